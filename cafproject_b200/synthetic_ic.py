@@ -1,0 +1,132 @@
+"""Synthetic LCDM-shaped initial conditions in CUBE's integer checkpoint format.
+
+The reference's ``ic.x`` (CUBE/utilities/initial_conditions.f90) cannot be run here (no Fortran, and its
+``seed_N.bin`` files replay gfortran's RNG), so *these* files are the "identical inputs" both the oracle
+and the GPU step consume.  Same conventions as initial_conditions.f90:509-580:
+
+* particles start on a simple-cubic lattice, ``np_nc`` per coarse cell per dim, at
+  ``q=(i-1)/np_nc + 0.5/ncell`` (:519), displaced by a Zel'dovich field;
+* ``xp = floor(frac(x)/x_resolution)`` truncated to int16 (:554);
+* ``vfield`` = per-coarse-cell mean velocity, ``vp = nint(N*atan(S*(v-vfield))/pi)`` (:556-557);
+* particles are packed tile-major, then k, j, i, in file order (Appendix B of SURVEY.md).
+
+Uses torch only as an array library (CPU for tests, CUDA for the large bench inputs).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+PI_F = float(np.float32(4) * np.arctan(np.float32(1)))
+
+
+def _bbks(k, gamma):
+    q = k / gamma
+    q = torch.clamp(q, min=1e-12)
+    t = torch.log(1 + 2.34 * q) / (2.34 * q) * (1 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+    return t
+
+
+def vfactor(a, omega_m=0.32, omega_l=0.68):
+    """initial_conditions.f90:754-763."""
+    lm = omega_l / omega_m
+    km = (1 - omega_m - omega_l) / omega_m
+    H = 2 / (3 * math.sqrt(a ** 3)) * math.sqrt(1 + a * km + a ** 3 * lm)
+    return a ** 2 * H
+
+
+def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_image=200.0, z_i=49.0,
+            n_s=0.9619, h=0.67, omega_m=0.32, device="cpu", velocity_boost=1.0):
+    """Return ``(states, sigma_vi, info)``; ``states[m]`` = dict(xp, vp, rhoc, vfield) numpy arrays in
+    file order for image ``m`` (image order x fastest, parameters.f90:200-203).
+
+    ``disp_rms``: rms Zel'dovich displacement per dimension in *fine* cells.
+    """
+    nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
+    ncell = 4
+    nt = nc // nnt
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    npd = [np_nc * nc * n for n in nn]            # particles per dim (x,y,z)
+    shape = (npd[2], npd[1], npd[0])
+    white = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
+    dk = torch.fft.rfftn(white)
+    del white
+    # wavenumbers in h/Mpc ; box length per dim = box_per_image*nn_d
+    def kvec(n, L, half=False):
+        f = torch.fft.rfftfreq(n, d=1.0 / n, device=dev) if half else torch.fft.fftfreq(n, d=1.0 / n, device=dev)
+        return (2 * math.pi / L) * f
+    kx = kvec(npd[0], box_per_image * nn[0], True)[None, None, :]
+    ky = kvec(npd[1], box_per_image * nn[1])[None, :, None]
+    kz = kvec(npd[2], box_per_image * nn[2])[:, None, None]
+    k2 = kx ** 2 + ky ** 2 + kz ** 2
+    k = torch.sqrt(k2)
+    pk = torch.where(k > 0, k ** n_s * _bbks(k, omega_m * h) ** 2, torch.zeros_like(k))
+    dk = dk * torch.sqrt(pk)
+    k2 = torch.where(k2 > 0, k2, torch.ones_like(k2))
+    psi = []
+    for kd in (kx, ky, kz):
+        psi.append(torch.fft.irfftn(dk * (1j * kd / k2), s=shape))
+    del dk
+    rms = torch.sqrt(sum((p.double() ** 2).mean() for p in psi) / 3).item()
+    scale = disp_rms / rms
+    a = 1.0 / (1.0 + z_i)
+    vf = vfactor(a, omega_m, 1 - omega_m) * velocity_boost
+    # positions in coarse cells (global), float64
+    ncg = [nc * n for n in nn]
+    idx = [torch.arange(npd[d], device=dev, dtype=torch.float64) for d in range(3)]
+    q = [idx[d] / np_nc + 0.5 / ncell for d in range(3)]
+    qb = (q[0][None, None, :], q[1][None, :, None], q[2][:, None, None])
+    cells, codes, vels = [], [], []
+    for d in range(3):
+        x = (qb[d] + psi[d].double() * (scale / ncell)).reshape(-1)
+        x = torch.remainder(x, float(ncg[d]))
+        c = torch.floor(x).clamp_(0, ncg[d] - 1)
+        u = torch.floor((x - c) * 65536.0).clamp_(0, 65535).to(torch.int64)
+        cells.append(c.to(torch.int64))
+        codes.append(u)
+        vels.append((psi[d].double() * (scale * vf)).reshape(-1))
+    del psi
+    # linear key: image (x fastest), tile (x fastest), k, j, i
+    img = [cells[d] // nc for d in range(3)]
+    loc = [cells[d] % nc for d in range(3)]
+    til = [loc[d] // nt for d in range(3)]
+    cel = [loc[d] % nt for d in range(3)]
+    m = img[0] + nn[0] * (img[1] + nn[1] * img[2])
+    t = til[0] + nnt * (til[1] + nnt * til[2])
+    cc = cel[0] + nt * (cel[1] + nt * cel[2])
+    ncell_img = nc ** 3
+    key = (m * (nnt ** 3) + t) * (nt ** 3) + cc
+    del img, loc, til, cel, m, t, cc, cells
+    nimg = nn[0] * nn[1] * nn[2]
+    order = torch.argsort(key, stable=True)
+    key_s = key[order]
+    counts = torch.bincount(key_s, minlength=nimg * ncell_img)
+    v_s = torch.stack([v[order] for v in vels], 1)          # (N,3) f64
+    u_s = torch.stack([c[order] for c in codes], 1)
+    del vels, codes, key
+    vsum = torch.zeros((nimg * ncell_img, 3), dtype=torch.float64, device=dev)
+    vsum.index_add_(0, key_s, v_s)
+    vfield = (vsum / counts.clamp(min=1)[:, None].double()).float()
+    res = v_s - vfield[key_s].double()
+    sigma_vi = np.float32(math.sqrt(float((res ** 2).sum(1).mean())) / math.sqrt(3.0))
+    S = float(np.float64(np.sqrt(np.float32(PI_F / 2), dtype=np.float32)) / (np.float64(sigma_vi) * 2.5))
+    vp = torch.round(65535.0 * torch.atan(S * res) / PI_F).clamp_(-32767, 32767).to(torch.int16)
+    xp = u_s.to(torch.int32)
+    xp = torch.where(xp >= 32768, xp - 65536, xp).to(torch.int16)
+    bounds = torch.cumsum(counts.view(nimg, -1).sum(1), 0).cpu().numpy()
+    starts = np.concatenate([[0], bounds[:-1]])
+    states = []
+    counts_c = counts.view(nimg, nnt, nnt, nnt, nt, nt, nt).to(torch.int32).cpu().numpy()
+    vfield_c = vfield.view(nimg, nnt, nnt, nnt, nt, nt, nt, 3).cpu().numpy()
+    xp_c = xp.cpu().numpy(); vp_c = vp.cpu().numpy()
+    for mi in range(nimg):
+        s, e = int(starts[mi]), int(bounds[mi])
+        states.append(dict(xp=np.ascontiguousarray(xp_c[s:e]), vp=np.ascontiguousarray(vp_c[s:e]),
+                           rhoc=np.ascontiguousarray(counts_c[mi]), vfield=np.ascontiguousarray(vfield_c[mi])))
+    info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, a=a, vf=vf, npglobal=int(xp_c.shape[0]), seed=seed,
+                disp_rms=disp_rms)
+    return states, sigma_vi, info
