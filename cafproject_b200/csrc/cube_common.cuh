@@ -1,0 +1,101 @@
+// cube_common.cuh -- geometry, code conversions and small device helpers shared by all kernels.
+//
+// Exact-arithmetic rules: every operation that feeds an integer code or a
+// cell index is written with the round-to-nearest intrinsics (__dadd_rn, __dmul_rn, __fmul_rn, ...)
+// so that nvcc can never contract a multiply-add into an FMA; the reference build (gfortran -O3,
+// x86-64 baseline) has no FMA.  f64 division, sqrt, ceil, floor and llround are IEEE-exact on the
+// device; f32 division uses __fdiv_rn.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cube {
+
+constexpr float PI_F = 3.14159274101257324f;  // parameters.f90:73  pi=4*atan(1.) (f32, 0x40490FDB)
+constexpr int NCB = 6;                        // parameters.f90:46
+constexpr int NCELL = 4;                      // parameters.f90:21
+constexpr int NFB = NCB * NCELL;              // parameters.f90:50
+
+struct Geom {
+  int nn[3];   // images per dim
+  int ic[3];   // this image's coordinates, 0-based (icx-1, icy-1, icz-1)
+  int nnt;     // tiles / image / dim
+  int nc;      // coarse cells / image / dim
+  int nt;      // coarse cells / tile / dim
+  int nte;     // nt + 2 ncb
+  int nft;     // 4 nt
+  int nfe;     // nft + 2 nfb
+  int ne;      // nc + 2 ncb : extended image grid (ghost layers alias the periodic image when nn_d == 1)
+  long long ncell_p;  // nc^3
+  long long ncell_e;  // ne^3
+};
+
+// ---- index helpers ---------------------------------------------------------------------------
+// file-order ("disjoint state") linear index of physical cell: tile-major, then k, j, i (0-based)
+__host__ __device__ inline long long phys_index(const Geom& g, int tx, int ty, int tz, int i, int j, int k) {
+  long long nt = g.nt;
+  return (((long long)(tz * g.nnt + ty) * g.nnt + tx) * nt * nt * nt) + ((long long)k * nt + j) * nt + i;
+}
+// inverse of phys_index
+__host__ __device__ inline void phys_decompose(const Geom& g, long long L, int& tx, int& ty, int& tz, int& i, int& j, int& k) {
+  long long nt = g.nt, nt3 = nt * nt * nt;
+  long long t = L / nt3, c = L - t * nt3;
+  tx = (int)(t % g.nnt); ty = (int)((t / g.nnt) % g.nnt); tz = (int)(t / ((long long)g.nnt * g.nnt));
+  i = (int)(c % nt); j = (int)((c / nt) % nt); k = (int)(c / (nt * nt));
+}
+// extended image grid index; x,y,z image-local 0-based in [-ncb, nc+ncb)
+__host__ __device__ inline long long ext_index(const Geom& g, int x, int y, int z) {
+  return ((long long)(z + NCB) * g.ne + (y + NCB)) * g.ne + (x + NCB);
+}
+
+// ---- codes -----------------------------------------------------------------------------------
+// int(xp+ishift,izipx)+rshift == u + 0.5 with u the raw 16-bit pattern (parameters.f90:14-15)
+__device__ __forceinline__ double xp_frac(short xp) {  // (u+0.5)*x_resolution, exact
+  return ((double)(unsigned short)xp + 0.5) * 0x1p-16;
+}
+// nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86)
+__device__ __forceinline__ short vp_encode(double v, double S) {
+  double t = __dmul_rn(65535.0, atan(__dmul_rn(S, v)));
+  return (short)llround(t / (double)PI_F);
+}
+// sqrt(pi/2)/(sigma_vi*vrel_boost): f32 sqrt promoted, f64 product (update_particle.f90:42)
+__host__ __device__ inline double vscale(float sigma) {
+  return (double)sqrtf(PI_F / 2) / ((double)sigma * 2.5);
+}
+
+// CIC split of an f32 coordinate (pm.f90:55-58): idx1=floor(x)+1, dx1=idx1-x, dx2=1-dx1
+__device__ __forceinline__ void cic_split(float tempx, int& idx1, float& dx1, float& dx2) {
+  idx1 = (int)floorf(tempx) + 1;
+  dx1 = __fsub_rn((float)idx1, tempx);
+  dx2 = __fsub_rn(1.0f, dx1);
+}
+
+// one CIC term of the kick: F*a_mid*dt/6/pi*wx*wy*wz, all f32, left to right (pm.f90:104)
+__device__ __forceinline__ float kick_term(float F, float a_mid, float dt, float wx, float wy, float wz) {
+  float t = __fmul_rn(F, a_mid);
+  t = __fmul_rn(t, dt);
+  t = __fdiv_rn(t, 6.0f);
+  t = __fdiv_rn(t, PI_F);
+  t = __fmul_rn(t, wx);
+  t = __fmul_rn(t, wy);
+  return __fmul_rn(t, wz);
+}
+
+// three 16-bit codes of one particle (AoS, 6-byte stride: only 2-byte alignment is guaranteed)
+struct Code3 { short x, y, z; };
+__device__ __forceinline__ Code3 load_code3(const short* __restrict__ a, long long p) {
+  const short* q = a + 3 * p;
+  Code3 c; c.x = __ldg(q); c.y = __ldg(q + 1); c.z = __ldg(q + 2);
+  return c;
+}
+__device__ __forceinline__ void store_code3(short* a, long long p, short x, short y, short z) {
+  short* q = a + 3 * p; q[0] = x; q[1] = y; q[2] = z;
+}
+
+// drift key: destination-minus-source cell offset per dim (5 bits each, biased by 16) + near-tie flag
+constexpr unsigned KEY_FLAG = 0x8000u;
+__host__ __device__ inline unsigned key_pack(int dx, int dy, int dz) {
+  return (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
+}
+
+}  // namespace cube

@@ -1,0 +1,651 @@
+// cube_gpu.cu -- host side of libcubegpu.so: the C ABI of include/cube_gpu.h.
+//
+// State lives in HBM between calls:
+//   disjoint state  : xp, vp (file order), rhoc_p, vfield_p, cstart_p           (what update_x leaves)
+//   buffered state  : + rhoc_e, cstart_e, vfield_e on the extended image grid   (what buffer builds)
+// See DESIGN.md for the layout and the per-kernel roofline.
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cube_gpu.h"
+#include "cube_kernels.cuh"
+
+using namespace cube;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define CF(call)                                                                                     \
+  do {                                                                                               \
+    cufftResult r_ = (call);                                                                         \
+    if (r_ != CUFFT_SUCCESS) return fail("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)r_, #call); \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+
+enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFFT, PH_FGREEN, PH_FIFFT, PH_FMAX, PH_FKICK,
+             PH_CDEP, PH_CFFT, PH_CKICK, PH_N };
+static const char* kPhaseNames[PH_N] = {"drift_key", "drift_count", "drift_scan", "drift_place", "buffer", "fine_deposit",
+                                        "fine_fft_fwd", "fine_green", "fine_fft_inv", "fine_f2max", "fine_kick",
+                                        "coarse_deposit", "coarse_fft_green", "coarse_kick"};
+
+struct cube_handle {
+  cube_params p;
+  Geom g;
+  cudaStream_t st = nullptr;
+  long long np_image_max = 0, np_tile_max = 0;
+  long long nplocal = 0, npglobal = 0;
+  float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
+  bool buffered = false;
+  // particles (double buffered)
+  short *xp = nullptr, *vp = nullptr, *xp2 = nullptr, *vp2 = nullptr;
+  unsigned short* key = nullptr;
+  // coarse-cell arrays, file order
+  int *rhoc_p = nullptr, *rhoc_p2 = nullptr;
+  float *vfield_p = nullptr, *vfield_p2 = nullptr;
+  long long *cstart_p = nullptr, *cstart_p2 = nullptr;
+  // extended image grid
+  int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
+  // scan scratch, reductions
+  long long* bsum = nullptr; int nscan_blocks = 0;
+  double* stat_partial = nullptr; double* stat3 = nullptr;
+  long long* tile_count = nullptr;
+  int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
+  // LUTs
+  float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f;
+  // fine mesh
+  int batch = 1; long long fvol = 0, fnk = 0;
+  float* rho = nullptr;      // [batch][nfe][nfe][nfe+2]  (in-place r2c)
+  float* force = nullptr;    // [3][batch][nfe][nfe][nfe+2]
+  float* kern_f = nullptr;   // [3][nk]
+  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_r2c1 = 0, plan_c2r1 = 0;
+  // coarse mesh
+  long long cvol = 0, cnk = 0;
+  float* r3 = nullptr; float* cforce = nullptr; float* kern_c = nullptr; float* fc = nullptr;
+  cufftHandle cplan_r2c = 0, cplan_c2r = 0;
+  // host pinned scalars
+  // profiling
+  bool prof = false; cudaEvent_t ev[2 * PH_N] = {}; float phase_ms[PH_N] = {}; long long launches = 0;
+  float last_f2max_fine = 0;
+};
+
+struct PhaseTimer {  // CUBEnu-style phase bracket (pm.f90:35,195,...) with CUDA events on the launch stream
+  cube_handle* h; int ph;
+  PhaseTimer(cube_handle* h_, int ph_) : h(h_), ph(ph_) { if (h->prof) cudaEventRecord(h->ev[2 * ph], h->st); }
+  ~PhaseTimer() {
+    if (h->prof) {
+      cudaEventRecord(h->ev[2 * ph + 1], h->st);
+      cudaEventSynchronize(h->ev[2 * ph + 1]);
+      float ms = 0; cudaEventElapsedTime(&ms, h->ev[2 * ph], h->ev[2 * ph + 1]);
+      h->phase_ms[ph] += ms;
+    }
+  }
+};
+
+template <class T> static cudaError_t dmalloc(T** p, long long n) { return cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T)); }
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// exclusive scan int32 -> int64, total returned in h->bsum[nb] (device)
+static int scan_counts(cube_handle* h, const int* in, long long n, long long* out) {
+  int nb = (int)((n + SCAN_B - 1) / SCAN_B);
+  k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum); CKL();
+  k_scan_bsums<<<1, 1024, 0, h->st>>>(h->bsum, nb); CKL();
+  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out); CKL();
+  h->launches += 3;
+  return 0;
+}
+
+static int build_dvlut(cube_handle* h, float sigma) {
+  if (h->lut_sigma == sigma) return 0;
+  k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, vscale(sigma), h->dvlut); CKL();
+  h->launches++;
+  h->lut_sigma = sigma;
+  return 0;
+}
+
+extern "C" const char* cube_gpu_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+static int build_kernels(cube_handle* h, const float* fk_table, const float* ck_table) {
+  const Geom& g = h->g;
+  float *d_fk = nullptr, *d_ck = nullptr;
+  CK(dmalloc(&d_fk, 16 * 16 * 16 * 3)); CK(dmalloc(&d_ck, 3 * 64));
+  CK(cudaMemcpyAsync(d_fk, fk_table, sizeof(float) * 16 * 16 * 16 * 3, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(d_ck, ck_table, sizeof(float) * 3 * 64, cudaMemcpyHostToDevice, h->st));
+  // kernel_f.f90:32-41
+  for (int d = 0; d < 3; d++) {
+    k_kernf_fill<<<nblk(h->fvol, 256), 256, 0, h->st>>>(g.nfe, d_fk, d, h->rho); CKL();
+    CF(cufftExecR2C(h->plan_r2c1, h->rho, (cufftComplex*)h->rho));
+    k_take_imag<<<nblk(h->fnk, 256), 256, 0, h->st>>>(h->fnk, (const float2*)h->rho, h->kern_f + d * h->fnk); CKL();
+  }
+  // kernel_c.f90:16-117 (single image: the coarse lattice is this image's nc^3)
+  float* pure = h->cforce;  // scratch [cvol]
+  for (int d = 0; d < 3; d++) {
+    k_kernc_fill<<<nblk(h->cvol, 256), 256, 0, h->st>>>(g.nc, d_ck, d, 1, h->r3); CKL();
+    CF(cufftExecR2C(h->cplan_r2c, h->r3, (cufftComplex*)h->r3));
+    k_take_imag<<<nblk(h->cnk, 256), 256, 0, h->st>>>(h->cnk, (const float2*)h->r3, h->kern_c + d * h->cnk); CKL();
+    k_kernc_fill<<<nblk(h->cvol, 256), 256, 0, h->st>>>(g.nc, d_ck, d, 0, pure); CKL();
+    CF(cufftExecR2C(h->cplan_r2c, pure, (cufftComplex*)pure));
+    k_kernc_lrck<<<nblk(h->cnk, 256), 256, 0, h->st>>>(g.nc, d, (const float2*)pure, h->kern_c + d * h->cnk); CKL();
+  }
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(d_fk); cudaFree(d_ck);
+  return 0;
+}
+
+extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const float* ck_table, const float* tanf_lut,
+                             const void* nccl_unique_id, cube_handle** out) {
+  if (!p || !fk_table || !ck_table || !tanf_lut || !out) return fail("cube_gpu_init: null argument");
+  if (p->izipx != 2 || p->izipv != 2) return fail("zip format incompatable: only izipx=izipv=2 is built (got %d,%d)", p->izipx, p->izipv);
+  if (p->ncell != NCELL || p->ncb != NCB) return fail("cube_gpu_init: ncell must be 4 and ncb 6");
+  if (p->nn[0] * p->nn[1] * p->nn[2] != 1 || nccl_unique_id)
+    return fail("cube_gpu_init: multi-image runs (nn>1) are not available in this build");
+  if (p->nnt < 1 || p->nc % p->nnt) return fail("cube_gpu_init: nc must be a multiple of nnt");
+  if (p->nc / p->nnt < 12 || p->nc < 24) return fail("cube_gpu_init: need nc>=24 and nt>=12 (parameters.f90:23-24)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("cube_gpu_init: no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(p->device));
+  cube_handle* h = new cube_handle();
+  h->p = *p;
+  Geom& g = h->g;
+  for (int d = 0; d < 3; d++) { g.nn[d] = p->nn[d]; }
+  g.ic[0] = p->rank % p->nn[0]; g.ic[1] = (p->rank / p->nn[0]) % p->nn[1]; g.ic[2] = p->rank / (p->nn[0] * p->nn[1]);
+  g.nnt = p->nnt; g.nc = p->nc; g.nt = p->nc / p->nnt;
+  g.nte = g.nt + 2 * NCB; g.nft = g.nt * NCELL; g.nfe = g.nft + 2 * NFB; g.ne = g.nc + 2 * NCB;
+  g.ncell_p = (long long)g.nc * g.nc * g.nc; g.ncell_e = (long long)g.ne * g.ne * g.ne;
+  // variables.f90:7-9 (real(4) arithmetic)
+  long long np_image = (long long)g.nc * p->np_nc; np_image = np_image * np_image * np_image;
+  float r = ((float)g.nte * 1.f) / (float)g.nt, r3 = r * r * r;
+  h->np_image_max = (long long)((float)np_image * r3 * p->image_buffer);
+  h->np_tile_max = (long long)((float)(np_image / ((long long)g.nnt * g.nnt * g.nnt)) * r3 * p->tile_buffer);
+  CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
+  const long long cap = h->np_image_max;
+  CK(dmalloc(&h->xp, 3 * cap)); CK(dmalloc(&h->vp, 3 * cap)); CK(dmalloc(&h->xp2, 3 * cap)); CK(dmalloc(&h->vp2, 3 * cap));
+  CK(dmalloc(&h->key, cap));
+  CK(dmalloc(&h->rhoc_p, g.ncell_p)); CK(dmalloc(&h->rhoc_p2, g.ncell_p));
+  CK(dmalloc(&h->vfield_p, 3 * g.ncell_p)); CK(dmalloc(&h->vfield_p2, 3 * g.ncell_p));
+  CK(dmalloc(&h->cstart_p, g.ncell_p)); CK(dmalloc(&h->cstart_p2, g.ncell_p));
+  CK(dmalloc(&h->rhoc_e, g.ncell_e)); CK(dmalloc(&h->cstart_e, g.ncell_e)); CK(dmalloc(&h->vfield_e, 3 * g.ncell_e));
+  h->nscan_blocks = (int)((g.ncell_p + SCAN_B - 1) / SCAN_B);
+  CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
+  CK(dmalloc(&h->stat_partial, 3 * (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 3));
+  CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
+  CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
+  CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536));
+  CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+  // fine mesh buffers: rho + 3 force arrays per tile in flight
+  const int ntile = g.nnt * g.nnt * g.nnt;
+  h->fvol = (long long)g.nfe * g.nfe * (g.nfe + 2);
+  h->fnk = (long long)g.nfe * g.nfe * (g.nfe / 2 + 1);
+  int batch = p->fine_batch;
+  if (batch <= 0) {
+    size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
+    // 4 arrays per tile plus cuFFT work area (~2 arrays per tile); stay below ~40% of free memory
+    long long per = h->fvol * 4 * 6;
+    batch = (int)std::max<long long>(1, std::min<long long>(8, (long long)(fr * 0.4) / per));
+  }
+  batch = std::min(batch, ntile);
+  h->batch = batch;
+  CK(dmalloc(&h->f2max, batch + 1));
+  CK(dmalloc(&h->rho, h->fvol * batch)); CK(dmalloc(&h->force, 3 * h->fvol * batch));
+  CK(dmalloc(&h->kern_f, 3 * h->fnk));
+  {
+    int n[3] = {g.nfe, g.nfe, g.nfe};
+    int rembed[3] = {g.nfe, g.nfe, g.nfe + 2}, cembed[3] = {g.nfe, g.nfe, g.nfe / 2 + 1};
+    CF(cufftPlanMany(&h->plan_r2c, 3, n, rembed, 1, (int)h->fvol, cembed, 1, (int)h->fnk, CUFFT_R2C, batch));
+    CF(cufftPlanMany(&h->plan_c2r, 3, n, cembed, 1, (int)h->fnk, rembed, 1, (int)h->fvol, CUFFT_C2R, 3 * batch));
+    CF(cufftPlanMany(&h->plan_r2c1, 3, n, rembed, 1, (int)h->fvol, cembed, 1, (int)h->fnk, CUFFT_R2C, 1));
+    CF(cufftPlanMany(&h->plan_c2r1, 3, n, cembed, 1, (int)h->fnk, rembed, 1, (int)h->fvol, CUFFT_C2R, 3));
+    CF(cufftSetStream(h->plan_r2c, h->st)); CF(cufftSetStream(h->plan_c2r, h->st));
+    CF(cufftSetStream(h->plan_r2c1, h->st)); CF(cufftSetStream(h->plan_c2r1, h->st));
+  }
+  // coarse mesh
+  h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
+  h->cnk = (long long)g.nc * g.nc * (g.nc / 2 + 1);
+  CK(dmalloc(&h->r3, h->cvol)); CK(dmalloc(&h->cforce, 3 * h->cvol)); CK(dmalloc(&h->kern_c, 3 * h->cnk));
+  CK(dmalloc(&h->fc, 3LL * (g.nc + 2) * (g.nc + 2) * (g.nc + 2)));
+  {
+    int n[3] = {g.nc, g.nc, g.nc};
+    int rembed[3] = {g.nc, g.nc, g.nc + 2}, cembed[3] = {g.nc, g.nc, g.nc / 2 + 1};
+    CF(cufftPlanMany(&h->cplan_r2c, 3, n, rembed, 1, (int)h->cvol, cembed, 1, (int)h->cnk, CUFFT_R2C, 1));
+    CF(cufftPlanMany(&h->cplan_c2r, 3, n, cembed, 1, (int)h->cnk, rembed, 1, (int)h->cvol, CUFFT_C2R, 3));
+    CF(cufftSetStream(h->cplan_r2c, h->st)); CF(cufftSetStream(h->cplan_c2r, h->st));
+  }
+  if (build_kernels(h, fk_table, ck_table)) { return 1; }
+  *out = h;
+  return 0;
+}
+
+extern "C" int cube_gpu_finalize(cube_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->p.device);
+  cudaStreamSynchronize(h->st);
+  void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->tile_count, h->maxoff, h->f2max,
+                  h->vmax_bits, h->tanlut, h->dvlut, h->rho, h->force, h->kern_f, h->r3, h->cforce, h->kern_c, h->fc};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  cufftHandle plans[] = {h->plan_r2c, h->plan_c2r, h->plan_r2c1, h->plan_c2r1, h->cplan_r2c, h->cplan_c2r};
+  for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
+  for (int i = 0; i < 2 * PH_N; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t* vp, const int32_t* rhoc_phys,
+                               const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  const Geom& g = h->g;
+  if (nplocal > h->np_image_max)
+    return fail("error: too many particles in this image+buffer: %lld > %lld; please set image_buffer larger", (long long)nplocal, h->np_image_max);
+  CK(cudaMemcpyAsync(h->xp, xp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->vp, vp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->rhoc_p, rhoc_phys, sizeof(int) * g.ncell_p, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->vfield_p, vfield_phys, sizeof(float) * 3 * g.ncell_p, cudaMemcpyHostToDevice, h->st));
+  if (scan_counts(h, h->rhoc_p, g.ncell_p, h->cstart_p)) return 1;
+  long long tot = 0;
+  CK(cudaMemcpyAsync(&tot, h->bsum + h->nscan_blocks, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (tot != nplocal) return fail("cube_gpu_upload: sum(rhoc)=%lld differs from nplocal=%lld", tot, (long long)nplocal);
+  h->nplocal = nplocal; h->npglobal = npglobal;
+  h->sigma_vi = h->sigma_vi_new = sigma_vi;
+  // mass_p=real((nf*nn)**3)/npglobal  (particle_initialization.f90:72)
+  long long nf = (long long)g.nc * NCELL;
+  h->mass_p = (float)((nf * g.nn[0]) * (nf * g.nn[1]) * (nf * g.nn[2])) / (float)npglobal;
+  h->buffered = false;
+  return 0;
+}
+
+extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32_t* rhoc_phys, float* vfield_phys,
+                                 int64_t* nplocal, float* sigma_vi) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  const Geom& g = h->g;
+  if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
+  if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
+  if (rhoc_phys) CK(cudaMemcpyAsync(rhoc_phys, h->rhoc_p, sizeof(int) * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
+  if (vfield_phys) CK(cudaMemcpyAsync(vfield_phys, h->vfield_p, sizeof(float) * 3 * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (nplocal) *nplocal = h->nplocal;
+  if (sigma_vi) *sigma_vi = h->sigma_vi;
+  return 0;
+}
+
+extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_v, float* overhead_image) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  const Geom& g = h->g;
+  (void)do_x; (void)do_v;  // single image: ghost particles alias the periodic image, nothing to copy
+  if (do_density) {
+    PhaseTimer pt(h, PH_BUFFER);
+    k_build_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g, h->rhoc_p, h->cstart_p, h->vfield_p, h->rhoc_e, h->cstart_e, h->vfield_e); CKL();
+    k_tile_counts<<<g.nnt * g.nnt * g.nnt, 256, 0, h->st>>>(g, h->rhoc_e, h->tile_count); CKL();
+    h->launches += 2;
+    h->buffered = true;
+  }
+  if (overhead_image) {
+    // overhead_image=sum(rhoc)/np_image_max over the buffered rhoc of all tiles (buffer_density.f90:75)
+    const int ntile = g.nnt * g.nnt * g.nnt;
+    std::vector<long long> tc(ntile);
+    CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    long long s = 0; for (long long v : tc) s += v;
+    *overhead_image = (float)((double)s / (double)h->np_image_max);
+    if ((double)*overhead_image > 1.0)
+      return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", s, h->np_image_max, h->p.rank + 1);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t* nplocal, float* sigma_vi_new,
+                                 double std_vsim[3], float* overhead_tile) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("cube_gpu_update_x: state is not buffered (call cube_gpu_buffer first, cafcube.f90:17-19)");
+  const Geom& g = h->g;
+  const float dt_mid_f = (dt_old + dt) / 2;  // update_particle.f90:16
+  const double dt_mid = (double)dt_mid_f, S = vscale(h->sigma_vi);
+  if (build_dvlut(h, h->sigma_vi)) return 1;
+  // tile overflow check (update_particle.f90:60-67): particles in each tile's extended region
+  const int ntile = g.nnt * g.nnt * g.nnt;
+  std::vector<long long> tc(ntile);
+  CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemsetAsync(h->maxoff, 0, sizeof(int), h->st));
+  int maxoff = 0;
+  {
+    PhaseTimer pt(h, PH_KEY);
+    k_drift_key<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->maxoff); CKL();
+    h->launches++;
+    CK(cudaMemcpyAsync(&maxoff, h->maxoff, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  float ovh = 0;
+  for (int t = 0; t < ntile; t++) {
+    ovh = std::max(ovh, (float)tc[t] / (float)h->np_tile_max);
+    if (tc[t] > h->np_tile_max)
+      return fail("error: too many particles in this tile+buffer: %lld > %lld on image %d tile %d %d %d; please set tile_buffer larger",
+                  tc[t], h->np_tile_max, h->p.rank + 1, t % g.nnt + 1, (t / g.nnt) % g.nnt + 1, t / (g.nnt * g.nnt) + 1);
+  }
+  if (maxoff > NCB) return fail("cube_gpu_update_x: a particle moves %d coarse cells in one step (> ncb=%d): outside the tile buffer", maxoff, NCB);
+  const int r = maxoff;
+  const unsigned nb = nblk(g.ncell_p, 128);
+  {
+    PhaseTimer pt(h, PH_COUNT);
+    k_drift_gather<false><<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, S,
+                                                h->rhoc_p2, h->vfield_p2, nullptr, nullptr, nullptr, nullptr); CKL();
+    h->launches++;
+  }
+  {
+    PhaseTimer pt(h, PH_SCAN);
+    if (scan_counts(h, h->rhoc_p2, g.ncell_p, h->cstart_p2)) return 1;
+  }
+  long long tot = 0;
+  CK(cudaMemcpyAsync(&tot, h->bsum + h->nscan_blocks, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (tot > h->np_image_max)
+    return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", tot, h->np_image_max, h->p.rank + 1);
+  {
+    PhaseTimer pt(h, PH_PLACE);
+    k_drift_gather<true><<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, S,
+                                               h->rhoc_p2, h->vfield_p2, h->cstart_p2, h->xp2, h->vp2, h->stat_partial); CKL();
+    k_reduce3<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, h->stat3); CKL();
+    h->launches += 2;
+  }
+  double st[3];
+  CK(cudaMemcpyAsync(st, h->stat3, sizeof st, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  std::swap(h->xp, h->xp2); std::swap(h->vp, h->vp2);
+  std::swap(h->rhoc_p, h->rhoc_p2); std::swap(h->vfield_p, h->vfield_p2); std::swap(h->cstart_p, h->cstart_p2);
+  h->nplocal = tot;
+  h->buffered = false;
+  // update_particle.f90:170-175 (single image: no co_sum)
+  const double nglob = (double)h->npglobal;
+  const double sv = std::sqrt(st[0] / nglob);
+  const double svc = std::sqrt(st[1] / (double)g.nc / (double)g.nc / (double)g.nc / (double)g.nn[0] / (double)g.nn[1] / (double)g.nn[2]);
+  const double svr = std::sqrt(st[2] / nglob);
+  h->sigma_vi_new = (float)(svr / (double)sqrtf(3.f));
+  if (nplocal) *nplocal = tot;
+  if (sigma_vi_new) *sigma_vi_new = h->sigma_vi_new;
+  if (std_vsim) { std_vsim[0] = sv; std_vsim[1] = svc; std_vsim[2] = svr; }
+  if (overhead_tile) *overhead_tile = ovh;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fine mesh of tiles [tile0, tile0+nb): deposit -> r2c -> green -> 3 c2r  (pm.f90:44-84)
+static int fine_mesh(cube_handle* h, int tile0, int nb, bool through_force) {
+  const Geom& g = h->g;
+  {
+    PhaseTimer pt(h, PH_FDEP);
+    const int nbx = (g.nte + DB_X - 1) / DB_X, nby = (g.nte + DB_Y - 1) / DB_Y, nbz = (g.nte + DB_Z - 1) / DB_Z;
+    dim3 grid(nbx * nby * nbz, nb);
+    k_fine_deposit<<<grid, DB_T, 0, h->st>>>(g, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->rho); CKL();
+    h->launches++;
+  }
+  if (!through_force) return 0;
+  const bool full = (nb == h->batch);
+  {
+    PhaseTimer pt(h, PH_FFFT);
+    if (full) CF(cufftExecR2C(h->plan_r2c, h->rho, (cufftComplex*)h->rho));
+    else for (int b = 0; b < nb; b++) CF(cufftExecR2C(h->plan_r2c1, h->rho + b * h->fvol, (cufftComplex*)(h->rho + b * h->fvol)));
+  }
+  {
+    PhaseTimer pt(h, PH_FGREEN);
+    const float scale = 1.0f / ((float)g.nfe * (float)g.nfe * (float)g.nfe);
+    k_green<<<nblk(h->fnk, 256), 256, 0, h->st>>>(h->fnk, nb, (const float2*)h->rho, h->kern_f, scale, (float2*)h->force); CKL();
+    h->launches++;
+  }
+  {
+    PhaseTimer pt(h, PH_FIFFT);
+    if (full) CF(cufftExecC2R(h->plan_c2r, (cufftComplex*)h->force, h->force));
+    else if (nb == 1) CF(cufftExecC2R(h->plan_c2r1, (cufftComplex*)h->force, h->force));
+    else {
+      // force is [3][nb][vol]: transform each (d,b) slab with the 3-batch plan is not contiguous -> one by one
+      for (int q = 0; q < 3 * nb; q += 3) CF(cufftExecC2R(h->plan_c2r1, (cufftComplex*)(h->force + q * h->fvol), h->force + q * h->fvol));
+    }
+  }
+  return 0;
+}
+
+static int fine_f2max(cube_handle* h, int nb, float* out /*host, nb*/) {
+  const Geom& g = h->g;
+  PhaseTimer pt(h, PH_FMAX);
+  CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
+  dim3 grid(592, nb);
+  k_f2max_fine<<<grid, 256, 0, h->st>>>(g, nb, h->force, h->f2max); CKL();
+  h->launches++;
+  CK(cudaMemcpyAsync(out, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
+  return 0;
+}
+
+static int coarse_mesh(cube_handle* h, bool through_force) {
+  const Geom& g = h->g;
+  {
+    PhaseTimer pt(h, PH_CDEP);
+    k_coarse_deposit<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3); CKL();
+    h->launches++;
+  }
+  if (!through_force) return 0;
+  PhaseTimer pt(h, PH_CFFT);
+  CF(cufftExecR2C(h->cplan_r2c, h->r3, (cufftComplex*)h->r3));
+  // rxyz = i*kern_c*crho_c ; r3=r3/ng_global^3 (pm.f90:172-175, pencil_fft.f90:58)
+  const float scale = 1.0f / ((float)g.nc * g.nn[0]) / ((float)g.nc * g.nn[1]) / ((float)g.nc * g.nn[2]);
+  k_green<<<nblk(h->cnk, 256), 256, 0, h->st>>>(h->cnk, 1, (const float2*)h->r3, h->kern_c, scale, (float2*)h->cforce); CKL();
+  CF(cufftExecC2R(h->cplan_c2r, (cufftComplex*)h->cforce, h->cforce));
+  const long long m = g.nc + 2;
+  k_force_c_assemble<<<nblk(m * m * m, 256), 256, 0, h->st>>>(g, h->cforce, h->fc); CKL();
+  h->launches += 2;
+  return 0;
+}
+
+extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, float* dt_fine, float* dt_coarse,
+                                      float* dt_vmax, float* vmax_out) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("cube_gpu_particle_mesh: state is not buffered (call cube_gpu_buffer first)");
+  const Geom& g = h->g;
+  const int ntile = g.nnt * g.nnt * g.nnt;
+  const long long nt3 = (long long)g.nt * g.nt * g.nt;
+  if (build_dvlut(h, h->sigma_vi)) return 1;
+  const double S_new = vscale(h->sigma_vi_new);
+  std::vector<float> f2(ntile, 0.f);
+  for (int t0 = 0; t0 < ntile; t0 += h->batch) {
+    const int nb = std::min(h->batch, ntile - t0);
+    if (fine_mesh(h, t0, nb, true)) return 1;
+    if (fine_f2max(h, nb, f2.data() + t0)) return 1;
+    PhaseTimer pt(h, PH_FKICK);
+    dim3 grid(nblk(nt3, 128), nb);
+    k_fine_kick<<<grid, 128, 0, h->st>>>(g, t0, nb, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->force, h->dvlut, S_new, a_mid, dt); CKL();
+    h->launches++;
+  }
+  h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
+  if (build_dvlut(h, h->sigma_vi)) return 1;
+  if (coarse_mesh(h, true)) return 1;
+  const long long m = g.nc + 2;
+  float f2c = 0; unsigned long long vb = 0;
+  {
+    PhaseTimer pt(h, PH_CKICK);
+    CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
+    CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
+    k_f2max_aos<<<592, 256, 0, h->st>>>(m * m * m, h->fc, h->f2max + h->batch); CKL();
+    k_coarse_kick<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->fc, h->dvlut,
+                                                         vscale(h->sigma_vi), a_mid, dt, h->vmax_bits); CKL();
+    h->launches += 2;
+    CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  double vmd; memcpy(&vmd, &vb, sizeof vmd);
+  const float vmax = (float)vmd;  // f32 <- max(f32, f64) is monotone, so one final rounding is the same
+  float f2f = 0; for (float v : f2) f2f = std::max(f2f, v);
+  h->last_f2max_fine = f2f;
+  // pm.f90:233-236, all f32
+  const float GG = 1.0f / 6.0f / PI_F;
+  if (dt_fine) *dt_fine = sqrtf(1.0f / (sqrtf(f2f) * a_mid * GG));
+  if (dt_coarse) *dt_coarse = sqrtf((float)NCELL / (sqrtf(f2c) * a_mid * GG));
+  if (dt_vmax) *dt_vmax = 0.9f * 20 / vmax;
+  if (vmax_out) *vmax_out = vmax;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
+  if (!h || !what) return -1;
+  std::string w(what);
+  if (w == "np_image_max") return h->np_image_max;
+  if (w == "np_tile_max") return h->np_tile_max;
+  if (w == "nfe") return h->g.nfe;
+  if (w == "nft") return h->g.nft;
+  if (w == "nt") return h->g.nt;
+  if (w == "fine_batch") return h->batch;
+  if (w == "kernel_launches") return h->launches;
+  if (w == "nplocal") return h->nplocal;
+  return -1;
+}
+extern "C" int cube_gpu_get_kern_f(cube_handle* h, float* out) {
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaMemcpy(out, h->kern_f, sizeof(float) * 3 * h->fnk, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int cube_gpu_get_kern_c(cube_handle* h, float* out) {
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaMemcpy(out, h->kern_c, sizeof(float) * 3 * h->cnk, cudaMemcpyDeviceToHost));
+  return 0;
+}
+static int tile_index(cube_handle* h, int itx, int ity, int itz, int* t) {
+  const int n = h->g.nnt;
+  if (itx < 1 || ity < 1 || itz < 1 || itx > n || ity > n || itz > n) return fail("tile index out of range");
+  *t = ((itz - 1) * n + (ity - 1)) * n + (itx - 1);
+  return 0;
+}
+extern "C" int cube_gpu_fine_density(cube_handle* h, int itx, int ity, int itz, float* rho_f) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
+  if (fine_mesh(h, t, 1, false)) return 1;
+  CK(cudaMemcpyAsync(rho_f, h->rho, sizeof(float) * h->fvol, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+// crop the three padded inverse transforms of batch slot 0 into force_f(3,nft+2,nft+2,nft+2)
+__global__ void k_crop_force(Geom g, int nbatch, const float* __restrict__ F, float* __restrict__ out) {
+  const int m = g.nft + 2;
+  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
+  long long o = ((long long)z * g.nfe + y) * ld + x;
+  for (int d = 0; d < 3; d++) out[3 * q + d] = F[(long long)d * nbatch * vol + o];
+}
+__global__ void k_uncrop_force(Geom g, int nbatch, const float* __restrict__ in, float* __restrict__ F) {
+  const int m = g.nft + 2;
+  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
+  long long o = ((long long)z * g.nfe + y) * ld + x;
+  for (int d = 0; d < 3; d++) F[(long long)d * nbatch * vol + o] = in[3 * q + d];
+}
+extern "C" int cube_gpu_fine_force(cube_handle* h, int itx, int ity, int itz, float* force_f) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
+  if (fine_mesh(h, t, 1, true)) return 1;
+  const long long m = h->g.nft + 2, n = m * m * m;
+  float* tmp = h->rho;  // rho is free after the forward transform has been consumed
+  if (3 * n > h->fvol * h->batch) return fail("scratch too small");
+  k_crop_force<<<nblk(n, 256), 256, 0, h->st>>>(h->g, 1, h->force, tmp); CKL();
+  CK(cudaMemcpyAsync(force_f, tmp, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz, const float* force_f, float a_mid, float dt,
+                                       float sigma_vi, float sigma_vi_new, float* f2_max) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
+  const Geom& g = h->g;
+  const long long m = g.nft + 2, n = m * m * m, nt3 = (long long)g.nt * g.nt * g.nt;
+  float* tmp = h->rho;
+  if (3 * n > h->fvol * h->batch) return fail("scratch too small");
+  CK(cudaMemcpyAsync(tmp, force_f, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->force, 0, sizeof(float) * 3 * h->fvol, h->st));
+  k_uncrop_force<<<nblk(n, 256), 256, 0, h->st>>>(g, 1, tmp, h->force); CKL();
+  if (build_dvlut(h, sigma_vi)) return 1;
+  float f2 = 0;
+  if (fine_f2max(h, 1, &f2)) return 1;
+  dim3 grid(nblk(nt3, 128), 1);
+  k_fine_kick<<<grid, 128, 0, h->st>>>(g, t, 1, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->force, h->dvlut, vscale(sigma_vi_new), a_mid, dt); CKL();
+  CK(cudaStreamSynchronize(h->st));
+  if (f2_max) *f2_max = f2;
+  return 0;
+}
+extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  const Geom& g = h->g;
+  if (coarse_mesh(h, false)) return 1;
+  CK(cudaMemcpy2DAsync(r3, sizeof(float) * g.nc, h->r3, sizeof(float) * (g.nc + 2), sizeof(float) * g.nc, (size_t)g.nc * g.nc,
+                       cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+extern "C" int cube_gpu_coarse_force(cube_handle* h, float* force_c) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  if (coarse_mesh(h, true)) return 1;
+  const long long m = h->g.nc + 2;
+  CK(cudaMemcpyAsync(force_c, h->fc, sizeof(float) * 3 * m * m * m, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, float a_mid, float dt, float sigma_vi, float* vmax,
+                                         float* f2_max) {
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("state is not buffered");
+  const Geom& g = h->g;
+  const long long m = g.nc + 2;
+  CK(cudaMemcpyAsync(h->fc, force_c, sizeof(float) * 3 * m * m * m, cudaMemcpyHostToDevice, h->st));
+  if (build_dvlut(h, sigma_vi)) return 1;
+  CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
+  k_f2max_aos<<<592, 256, 0, h->st>>>(m * m * m, h->fc, h->f2max + h->batch); CKL();
+  k_coarse_kick<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->fc, h->dvlut,
+                                                       vscale(sigma_vi), a_mid, dt, h->vmax_bits); CKL();
+  float f2c = 0; unsigned long long vb = 0;
+  CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  double vmd; memcpy(&vmd, &vb, sizeof vmd);
+  if (vmax) *vmax = (float)vmd;
+  if (f2_max) *f2_max = f2c;
+  return 0;
+}
+extern "C" int cube_gpu_phase_count(void) { return PH_N; }
+extern "C" const char* cube_gpu_phase_name(int i) { return (i >= 0 && i < PH_N) ? kPhaseNames[i] : ""; }
+extern "C" int cube_gpu_phase_times(cube_handle* h, float* ms) {
+  for (int i = 0; i < PH_N; i++) { ms[i] = h->phase_ms[i]; h->phase_ms[i] = 0; }
+  return 0;
+}
+extern "C" int cube_gpu_set_profiling(cube_handle* h, int on) { h->prof = on != 0; return 0; }

@@ -1,0 +1,622 @@
+// cube_kernels.cuh -- sm_100a kernels of the CUBE particle-mesh step.
+//
+// All particle kernels exploit CUBE's cell-ordered storage: a coarse cell's particles are the
+// contiguous run [cstart, cstart+rhoc) of the AoS int16 arrays.  Every mesh value is produced by
+// exactly one thread that pulls ("gathers") its contributions in the reference's traversal order
+// (tile-local k, j, i, then storage order inside a cell), so there are no float atomics and the
+// results do not depend on scheduling; for the densities they are bit-identical to the reference's
+// sequential scatter loop.
+#pragma once
+#include "cube_common.cuh"
+
+namespace cube {
+
+// =============================================================================================
+// scan: exclusive prefix sum int32 -> int64 (cumsum6 of variables.f90:90-110, in file order)
+// =============================================================================================
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* smem /*>=33*/, long long& total) {
+  // inclusive warp scan
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    long long s = (lane < (blockDim.x >> 5)) ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    smem[lane] = s;  // inclusive over warps
+  }
+  __syncthreads();
+  long long woff = w ? smem[w - 1] : 0;
+  total = smem[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return woff + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_blocksum(const int* __restrict__ in, long long n, long long* __restrict__ bsum) {
+  __shared__ long long sm[33];
+  long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
+  long long s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_I; q++) if (base + q < n) s += in[base + q];
+  long long tot;
+  block_exclusive_scan(s, sm, tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+// single block: exclusive scan of the block sums in place; total -> bsum[nb]
+__global__ void __launch_bounds__(1024) k_scan_bsums(long long* bsum, int nb) {
+  __shared__ long long sm[33];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
+    int q = b0 + threadIdx.x;
+    long long v = q < nb ? bsum[q] : 0, tot;
+    long long ex = block_exclusive_scan(v, sm, tot);
+    if (q < nb) bsum[q] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[nb] = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ in, long long n, const long long* __restrict__ bsum,
+                                                       long long* __restrict__ out) {
+  __shared__ long long sm[33];
+  long long base = (long long)blockIdx.x * SCAN_B + (long long)threadIdx.x * SCAN_I;
+  int v[SCAN_I];
+  long long s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_I; q++) { v[q] = (base + q < n) ? in[base + q] : 0; s += v[q]; }
+  long long tot;
+  long long ex = block_exclusive_scan(s, sm, tot) + bsum[blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < SCAN_I; q++) { if (base + q < n) out[base + q] = ex; ex += v[q]; }
+}
+
+// =============================================================================================
+// buffered state: extended image grid (buffer_density.f90 for one image: ghost layers alias the
+// periodic image, so ghost particles are never copied)
+// =============================================================================================
+__global__ void k_build_ext(Geom g, const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
+                            const float* __restrict__ vfield_p, int* __restrict__ rhoc_e, long long* __restrict__ cstart_e,
+                            float* __restrict__ vfield_e) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.ncell_e) return;
+  int x = (int)(e % g.ne) - NCB, y = (int)((e / g.ne) % g.ne) - NCB, z = (int)(e / ((long long)g.ne * g.ne)) - NCB;
+  // nn_d == 1: neighbour image is this image (inx=ipx=icx), parameters.f90:189-194
+  int xw = (x + g.nc) % g.nc, yw = (y + g.nc) % g.nc, zw = (z + g.nc) % g.nc;
+  long long L = phys_index(g, xw / g.nt, yw / g.nt, zw / g.nt, xw % g.nt, yw % g.nt, zw % g.nt);
+  rhoc_e[e] = rhoc_p[L];
+  cstart_e[e] = cstart_p[L];
+  vfield_e[3 * e + 0] = vfield_p[3 * L + 0];
+  vfield_e[3 * e + 1] = vfield_p[3 * L + 1];
+  vfield_e[3 * e + 2] = vfield_p[3 * L + 2];
+}
+
+// particles in each tile's extended region (cume(nt+2ncb,...) of update_particle.f90:60)
+__global__ void k_tile_counts(Geom g, const int* __restrict__ rhoc_e, long long* __restrict__ tile_count) {
+  __shared__ long long sm[33];
+  int t = blockIdx.x;
+  int tx = t % g.nnt, ty = (t / g.nnt) % g.nnt, tz = t / (g.nnt * g.nnt);
+  long long n = (long long)g.nte * g.nte * g.nte, s = 0;
+  for (long long q = threadIdx.x; q < n; q += blockDim.x) {
+    int i = (int)(q % g.nte), j = (int)((q / g.nte) % g.nte), k = (int)(q / ((long long)g.nte * g.nte));
+    s += rhoc_e[ext_index(g, tx * g.nt + i - NCB, ty * g.nt + j - NCB, tz * g.nt + k - NCB)];
+  }
+  long long tot;
+  block_exclusive_scan(s, sm, tot);
+  if (threadIdx.x == 0) tile_count[t] = tot;
+}
+
+// dv table: dble(tan((pi*real(vp))/real(nvbin-1))) / (sqrt(pi/2)/(sigma_vi*vrel_boost))
+__global__ void k_build_dvlut(const float* __restrict__ tanlut, double S, double* __restrict__ dvlut) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < 65536) dvlut[u] = (double)tanlut[u] / S;
+}
+
+// =============================================================================================
+// drift (update_particle.f90)
+// =============================================================================================
+constexpr double TIE_EPS = 1e-9;
+
+// destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
+__device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
+  double xq = __dadd_rn((double)(cell1 - 1), xp_frac(xp));
+  double dx = __dmul_rn(__dmul_rn(dt_mid, v), 0.25);  // (dt_mid*vreal)/ncell, ncell=4: exact scaling
+  double s = __dadd_rn(xq, dx);
+  double c = ceil(s);
+  tie = tie || (c - s < TIE_EPS) || (s - (c - 1.0) < TIE_EPS);
+  return (int)c;
+}
+
+// pass 0: one thread per storage-owning cell; key = destination offset of every particle
+__global__ void __launch_bounds__(128) k_drift_key(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                   const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
+                                                   const float* __restrict__ vfield_p, const double* __restrict__ dvlut,
+                                                   double dt_mid, unsigned short* __restrict__ key, int* __restrict__ maxoff) {
+  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int m = 0;
+  if (L < g.ncell_p) {
+    int tx, ty, tz, i, j, k;
+    phys_decompose(g, L, tx, ty, tz, i, j, k);
+    const int n = rhoc_p[L];
+    const long long s = cstart_p[L];
+    const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
+    for (int l = 0; l < n; l++) {
+      Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
+      bool tie = false;
+      int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
+      int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
+      int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
+      m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
+      ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
+      key[s + l] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
+    }
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
+}
+
+// pass 1 (PLACE=false): count + vfield_new chain;  pass 2 (PLACE=true): rank + write + statistics.
+// One thread per destination cell; sources are visited in the reference's traversal order.
+template <bool PLACE>
+__global__ void __launch_bounds__(128) k_drift_gather(
+    Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp, const unsigned short* __restrict__ key,
+    const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
+    const double* __restrict__ dvlut, double dt_mid, double S, int* __restrict__ rhoc_new, float* __restrict__ vfield_new,
+    const long long* __restrict__ cstart_new, short* __restrict__ xp_new, short* __restrict__ vp_new,
+    double* __restrict__ stat_partial) {
+  const double weight_v = (double)0.1f;  // update_particle.f90:10
+  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double st_tot = 0, st_c = 0, st_res = 0;
+  if (L < g.ncell_p) {
+    int tx, ty, tz, i, j, k;
+    phys_decompose(g, L, tx, ty, tz, i, j, k);
+    const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
+    float vfn0, vfn1, vfn2;
+    int cnt = 0;
+    long long pos = 0;
+    if (!PLACE) {
+      long long e = ext_index(g, X0 + i, Y0 + j, Z0 + k);
+      vfn0 = (float)__dmul_rn((double)vfield_e[3 * e], weight_v);  // :27
+      vfn1 = (float)__dmul_rn((double)vfield_e[3 * e + 1], weight_v);
+      vfn2 = (float)__dmul_rn((double)vfield_e[3 * e + 2], weight_v);
+    } else {
+      vfn0 = vfield_new[3 * L]; vfn1 = vfield_new[3 * L + 1]; vfn2 = vfield_new[3 * L + 2];
+      pos = cstart_new[L];
+      st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
+    }
+    for (int sk = k - r; sk <= k + r; sk++)
+      for (int sj = j - r; sj <= j + r; sj++)
+        for (int si = i - r; si <= i + r; si++) {
+          const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
+          const int n = rhoc_e[e];
+          if (n == 0) continue;
+          const long long s = cstart_e[e];
+          const unsigned want = key_pack(i - si, j - sj, k - sk);
+          const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
+          for (int l = 0; l < n; l++) {
+            const unsigned kk = key[s + l];
+            if (!(kk & KEY_FLAG) && kk != want) continue;
+            Code3 vc = load_code3(vp, s + l);
+            const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], vf0);
+            const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], vf1);
+            const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], vf2);
+            Code3 xc;
+            if (PLACE || (kk & KEY_FLAG)) xc = load_code3(xp, s + l);
+            if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
+              bool t = false;
+              if (drift_dest(si + 1, xc.x, v0, dt_mid, t) != i + 1) continue;
+              if (drift_dest(sj + 1, xc.y, v1, dt_mid, t) != j + 1) continue;
+              if (drift_dest(sk + 1, xc.z, v2, dt_mid, t) != k + 1) continue;
+            }
+            if (!PLACE) {
+              cnt++;
+              vfn0 = (float)__dadd_rn((double)vfn0, v0);  // :47, f32 store after each f64 add
+              vfn1 = (float)__dadd_rn((double)vfn1, v1);
+              vfn2 = (float)__dadd_rn((double)vfn2, v2);
+            } else {
+              // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
+              short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
+              short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
+              short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
+              short w0 = vp_encode(__dsub_rn(v0, (double)vfn0), S);  // :85-86
+              short w1 = vp_encode(__dsub_rn(v1, (double)vfn1), S);
+              short w2 = vp_encode(__dsub_rn(v2, (double)vfn2), S);
+              store_code3(xp_new, pos, x0, x1, x2);
+              store_code3(vp_new, pos, w0, w1, w2);
+              pos++;
+              // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
+              double a0 = dvlut[(unsigned short)w0], a1 = dvlut[(unsigned short)w1], a2 = dvlut[(unsigned short)w2];
+              st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+              a0 = __dadd_rn(a0, (double)vfn0); a1 = __dadd_rn(a1, (double)vfn1); a2 = __dadd_rn(a2, (double)vfn2);
+              st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+            }
+          }
+        }
+    if (!PLACE) {
+      const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
+      rhoc_new[L] = cnt;
+      vfield_new[3 * L] = (float)((double)vfn0 / den);
+      vfield_new[3 * L + 1] = (float)((double)vfn1 / den);
+      vfield_new[3 * L + 2] = (float)((double)vfn2 / den);
+    }
+  }
+  if (PLACE) {  // deterministic block reduction of the three sums
+    __shared__ double sm[3][4];
+    for (int o = 16; o; o >>= 1) {
+      st_tot += __shfl_down_sync(0xffffffffu, st_tot, o);
+      st_c += __shfl_down_sync(0xffffffffu, st_c, o);
+      st_res += __shfl_down_sync(0xffffffffu, st_res, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = st_tot; sm[1][threadIdx.x >> 5] = st_c; sm[2][threadIdx.x >> 5] = st_res; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double s = ((sm[threadIdx.x][0] + sm[threadIdx.x][1]) + sm[threadIdx.x][2]) + sm[threadIdx.x][3];
+      stat_partial[3 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+  }
+}
+
+// fixed-order final reduction of per-block partial sums (3 interleaved series)
+__global__ void __launch_bounds__(1024) k_reduce3(const double* __restrict__ part, long long nb, double* __restrict__ out) {
+  __shared__ double sm[3][32];
+  double s[3] = {0, 0, 0};
+  for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
+    s[0] += part[3 * b]; s[1] += part[3 * b + 1]; s[2] += part[3 * b + 2];
+  }
+  for (int c = 0; c < 3; c++) {
+    for (int o = 16; o; o >>= 1) s[c] += __shfl_down_sync(0xffffffffu, s[c], o);
+    if ((threadIdx.x & 31) == 0) sm[c][threadIdx.x >> 5] = s[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sm[threadIdx.x][w];
+    out[threadIdx.x] = t;
+  }
+}
+
+// =============================================================================================
+// fine mesh (pm.f90:44-118)
+// =============================================================================================
+constexpr int DB_X = 8, DB_Y = 4, DB_Z = 4, DB_T = DB_X * DB_Y * DB_Z;  // deposit brick (coarse cells)
+
+// tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution, rounded to f32 (pm.f90:54)
+__device__ __forceinline__ float fine_tempx(int cell1, short xp) {
+  return __double2float_rn((double)(4 * (cell1 - 1)) + ((double)(unsigned short)xp + 0.5) * 0x1p-14);
+}
+
+// One thread per OUTPUT coarse cell of the tile's extended region: it owns that cell's 4x4x4 fine
+// cells (private accumulators in shared memory, bank = thread id) and walks the (up to) eight
+// source coarse cells that can reach them, in the reference's k,j,i order.  Every fine cell is
+// written exactly once, so rho_f needs no zero-fill and no atomics.
+__global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, int tile0, const short* __restrict__ xp,
+                                                       const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
+                                                       float mass_p, float* __restrict__ rho /*[batch][nfe][nfe][nfe+2]*/) {
+  __shared__ float acc[64 * DB_T];
+  const int t = threadIdx.x;
+  const int tile = tile0 + blockIdx.y;
+  const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
+  const int nbx = (g.nte + DB_X - 1) / DB_X, nby = (g.nte + DB_Y - 1) / DB_Y;
+  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
+  const int cx = t % DB_X, cy = (t / DB_X) % DB_Y, cz = t / (DB_X * DB_Y);
+  // tile-local Fortran index of my output cell: 1-ncb .. nt+ncb
+  const int i = bx * DB_X + cx + 1 - NCB, j = by * DB_Y + cy + 1 - NCB, k = bz * DB_Z + cz + 1 - NCB;
+#pragma unroll
+  for (int q = 0; q < 64; q++) acc[q * DB_T + t] = 0.f;
+  const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
+  if (i <= g.nt + NCB && j <= g.nt + NCB && k <= g.nt + NCB) {
+    const int X0 = tx * g.nt - 1, Y0 = ty * g.nt - 1, Z0 = tz * g.nt - 1;  // image-local = X0 + Fortran local
+    for (int sk = k - 1; sk <= k; sk++) {
+      if (sk < lo || sk > hi) continue;
+      for (int sj = j - 1; sj <= j; sj++) {
+        if (sj < lo || sj > hi) continue;
+        for (int si = i - 1; si <= i; si++) {
+          if (si < lo || si > hi) continue;
+          const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
+          const int n = rhoc_e[e];
+          if (n == 0) continue;
+          const long long s = cstart_e[e];
+          // conservative early reject: a lower neighbour only reaches me from its top quarter
+          const unsigned rx = si < i ? 0xB000u : 0u, ry = sj < j ? 0xB000u : 0u, rz = sk < k ? 0xB000u : 0u;
+          for (int l = 0; l < n; l++) {
+            Code3 c = load_code3(xp, s + l);
+            if ((unsigned short)c.x < rx || (unsigned short)c.y < ry || (unsigned short)c.z < rz) continue;
+            int i1, j1, k1; float ax1, ax2, ay1, ay2, az1, az2;
+            cic_split(fine_tempx(si, c.x), i1, ax1, ax2);
+            cic_split(fine_tempx(sj, c.y), j1, ay1, ay2);
+            cic_split(fine_tempx(sk, c.z), k1, az1, az2);
+            // fine index (without nfb) relative to my first fine cell 4(i-1)+1
+            const int fa = i1 - (4 * (i - 1) + 1), fb = j1 - (4 * (j - 1) + 1), fc = k1 - (4 * (k - 1) + 1);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
+              const int a = fa + qa, b = fb + qb, cc = fc + qc;
+              if ((unsigned)a < 4u && (unsigned)b < 4u && (unsigned)cc < 4u) {
+                // dx(1)*dx(2)*dx(3)*mass_p, left to right (pm.f90:61-68)
+                float w = __fmul_rn(__fmul_rn(__fmul_rn(qa ? ax2 : ax1, qb ? ay2 : ay1), qc ? az2 : az1), mass_p);
+                float* p = &acc[((cc * 4 + b) * 4 + a) * DB_T + t];
+                *p = __fadd_rn(*p, w);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // write the brick's fine region, one 32-float row per warp iteration
+  const int lane = t & 31, w = t >> 5, nw = DB_T >> 5;
+  const long long ld = g.nfe + 2;
+  float* out = rho + (long long)blockIdx.y * g.nfe * g.nfe * ld;
+  for (int row = w; row < 16 * DB_Y * DB_Z; row += nw) {
+    const int fy = row % (4 * DB_Y), fz = row / (4 * DB_Y);
+    const int ocx = lane >> 2, a = lane & 3, ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
+    const int gx = (bx * DB_X + ocx) * 4 + a, gy = (by * DB_Y + ocy) * 4 + b, gz = (bz * DB_Z + ocz) * 4 + cc;
+    if (gx < g.nfe && gy < g.nfe && gz < g.nfe)
+      out[((long long)gz * g.nfe + gy) * ld + gx] = acc[((cc * 4 + b) * 4 + a) * DB_T + ((ocz * DB_Y + ocy) * DB_X + ocx)];
+  }
+}
+
+// k-space: F_d = i * kern_d * rho_k (pm.f90:79-80), with the 1/nfe^3 of pm.f90:82 folded in.
+// One thread per k-space element, looping over the tiles of the batch so that kern is read once.
+__global__ void __launch_bounds__(256) k_green(long long nk, int nbatch, const float2* __restrict__ crho,
+                                               const float* __restrict__ kern /*[3][nk]*/, float scale,
+                                               float2* __restrict__ out /*[3][batch][nk]*/) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nk) return;
+  const float k0 = kern[q] * scale, k1 = kern[nk + q] * scale, k2 = kern[2 * nk + q] * scale;
+  for (int b = 0; b < nbatch; b++) {
+    const float2 c = crho[(long long)b * nk + q];
+    out[((long long)0 * nbatch + b) * nk + q] = make_float2(-c.y * k0, c.x * k0);
+    out[((long long)1 * nbatch + b) * nk + q] = make_float2(-c.y * k1, c.x * k1);
+    out[((long long)2 * nbatch + b) * nk + q] = make_float2(-c.y * k2, c.x * k2);
+  }
+}
+
+// f2_max_fine(tile)=maxval(sum(force_f**2,1)) over force_f(:,nfb:nfe-nfb+1,...)  (pm.f90:85)
+__global__ void __launch_bounds__(256) k_f2max_fine(Geom g, int nbatch, const float* __restrict__ F /*[3][batch][..]*/,
+                                                    unsigned* __restrict__ f2max /*[batch] as float bits*/) {
+  const int b = blockIdx.y;
+  const int m = g.nft + 2;
+  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
+  float best = 0.f;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
+    long long o = ((long long)z * g.nfe + y) * ld + x;
+    float f0 = F[((long long)0 * nbatch + b) * vol + o], f1 = F[((long long)1 * nbatch + b) * vol + o], f2 = F[((long long)2 * nbatch + b) * vol + o];
+    float s = __fadd_rn(__fadd_rn(__fmul_rn(f0, f0), __fmul_rn(f1, f1)), __fmul_rn(f2, f2));
+    best = fmaxf(best, s);
+  }
+  best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));  // non-negative floats order as uints
+  if ((threadIdx.x & 31) == 0) atomicMax(&f2max[b], __float_as_uint(best));
+}
+
+// fine kick (pm.f90:88-118): one thread per physical coarse cell of the tile
+__global__ void __launch_bounds__(128) k_fine_kick(Geom g, int tile0, int nbatch, const short* __restrict__ xp, short* __restrict__ vp,
+                                                   const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
+                                                   const float* __restrict__ F /*[3][batch][nfe][nfe][nfe+2]*/,
+                                                   const double* __restrict__ dvlut, double S_new, float a_mid, float dt) {
+  const long long nt3 = (long long)g.nt * g.nt * g.nt;
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nt3) return;
+  const int b = blockIdx.y;
+  const long long L = (long long)(tile0 + b) * nt3 + c;
+  const int n = rhoc_p[L];
+  if (n == 0) return;
+  const int i = (int)(c % g.nt) + 1, j = (int)((c / g.nt) % g.nt) + 1, k = (int)(c / ((long long)g.nt * g.nt)) + 1;
+  const long long s = cstart_p[L], ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
+  const float* F0 = F + ((long long)0 * nbatch + b) * vol;
+  const float* F1 = F + ((long long)1 * nbatch + b) * vol;
+  const float* F2 = F + ((long long)2 * nbatch + b) * vol;
+  for (int l = 0; l < n; l++) {
+    Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
+    int i1, j1, k1; float ax[2], ay[2], az[2];
+    cic_split(fine_tempx(i, xc.x), i1, ax[0], ax[1]);
+    cic_split(fine_tempx(j, xc.y), j1, ay[0], ay[1]);
+    cic_split(fine_tempx(k, xc.z), k1, az[0], az[1]);
+    i1 += NFB - 1; j1 += NFB - 1; k1 += NFB - 1;  // 0-based index into the padded array
+    double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
+    // corner order of pm.f90:104-111
+    const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const long long o = ((long long)(k1 + qz[q]) * g.nfe + (j1 + qy[q])) * ld + (i1 + qx[q]);
+      const float wx = ax[qx[q]], wy = ay[qy[q]], wz = az[qz[q]];
+      v0 = __dadd_rn(v0, (double)kick_term(__ldg(F0 + o), a_mid, dt, wx, wy, wz));
+      v1 = __dadd_rn(v1, (double)kick_term(__ldg(F1 + o), a_mid, dt, wx, wy, wz));
+      v2 = __dadd_rn(v2, (double)kick_term(__ldg(F2 + o), a_mid, dt, wx, wy, wz));
+    }
+    store_code3(vp, s + l, vp_encode(v0, S_new), vp_encode(v1, S_new), vp_encode(v2, S_new));
+  }
+}
+
+// =============================================================================================
+// coarse mesh (pm.f90:127-228)
+// =============================================================================================
+// tempx=((/i,j,k/)-1)+(...)*x_resolution-0.5 -> f32 (pm.f90:142); cell0 = Fortran index - 1
+__device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
+  return __double2float_rn(__dsub_rn(__dadd_rn((double)cell0, xp_frac(xp)), 0.5));
+}
+
+// one thread per physical coarse cell: gathers from the 27 surrounding source cells in the tile's
+// frame, in k,j,i order => identical summation order to the r3t scatter loop
+__global__ void __launch_bounds__(128) k_coarse_deposit(Geom g, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
+                                                        const long long* __restrict__ cstart_e, float mass_p,
+                                                        float* __restrict__ r3 /*[nc][nc][nc+2]*/) {
+  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= g.ncell_p) return;
+  int tx, ty, tz, i, j, k;
+  phys_decompose(g, L, tx, ty, tz, i, j, k);
+  const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
+  float acc = 0.f;
+  const int ti = i + 1, tj = j + 1, tk = k + 1;  // my r3t index (Fortran)
+  for (int sk = k - 1; sk <= k + 1; sk++)
+    for (int sj = j - 1; sj <= j + 1; sj++)
+      for (int si = i - 1; si <= i + 1; si++) {
+        const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
+        const int n = rhoc_e[e];
+        if (n == 0) continue;
+        const long long s = cstart_e[e];
+        for (int l = 0; l < n; l++) {
+          Code3 c = load_code3(xp, s + l);
+          int i1, j1, k1; float ax1, ax2, ay1, ay2, az1, az2;
+          cic_split(coarse_tempx(si, c.x), i1, ax1, ax2);  // si is 0-based = Fortran cell - 1
+          const int da = ti - i1;
+          if ((unsigned)da > 1u) continue;
+          cic_split(coarse_tempx(sj, c.y), j1, ay1, ay2);
+          const int db = tj - j1;
+          if ((unsigned)db > 1u) continue;
+          cic_split(coarse_tempx(sk, c.z), k1, az1, az2);
+          const int dc = tk - k1;
+          if ((unsigned)dc > 1u) continue;
+          float w = __fmul_rn(__fmul_rn(__fmul_rn(da ? ax2 : ax1, db ? ay2 : ay1), dc ? az2 : az1), mass_p);
+          acc = __fadd_rn(acc, w);
+        }
+      }
+  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * (g.nc + 2) + (X0 + i)] = acc;
+}
+
+// force_c(3,0:nc+1,0:nc+1,0:nc+1) from the three inverse transforms + periodic 1-cell halo
+// (pm.f90:176-189, single image: neighbour = self)
+__global__ void k_force_c_assemble(Geom g, const float* __restrict__ F /*[3][nc][nc][nc+2]*/, float* __restrict__ fc) {
+  const int m = g.nc + 2;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)m * m * m) return;
+  int x = (int)(q % m) - 1, y = (int)((q / m) % m) - 1, z = (int)(q / ((long long)m * m)) - 1;
+  x = (x + g.nc) % g.nc; y = (y + g.nc) % g.nc; z = (z + g.nc) % g.nc;
+  const long long vol = (long long)g.nc * g.nc * (g.nc + 2), o = ((long long)z * g.nc + y) * (g.nc + 2) + x;
+  fc[3 * q] = F[o]; fc[3 * q + 1] = F[vol + o]; fc[3 * q + 2] = F[2 * vol + o];
+}
+
+__global__ void __launch_bounds__(256) k_f2max_aos(long long n, const float* __restrict__ f, unsigned* __restrict__ f2max) {
+  float best = 0.f;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    float f0 = f[3 * q], f1 = f[3 * q + 1], f2 = f[3 * q + 2];
+    best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0, f0), __fmul_rn(f1, f1)), __fmul_rn(f2, f2)));
+  }
+  best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
+  if ((threadIdx.x & 31) == 0) atomicMax(f2max, __float_as_uint(best));
+}
+
+// coarse kick (pm.f90:196-228): one thread per physical coarse cell, image-local coordinates
+__global__ void __launch_bounds__(128) k_coarse_kick(Geom g, const short* __restrict__ xp, short* __restrict__ vp,
+                                                     const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
+                                                     const float* __restrict__ vfield_p, const float* __restrict__ fc,
+                                                     const double* __restrict__ dvlut, double S, float a_mid, float dt,
+                                                     unsigned long long* __restrict__ vmax_bits) {
+  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double vm = 0.0;
+  if (L < g.ncell_p) {
+    const int n = rhoc_p[L];
+    if (n) {
+      int tx, ty, tz, i, j, k;
+      phys_decompose(g, L, tx, ty, tz, i, j, k);
+      const int X = tx * g.nt + i, Y = ty * g.nt + j, Z = tz * g.nt + k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
+      const long long s = cstart_p[L];
+      const int m = g.nc + 2;
+      const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
+      for (int l = 0; l < n; l++) {
+        Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
+        int i1, j1, k1; float ax[2], ay[2], az[2];
+        cic_split(coarse_tempx(X, xc.x), i1, ax[0], ax[1]);
+        cic_split(coarse_tempx(Y, xc.y), j1, ay[0], ay[1]);
+        cic_split(coarse_tempx(Z, xc.z), k1, az[0], az[1]);
+        double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
+        const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float* f = fc + 3 * (((long long)(k1 + qz[q]) * m + (j1 + qy[q])) * m + (i1 + qx[q]));
+          const float wx = ax[qx[q]], wy = ay[qy[q]], wz = az[qz[q]];
+          v0 = __dadd_rn(v0, (double)kick_term(__ldg(f), a_mid, dt, wx, wy, wz));
+          v1 = __dadd_rn(v1, (double)kick_term(__ldg(f + 1), a_mid, dt, wx, wy, wz));
+          v2 = __dadd_rn(v2, (double)kick_term(__ldg(f + 2), a_mid, dt, wx, wy, wz));
+        }
+        // vmax=max(vmax,maxval(vreal+vfield(:,i,j,k,...)))  (no abs, pm.f90:220)
+        vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));
+        store_code3(vp, s + l, vp_encode(v0, S), vp_encode(v1, S), vp_encode(v2, S));
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(0xffffffffu, vm, o));
+  if ((threadIdx.x & 31) == 0 && vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
+}
+
+// =============================================================================================
+// kernel construction (kernel_f.f90, kernel_c.f90) -- init only
+// =============================================================================================
+// rho_f <- 16^3 table mirrored into 8 octants, odd along the force's own axis (kernel_f.f90:32-38)
+__global__ void k_kernf_fill(int nfe, const float* __restrict__ tab /*(16,16,16,3) Fortran*/, int dim, float* __restrict__ rho) {
+  const long long ld = nfe + 2, n = (long long)nfe * nfe * ld;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int x = (int)(q % ld), y = (int)((q / ld) % nfe), z = (int)(q / (ld * nfe));
+  float v = 0.f;
+  if (x < nfe) {
+    int ox = x < 16 ? x : x - nfe, oy = y < 16 ? y : y - nfe, oz = z < 16 ? z : z - nfe;
+    if (ox > -16 && oy > -16 && oz > -16 && ox < 16 && oy < 16 && oz < 16) {
+      int o[3] = {ox, oy, oz};
+      v = tab[(((long long)dim * 16 + abs(oz)) * 16 + abs(oy)) * 16 + abs(ox)];
+      if (o[dim] < 0) v = -v;
+    }
+  }
+  rho[q] = v;
+}
+__global__ void k_take_imag(long long nk, const float2* __restrict__ c, float* __restrict__ out) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nk) out[q] = c[q].y;
+}
+
+__device__ __forceinline__ int signed_index(int g, int n) { return (g + n / 2) % n - n / 2; }
+
+// ck(dim) on the (single-image) coarse lattice: -r/r^3 with the 4^3 table in the 8 corners when
+// `corrected` (kernel_c.f90:16-72)
+__global__ void k_kernc_fill(int nc, const float* __restrict__ tab /*(3,4,4,4) Fortran*/, int dim, int corrected, float* __restrict__ r3) {
+  const long long ld = nc + 2, n = (long long)nc * nc * ld;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int x = (int)(q % ld), y = (int)((q / ld) % nc), z = (int)(q / (ld * nc));
+  float v = 0.f;
+  if (x < nc) {
+    int o[3] = {signed_index(x, nc), signed_index(y, nc), signed_index(z, nc)};
+    float rx = 4.f * o[0], ry = 4.f * o[1], rz = 4.f * o[2];
+    float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
+    float rr[3] = {rx, ry, rz};
+    v = (r == 0.f) ? 0.f : __fdiv_rn(-rr[dim], __fmul_rn(__fmul_rn(r, r), r));
+    if (corrected && o[0] > -4 && o[0] < 4 && o[1] > -4 && o[1] < 4 && o[2] > -4 && o[2] < 4) {
+      // positive side uses table index 0..3, negative side (offsets -3..-1) mirrors 3..1
+      v = tab[dim + 3 * (abs(o[0]) + 4 * (abs(o[1]) + 4 * abs(o[2])))];
+      if (o[dim] < 0) v = -v;
+    }
+  }
+  r3[q] = v;
+}
+// LRCKCORR (kernel_c.f90:76-117) on the half-x k-space grid of a single image
+__global__ void k_kernc_lrck(int nc, int dim, const float2* __restrict__ cpure, float* __restrict__ kern) {
+  const int nh = nc / 2 + 1;
+  long long nk = (long long)nh * nc * nc;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nk) return;
+  int x = (int)(q % nh), y = (int)((q / nh) % nc), z = (int)(q / ((long long)nh * nc));
+  float kx[3] = {(float)signed_index(x, nc), (float)signed_index(y, nc), (float)signed_index(z, nc)};
+  float kr = sqrtf(kx[0] * kx[0] + kx[1] * kx[1] + kx[2] * kx[2]);
+  if (kr > 8.0f || kx[dim] == 0.f) return;
+  float ks[3];
+  for (int d = 0; d < 3; d++) ks[d] = 2.f * sinf(PI_F * kx[d] / (float)nc);
+  float ssum = ks[0] * ks[0] + ks[1] * ks[1] + ks[2] * ks[2];
+  kern[q] = kern[q] * 0.25f * PI_F * ks[dim] / ssum / cpure[q].y;
+}
+
+}  // namespace cube

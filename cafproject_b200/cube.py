@@ -1,0 +1,251 @@
+"""Host-side mirror of CUBE's step loop on top of the C ABI (``include/cube_gpu.h``).
+
+The reference's "operator interface" for the hot path is the sequence of argument-less subroutine
+calls in ``CUBE/main/cafcube.f90:25-46`` working on module globals.  :class:`CubeGPU` offers the same
+names (``update_particle``, ``buffer_density``, ``buffer_x``, ``buffer_v``, ``particle_mesh``,
+``checkpoint``) over ``libcubegpu.so``; the state lives in HBM between calls.  There is no CPU
+fallback: importing works without a GPU (so that the symbol table can be checked), every compute
+call raises if the CUDA library or a device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcubegpu.so")
+
+F32 = np.float32
+PI_F = F32(4) * np.arctan(F32(1.0), dtype=F32)
+
+
+class CubeParams(C.Structure):
+    """``cube_params`` of include/cube_gpu.h."""
+    _fields_ = [("nn", C.c_int32 * 3), ("rank", C.c_int32), ("nnt", C.c_int32), ("nc", C.c_int32),
+                ("ncell", C.c_int32), ("ncb", C.c_int32), ("izipx", C.c_int32), ("izipv", C.c_int32),
+                ("np_nc", C.c_int32), ("image_buffer", C.c_float), ("tile_buffer", C.c_float),
+                ("device", C.c_int32), ("fine_batch", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class CubeGPUError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libcubegpu.so and declare every prototype of include/cube_gpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CubeGPUError("libcubegpu.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, f32, i32 = C.c_void_p, C.c_int64, C.c_float, C.c_int
+    L.cube_gpu_init.argtypes = [C.POINTER(CubeParams), vp, vp, vp, vp, C.POINTER(vp)]
+    L.cube_gpu_upload.argtypes = [vp, vp, vp, vp, vp, i64, i64, f32]
+    L.cube_gpu_update_x.argtypes = [vp, f32, f32, C.POINTER(i64), C.POINTER(f32), C.POINTER(C.c_double * 3), C.POINTER(f32)]
+    L.cube_gpu_buffer.argtypes = [vp, i32, i32, i32, C.POINTER(f32)]
+    L.cube_gpu_particle_mesh.argtypes = [vp, f32, f32] + [C.POINTER(f32)] * 4
+    L.cube_gpu_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(f32)]
+    L.cube_gpu_finalize.argtypes = [vp]
+    L.cube_gpu_last_error.restype = C.c_char_p
+    L.cube_gpu_query.restype = i64
+    L.cube_gpu_query.argtypes = [vp, C.c_char_p]
+    L.cube_gpu_get_kern_f.argtypes = [vp, vp]
+    L.cube_gpu_get_kern_c.argtypes = [vp, vp]
+    L.cube_gpu_fine_density.argtypes = [vp, i32, i32, i32, vp]
+    L.cube_gpu_fine_force.argtypes = [vp, i32, i32, i32, vp]
+    L.cube_gpu_fine_kick_with.argtypes = [vp, i32, i32, i32, vp, f32, f32, f32, f32, C.POINTER(f32)]
+    L.cube_gpu_coarse_density.argtypes = [vp, vp]
+    L.cube_gpu_coarse_force.argtypes = [vp, vp]
+    L.cube_gpu_coarse_kick_with.argtypes = [vp, vp, f32, f32, f32, C.POINTER(f32), C.POINTER(f32)]
+    L.cube_gpu_phase_count.restype = i32
+    L.cube_gpu_phase_name.restype = C.c_char_p
+    L.cube_gpu_phase_name.argtypes = [i32]
+    L.cube_gpu_phase_times.argtypes = [vp, vp]
+    L.cube_gpu_set_profiling.argtypes = [vp, i32]
+    _lib = L
+    return L
+
+
+#: every symbol include/cube_gpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "cube_gpu_init", "cube_gpu_upload", "cube_gpu_update_x", "cube_gpu_buffer", "cube_gpu_particle_mesh",
+    "cube_gpu_download", "cube_gpu_finalize", "cube_gpu_last_error", "cube_gpu_query", "cube_gpu_get_kern_f",
+    "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
+    "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
+    "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling",
+]
+
+
+def host_tanf_lut() -> np.ndarray:
+    """``tan((pi*real(v))/real(nvbin-1))`` for all 65536 codes with the *host's* libm ``tanf``
+    (what the Fortran host passes to ``cube_gpu_init``).  Uses libm through ctypes, not the oracle."""
+    libm = C.CDLL("libm.so.6")
+    libm.tanf.restype = C.c_float
+    libm.tanf.argtypes = [C.c_float]
+    codes = np.arange(65536, dtype=np.uint16).view(np.int16).astype(F32)
+    arg = (PI_F * codes) / F32(65535.0)
+    return np.array([libm.tanf(float(a)) for a in arg], dtype=F32)
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+class CubeGPU:
+    """One image of a CUBE run on one B200.  Mirrors the step subroutines of CUBE/main."""
+
+    def __init__(self, nc, nnt, fk_table, ck_table, nn=(1, 1, 1), rank=0, np_nc=2, image_buffer=1.5, tile_buffer=2.5,
+                 device=0, fine_batch=0, tanf_lut=None):
+        L = load_library()
+        self.L = L
+        nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
+        p = CubeParams()
+        p.nn[:] = nn
+        p.rank, p.nnt, p.nc, p.ncell, p.ncb = rank, nnt, nc, 4, 6
+        p.izipx = p.izipv = 2
+        p.np_nc, p.image_buffer, p.tile_buffer, p.device, p.fine_batch = np_nc, image_buffer, tile_buffer, device, fine_batch
+        self.params = p
+        self.nn, self.nc, self.nnt, self.nt = nn, nc, nnt, nc // nnt
+        self.nft = 4 * self.nt
+        self.nfe = self.nft + 48
+        # reference layouts: fk_table(16,16,16,3) [dim slowest], ck_table(3,4,4,4) [dim fastest]
+        fk = np.ascontiguousarray(np.moveaxis(np.asarray(fk_table, F32), 3, 0))  # fixture is [k][j][i][dim]
+        ck = np.ascontiguousarray(np.asarray(ck_table, F32))
+        lut = np.ascontiguousarray(host_tanf_lut() if tanf_lut is None else tanf_lut, F32)
+        assert lut.shape == (65536,)
+        h = C.c_void_p()
+        self.h = None
+        self._ck(L.cube_gpu_init(C.byref(p), _p(fk), _p(ck), _p(lut), None, C.byref(h)))
+        self.h = h
+        self.nplocal = 0
+        self.sigma_vi = F32(0)
+        self.dt_fine = self.dt_coarse = self.dt_vmax = self.dt_pp = F32(1000)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CubeGPUError(self.L.cube_gpu_last_error().decode())
+
+    def close(self):
+        if self.h is not None:
+            self.L.cube_gpu_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, what):
+        return int(self.L.cube_gpu_query(self.h, what.encode()))
+
+    # ---- particle_initialization / checkpoint ------------------------------------------------
+    def particle_initialization(self, state, sigma_vi, npglobal=None):
+        xp = np.ascontiguousarray(state["xp"], np.int16); vp = np.ascontiguousarray(state["vp"], np.int16)
+        rc = np.ascontiguousarray(state["rhoc"], np.int32); vf = np.ascontiguousarray(state["vfield"], np.float32)
+        n = xp.shape[0]
+        self._ck(self.L.cube_gpu_upload(self.h, _p(xp), _p(vp), _p(rc), _p(vf), n, npglobal or n, F32(sigma_vi)))
+        self.nplocal = n
+        self.sigma_vi = F32(sigma_vi)
+
+    def checkpoint(self):
+        """Disjoint state back on the host (what checkpoint.f90 writes)."""
+        n = self.query("nplocal")
+        shp = (self.nnt,) * 3 + (self.nt,) * 3
+        xp = np.empty((n, 3), np.int16); vp = np.empty((n, 3), np.int16)
+        rc = np.empty(shp, np.int32); vf = np.empty(shp + (3,), np.float32)
+        npl = C.c_int64(); sig = C.c_float()
+        self._ck(self.L.cube_gpu_download(self.h, _p(xp), _p(vp), _p(rc), _p(vf), C.byref(npl), C.byref(sig)))
+        return dict(xp=xp, vp=vp, rhoc=rc, vfield=vf), F32(sig.value)
+
+    # ---- step subroutines -------------------------------------------------------------------
+    def update_particle(self, dt_old, dt):
+        npl = C.c_int64(); sig = C.c_float(); ovh = C.c_float(); st = (C.c_double * 3)()
+        self._ck(self.L.cube_gpu_update_x(self.h, F32(dt_old), F32(dt), C.byref(npl), C.byref(sig), C.byref(st), C.byref(ovh)))
+        self.nplocal = npl.value
+        return dict(nplocal=npl.value, sigma_vi_new=F32(sig.value), std_vsim=st[0], std_vsim_c=st[1], std_vsim_res=st[2],
+                    overhead_tile=F32(ovh.value))
+
+    def buffer_density(self):
+        ovh = C.c_float()
+        self._ck(self.L.cube_gpu_buffer(self.h, 1, 0, 0, C.byref(ovh)))
+        return F32(ovh.value)
+
+    def buffer_x(self):
+        self._ck(self.L.cube_gpu_buffer(self.h, 0, 1, 0, None))
+
+    def buffer_v(self):
+        self._ck(self.L.cube_gpu_buffer(self.h, 0, 0, 1, None))
+
+    def particle_mesh(self, a_mid, dt):
+        o = [C.c_float() for _ in range(4)]
+        self._ck(self.L.cube_gpu_particle_mesh(self.h, F32(a_mid), F32(dt), *[C.byref(v) for v in o]))
+        self.dt_fine, self.dt_coarse, self.dt_vmax = (F32(v.value) for v in o[:3])
+        return dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000), vmax=F32(o[3].value))
+
+    def step(self, dt_old, dt, a_mid):
+        """cafcube.f90:27-31."""
+        up = self.update_particle(dt_old, dt)
+        self.buffer_density(); self.buffer_x()
+        pm = self.particle_mesh(a_mid, dt)
+        self.buffer_v()
+        return up, pm
+
+    # ---- diagnostics -------------------------------------------------------------------------
+    def kern_f(self):
+        out = np.empty((3, self.nfe, self.nfe, self.nfe // 2 + 1), F32)
+        self._ck(self.L.cube_gpu_get_kern_f(self.h, _p(out)))
+        return out
+
+    def kern_c(self):
+        out = np.empty((3, self.nc, self.nc, self.nc // 2 + 1), F32)
+        self._ck(self.L.cube_gpu_get_kern_c(self.h, _p(out)))
+        return out
+
+    def fine_density(self, itx, ity, itz):
+        out = np.empty((self.nfe, self.nfe, self.nfe + 2), F32)
+        self._ck(self.L.cube_gpu_fine_density(self.h, itx, ity, itz, _p(out)))
+        return out
+
+    def fine_force(self, itx, ity, itz):
+        m = self.nft + 2
+        out = np.empty((m, m, m, 3), F32)
+        self._ck(self.L.cube_gpu_fine_force(self.h, itx, ity, itz, _p(out)))
+        return out
+
+    def fine_kick_with(self, itx, ity, itz, force_f, a_mid, dt, sigma_vi, sigma_vi_new):
+        f = np.ascontiguousarray(force_f, F32); f2 = C.c_float()
+        self._ck(self.L.cube_gpu_fine_kick_with(self.h, itx, ity, itz, _p(f), F32(a_mid), F32(dt), F32(sigma_vi), F32(sigma_vi_new), C.byref(f2)))
+        return F32(f2.value)
+
+    def coarse_density(self):
+        out = np.empty((self.nc,) * 3, F32)
+        self._ck(self.L.cube_gpu_coarse_density(self.h, _p(out)))
+        return out
+
+    def coarse_force(self):
+        m = self.nc + 2
+        out = np.empty((m, m, m, 3), F32)
+        self._ck(self.L.cube_gpu_coarse_force(self.h, _p(out)))
+        return out
+
+    def coarse_kick_with(self, force_c, a_mid, dt, sigma_vi):
+        f = np.ascontiguousarray(force_c, F32); vm = C.c_float(); f2 = C.c_float()
+        self._ck(self.L.cube_gpu_coarse_kick_with(self.h, _p(f), F32(a_mid), F32(dt), F32(sigma_vi), C.byref(vm), C.byref(f2)))
+        return F32(vm.value), F32(f2.value)
+
+    def set_profiling(self, on=True):
+        self.L.cube_gpu_set_profiling(self.h, int(on))
+
+    def phase_times(self):
+        n = self.L.cube_gpu_phase_count()
+        ms = np.zeros(n, F32)
+        self.L.cube_gpu_phase_times(self.h, _p(ms))
+        return {self.L.cube_gpu_phase_name(i).decode(): float(ms[i]) for i in range(n)}

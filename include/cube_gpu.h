@@ -1,0 +1,119 @@
+/*
+ * cube_gpu.h -- C ABI of the B200-native CUBE particle-mesh step (libcubegpu.so).
+ *
+ * The reference (yuhaoran/cafproject, Coarray Fortran) has no plugin/FFI interface: its step loop
+ * calls argument-less subroutines that work on module globals (CUBE/main/cafcube.f90:25-46,
+ * CUBE/main/variables.f90:17-68).  This header is the boundary *cut* at those calls; each entry
+ * point names the reference routine it replaces.  The Fortran side binds them with ISO_C_BINDING
+ * (fortran/cube_gpu.f90) and passes its globals explicitly.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all arrays are host memory owned by the caller and touched
+ *    only inside the call; the authoritative state lives in HBM between upload and download.
+ *  - arrays use the reference's own memory layout (Fortran column-major, first index fastest):
+ *      xp, vp            integer(2)  (3, nplocal)                          variables.f90:41-42
+ *      rhoc_phys         integer(4)  (nt,nt,nt,nnt,nnt,nnt)   = rhoc(1:nt,1:nt,1:nt,:,:,:)   checkpoint.f90:35
+ *      vfield_phys       real(4)     (3,nt,nt,nt,nnt,nnt,nnt) = vfield(:,1:nt,1:nt,1:nt,:,:,:) checkpoint.f90:40
+ *    i.e. exactly what the reference writes to zip0/zip1/zip2/vfield ("disjoint state").
+ *  - every function returns 0 on success; non-zero = error, message in cube_gpu_last_error().
+ *    Capacity overflows are reported with the reference's own wording (update_particle.f90:61-67,
+ *    buffer_density.f90:87-93) instead of `stop`.
+ *  - single caller per handle; calls are not re-entrant (the reference's step calls never overlap).
+ *  - there is no CPU fallback: every call fails if no CUDA device is usable.
+ */
+#ifndef CUBE_GPU_H
+#define CUBE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Compile-time constants of CUBE/main/parameters.f90:13-60 passed at run time. */
+typedef struct cube_params {
+  int32_t nn[3];        /* images per dimension (reference: nn,nn,nn; parameters.f90:20)            */
+  int32_t rank;         /* this image, 0-based = this_image()-1 (parameters.f90:180)               */
+  int32_t nnt;          /* tiles / image / dim                         parameters.f90:22           */
+  int32_t nc;           /* coarse cells / image / dim                  parameters.f90:23           */
+  int32_t ncell;        /* fine cells per coarse cell / dim (must be 4) parameters.f90:21           */
+  int32_t ncb;          /* buffer depth in coarse cells (must be 6)    parameters.f90:46           */
+  int32_t izipx, izipv; /* bytes per position / velocity code (must be 2,2)  universe*.fh          */
+  int32_t np_nc;        /* particles / coarse cell / dim (capacity sizing) parameters.f90:55       */
+  float image_buffer;   /* parameters.f90:59 */
+  float tile_buffer;    /* parameters.f90:60 */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t fine_batch;   /* tiles per batched fine-mesh FFT, 0 = choose automatically */
+  int32_t reserved[4];
+} cube_params;
+
+typedef struct cube_handle cube_handle;
+
+/* initialize.f90:1-56: geometry, FFT plans, kernel_f (kernel_f.f90), kernel_c (kernel_c.f90).
+ *   fk_table  real(4) (16,16,16,3)  = fk_table(i,j,k,dim) as read from ../kernels/wfxyzf.3.ascii
+ *   ck_table  real(4) (3,4,4,4)     = ck_table(dim,i,j,k) as read from ../kernels/wfxyzc.2.ascii
+ *   tanf_lut  real(4) (0:65535)     tan((pi*real(v))/real(nvbin-1)) evaluated BY THE HOST's libm for
+ *                                   v = int(u,2) (u = raw 16-bit pattern) -- makes velocity decoding
+ *                                   bit-identical to the host build (pm.f90:102, update_particle.f90:42)
+ *   nccl_unique_id  NULL for a single image; otherwise the 128-byte ncclUniqueId shared by all images. */
+int cube_gpu_init(const cube_params *p, const float *fk_table, const float *ck_table, const float *tanf_lut,
+                  const void *nccl_unique_id, cube_handle **h);
+
+/* particle_initialization.f90:11-72: take the disjoint state (file order). mass_p = nf_global^3/npglobal. */
+int cube_gpu_upload(cube_handle *h, const int16_t *xp, const int16_t *vp, const int32_t *rhoc_phys,
+                    const float *vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi);
+
+/* update_particle (update_particle.f90:1-213): drift + cell re-sort + vfield rebuild + sigma statistics.
+ * in: buffered state; out: disjoint state.  std_vsim = {std_vsim, std_vsim_c, std_vsim_res}. */
+int cube_gpu_update_x(cube_handle *h, float dt_old, float dt, int64_t *nplocal, float *sigma_vi_new,
+                      double std_vsim[3], float *overhead_tile);
+
+/* buffer_density / buffer_x / buffer_v (buffer_density.f90, buffer_x.f90, buffer_v.f90):
+ * disjoint -> buffered state.  Flags select which of the three reference calls this stands for. */
+int cube_gpu_buffer(cube_handle *h, int do_density, int do_x, int do_v, float *overhead_image);
+
+/* particle_mesh (pm.f90:1-247): fine + coarse PM force, both kicks, time-step limits. */
+int cube_gpu_particle_mesh(cube_handle *h, float a_mid, float dt, float *dt_fine, float *dt_coarse,
+                           float *dt_vmax, float *vmax);
+
+/* checkpoint.f90:33-70: bring the disjoint state back.  Pass NULL for anything not wanted.
+ * Capacity of xp/vp must be >= nplocal as returned by the last update_x/upload. */
+int cube_gpu_download(cube_handle *h, int16_t *xp, int16_t *vp, int32_t *rhoc_phys, float *vfield_phys,
+                      int64_t *nplocal, float *sigma_vi);
+
+int cube_gpu_finalize(cube_handle *h);
+const char *cube_gpu_last_error(void);
+
+/* ---- diagnostics used by the parity tests and the benchmark (not part of the step loop) -------- */
+
+/* derived sizes: what[] = "np_image_max","np_tile_max","nfe","nft","nt","fine_batch","kernel_launches" */
+int64_t cube_gpu_query(cube_handle *h, const char *what);
+/* kern_f(nfe/2+1,nfe,nfe,3) and kern_c(nc*nn/2+1,nc,nc,3) (single image) as built at init, unscaled */
+int cube_gpu_get_kern_f(cube_handle *h, float *out);
+int cube_gpu_get_kern_c(cube_handle *h, float *out);
+/* rho_f(nfe+2,nfe,nfe) of tile (itx,ity,itz) (1-based) from the current buffered state  pm.f90:44-72 */
+int cube_gpu_fine_density(cube_handle *h, int itx, int ity, int itz, float *rho_f);
+/* force_f(3,nft+2,nft+2,nft+2) of that tile  pm.f90:75-84 */
+int cube_gpu_fine_force(cube_handle *h, int itx, int ity, int itz, float *force_f);
+/* fine kick of one tile with a caller-supplied force_f (parity: identical F => identical vp) pm.f90:88-118 */
+int cube_gpu_fine_kick_with(cube_handle *h, int itx, int ity, int itz, const float *force_f, float a_mid,
+                            float dt, float sigma_vi, float sigma_vi_new, float *f2_max);
+/* r3(nc,nc,nc)  pm.f90:130-163 */
+int cube_gpu_coarse_density(cube_handle *h, float *r3);
+/* force_c(3,0:nc+1,0:nc+1,0:nc+1) incl. halo  pm.f90:168-189 */
+int cube_gpu_coarse_force(cube_handle *h, float *force_c);
+/* coarse kick with a caller-supplied force_c  pm.f90:192-228 */
+int cube_gpu_coarse_kick_with(cube_handle *h, const float *force_c, float a_mid, float dt, float sigma_vi,
+                              float *vmax, float *f2_max);
+/* per-phase device times (ms) of the last update_x / particle_mesh, CUBEnu-style phase brackets
+ * (CUBEnu/work/main/pm.f90:35,195,268,299,388): names returned via cube_gpu_phase_name(i) */
+int cube_gpu_phase_count(void);
+const char *cube_gpu_phase_name(int i);
+int cube_gpu_phase_times(cube_handle *h, float *ms);
+/* enable (1) / disable (0) per-phase event timing (off by default; costs a few event records) */
+int cube_gpu_set_profiling(cube_handle *h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBE_GPU_H */

@@ -1,0 +1,145 @@
+"""GPU parity tests: libcubegpu.so (through the C ABI) against the CPU oracle on identical inputs.
+
+Parity is unpinned by the reference (no golden vectors upstream); the oracle restates it line by line.
+Gates: integer codes / counts bit-exact; densities and forces <= 1e-5 norm-relative
+(in fact the densities are bit-exact because the deposit kernels keep the reference's summation order).
+"""
+import numpy as np
+import pytest
+
+from conftest import norm_rel, physical
+
+pytestmark = pytest.mark.gpu
+
+NC, NNT, NP_NC = 32, 2, 2
+
+
+@pytest.fixture(scope="module")
+def setup(tables):
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    states, sig, info = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=11, disp_rms=0.8)
+    O = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+    G.particle_initialization(states[0], sig)
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    yield O, G, states, sig
+    G.close(); O.close()
+
+
+def test_host_tanf_lut_matches_oracle():
+    from cafproject_b200.cube import host_tanf_lut
+    from oracle import cube_oracle as co
+    assert np.array_equal(host_tanf_lut().view(np.uint32), co.tanf_lut().view(np.uint32))
+
+
+def test_kernels(setup):
+    O, G, _, _ = setup
+    assert norm_rel(G.kern_f(), O.kern_f) < 1e-5
+    assert norm_rel(G.kern_c(), O.kern_c) < 1e-5
+
+
+def test_fine_density_bit_exact(setup):
+    O, G, _, _ = setup
+    for t in [(1, 1, 1), (2, 1, 2), (2, 2, 2)]:
+        ro = O.fine_density(0, *t)
+        rg = G.fine_density(*t)
+        assert abs(float(rg[:, :, :O.nfe].sum(dtype=np.float64)) - float(ro[:, :, :O.nfe].sum(dtype=np.float64))) < 1e-3
+        assert np.array_equal(ro[:, :, :O.nfe], rg[:, :, :O.nfe]), t
+
+
+def test_fine_force(setup):
+    O, G, _, _ = setup
+    for t in [(1, 1, 1), (2, 2, 1)]:
+        fo = O.fine_force(O.fine_density(0, *t))
+        fg = G.fine_force(*t)
+        assert norm_rel(fg, fo) < 1e-5, t
+
+
+def test_coarse_density_bit_exact(setup):
+    O, G, _, _ = setup
+    assert np.array_equal(O.coarse_density(), G.coarse_density())
+
+
+def test_coarse_force(setup):
+    O, G, _, _ = setup
+    fo = O.force_c_image(O.coarse_force(O.coarse_density()), 0)
+    assert norm_rel(G.coarse_force(), fo) < 1e-5
+
+
+def test_drift_then_kicks_bit_exact(setup):
+    """update_particle -> buffers -> both kicks with the ORACLE's forces: every code must match."""
+    O, G, _, sig = setup
+    dt_old, dt, a_mid = np.float32(0.0), np.float32(1.0), np.float32(0.021)
+    uo = O.update_particle(dt_old, dt)
+    ug = G.update_particle(dt_old, dt)
+    assert ug["nplocal"] == O.nplocal(0)
+    so = O.store(0)
+    sg, _ = G.checkpoint()
+    assert np.array_equal(so["rhoc"], sg["rhoc"])
+    assert np.array_equal(so["xp"], sg["xp"])
+    assert np.array_equal(so["vfield"].view(np.uint32), sg["vfield"].view(np.uint32))
+    assert np.array_equal(so["vp"], sg["vp"])
+    assert ug["sigma_vi_new"] == uo["sigma_vi_new"]
+    assert ug["overhead_tile"] == uo["overhead_tile"]
+    for k in ("std_vsim", "std_vsim_c", "std_vsim_res"):
+        assert abs(ug[k] - uo[k]) <= 1e-12 * abs(uo[k])
+    ovo = O.buffer_density(); O.buffer_x()
+    ovg = G.buffer_density(); G.buffer_x()
+    assert ovo == ovg
+    sig_old, sig_new = O.sigma_vi, O.sigma_vi_new
+    pm = O.particle_mesh(a_mid, dt, keep=True)
+    f2 = []
+    for tz in range(1, NNT + 1):
+        for ty in range(1, NNT + 1):
+            for tx in range(1, NNT + 1):
+                f2.append(G.fine_kick_with(tx, ty, tz, pm["meshes"]["force_f"][(0, tx, ty, tz)], a_mid, dt, sig_old, sig_new))
+    assert np.float32(max(f2)) == pm["f2_max_fine"]
+    vmax, f2c = G.coarse_kick_with(O.force_c_image(pm["meshes"]["force_c"], 0), a_mid, dt, sig_new)
+    assert vmax == pm["vmax"][0]
+    assert f2c == pm["f2_max_coarse"][0]
+    sg, _ = G.checkpoint()
+    assert np.array_equal(physical(O, "xp"), sg["xp"])
+    assert np.array_equal(physical(O, "vp"), sg["vp"])
+
+
+def test_full_steps(tables):
+    """Three full steps, each side with its own FFT: positions/counts are bit-exact after step 1 (the drift
+    uses only input velocities); velocity codes may differ by one unit where FFT round-off crosses a
+    rounding boundary of the arctan quantiser."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=5, disp_rms=0.6)
+    O = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+    G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+    ts = co.TimeStepper(co.Cosmology(), [0.0])
+    for it in range(3):
+        dt_old, dt, a_mid = ts.step()
+        uo, po = O.step(dt_old, dt, a_mid)
+        ug, pg = G.step(dt_old, dt, a_mid)
+        sg, _ = G.checkpoint()
+        xp_o, vp_o = physical(O, "xp"), physical(O, "vp")
+        assert ug["nplocal"] == O.nplocal(0) == xp_o.shape[0]
+        same_cells = np.array_equal(O.store(0)["rhoc"], sg["rhoc"])
+        if it == 0:
+            assert same_cells
+            assert np.array_equal(xp_o, sg["xp"])
+        if same_cells:
+            dv = np.abs(vp_o.astype(np.int32) - sg["vp"].astype(np.int32))
+            # step 1: a code can only flip by one unit; later steps inherit earlier flips through vfield
+            assert dv.max() <= (1 if it == 0 else 4)
+            assert (dv != 0).mean() < (2e-3 if it == 0 else 2e-2)
+        else:
+            assert int(np.abs(O.store(0)["rhoc"] - sg["rhoc"]).sum()) < 1e-4 * xp_o.shape[0]
+        for k in ("dt_fine", "dt_coarse", "dt_vmax"):
+            assert abs(float(pg[k]) - float(po[k])) <= 1e-4 * abs(float(po[k])), k
+        ts.dt_fine, ts.dt_coarse, ts.dt_vmax = po["dt_fine"], po["dt_coarse"], po["dt_vmax"]
+    G.close(); O.close()
