@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of one CUBE PM step (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nc NC --nnt NNT]
+
+A "step" is one pass of the hot path over the resident state (cafcube.f90:27-31):
+update_particle -> buffer_density -> buffer_x -> particle_mesh -> buffer_v.  Workload at N=1 is
+BASELINE.json configs[1]: CUBE LCDM 512^3 particles, 1 image (nc=256, nnt=4 => nt=64, nfe=304, np_nc=2),
+synthetic Zel'dovich LCDM-shaped initial conditions at z=49.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the state resident in HBM;
+`e2e` = same metric through the C ABI with the disjoint state in pinned host memory, upload and download
+inside the timed region; `roofline` = the dominant phase of the step against MEASURED_PEAKS.json;
+`cpu_baseline` = the CPU oracle (restated reference path, kind "port") on a bounded sample.
+`--impl reference` times that CPU port alone, with all host threads, on the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec per PM step"
+UNIT = "particle-updates/s"
+
+
+def tables():
+    g = os.path.join(ROOT, "tests", "golden")
+    return np.load(os.path.join(g, "fk_table.npy")), np.load(os.path.join(g, "ck_table.npy"))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU port (the oracle): bounded sample, one independent single-tile image per host thread --
+# the way the reference is deployed (one coarray image per core, CUBE/main/run.sh)
+# ---------------------------------------------------------------------------------------------
+def cpu_port_throughput(nt, steps=1, warmup=0, max_threads=32):
+    from oracle import cube_oracle as co
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables()
+    ncores = os.cpu_count() or 1
+    nth = max(1, min(ncores, max_threads))
+    os.environ["CUBE_ORACLE_THREADS"] = "1"
+    states, sig, _ = make_ic(nn=1, nc=nt, nnt=1, np_nc=2, seed=7)
+    npart = states[0]["xp"].shape[0]
+    kf = co.kernel_f(fk, 4 * nt + 48)
+    kc = co.kernel_c(ck, nt)
+    sims = []
+    for _ in range(nth):
+        O = co.Oracle(nn=1, nnt=1, nc=nt, np_nc=2)
+        O.kern_f, O.kern_c = kf, kc
+        O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+        sims.append(O)
+    dt_old, dt, a_mid = np.float32(0.0), np.float32(1.0), np.float32(0.021)
+
+    def run(O, n):
+        for _ in range(n):
+            O.step(dt_old, dt, a_mid)
+
+    def timed(n):
+        th = [threading.Thread(target=run, args=(O, n)) for O in sims]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        return time.perf_counter() - t0
+
+    if warmup:
+        timed(warmup)
+    sec = timed(steps)
+    for O in sims:
+        O.close()
+    value = nth * npart * steps / sec
+    sample = ("%d independent single-tile images (nc=nt=%d, nfe=%d, %d particles each = 1/%s of the GPU workload's tiles), "
+              "one per host thread, %d step(s)" % (nth, nt, 4 * nt + 48, npart, "64", steps))
+    return dict(value=value, unit=UNIT, cores=nth, kind="port", sample=sample, seconds=sec, ms_per_step=1e3 * sec / steps)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    nt = args.nc // args.nnt
+    r = cpu_port_throughput(nt, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 mesh / f64 particle update / int16 codes", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "restated CPU path (C + pocketfft port of CUBE/main), not the coarray-Fortran binary: no Fortran compiler exists here"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    nt = args.nc // args.nnt
+    return {"workload": "CUBE LCDM %d^3 particles per image, %d image(s), nc=%d nnt=%d nt=%d nfe=%d np_nc=2 izipx=izipv=2, z=49 Zel'dovich ICs"
+                        % (2 * args.nc, world, args.nc, args.nnt, nt, 4 * nt + 48),
+            "step": "update_particle+buffer_density+buffer_x+particle_mesh+buffer_v (cafcube.f90:27-31)",
+            "l2": "state and meshes (>1.5 GB) exceed the 126 MB L2; no flush needed",
+            "parallelism": "1 image" if world == 1 else "%d independent periodic images, one per GPU (ghost exchange over NCCL not built yet)" % world}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nc", type=int, default=256)
+    ap.add_argument("--nnt", type=int, default=4)
+    ap.add_argument("--fine-batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cafproject_b200.cube import CubeGPU, host_tanf_lut
+    from cafproject_b200.synthetic_ic import make_ic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fk, ck = tables()
+    nc, nnt = args.nc, args.nnt
+    states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=1000 * 2 + rank, device="cuda")
+    torch.cuda.empty_cache()
+    st = states[0]
+    npart = st["xp"].shape[0]
+    G = CubeGPU(nc, nnt, fk, ck, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut())
+    G.particle_initialization(st, sig)
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    # fixed small time step so that every timed step does the same work (dt from the first PM limits)
+    dt, a_mid = np.float32(0.5), np.float32(0.0205)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(dt_old):
+        G.step(dt_old, dt, a_mid)
+
+    one_step(np.float32(0.0))
+    for _ in range(max(0, args.warmup - 1)):
+        one_step(dt)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = G.query("kernel_launches")
+    barrier()
+    G.timer_start()
+    for _ in range(args.steps):
+        one_step(dt)
+    ms = G.timer_stop()
+    barrier()
+    launches = G.query("kernel_launches") - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * npart / (ms_per_step * 1e-3)
+
+    # ---- per-phase timing (CUDA events on the library stream) -> dominant kernel + roofline ----
+    G.set_profiling(True); G.phase_times()
+    nprof = 2
+    for _ in range(nprof):
+        one_step(dt)
+    phases = {k: v / nprof for k, v in G.phase_times().items()}
+    G.set_profiling(False)
+    nt = nc // nnt; nfe = 4 * nt + 48
+    ntile = nnt ** 3
+    batch = G.query("fine_batch")
+    nfine = ntile * nfe ** 3
+    # algorithmic bytes per step of each phase (DESIGN.md "roofline")
+    alg = {"drift_key": 12 * npart, "drift_count": 6 * npart, "drift_place": 24 * npart, "drift_scan": 12 * nc ** 3,
+           "buffer": 32 * nc ** 3, "fine_deposit": 6 * npart * (1 + 12 / nt) ** 3 + 4 * nfine, "fine_fft_fwd": 8 * nfine,
+           "fine_green": 18 * nfine, "fine_fft_inv": 24 * nfine, "fine_f2max": 0, "fine_kick": 18 * npart + 12 * ntile * (4 * nt + 2) ** 3,
+           "coarse_deposit": 6 * npart + 4 * nc ** 3, "coarse_fft_green": 50 * nc ** 3, "coarse_kick": 18 * npart + 12 * nc ** 3}
+    launches_per_step = {k: (ntile + batch - 1) // batch if k.startswith("fine") else 1 for k in phases}
+    dom = max(phases, key=lambda k: phases[k])
+    peak, which = measured_peak()
+    dom_ms_per_launch = phases[dom] / launches_per_step[dom]
+    achieved = alg[dom] / launches_per_step[dom] / (dom_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "ms_per_launch": dom_ms_per_launch,
+                "algorithmic_bytes_per_launch": alg[dom] / launches_per_step[dom]}
+    bytes_step = 48 * npart + 42 * nfine + 82 * nc ** 3
+    step_roof = {"bytes_step": bytes_step, "achieved": bytes_step / (ms_per_step * 1e-3) / 1e9,
+                 "frac": bytes_step / (ms_per_step * 1e-3) / 1e9 / peak, "formula": "48*Np+42*Nfine_ext+82*Ncoarse (BASELINE.md sec.2)"}
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        cur, sig_cur = G.checkpoint()
+        pin = {k: torch.from_numpy(v).pin_memory() for k, v in cur.items()}
+        host = {k: v.numpy() for k, v in pin.items()}
+        n_e2e = max(2, min(args.steps, 3))
+        h2d = sum(v.nbytes for v in host.values()); d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            G.particle_initialization(host, sig_cur, npglobal=npart)
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+            one_step(dt)
+            out, sig_cur = G.checkpoint(out=host)   # result lands in the same pinned buffers = next step's input
+            d2h = sum(v.nbytes for v in out.values())
+        barrier()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); sec = float(t.item())
+        e2e = {"value": world * npart * n_e2e / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * sec / n_e2e, "steps": n_e2e}
+    G.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_port_throughput(nt, steps=1, warmup=0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 mesh / f64 particle update / int16 codes", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "step_roofline": step_roof, "phases_ms_per_step": phases, "cpu_baseline": cpu,
+                "particles_per_gpu": int(npart)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,7 @@ struct cube_handle {
   cufftHandle cplan_r2c = 0, cplan_c2r = 0;
   // host pinned scalars
   // profiling
+  cudaEvent_t tev[2] = {};
   bool prof = false; cudaEvent_t ev[2 * PH_N] = {}; float phase_ms[PH_N] = {}; long long launches = 0;
   float last_f2max_fine = 0;
 };
@@ -176,6 +177,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   h->np_tile_max = (long long)((float)(np_image / ((long long)g.nnt * g.nnt * g.nnt)) * r3 * p->tile_buffer);
   CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
+  CK(cudaEventCreate(&h->tev[0])); CK(cudaEventCreate(&h->tev[1]));
   const long long cap = h->np_image_max;
   CK(dmalloc(&h->xp, 3 * cap)); CK(dmalloc(&h->vp, 3 * cap)); CK(dmalloc(&h->xp2, 3 * cap)); CK(dmalloc(&h->vp2, 3 * cap));
   CK(dmalloc(&h->key, cap));
@@ -646,6 +648,15 @@ extern "C" int cube_gpu_phase_count(void) { return PH_N; }
 extern "C" const char* cube_gpu_phase_name(int i) { return (i >= 0 && i < PH_N) ? kPhaseNames[i] : ""; }
 extern "C" int cube_gpu_phase_times(cube_handle* h, float* ms) {
   for (int i = 0; i < PH_N; i++) { ms[i] = h->phase_ms[i]; h->phase_ms[i] = 0; }
+  return 0;
+}
+extern "C" int cube_gpu_timer(cube_handle* h, int start, float* ms) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  if (start) { CK(cudaEventRecord(h->tev[0], h->st)); return 0; }
+  CK(cudaEventRecord(h->tev[1], h->st));
+  CK(cudaEventSynchronize(h->tev[1]));
+  if (ms) CK(cudaEventElapsedTime(ms, h->tev[0], h->tev[1]));
   return 0;
 }
 extern "C" int cube_gpu_set_profiling(cube_handle* h, int on) { h->prof = on != 0; return 0; }

@@ -69,6 +69,7 @@ def load_library():
     L.cube_gpu_phase_name.argtypes = [i32]
     L.cube_gpu_phase_times.argtypes = [vp, vp]
     L.cube_gpu_set_profiling.argtypes = [vp, i32]
+    L.cube_gpu_timer.argtypes = [vp, i32, C.POINTER(f32)]
     _lib = L
     return L
 
@@ -79,7 +80,7 @@ ABI_SYMBOLS = [
     "cube_gpu_download", "cube_gpu_finalize", "cube_gpu_last_error", "cube_gpu_query", "cube_gpu_get_kern_f",
     "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
-    "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling",
+    "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer",
 ]
 
 
@@ -155,15 +156,21 @@ class CubeGPU:
         self.nplocal = n
         self.sigma_vi = F32(sigma_vi)
 
-    def checkpoint(self):
-        """Disjoint state back on the host (what checkpoint.f90 writes)."""
+    def checkpoint(self, out=None):
+        """Disjoint state back on the host (what checkpoint.f90 writes).  ``out`` may hold preallocated
+        (e.g. pinned) arrays xp, vp (capacity >= nplocal rows), rhoc, vfield."""
         n = self.query("nplocal")
         shp = (self.nnt,) * 3 + (self.nt,) * 3
-        xp = np.empty((n, 3), np.int16); vp = np.empty((n, 3), np.int16)
-        rc = np.empty(shp, np.int32); vf = np.empty(shp + (3,), np.float32)
+        if out is None:
+            out = dict(xp=np.empty((n, 3), np.int16), vp=np.empty((n, 3), np.int16), rhoc=np.empty(shp, np.int32),
+                       vfield=np.empty(shp + (3,), np.float32))
+        assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n
         npl = C.c_int64(); sig = C.c_float()
-        self._ck(self.L.cube_gpu_download(self.h, _p(xp), _p(vp), _p(rc), _p(vf), C.byref(npl), C.byref(sig)))
-        return dict(xp=xp, vp=vp, rhoc=rc, vfield=vf), F32(sig.value)
+        self._ck(self.L.cube_gpu_download(self.h, _p(out["xp"]), _p(out["vp"]), _p(out["rhoc"]), _p(out["vfield"]),
+                                          C.byref(npl), C.byref(sig)))
+        if out["xp"].shape[0] != n:
+            out = dict(out, xp=out["xp"][:n], vp=out["vp"][:n])
+        return out, F32(sig.value)
 
     # ---- step subroutines -------------------------------------------------------------------
     def update_particle(self, dt_old, dt):
@@ -240,6 +247,14 @@ class CubeGPU:
         f = np.ascontiguousarray(force_c, F32); vm = C.c_float(); f2 = C.c_float()
         self._ck(self.L.cube_gpu_coarse_kick_with(self.h, _p(f), F32(a_mid), F32(dt), F32(sigma_vi), C.byref(vm), C.byref(f2)))
         return F32(vm.value), F32(f2.value)
+
+    def timer_start(self):
+        self._ck(self.L.cube_gpu_timer(self.h, 1, None))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.cube_gpu_timer(self.h, 0, C.byref(ms)))
+        return float(ms.value)
 
     def set_profiling(self, on=True):
         self.L.cube_gpu_set_profiling(self.h, int(on))

@@ -110,6 +110,9 @@ int cube_gpu_coarse_kick_with(cube_handle *h, const float *force_c, float a_mid,
 int cube_gpu_phase_count(void);
 const char *cube_gpu_phase_name(int i);
 int cube_gpu_phase_times(cube_handle *h, float *ms);
+/* device-side stopwatch on the library's own launch stream (CUDA events): start=1 records the start event,
+ * start=0 records the stop event, waits for it and returns the elapsed milliseconds in *ms. */
+int cube_gpu_timer(cube_handle *h, int start, float *ms);
 /* enable (1) / disable (0) per-phase event timing (off by default; costs a few event records) */
 int cube_gpu_set_profiling(cube_handle *h, int on);
 
