@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--fine-batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,10 +210,14 @@ def main():
         sampler.start()
     l0 = G.query("kernel_launches")
     barrier()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStart()
     G.timer_start()
     for _ in range(args.steps):
         one_step(dt)
     ms = G.timer_stop()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     launches = G.query("kernel_launches") - l0
     clocks = sampler.stop() if rank == 0 else None
