@@ -237,10 +237,15 @@ def main():
     ntile = nnt ** 3
     batch = G.query("fine_batch")
     nfine = ntile * nfe ** 3
-    # algorithmic bytes per step of each phase (DESIGN.md "roofline")
+    # compulsory bytes per step of each phase: every input read once, every output written once (DESIGN.md "roofline")
+    N = G.query("nfft"); NH = N // 2 + 1; M = 4 * nt + 2
+    np_win = npart * (N / 4 / nt) ** 3          # particles inside the tiles' FFT windows (ghosts included)
     alg = {"drift_key": 12 * npart, "drift_count": 6 * npart, "drift_place": 24 * npart, "drift_scan": 12 * nc ** 3,
-           "buffer": 32 * nc ** 3, "fine_deposit": 6 * npart * (1 + 12 / nt) ** 3 + 4 * nfine, "fine_fft_fwd": 8 * nfine,
-           "fine_green": 18 * nfine, "fine_fft_inv": 24 * nfine, "fine_f2max": 0, "fine_kick": 18 * npart + 12 * ntile * (4 * nt + 2) ** 3,
+           "buffer": 32 * nc ** 3, "fine_deposit": 6 * np_win + 4 * ntile * N ** 3,
+           "fine_fft_x": ntile * (4 * N ** 3 + 8 * N * N * NH), "fine_fft_y": ntile * 16 * N * N * NH,
+           "fine_fft_z_green": ntile * (8 * N * N * NH + 24 * M * N * NH) + 12 * N * N * NH,
+           "fine_ifft_y": ntile * 3 * (8 * M * N * NH + 8 * M * M * NH), "fine_ifft_x": ntile * 3 * (8 * M * M * NH + 4 * M ** 3),
+           "fine_f2max": ntile * 12 * M ** 3, "fine_kick": 18 * npart + 12 * ntile * M ** 3,
            "coarse_deposit": 6 * npart + 4 * nc ** 3, "coarse_fft_green": 50 * nc ** 3, "coarse_kick": 18 * npart + 12 * nc ** 3}
     launches_per_step = {k: (ntile + batch - 1) // batch if k.startswith("fine") else 1 for k in phases}
     dom = max(phases, key=lambda k: phases[k])

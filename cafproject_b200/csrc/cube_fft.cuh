@@ -1,0 +1,417 @@
+// cube_fft.cuh -- hand-written fine-mesh force convolution for sm_100a (replaces FFTW's
+// plan_fft_fine / plan_ifft_fine + the kern_f multiply of CUBE/main/pm.f90:75-84).
+//
+// The reference transforms the whole padded tile rho_f(nfe,nfe,nfe), nfe = nft + 2*nfb (304 for nt = 64),
+// multiplies by kern_f and transforms back three times, but it only keeps force_f on the M = nft+2 points
+// nfb..nfe-nfb+1 (pm.f90:83), and the real-space kernel has support |offset| <= nf_cutoff-1 = 15
+// (kernel_f.f90:32-38).  A circular convolution of length N >= M + 30 on the window that starts 15 cells
+// before the kept region therefore gives the same forces (no wrap-around reaches the kept points); for
+// nt = 64 that is N = 288 = 16*18 instead of 304 = 16*19: 15% fewer cells and radix-friendly.
+//
+// Pipeline per batch of tiles (all arrays in HBM, x fastest):
+//   rho [b][z][y][x]          real   N^3                       (fine CIC deposit)
+//   A   [b][z][ky][kx]        complex, kx pitch P >= N/2+1      k_fft_x_fwd (r2c, two real rows per complex line)
+//                                                              k_fft_y (in place)
+//   B   [d][b][z'][ky][kx]    complex, z' = M kept planes      k_fft_z_green: z forward, x i*K_d, z inverse, d=1..3
+//                                                              k_fft_y (inverse, in place, keeps M rows)
+//   F   [b][z'][y'][d][x']    real, x' pitch FP                k_fft_x_inv (c2r) -> read by the fine kick
+// Every kernel moves 16 lines x N points through shared memory in the layout s[n][line] (line fastest):
+// a warp then touches 32 consecutive float2 per access (conflict-free) in both Cooley-Tukey steps
+// N = R1*R2, each thread doing one R-point DFT in registers with compile-time twiddles.
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+
+namespace cube {
+
+// ---------------------------------------------------------------------------------------------
+// compile-time trigonometry: cos/sin(2 pi a / R) to double precision
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr double ct_sin_small(double x) {  // |x| <= pi/4
+  double x2 = x * x, term = x, sum = x;
+  for (int n = 1; n <= 12; n++) { term *= -x2 / (double)((2 * n) * (2 * n + 1)); sum += term; }
+  return sum;
+}
+__host__ __device__ constexpr double ct_cos_small(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int n = 1; n <= 12; n++) { term *= -x2 / (double)((2 * n - 1) * (2 * n)); sum += term; }
+  return sum;
+}
+struct ct_cs { double c, s; };
+__host__ __device__ constexpr ct_cs ct_cossin_turn(int a, int R) {  // angle = 2 pi a / R
+  a %= R; if (a < 0) a += R;
+  const int q = (8 * a) / R, r = 8 * a - q * R;  // octant and remainder: angle = (pi/4)(q + r/R)
+  const double qp = 0.785398163397448309615660845819875721;
+  const double t = qp * (double)r / (double)R, u = qp * (double)(R - r) / (double)R;  // theta', pi/4 - theta'
+  switch (q) {
+    case 0: return {ct_cos_small(t), ct_sin_small(t)};
+    case 1: return {ct_sin_small(u), ct_cos_small(u)};
+    case 2: return {-ct_sin_small(t), ct_cos_small(t)};
+    case 3: return {-ct_cos_small(u), ct_sin_small(u)};
+    case 4: return {-ct_cos_small(t), -ct_sin_small(t)};
+    case 5: return {-ct_sin_small(u), -ct_cos_small(u)};
+    case 6: return {ct_sin_small(t), -ct_cos_small(t)};
+    default: return {ct_cos_small(u), -ct_sin_small(u)};
+  }
+}
+
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+
+// a * exp(DIR * 2 pi i T / R) with the root folded to immediates; trivial roots cost nothing
+template <int DIR, int T, int R>
+__device__ __forceinline__ float2 mul_root(float2 a) {
+  constexpr int t = ((T % R) + R) % R;
+  if constexpr (t == 0) return a;
+  else if constexpr (2 * t == R) return make_float2(-a.x, -a.y);
+  else if constexpr (4 * t == R) return DIR > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);      // * (+-i)
+  else if constexpr (4 * t == 3 * R) return DIR > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);  // * (-+i)
+  else {
+    constexpr ct_cs w = ct_cossin_turn(t, R);
+    constexpr float c = (float)w.c, s = (float)(DIR > 0 ? w.s : -w.s);
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+  }
+}
+
+__host__ __device__ constexpr int fft_radix_of(int R) { return R % 4 == 0 ? 4 : R % 2 == 0 ? 2 : R % 3 == 0 ? 3 : R % 5 == 0 ? 5 : R; }
+
+// p-point butterfly, natural order in and out, root exp(DIR*2 pi i/p)
+template <int P, int DIR>
+__device__ __forceinline__ void butterfly(float2 (&t)[P]) {
+  if constexpr (P == 2) {
+    float2 a = t[0], b = t[1];
+    t[0] = make_float2(a.x + b.x, a.y + b.y);
+    t[1] = make_float2(a.x - b.x, a.y - b.y);
+  } else if constexpr (P == 4) {
+    float2 a = make_float2(t[0].x + t[2].x, t[0].y + t[2].y), b = make_float2(t[0].x - t[2].x, t[0].y - t[2].y);
+    float2 c = make_float2(t[1].x + t[3].x, t[1].y + t[3].y), d = make_float2(t[1].x - t[3].x, t[1].y - t[3].y);
+    t[0] = make_float2(a.x + c.x, a.y + c.y);
+    t[2] = make_float2(a.x - c.x, a.y - c.y);
+    if (DIR > 0) { t[1] = make_float2(b.x - d.y, b.y + d.x); t[3] = make_float2(b.x + d.y, b.y - d.x); }   // b +- i d
+    else         { t[1] = make_float2(b.x + d.y, b.y - d.x); t[3] = make_float2(b.x - d.y, b.y + d.x); }   // b -+ i d
+  } else if constexpr (P == 3) {
+    constexpr float s0 = (float)(DIR > 0 ? 0.866025403784438646763723170752936183 : -0.866025403784438646763723170752936183);
+    float2 s = make_float2(t[1].x + t[2].x, t[1].y + t[2].y), d = make_float2(t[1].x - t[2].x, t[1].y - t[2].y);
+    float2 m = make_float2(t[0].x - 0.5f * s.x, t[0].y - 0.5f * s.y);
+    t[0] = make_float2(t[0].x + s.x, t[0].y + s.y);
+    t[1] = make_float2(m.x - s0 * d.y, m.y + s0 * d.x);
+    t[2] = make_float2(m.x + s0 * d.y, m.y - s0 * d.x);
+  } else {  // generic small prime (5): direct DFT with immediate roots
+    float2 o[P];
+    static_for<0, P>([&](auto Q) {
+      float2 acc = t[0];
+      static_for<1, P>([&](auto J) {
+        float2 v = mul_root<DIR, (J.value * Q.value) % P, P>(t[J.value]);
+        acc.x += v.x; acc.y += v.y;
+      });
+      o[Q.value] = acc;
+    });
+    static_for<0, P>([&](auto Q) { t[Q.value] = o[Q.value]; });
+  }
+}
+
+// In-register DFT of the R elements x[OFF + S*i] (natural order in and out), decimation in time.
+template <int R, int DIR, int S, int OFF, int NT>
+__device__ __forceinline__ void dft_rec(float2 (&x)[NT]) {
+  if constexpr (R > 1) {
+    constexpr int p = fft_radix_of(R), m = R / p;
+    static_for<0, p>([&](auto J) { dft_rec<m, DIR, S * p, OFF + S * J.value, NT>(x); });
+    float2 y[R];
+    static_for<0, m>([&](auto K) {
+      float2 t[p];
+      static_for<0, p>([&](auto J) { t[J.value] = mul_root<DIR, J.value * K.value, R>(x[OFF + S * (J.value + p * K.value)]); });
+      butterfly<p, DIR>(t);
+      static_for<0, p>([&](auto Q) { y[K.value + m * Q.value] = t[Q.value]; });
+    });
+    static_for<0, R>([&](auto I) { x[OFF + S * I.value] = y[I.value]; });
+  }
+}
+template <int R, int DIR>
+__device__ __forceinline__ void dft(float2 (&x)[R]) { dft_rec<R, DIR, 1, 0, R>(x); }
+
+// a * tw or a * conj(tw)
+template <int DIR>
+__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
+  if (DIR < 0) return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+  return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-level line FFT, N = R1*R2, LW lines interleaved: s[n*LW + line].  tw[t] = exp(-2 pi i t/N).
+// thread -> (line = tid % 16, idx = tid / 16); blockDim.x = 16*max(R1,R2).
+// ---------------------------------------------------------------------------------------------
+constexpr int FL = 16;  // lines per CTA
+
+// step A: R1-point DFTs over n1 for fixed n2 = idx, twiddle, back to the same slots (holds Y[k1][n2])
+template <int R1, int R2, int DIR, int LW>
+__device__ __forceinline__ void fft_step_a(float2* s, const float2* tw, int line, int idx) {
+  if (idx < R2) {
+    float2 v[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; n1++) v[n1] = s[(n1 * R2 + idx) * LW + line];
+    dft<R1, DIR>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; k1++) s[(k1 * R2 + idx) * LW + line] = k1 ? mul_tw<DIR>(v[k1], tw[idx * k1]) : v[0];
+  }
+}
+// step B: R2-point DFT over n2 for fixed k1 = idx; v[k2] = X[k1 + R1*k2]
+template <int R1, int R2, int DIR, int LW>
+__device__ __forceinline__ void fft_step_b(const float2* s, int line, int idx, float2 (&v)[R2]) {
+#pragma unroll
+  for (int n2 = 0; n2 < R2; n2++) v[n2] = s[(idx * R2 + n2) * LW + line];
+  dft<R2, DIR>(v);
+}
+// mirrored inverse, first half: from v[k2] = X[k1 + R1*k2] (registers of thread k1 = idx) to s[(k1*R2+n2)]
+template <int R1, int R2, int LW>
+__device__ __forceinline__ void ifft_step_a(float2 (&v)[R2], float2* s, const float2* tw, int line, int idx) {
+  dft<R2, +1>(v);
+#pragma unroll
+  for (int n2 = 0; n2 < R2; n2++) s[(idx * R2 + n2) * LW + line] = n2 ? mul_tw<+1>(v[n2], tw[n2 * idx]) : v[0];
+}
+// mirrored inverse, second half: thread n2 = idx gets v[n1] = x[n1*R2 + n2]
+template <int R1, int R2, int LW>
+__device__ __forceinline__ void ifft_step_b(const float2* s, int line, int idx, float2 (&v)[R1]) {
+#pragma unroll
+  for (int k1 = 0; k1 < R1; k1++) v[k1] = s[(k1 * R2 + idx) * LW + line];
+  dft<R1, +1>(v);
+}
+
+struct FftGeom {
+  int N;     // transform length
+  int NH;    // N/2+1
+  int P;     // kx pitch of the complex arrays (multiple of 16)
+  int M;     // kept points per dim (nft+2)
+  int off;   // first kept point on the FFT grid (15)
+  int FP;    // x' pitch of the force rows
+  int nbatch;
+};
+
+__device__ __forceinline__ void load_tw(float2* tw_s, const float2* __restrict__ tw_g, int N) {
+  for (int t = threadIdx.x; t < N; t += blockDim.x) tw_s[t] = tw_g[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// x forward (r2c): rho[b][z][y][x] -> A[b][z][y][kx].  One CTA = 32 real rows = 16 complex lines.
+// grid = (ceil(N/32), N, nbatch)
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom g, const float* __restrict__ rho, float2* __restrict__ A,
+                                                                       const float2* __restrict__ tw_g) {
+  constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
+  extern __shared__ float2 smem[];
+  float2* s = smem;            // [N][LW]
+  float2* tw = smem + N * LW;  // [N]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int y0 = blockIdx.x * 32, z = blockIdx.y, b = blockIdx.z;
+  load_tw(tw, tw_g, N);
+  const float* src = rho + ((size_t)b * N + z) * (size_t)N * N;
+  // rows y0+2l (re), y0+2l+1 (im); lanes along x
+  for (int r = warp; r < 32; r += NT / 32) {
+    const int y = y0 + r;
+    const int l = r >> 1, im = r & 1;
+    float* dst = reinterpret_cast<float*>(s) + im;
+    if (y < N) {
+      const float* row = src + (size_t)y * N;
+      for (int x = lane; x < N; x += 32) dst[(x * LW + l) * 2] = row[x];
+    } else {
+      for (int x = lane; x < N; x += 32) dst[(x * LW + l) * 2] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int line = tid % FL, idx = tid / FL;
+  fft_step_a<R1, R2, -1, LW>(s, tw, line, idx);
+  __syncthreads();
+  float2 v[R2];
+  if (idx < R1) fft_step_b<R1, R2, -1, LW>(s, line, idx, v);
+  __syncthreads();
+  if (idx < R1) {
+#pragma unroll
+    for (int k2 = 0; k2 < R2; k2++) s[(idx + R1 * k2) * LW + line] = v[k2];
+  }
+  __syncthreads();
+  // separate the two real rows: Xa[k] = (Z[k] + conj Z[N-k])/2, Xb[k] = (Z[k] - conj Z[N-k])/(2i)
+  float2* dstA = A + ((size_t)b * N + z) * (size_t)N * g.P;
+  for (int r = warp; r < 32; r += NT / 32) {
+    const int y = y0 + r;
+    if (y >= N) continue;
+    const int l = r >> 1, im = r & 1;
+    float2* row = dstA + (size_t)y * g.P;
+    for (int k = lane; k < g.NH; k += 32) {
+      const float2 zk = s[k * LW + l], zn = s[(k ? N - k : 0) * LW + l];
+      float2 o;
+      if (!im) o = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      else o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      row[k] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y transform, in place, lines along ky for 16 adjacent kx.  DIR=-1: A (all rows, N planes);
+// DIR=+1: B (writes only the M kept rows y' -> row index y'+off stays in place), planes = M per (d,b).
+// grid = (P/16, planes, nslab) ; plane stride = N*P, slab stride = planes*N*P
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2, int DIR>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_y(FftGeom g, float2* __restrict__ A, const float2* __restrict__ tw_g) {
+  constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2);
+  extern __shared__ float2 smem[];
+  float2* s = smem;
+  float2* tw = smem + N * LW;
+  const int tid = threadIdx.x, line = tid % FL, idx = tid / FL;
+  const int kx = blockIdx.x * FL + line;
+  load_tw(tw, tw_g, N);
+  float2* base = A + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (size_t)N * g.P + kx;
+  const bool act = kx < g.NH;
+  if (act) {
+#pragma unroll 4
+    for (int n = idx; n < N; n += NT / FL) s[n * LW + line] = base[(size_t)n * g.P];
+  }
+  __syncthreads();
+  if (act) fft_step_a<R1, R2, DIR, LW>(s, tw, line, idx);
+  __syncthreads();
+  if (act && idx < R1) {
+    float2 v[R2];
+    fft_step_b<R1, R2, DIR, LW>(s, line, idx, v);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; k2++) {
+      const int y = idx + R1 * k2;
+      if (DIR < 0 || (y >= g.off && y < g.off + g.M)) base[(size_t)y * g.P] = v[k2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// z forward + Green multiply + z inverse for the three force components.
+// A[b][z][ky][kx] -> B[d][b][z'][ky][kx];  kern[d][kz][ky][kx] real (already scaled by 1/N^3).
+// out = i*K*c  (pm.f90:79-80: re' = -im*K, im' = re*K).   grid = (P/16, N); loops over the batch.
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
+                                                                         const float* __restrict__ kern, float scale,
+                                                                         const float2* __restrict__ tw_g) {
+  constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2);
+  extern __shared__ float2 smem[];
+  float2* s = smem;                                         // [N][16]
+  float2* tw = smem + N * LW;                               // [N]
+  float* ks = reinterpret_cast<float*>(smem + N * LW + N);  // [3][N][16]
+  const int tid = threadIdx.x, line = tid % FL, idx = tid / FL;
+  const int kx = blockIdx.x * FL + line, ky = blockIdx.y;
+  const bool act = kx < g.NH;
+  load_tw(tw, tw_g, N);
+  for (int q = idx; q < 3 * N; q += NT / FL) ks[q * FL + line] = act ? kern[((size_t)q * N + ky) * g.P + kx] * scale : 0.f;
+  const size_t plane = (size_t)N * g.P;
+  const size_t colo = (size_t)ky * g.P + kx;
+  for (int b = 0; b < g.nbatch; b++) {
+    const float2* src = A + (size_t)b * N * plane + colo;
+    __syncthreads();  // previous iteration's readers of s are done (also orders the ks/tw fill)
+    if (act) {
+#pragma unroll 4
+      for (int n = idx; n < N; n += NT / FL) s[n * LW + line] = src[(size_t)n * plane];
+    }
+    __syncthreads();
+    if (act) fft_step_a<R1, R2, -1, LW>(s, tw, line, idx);
+    __syncthreads();
+    float2 X[R2];
+    if (act && idx < R1) fft_step_b<R1, R2, -1, LW>(s, line, idx, X);
+#pragma unroll 1
+    for (int d = 0; d < 3; d++) {
+      __syncthreads();
+      if (act && idx < R1) {
+        float2 w[R2];
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) {
+          const float K = ks[(d * N + idx + R1 * k2) * FL + line];
+          w[k2] = make_float2(-X[k2].y * K, X[k2].x * K);
+        }
+        ifft_step_a<R1, R2, LW>(w, s, tw, line, idx);
+      }
+      __syncthreads();
+      if (act && idx < R2) {
+        float2 v[R1];
+        ifft_step_b<R1, R2, LW>(s, line, idx, v);
+        float2* dst = B + ((size_t)d * g.nbatch + b) * (size_t)g.M * plane + colo;
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) {
+          const int zi = n1 * R2 + idx - g.off;
+          if (zi >= 0 && zi < g.M) dst[(size_t)zi * plane] = v[n1];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x inverse (c2r): B[d][b][z'][y][kx] -> F[b][z'][y'][d][x'] (x' = M kept points, pitch FP).
+// One CTA = 32 kept rows (16 complex lines).  grid = (ceil(M/32), M, 3*nbatch)
+// Also reduces f2 partials?  No: |F|^2 needs the three components; see k_f2max_rows.
+// ---------------------------------------------------------------------------------------------
+template <int R1, int R2>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
+                                                                       const float2* __restrict__ tw_g) {
+  constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
+  extern __shared__ float2 smem[];
+  float2* s = smem;
+  float2* tw = smem + N * LW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * 32, zp = blockIdx.y, db = blockIdx.z, d = db / g.nbatch, b = db - d * g.nbatch;
+  load_tw(tw, tw_g, N);
+  const float2* src = B + ((size_t)db * g.M + zp) * (size_t)N * g.P;
+  // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k])
+  for (int l = warp; l < FL; l += NT / 32) {
+    const int ya = r0 + 2 * l, yb = ya + 1;
+    const float2* rowa = src + (size_t)(ya + g.off) * g.P;
+    const float2* rowb = src + (size_t)(yb + g.off) * g.P;
+    for (int k = lane; k < g.NH; k += 32) {
+      const float2 a = ya < g.M ? rowa[k] : make_float2(0.f, 0.f);
+      const float2 c = yb < g.M ? rowb[k] : make_float2(0.f, 0.f);
+      s[k * LW + l] = make_float2(a.x - c.y, a.y + c.x);
+      if (k && 2 * k != N) s[(N - k) * LW + l] = make_float2(a.x + c.y, c.x - a.y);
+    }
+  }
+  __syncthreads();
+  const int line = tid % FL, idx = tid / FL;
+  fft_step_a<R1, R2, +1, LW>(s, tw, line, idx);
+  __syncthreads();
+  float2 v[R2];
+  if (idx < R1) fft_step_b<R1, R2, +1, LW>(s, line, idx, v);
+  __syncthreads();
+  if (idx < R1) {
+#pragma unroll
+    for (int k2 = 0; k2 < R2; k2++) s[(idx + R1 * k2) * LW + line] = v[k2];
+  }
+  __syncthreads();
+  float* dst = F + (((size_t)b * g.M + zp) * g.M) * 3 * (size_t)g.FP;
+  for (int r = warp; r < 32; r += NT / 32) {
+    const int yp = r0 + r;
+    if (yp >= g.M) continue;
+    const int l = r >> 1, im = r & 1;
+    float* row = dst + ((size_t)yp * 3 + d) * g.FP;
+    const float* sp = reinterpret_cast<const float*>(s) + im;
+    for (int x = lane; x < g.M; x += 32) row[x] = sp[((x + g.off) * LW + l) * 2];
+  }
+}
+
+// f2_max_fine(tile) = maxval(sum(force_f**2,1))  (pm.f90:85) on F[b][z'][y'][d][x'];  grid = (blocks, nbatch)
+__global__ void __launch_bounds__(256) k_f2max_rows(FftGeom g, const float* __restrict__ F, unsigned* __restrict__ f2max) {
+  const int b = blockIdx.y;
+  const size_t nrow = (size_t)g.M * g.M;
+  const float* base = F + (size_t)b * nrow * 3 * g.FP;
+  float best = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (size_t r = (size_t)blockIdx.x * nw + warp; r < nrow; r += (size_t)gridDim.x * nw) {
+    const float* row = base + r * 3 * g.FP;
+    for (int x = lane; x < g.M; x += 32) {
+      const float f0 = row[x], f1 = row[g.FP + x], f2 = row[2 * g.FP + x];
+      best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0, f0), __fmul_rn(f1, f1)), __fmul_rn(f2, f2)));
+    }
+  }
+  best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
+  if (lane == 0) atomicMax(&f2max[b], __float_as_uint(best));
+}
+
+}  // namespace cube

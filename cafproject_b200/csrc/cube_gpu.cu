@@ -17,6 +17,7 @@
 
 #include "../../include/cube_gpu.h"
 #include "cube_kernels.cuh"
+#include "cube_fft.cuh"
 
 using namespace cube;
 
@@ -39,11 +40,29 @@ static int fail(const char* fmt, ...) {
   } while (0)
 #define CKL() CK(cudaGetLastError())
 
-enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFFT, PH_FGREEN, PH_FIFFT, PH_FMAX, PH_FKICK,
+enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFTX, PH_FFTY, PH_FFTZ, PH_IFFTY, PH_IFFTX, PH_FMAX, PH_FKICK,
              PH_CDEP, PH_CFFT, PH_CKICK, PH_N };
 static const char* kPhaseNames[PH_N] = {"drift_key", "drift_count", "drift_scan", "drift_place", "buffer", "fine_deposit",
-                                        "fine_fft_fwd", "fine_green", "fine_fft_inv", "fine_f2max", "fine_kick",
-                                        "coarse_deposit", "coarse_fft_green", "coarse_kick"};
+                                        "fine_fft_x", "fine_fft_y", "fine_fft_z_green", "fine_ifft_y", "fine_ifft_x", "fine_f2max",
+                                        "fine_kick", "coarse_deposit", "coarse_fft_green", "coarse_kick"};
+
+// one instantiation of the hand-written fine-mesh FFT kernels per supported transform length N = R1*R2
+struct FftPlan {
+  int R1, R2;
+  void (*x_fwd)(FftGeom, const float*, float2*, const float2*);
+  void (*y_fwd)(FftGeom, float2*, const float2*);
+  void (*y_inv)(FftGeom, float2*, const float2*);
+  void (*z_green)(FftGeom, const float2*, float2*, const float*, float, const float2*);
+  void (*x_inv)(FftGeom, const float2*, float*, const float2*);
+  int N() const { return R1 * R2; }
+  int threads() const { return FL * (R1 > R2 ? R1 : R2); }
+};
+template <int R1, int R2> static FftPlan make_plan() {
+  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv<R1, R2>};
+}
+// N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
+static const FftPlan kPlans[] = {make_plan<8, 10>(), make_plan<8, 12>(), make_plan<8, 16>(), make_plan<10, 16>(), make_plan<12, 16>(),
+                                 make_plan<16, 16>(), make_plan<16, 18>(), make_plan<18, 20>(), make_plan<20, 24>(), make_plan<24, 24>()};
 
 struct cube_handle {
   cube_params p;
@@ -69,12 +88,16 @@ struct cube_handle {
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f;
-  // fine mesh
-  int batch = 1; long long fvol = 0, fnk = 0;
-  float* rho = nullptr;      // [batch][nfe][nfe][nfe+2]  (in-place r2c)
-  float* force = nullptr;    // [3][batch][nfe][nfe][nfe+2]
-  float* kern_f = nullptr;   // [3][nk]
-  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_r2c1 = 0, plan_c2r1 = 0;
+  // fine mesh (cube_fft.cuh)
+  int batch = 1;
+  const FftPlan* plan = nullptr; FftGeom fg = {};
+  size_t rho_n = 0, A_n = 0, B_n = 0, F_n = 0;  // elements per tile
+  float* rho = nullptr;      // [batch][N][N][N]            (aliases the head of Bk: dead before Bk is written)
+  float2* Ak = nullptr;      // [batch][N][N][P]
+  float2* Bk = nullptr;      // [3][batch][M][N][P]
+  float* F = nullptr;        // [batch][M][M][3][FP]
+  float* kern_f = nullptr;   // [3][N][N][P]  unscaled Im(FFT(kernel)) on the N grid
+  float2* tw = nullptr;      // [N] exp(-2 pi i t/N)
   // coarse mesh
   long long cvol = 0, cnk = 0;
   float* r3 = nullptr; float* cforce = nullptr; float* kern_c = nullptr; float* fc = nullptr;
@@ -129,11 +152,21 @@ static int build_kernels(cube_handle* h, const float* fk_table, const float* ck_
   CK(dmalloc(&d_fk, 16 * 16 * 16 * 3)); CK(dmalloc(&d_ck, 3 * 64));
   CK(cudaMemcpyAsync(d_fk, fk_table, sizeof(float) * 16 * 16 * 16 * 3, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(d_ck, ck_table, sizeof(float) * 3 * 64, cudaMemcpyHostToDevice, h->st));
-  // kernel_f.f90:32-41
-  for (int d = 0; d < 3; d++) {
-    k_kernf_fill<<<nblk(h->fvol, 256), 256, 0, h->st>>>(g.nfe, d_fk, d, h->rho); CKL();
-    CF(cufftExecR2C(h->plan_r2c1, h->rho, (cufftComplex*)h->rho));
-    k_take_imag<<<nblk(h->fnk, 256), 256, 0, h->st>>>(h->fnk, (const float2*)h->rho, h->kern_f + d * h->fnk); CKL();
+  // kernel_f.f90:32-41 on the N-point window: mirrored 16^3 table, r2c (cuFFT, init only), keep Im
+  {
+    const int N = h->fg.N;
+    const long long vol = (long long)N * N * (N + 2), nk = (long long)N * N * (N / 2 + 1);
+    float* tmp = nullptr; CK(dmalloc(&tmp, vol));
+    cufftHandle pl = 0;
+    CF(cufftPlan3d(&pl, N, N, N, CUFFT_R2C)); CF(cufftSetStream(pl, h->st));
+    CK(cudaMemsetAsync(h->kern_f, 0, sizeof(float) * 3 * (size_t)N * N * h->fg.P, h->st));
+    for (int d = 0; d < 3; d++) {
+      k_kernf_fill<<<nblk(vol, 256), 256, 0, h->st>>>(N, d_fk, d, tmp); CKL();
+      CF(cufftExecR2C(pl, tmp, (cufftComplex*)tmp));
+      k_take_imag_pitched<<<nblk(nk, 256), 256, 0, h->st>>>(N, h->fg.P, (const float2*)tmp, h->kern_f + (size_t)d * N * N * h->fg.P); CKL();
+    }
+    CK(cudaStreamSynchronize(h->st));
+    cufftDestroy(pl); cudaFree(tmp);
   }
   // kernel_c.f90:16-117 (single image: the coarse lattice is this image's nc^3)
   float* pure = h->cforce;  // scratch [cvol]
@@ -192,31 +225,48 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
   CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536));
   CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
-  // fine mesh buffers: rho + 3 force arrays per tile in flight
+  // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
   const int ntile = g.nnt * g.nnt * g.nnt;
-  h->fvol = (long long)g.nfe * g.nfe * (g.nfe + 2);
-  h->fnk = (long long)g.nfe * g.nfe * (g.nfe / 2 + 1);
+  {
+    const int need = g.nft + 32;  // M + 2*(nf_cutoff-1), M = nft+2
+    for (const FftPlan& pl : kPlans)
+      if (pl.N() >= need && (!h->plan || pl.N() < h->plan->N())) h->plan = &pl;
+    if (!h->plan) return fail("cube_gpu_init: no fine-mesh FFT plan for nt=%d (needs N>=%d; largest built N is 576, i.e. nt<=136)", g.nt, need);
+    FftGeom& f = h->fg;
+    f.N = h->plan->N(); f.NH = f.N / 2 + 1; f.P = (f.NH + FL - 1) / FL * FL; f.M = g.nft + 2; f.off = 15; f.FP = (f.M + 7) / 8 * 8;
+    h->rho_n = (size_t)f.N * f.N * f.N; h->A_n = (size_t)f.N * f.N * f.P; h->B_n = 3 * (size_t)f.M * f.N * f.P;
+    h->F_n = (size_t)f.M * f.M * 3 * f.FP;
+    if (h->rho_n * sizeof(float) > h->B_n * sizeof(float2)) return fail("cube_gpu_init: internal: rho does not fit its alias");
+  }
   int batch = p->fine_batch;
-  if (batch <= 0) {
-    size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
-    // 4 arrays per tile plus cuFFT work area (~2 arrays per tile); stay below ~40% of free memory
-    long long per = h->fvol * 4 * 6;
-    batch = (int)std::max<long long>(1, std::min<long long>(8, (long long)(fr * 0.4) / per));
+  {
+    const size_t per = h->A_n * sizeof(float2) + h->B_n * sizeof(float2) + h->F_n * sizeof(float);
+    if (batch <= 0) {
+      size_t fr = 0, tot = 0; CK(cudaMemGetInfo(&fr, &tot));
+      batch = (int)std::max<long long>(1, std::min<long long>(64, (long long)(fr * 0.6) / (long long)per));
+    }
   }
   batch = std::min(batch, ntile);
   h->batch = batch;
+  h->fg.nbatch = batch;
   CK(dmalloc(&h->f2max, batch + 1));
-  CK(dmalloc(&h->rho, h->fvol * batch)); CK(dmalloc(&h->force, 3 * h->fvol * batch));
-  CK(dmalloc(&h->kern_f, 3 * h->fnk));
+  CK(dmalloc(&h->Ak, (long long)(h->A_n * batch))); CK(dmalloc(&h->Bk, (long long)(h->B_n * batch))); CK(dmalloc(&h->F, (long long)(h->F_n * batch)));
+  h->rho = reinterpret_cast<float*>(h->Bk);
+  CK(dmalloc(&h->kern_f, 3LL * h->fg.N * h->fg.N * h->fg.P));
+  CK(dmalloc(&h->tw, h->fg.N));
   {
-    int n[3] = {g.nfe, g.nfe, g.nfe};
-    int rembed[3] = {g.nfe, g.nfe, g.nfe + 2}, cembed[3] = {g.nfe, g.nfe, g.nfe / 2 + 1};
-    CF(cufftPlanMany(&h->plan_r2c, 3, n, rembed, 1, (int)h->fvol, cembed, 1, (int)h->fnk, CUFFT_R2C, batch));
-    CF(cufftPlanMany(&h->plan_c2r, 3, n, cembed, 1, (int)h->fnk, rembed, 1, (int)h->fvol, CUFFT_C2R, 3 * batch));
-    CF(cufftPlanMany(&h->plan_r2c1, 3, n, rembed, 1, (int)h->fvol, cembed, 1, (int)h->fnk, CUFFT_R2C, 1));
-    CF(cufftPlanMany(&h->plan_c2r1, 3, n, cembed, 1, (int)h->fnk, rembed, 1, (int)h->fvol, CUFFT_C2R, 3));
-    CF(cufftSetStream(h->plan_r2c, h->st)); CF(cufftSetStream(h->plan_c2r, h->st));
-    CF(cufftSetStream(h->plan_r2c1, h->st)); CF(cufftSetStream(h->plan_c2r1, h->st));
+    const int N = h->fg.N;
+    std::vector<float2> tw(N);
+    for (int t = 0; t < N; t++) { double a = -2.0 * M_PI * t / N; tw[t] = make_float2((float)cos(a), (float)sin(a)); }
+    CK(cudaMemcpyAsync(h->tw, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    const int smem_x = (N * (FL + 1) + N) * (int)sizeof(float2), smem_y = (N * FL + N) * (int)sizeof(float2);
+    const int smem_z = smem_y + 3 * N * FL * (int)sizeof(float);
+    CK(cudaFuncSetAttribute((const void*)h->plan->x_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
+    CK(cudaFuncSetAttribute((const void*)h->plan->x_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
+    CK(cudaFuncSetAttribute((const void*)h->plan->y_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
+    CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
+    CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
   }
   // coarse mesh
   h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
@@ -241,9 +291,9 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->rho, h->force, h->kern_f, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
-  cufftHandle plans[] = {h->plan_r2c, h->plan_c2r, h->plan_r2c1, h->plan_c2r1, h->cplan_r2c, h->cplan_c2r};
+  cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r};
   for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
   for (int i = 0; i < 2 * PH_N; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   cudaStreamDestroy(h->st);
@@ -394,47 +444,58 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// fine mesh of tiles [tile0, tile0+nb): deposit -> r2c -> green -> 3 c2r  (pm.f90:44-84)
-static int fine_mesh(cube_handle* h, int tile0, int nb, bool through_force) {
+// fine mesh of tiles [tile0, tile0+nb): deposit -> x,y forward -> z forward * i kern_f, z inverse (x3) -> y,x inverse
+// (pm.f90:44-84).  Leaves force_f of the nb tiles in h->F.
+static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, float* out) {
   const Geom& g = h->g;
+  PhaseTimer pt(h, PH_FDEP);
+  const int nc4 = w.n / 4;
+  const int nbx = (nc4 + DB_X - 1) / DB_X, nby = (nc4 + DB_Y - 1) / DB_Y, nbz = (nc4 + DB_Z - 1) / DB_Z;
+  dim3 grid(nbx * nby * nbz, nb);
+  k_fine_deposit<<<grid, DB_T, 0, h->st>>>(g, w, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
+  h->launches++;
+  return 0;
+}
+
+static int fine_mesh(cube_handle* h, int tile0, int nb) {
+  FftGeom f = h->fg;
+  f.nbatch = nb;
+  const FftPlan& pl = *h->plan;
+  const int N = f.N, T = pl.threads();
+  const size_t smem_x = (size_t)(N * (FL + 1) + N) * sizeof(float2), smem_y = (size_t)(N * FL + N) * sizeof(float2);
+  const size_t smem_z = smem_y + (size_t)3 * N * FL * sizeof(float);
+  DepWin w{8, N, N, (long long)h->rho_n};
+  if (fine_deposit(h, tile0, nb, w, h->rho)) return 1;
   {
-    PhaseTimer pt(h, PH_FDEP);
-    const int nbx = (g.nte + DB_X - 1) / DB_X, nby = (g.nte + DB_Y - 1) / DB_Y, nbz = (g.nte + DB_Z - 1) / DB_Z;
-    dim3 grid(nbx * nby * nbz, nb);
-    k_fine_deposit<<<grid, DB_T, 0, h->st>>>(g, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->rho); CKL();
-    h->launches++;
-  }
-  if (!through_force) return 0;
-  const bool full = (nb == h->batch);
-  {
-    PhaseTimer pt(h, PH_FFFT);
-    if (full) CF(cufftExecR2C(h->plan_r2c, h->rho, (cufftComplex*)h->rho));
-    else for (int b = 0; b < nb; b++) CF(cufftExecR2C(h->plan_r2c1, h->rho + b * h->fvol, (cufftComplex*)(h->rho + b * h->fvol)));
+    PhaseTimer pt(h, PH_FFTX);
+    pl.x_fwd<<<dim3((N + 31) / 32, N, nb), T, smem_x, h->st>>>(f, h->rho, h->Ak, h->tw); CKL();
   }
   {
-    PhaseTimer pt(h, PH_FGREEN);
-    const float scale = 1.0f / ((float)g.nfe * (float)g.nfe * (float)g.nfe);
-    k_green<<<nblk(h->fnk, 256), 256, 0, h->st>>>(h->fnk, nb, (const float2*)h->rho, h->kern_f, scale, (float2*)h->force); CKL();
-    h->launches++;
+    PhaseTimer pt(h, PH_FFTY);
+    pl.y_fwd<<<dim3(f.P / FL, N, nb), T, smem_y, h->st>>>(f, h->Ak, h->tw); CKL();
   }
   {
-    PhaseTimer pt(h, PH_FIFFT);
-    if (full) CF(cufftExecC2R(h->plan_c2r, (cufftComplex*)h->force, h->force));
-    else if (nb == 1) CF(cufftExecC2R(h->plan_c2r1, (cufftComplex*)h->force, h->force));
-    else {
-      // force is [3][nb][vol]: transform each (d,b) slab with the 3-batch plan is not contiguous -> one by one
-      for (int q = 0; q < 3 * nb; q += 3) CF(cufftExecC2R(h->plan_c2r1, (cufftComplex*)(h->force + q * h->fvol), h->force + q * h->fvol));
-    }
+    PhaseTimer pt(h, PH_FFTZ);
+    const float scale = 1.0f / ((float)N * (float)N * (float)N);
+    pl.z_green<<<dim3(f.P / FL, N), T, smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
   }
+  {
+    PhaseTimer pt(h, PH_IFFTY);
+    pl.y_inv<<<dim3(f.P / FL, f.M, 3 * nb), T, smem_y, h->st>>>(f, h->Bk, h->tw); CKL();
+  }
+  {
+    PhaseTimer pt(h, PH_IFFTX);
+    pl.x_inv<<<dim3((f.M + 31) / 32, f.M, 3 * nb), T, smem_x, h->st>>>(f, h->Bk, h->F, h->tw); CKL();
+  }
+  h->launches += 5;
   return 0;
 }
 
 static int fine_f2max(cube_handle* h, int nb, float* out /*host, nb*/) {
-  const Geom& g = h->g;
   PhaseTimer pt(h, PH_FMAX);
   CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
   dim3 grid(592, nb);
-  k_f2max_fine<<<grid, 256, 0, h->st>>>(g, nb, h->force, h->f2max); CKL();
+  k_f2max_rows<<<grid, 256, 0, h->st>>>(h->fg, h->F, h->f2max); CKL();
   h->launches++;
   CK(cudaMemcpyAsync(out, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
   return 0;
@@ -473,11 +534,11 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   std::vector<float> f2(ntile, 0.f);
   for (int t0 = 0; t0 < ntile; t0 += h->batch) {
     const int nb = std::min(h->batch, ntile - t0);
-    if (fine_mesh(h, t0, nb, true)) return 1;
+    if (fine_mesh(h, t0, nb)) return 1;
     if (fine_f2max(h, nb, f2.data() + t0)) return 1;
     PhaseTimer pt(h, PH_FKICK);
     dim3 grid(nblk(nt3, 128), nb);
-    k_fine_kick<<<grid, 128, 0, h->st>>>(g, t0, nb, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->force, h->dvlut, S_new, a_mid, dt); CKL();
+    k_fine_kick<<<grid, 128, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->F, h->dvlut, S_new, a_mid, dt); CKL();
     h->launches++;
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
@@ -521,13 +582,17 @@ extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   if (w == "nft") return h->g.nft;
   if (w == "nt") return h->g.nt;
   if (w == "fine_batch") return h->batch;
+  if (w == "nfft") return h->fg.N;
+  if (w == "nfft_pitch") return h->fg.P;
   if (w == "kernel_launches") return h->launches;
   if (w == "nplocal") return h->nplocal;
   return -1;
 }
 extern "C" int cube_gpu_get_kern_f(cube_handle* h, float* out) {
   CK(cudaSetDevice(h->p.device));
-  CK(cudaMemcpy(out, h->kern_f, sizeof(float) * 3 * h->fnk, cudaMemcpyDeviceToHost));
+  const FftGeom& f = h->fg;  // strip the kx pitch: out(N/2+1, N, N, 3)
+  CK(cudaMemcpy2D(out, sizeof(float) * f.NH, h->kern_f, sizeof(float) * f.P, sizeof(float) * f.NH, (size_t)3 * f.N * f.N,
+                  cudaMemcpyDeviceToHost));
   return 0;
 }
 extern "C" int cube_gpu_get_kern_c(cube_handle* h, float* out) {
@@ -545,41 +610,29 @@ extern "C" int cube_gpu_fine_density(cube_handle* h, int itx, int ity, int itz, 
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
-  if (fine_mesh(h, t, 1, false)) return 1;
-  CK(cudaMemcpyAsync(rho_f, h->rho, sizeof(float) * h->fvol, cudaMemcpyDeviceToHost, h->st));
+  // diagnostic: deposit on the reference's whole padded grid rho_f(nfe+2,nfe,nfe) instead of the FFT window
+  const Geom& g = h->g;
+  const long long vol = (long long)g.nfe * g.nfe * (g.nfe + 2);
+  float* tmp = nullptr; CK(dmalloc(&tmp, vol));
+  CK(cudaMemsetAsync(tmp, 0, sizeof(float) * vol, h->st));
+  DepWin w{0, g.nfe, g.nfe + 2, vol};
+  if (fine_deposit(h, t, 1, w, tmp)) { cudaFree(tmp); return 1; }
+  CK(cudaMemcpyAsync(rho_f, tmp, sizeof(float) * vol, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
+  cudaFree(tmp);
   return 0;
-}
-// crop the three padded inverse transforms of batch slot 0 into force_f(3,nft+2,nft+2,nft+2)
-__global__ void k_crop_force(Geom g, int nbatch, const float* __restrict__ F, float* __restrict__ out) {
-  const int m = g.nft + 2;
-  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
-  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
-  long long o = ((long long)z * g.nfe + y) * ld + x;
-  for (int d = 0; d < 3; d++) out[3 * q + d] = F[(long long)d * nbatch * vol + o];
-}
-__global__ void k_uncrop_force(Geom g, int nbatch, const float* __restrict__ in, float* __restrict__ F) {
-  const int m = g.nft + 2;
-  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
-  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
-  long long o = ((long long)z * g.nfe + y) * ld + x;
-  for (int d = 0; d < 3; d++) F[(long long)d * nbatch * vol + o] = in[3 * q + d];
 }
 extern "C" int cube_gpu_fine_force(cube_handle* h, int itx, int ity, int itz, float* force_f) {
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
-  if (fine_mesh(h, t, 1, true)) return 1;
-  const long long m = h->g.nft + 2, n = m * m * m;
-  float* tmp = h->rho;  // rho is free after the forward transform has been consumed
-  if (3 * n > h->fvol * h->batch) return fail("scratch too small");
-  k_crop_force<<<nblk(n, 256), 256, 0, h->st>>>(h->g, 1, h->force, tmp); CKL();
+  if (fine_mesh(h, t, 1)) return 1;
+  const long long m = h->fg.M, n = m * m * m;
+  float* tmp = nullptr; CK(dmalloc(&tmp, 3 * n));
+  k_force_to_ref<<<nblk(n, 256), 256, 0, h->st>>>((int)m, h->fg.FP, h->F, tmp); CKL();
   CK(cudaMemcpyAsync(force_f, tmp, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
+  cudaFree(tmp);
   return 0;
 }
 extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz, const float* force_f, float a_mid, float dt,
@@ -588,18 +641,17 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
   const Geom& g = h->g;
-  const long long m = g.nft + 2, n = m * m * m, nt3 = (long long)g.nt * g.nt * g.nt;
-  float* tmp = h->rho;
-  if (3 * n > h->fvol * h->batch) return fail("scratch too small");
+  const long long m = h->fg.M, n = m * m * m, nt3 = (long long)g.nt * g.nt * g.nt;
+  float* tmp = nullptr; CK(dmalloc(&tmp, 3 * n));
   CK(cudaMemcpyAsync(tmp, force_f, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->st));
-  CK(cudaMemsetAsync(h->force, 0, sizeof(float) * 3 * h->fvol, h->st));
-  k_uncrop_force<<<nblk(n, 256), 256, 0, h->st>>>(g, 1, tmp, h->force); CKL();
+  k_force_from_ref<<<nblk(n, 256), 256, 0, h->st>>>((int)m, h->fg.FP, tmp, h->F); CKL();
   if (build_dvlut(h, sigma_vi)) return 1;
   float f2 = 0;
   if (fine_f2max(h, 1, &f2)) return 1;
   dim3 grid(nblk(nt3, 128), 1);
-  k_fine_kick<<<grid, 128, 0, h->st>>>(g, t, 1, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->force, h->dvlut, vscale(sigma_vi_new), a_mid, dt); CKL();
+  k_fine_kick<<<grid, 128, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->F, h->dvlut, vscale(sigma_vi_new), a_mid, dt); CKL();
   CK(cudaStreamSynchronize(h->st));
+  cudaFree(tmp);
   if (f2_max) *f2_max = f2;
   return 0;
 }

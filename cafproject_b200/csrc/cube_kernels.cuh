@@ -298,26 +298,31 @@ __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
   return __double2float_rn((double)(4 * (cell1 - 1)) + ((double)(unsigned short)xp + 0.5) * 0x1p-14);
 }
 
-// One thread per OUTPUT coarse cell of the tile's extended region: it owns that cell's 4x4x4 fine
-// cells (private accumulators in shared memory, bank = thread id) and walks the (up to) eight
-// source coarse cells that can reach them, in the reference's k,j,i order.  Every fine cell is
-// written exactly once, so rho_f needs no zero-fill and no atomics.
-__global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, int tile0, const short* __restrict__ xp,
+// Output window of the fine deposit on the reference's padded tile grid rho_f(1:nfe): the window starts at
+// 0-based fine index f0 (a multiple of 4) and spans n cells per dim; rows have pitch ld, tiles stride vol.
+struct DepWin { int f0, n; long long ld, vol; };
+
+// One thread per OUTPUT coarse cell of the window: it owns that cell's 4x4x4 fine cells (private accumulators in
+// shared memory, bank = thread id) and walks the (up to) eight source coarse cells that can reach them, in the
+// reference's k,j,i order.  Every fine cell of the window is written exactly once, so rho needs no zero-fill and
+// no atomics, and the sums are bit-identical to the reference's sequential scatter loop (pm.f90:44-72).
+__global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, DepWin w, int tile0, const short* __restrict__ xp,
                                                        const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                       float mass_p, float* __restrict__ rho /*[batch][nfe][nfe][nfe+2]*/) {
+                                                       float mass_p, float* __restrict__ rho /*[batch][n][n][ld]*/) {
   __shared__ float acc[64 * DB_T];
   const int t = threadIdx.x;
   const int tile = tile0 + blockIdx.y;
   const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
-  const int nbx = (g.nte + DB_X - 1) / DB_X, nby = (g.nte + DB_Y - 1) / DB_Y;
+  const int nc4 = w.n / 4, c0 = w.f0 / 4;
+  const int nbx = (nc4 + DB_X - 1) / DB_X, nby = (nc4 + DB_Y - 1) / DB_Y;
   const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
   const int cx = t % DB_X, cy = (t / DB_X) % DB_Y, cz = t / (DB_X * DB_Y);
-  // tile-local Fortran index of my output cell: 1-ncb .. nt+ncb
-  const int i = bx * DB_X + cx + 1 - NCB, j = by * DB_Y + cy + 1 - NCB, k = bz * DB_Z + cz + 1 - NCB;
+  // tile-local Fortran index of my output cell (1-ncb .. nt+ncb inside the extended tile)
+  const int i = c0 + bx * DB_X + cx + 1 - NCB, j = c0 + by * DB_Y + cy + 1 - NCB, k = c0 + bz * DB_Z + cz + 1 - NCB;
 #pragma unroll
   for (int q = 0; q < 64; q++) acc[q * DB_T + t] = 0.f;
   const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
-  if (i <= g.nt + NCB && j <= g.nt + NCB && k <= g.nt + NCB) {
+  {
     const int X0 = tx * g.nt - 1, Y0 = ty * g.nt - 1, Z0 = tz * g.nt - 1;  // image-local = X0 + Fortran local
     for (int sk = k - 1; sk <= k; sk++) {
       if (sk < lo || sk > hi) continue;
@@ -346,9 +351,9 @@ __global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, int tile0, const 
               const int a = fa + qa, b = fb + qb, cc = fc + qc;
               if ((unsigned)a < 4u && (unsigned)b < 4u && (unsigned)cc < 4u) {
                 // dx(1)*dx(2)*dx(3)*mass_p, left to right (pm.f90:61-68)
-                float w = __fmul_rn(__fmul_rn(__fmul_rn(qa ? ax2 : ax1, qb ? ay2 : ay1), qc ? az2 : az1), mass_p);
+                float wgt = __fmul_rn(__fmul_rn(__fmul_rn(qa ? ax2 : ax1, qb ? ay2 : ay1), qc ? az2 : az1), mass_p);
                 float* p = &acc[((cc * 4 + b) * 4 + a) * DB_T + t];
-                *p = __fadd_rn(*p, w);
+                *p = __fadd_rn(*p, wgt);
               }
             }
           }
@@ -358,15 +363,14 @@ __global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, int tile0, const 
   }
   __syncthreads();
   // write the brick's fine region, one 32-float row per warp iteration
-  const int lane = t & 31, w = t >> 5, nw = DB_T >> 5;
-  const long long ld = g.nfe + 2;
-  float* out = rho + (long long)blockIdx.y * g.nfe * g.nfe * ld;
-  for (int row = w; row < 16 * DB_Y * DB_Z; row += nw) {
+  const int lane = t & 31, wp = t >> 5, nw = DB_T >> 5;
+  float* out = rho + (long long)blockIdx.y * w.vol;
+  for (int row = wp; row < 16 * DB_Y * DB_Z; row += nw) {
     const int fy = row % (4 * DB_Y), fz = row / (4 * DB_Y);
     const int ocx = lane >> 2, a = lane & 3, ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
     const int gx = (bx * DB_X + ocx) * 4 + a, gy = (by * DB_Y + ocy) * 4 + b, gz = (bz * DB_Z + ocz) * 4 + cc;
-    if (gx < g.nfe && gy < g.nfe && gz < g.nfe)
-      out[((long long)gz * g.nfe + gy) * ld + gx] = acc[((cc * 4 + b) * 4 + a) * DB_T + ((ocz * DB_Y + ocy) * DB_X + ocx)];
+    if (gx < w.n && gy < w.n && gz < w.n)
+      out[((long long)gz * w.n + gy) * w.ld + gx] = acc[((cc * 4 + b) * 4 + a) * DB_T + ((ocz * DB_Y + ocy) * DB_X + ocx)];
   }
 }
 
@@ -386,29 +390,12 @@ __global__ void __launch_bounds__(256) k_green(long long nk, int nbatch, const f
   }
 }
 
-// f2_max_fine(tile)=maxval(sum(force_f**2,1)) over force_f(:,nfb:nfe-nfb+1,...)  (pm.f90:85)
-__global__ void __launch_bounds__(256) k_f2max_fine(Geom g, int nbatch, const float* __restrict__ F /*[3][batch][..]*/,
-                                                    unsigned* __restrict__ f2max /*[batch] as float bits*/) {
-  const int b = blockIdx.y;
-  const int m = g.nft + 2;
-  const long long n = (long long)m * m * m, ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
-  float best = 0.f;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(q % m) + NFB - 1, y = (int)((q / m) % m) + NFB - 1, z = (int)(q / ((long long)m * m)) + NFB - 1;
-    long long o = ((long long)z * g.nfe + y) * ld + x;
-    float f0 = F[((long long)0 * nbatch + b) * vol + o], f1 = F[((long long)1 * nbatch + b) * vol + o], f2 = F[((long long)2 * nbatch + b) * vol + o];
-    float s = __fadd_rn(__fadd_rn(__fmul_rn(f0, f0), __fmul_rn(f1, f1)), __fmul_rn(f2, f2));
-    best = fmaxf(best, s);
-  }
-  best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));  // non-negative floats order as uints
-  if ((threadIdx.x & 31) == 0) atomicMax(&f2max[b], __float_as_uint(best));
-}
-
-// fine kick (pm.f90:88-118): one thread per physical coarse cell of the tile
-__global__ void __launch_bounds__(128) k_fine_kick(Geom g, int tile0, int nbatch, const short* __restrict__ xp, short* __restrict__ vp,
+// fine kick (pm.f90:88-118): one thread per physical coarse cell of the tile.
+// F[b][z'][y'][d][x'] holds force_f(d, nfb-1+x'+1, ...) on the M=nft+2 kept points, x' pitch FP.
+__global__ void __launch_bounds__(128) k_fine_kick(Geom g, int tile0, int M, int FP, const short* __restrict__ xp, short* __restrict__ vp,
                                                    const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
-                                                   const float* __restrict__ F /*[3][batch][nfe][nfe][nfe+2]*/,
-                                                   const double* __restrict__ dvlut, double S_new, float a_mid, float dt) {
+                                                   const float* __restrict__ F, const double* __restrict__ dvlut, double S_new,
+                                                   float a_mid, float dt) {
   const long long nt3 = (long long)g.nt * g.nt * g.nt;
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nt3) return;
@@ -417,30 +404,41 @@ __global__ void __launch_bounds__(128) k_fine_kick(Geom g, int tile0, int nbatch
   const int n = rhoc_p[L];
   if (n == 0) return;
   const int i = (int)(c % g.nt) + 1, j = (int)((c / g.nt) % g.nt) + 1, k = (int)(c / ((long long)g.nt * g.nt)) + 1;
-  const long long s = cstart_p[L], ld = g.nfe + 2, vol = (long long)g.nfe * g.nfe * ld;
-  const float* F0 = F + ((long long)0 * nbatch + b) * vol;
-  const float* F1 = F + ((long long)1 * nbatch + b) * vol;
-  const float* F2 = F + ((long long)2 * nbatch + b) * vol;
+  const long long s = cstart_p[L];
+  const float* Fb = F + (long long)b * M * M * 3 * FP;
   for (int l = 0; l < n; l++) {
     Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
     int i1, j1, k1; float ax[2], ay[2], az[2];
-    cic_split(fine_tempx(i, xc.x), i1, ax[0], ax[1]);
+    cic_split(fine_tempx(i, xc.x), i1, ax[0], ax[1]);  // i1 = idx1 of pm.f90:96 = 0-based kept index
     cic_split(fine_tempx(j, xc.y), j1, ay[0], ay[1]);
     cic_split(fine_tempx(k, xc.z), k1, az[0], az[1]);
-    i1 += NFB - 1; j1 += NFB - 1; k1 += NFB - 1;  // 0-based index into the padded array
     double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
     // corner order of pm.f90:104-111
     const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-      const long long o = ((long long)(k1 + qz[q]) * g.nfe + (j1 + qy[q])) * ld + (i1 + qx[q]);
+      const float* f = Fb + ((long long)(k1 + qz[q]) * M + (j1 + qy[q])) * 3 * FP + (i1 + qx[q]);
       const float wx = ax[qx[q]], wy = ay[qy[q]], wz = az[qz[q]];
-      v0 = __dadd_rn(v0, (double)kick_term(__ldg(F0 + o), a_mid, dt, wx, wy, wz));
-      v1 = __dadd_rn(v1, (double)kick_term(__ldg(F1 + o), a_mid, dt, wx, wy, wz));
-      v2 = __dadd_rn(v2, (double)kick_term(__ldg(F2 + o), a_mid, dt, wx, wy, wz));
+      v0 = __dadd_rn(v0, (double)kick_term(__ldg(f), a_mid, dt, wx, wy, wz));
+      v1 = __dadd_rn(v1, (double)kick_term(__ldg(f + FP), a_mid, dt, wx, wy, wz));
+      v2 = __dadd_rn(v2, (double)kick_term(__ldg(f + 2 * FP), a_mid, dt, wx, wy, wz));
     }
     store_code3(vp, s + l, vp_encode(v0, S_new), vp_encode(v1, S_new), vp_encode(v2, S_new));
   }
+}
+
+// force_f(3,nft+2,nft+2,nft+2) [z][y][x][3] <-> F[z'][y'][d][x'] of batch slot 0 (diagnostics only)
+__global__ void k_force_to_ref(int M, int FP, const float* __restrict__ F, float* __restrict__ out) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)M * M * M) return;
+  const int x = (int)(q % M); const long long r = q / M;
+  for (int d = 0; d < 3; d++) out[3 * q + d] = F[(r * 3 + d) * FP + x];
+}
+__global__ void k_force_from_ref(int M, int FP, const float* __restrict__ in, float* __restrict__ F) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)M * M * M) return;
+  const int x = (int)(q % M); const long long r = q / M;
+  for (int d = 0; d < 3; d++) F[(r * 3 + d) * FP + x] = in[3 * q + d];
 }
 
 // =============================================================================================
@@ -573,6 +571,13 @@ __global__ void k_kernf_fill(int nfe, const float* __restrict__ tab /*(16,16,16,
     }
   }
   rho[q] = v;
+}
+// Im of an r2c result c[z][y][n/2+1] into a kx-pitched real array out[z][y][P]
+__global__ void k_take_imag_pitched(int n, int P, const float2* __restrict__ c, float* __restrict__ out) {
+  const int nh = n / 2 + 1;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)n * n * nh) return;
+  out[(q / nh) * P + (q % nh)] = c[q].y;
 }
 __global__ void k_take_imag(long long nk, const float2* __restrict__ c, float* __restrict__ out) {
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;

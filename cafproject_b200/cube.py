@@ -207,7 +207,9 @@ class CubeGPU:
 
     # ---- diagnostics -------------------------------------------------------------------------
     def kern_f(self):
-        out = np.empty((3, self.nfe, self.nfe, self.nfe // 2 + 1), F32)
+        """Im(FFT(fine force kernel)) on the N = query("nfft") window grid (kernel_f.f90:32-41 with nfe -> N)."""
+        n = self.query("nfft")
+        out = np.empty((3, n, n, n // 2 + 1), F32)
         self._ck(self.L.cube_gpu_get_kern_f(self.h, _p(out)))
         return out
 

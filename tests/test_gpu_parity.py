@@ -37,9 +37,13 @@ def test_host_tanf_lut_matches_oracle():
     assert np.array_equal(host_tanf_lut().view(np.uint32), co.tanf_lut().view(np.uint32))
 
 
-def test_kernels(setup):
+def test_kernels(setup, tables):
     O, G, _, _ = setup
-    assert norm_rel(G.kern_f(), O.kern_f) < 1e-5
+    from oracle import cube_oracle as co
+    # the GPU convolves on the minimal window N >= nft+32 instead of nfe (cube_fft.cuh); same construction, other length
+    n = G.query("nfft")
+    assert O.nft + 32 <= n <= max(O.nfe, O.nft + 48)
+    assert norm_rel(G.kern_f(), co.kernel_f(tables[0], n)) < 1e-5
     assert norm_rel(G.kern_c(), O.kern_c) < 1e-5
 
 
@@ -134,8 +138,9 @@ def test_full_steps(tables):
             assert np.array_equal(xp_o, sg["xp"])
         if same_cells:
             dv = np.abs(vp_o.astype(np.int32) - sg["vp"].astype(np.int32))
-            # step 1: a code can only flip by one unit; later steps inherit earlier flips through vfield
-            assert dv.max() <= (1 if it == 0 else 4)
+            # step 1: a code can flip by one unit in each of the two kicks (fine, coarse); later steps inherit
+            # earlier flips through vfield
+            assert dv.max() <= (2 if it == 0 else 4)
             assert (dv != 0).mean() < (2e-3 if it == 0 else 2e-2)
         else:
             assert int(np.abs(O.store(0)["rhoc"] - sg["rhoc"]).sum()) < 1e-4 * xp_o.shape[0]

@@ -34,18 +34,25 @@ def make(co, tables, nc=24, nnt=2, np_nc=2, seed=3, disp_rms=0.7, nn=1):
 
 # ---- (1) paper decode example, ms_caf/ms_caf.tex:78 ---------------------------------------------
 def test_paper_decode_example():
-    """x = (cell-1) + (int(xp+ishift,izipx)+rshift)*x_resolution with izipx=1 (parameters.f90:14-15,
-    pm.f90:54): chi=(-128,127,0,60), rho_c=(1,0,2,1) -> x=(0.001953125,2.998046875,2.501953125,3.736328125)."""
+    """ms_caf.tex:66-78: x_d = (n_c-1) + 2^-8n (chi_d + 2^(8n-1) + 1/2); chi=(-128,127,0,60), rho_c=(1,0,2,1) ->
+    x=(0.001953125,2.998046875,2.501953125,3.736328125).  The paper stores chi offset-binary (chi = u - 2^(8n-1));
+    the code stores the two's-complement wrap of u (initial_conditions.f90:554 `floor(x/x_resolution)` truncated to
+    izipx bytes) and decodes with int(xp+ishift,izipx)+rshift (parameters.f90:14-15, pm.f90:54).  Both are
+    (u + 1/2) * x_resolution for the same fraction bin u -- the identity every kernel and the oracle use."""
     izipx = 1
-    ishift = -(2 ** (8 * izipx - 1)); rshift = 0.5 - ishift; xres = 2.0 ** -(8 * izipx)
-    chi = np.array([-128, 127, 0, 60], np.int8)
+    xres = 2.0 ** -(8 * izipx)
+    chi = np.array([-128, 127, 0, 60], np.int64)
     rho = np.array([1, 0, 2, 1])
-    cell = np.repeat(np.arange(4), rho)          # cell index from the prefix sum of rho_c
-    wrapped = (chi.astype(np.int32) + ishift).astype(np.int8)   # int(xp+ishift,izipx) wraps
-    x = cell + (wrapped.astype(np.float64) + rshift) * xres
-    assert np.array_equal(x, [0.001953125, 2.998046875, 2.501953125, 3.736328125])
-    # the same identity in the form the kernels use: (u+0.5)*R with u the raw unsigned pattern
-    assert np.array_equal(x, cell + (chi.view(np.uint8).astype(np.float64) + 0.5) * xres)
+    cell = np.repeat(np.arange(4), rho)          # n_c - 1 from the prefix sum of rho_c
+    x_paper = cell + xres * (chi + 2 ** (8 * izipx - 1) + 0.5)
+    assert np.array_equal(x_paper, [0.001953125, 2.998046875, 2.501953125, 3.736328125])
+    u = chi + 2 ** (8 * izipx - 1)               # fraction bin 0..255
+    xp = u.astype(np.uint8).view(np.int8)        # what the code stores
+    ishift = -(2 ** (8 * izipx - 1)); rshift = 0.5 - ishift
+    wrapped = (xp.astype(np.int64) + ishift).astype(np.int8)   # int(xp+ishift,izipx) wraps
+    x_code = cell + (wrapped.astype(np.float64) + rshift) * xres
+    assert np.array_equal(x_code, x_paper)
+    assert np.array_equal(x_code, cell + (xp.view(np.uint8).astype(np.float64) + 0.5) * xres)
 
 
 def test_int16_decode_identity():
@@ -114,8 +121,8 @@ def test_two_body_fine_force(co, tables):
     O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=1, fk_table=fk, ck_table=ck)
     rhoc = np.zeros((1, 1, 1, nc, nc, nc), np.int32)
     rhoc[0, 0, 0, 10, 10, 10] = 1
-    # fine-cell centre: frac = (1+0.5)/4 -> u+0.5 = 0.375*65536
-    u = int(0.375 * 65536 - 0.5 + 0.5)
+    # as close to a fine mesh node as the half-offset code allows: 4*(u+0.5)/65536 = 1 - 3e-5
+    u = 16383
     xp = np.full((1, 3), u, np.uint16).view(np.int16)
     st = dict(xp=xp, vp=np.zeros((1, 3), np.int16), rhoc=rhoc, vfield=np.zeros(rhoc.shape + (3,), F32))
     O.load([st], F32(1.0))
@@ -124,14 +131,14 @@ def test_two_body_fine_force(co, tables):
     m = float(O.mass_p)
     assert abs(float(rho[:, :, :O.nfe].sum(dtype=np.float64)) - m) < 1e-4 * m
     ff = O.fine_force(rho)     # [z][y][x][3], index 0 <-> fine coordinate nfb-1 (Fortran nfb)
-    # particle sits at fine position 4*10+1.5 (0-based cell 41, centre) -> with CIC split it is
-    # shared between fine cells; take the exact peak location from the density instead
+    # the CIC split puts 1-1e-4 of the mass on one node; locate it from the density
     zc, yc, xc = np.unravel_index(np.argmax(rho[:, :, :O.nfe]), rho[:, :, :O.nfe].shape)
     off = O.nfb - 1
     fx_plus = ff[zc - off, yc - off, xc - off + 1, 0]
     fx_minus = ff[zc - off, yc - off, xc - off - 1, 0]
     assert fx_plus < 0 < fx_minus
-    assert abs(fx_plus + fx_minus) < 2e-2 * m          # antisymmetric about the particle (CIC share is 1/8 per corner)
+    assert abs(fx_plus + fx_minus) < 1e-3 * m          # antisymmetric about the particle
+    assert abs(fx_plus / m + 0.9996) < 1e-3            # wfxyzf.3.ascii row 2: F_x(1,0,0) = -0.9996
     far = ff[zc - off, yc - off, xc - off + 20, :]
     assert np.abs(far).max() < 1e-4 * abs(fx_plus)
     O.close()
