@@ -81,6 +81,25 @@ __device__ __forceinline__ float kick_term(float F, float a_mid, float dt, float
   return __fmul_rn(t, wz);
 }
 
+// IEEE-correct a/c for the constants c = 6 and c = pi_f without the generic division routine: q0 = RN(a*rc),
+// e = a - c*q0 (exact with an FMA), q = RN(q0 + e*rc) with rc = RN(1/c).  Verified exhaustively against a/c for
+// all 2^23 mantissas (tests/test_oracle_pins.py::test_fma_division_by_constants); tiny/huge operands take __fdiv_rn.
+__device__ __forceinline__ float div_const_rn(float a, float c, float rc) {
+  const float aa = fabsf(a);
+  if (aa != 0.f && (aa < 1e-30f || aa > 1e30f)) return __fdiv_rn(a, c);
+  const float q0 = __fmul_rn(a, rc);
+  const float e = __fmaf_rn(-c, q0, a);
+  return __fmaf_rn(e, rc, q0);
+}
+// F*a_mid*dt/6/pi in the reference's order (pm.f90:104): the per-node prefix of every kick term
+__device__ __forceinline__ float kick_prefix(float F, float a_mid, float dt) {
+  const float t = __fmul_rn(__fmul_rn(F, a_mid), dt);
+  return div_const_rn(div_const_rn(t, 6.0f, 1.0f / 6.0f), PI_F, 1.0f / PI_F);
+}
+__device__ __forceinline__ float kick_weight(float G, float wx, float wy, float wz) {
+  return __fmul_rn(__fmul_rn(__fmul_rn(G, wx), wy), wz);
+}
+
 // three 16-bit codes of one particle (AoS, 6-byte stride: only 2-byte alignment is guaranteed)
 struct Code3 { short x, y, z; };
 __device__ __forceinline__ Code3 load_code3(const short* __restrict__ a, long long p) {

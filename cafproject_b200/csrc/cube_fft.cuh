@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <type_traits>
+#include "cube_common.cuh"
 
 namespace cube {
 
@@ -347,28 +348,35 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_z_green(FftGeo
 
 // ---------------------------------------------------------------------------------------------
 // x inverse (c2r): B[d][b][z'][y][kx] -> F[b][z'][y'][d][x'] (x' = M kept points, pitch FP).
-// One CTA = 32 kept rows (16 complex lines).  grid = (ceil(M/32), M, 3*nbatch)
-// Also reduces f2 partials?  No: |F|^2 needs the three components; see k_f2max_rows.
+// One CTA = 32 kept rows (16 complex lines) of one component.  grid = (ceil(M/32), M, 3*nbatch)
 // ---------------------------------------------------------------------------------------------
 template <int R1, int R2>
 __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
                                                                        const float2* __restrict__ tw_g) {
   constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
+  constexpr int NHC = N / 2 + 1, NLD = (FL * NHC + NT - 1) / NT;  // loads per thread
   extern __shared__ float2 smem[];
   float2* s = smem;
   float2* tw = smem + N * LW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.x * 32, zp = blockIdx.y, db = blockIdx.z, d = db / g.nbatch, b = db - d * g.nbatch;
+  const float2* src = B + ((size_t)db * g.M + zp) * (size_t)N * g.P + (size_t)g.off * g.P;
+  // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k]); all loads are issued before the first use
+  float2 va[NLD], vb[NLD];
+#pragma unroll
+  for (int i = 0; i < NLD; i++) {
+    const int e = tid + NT * i, l = e / NHC, k = e - l * NHC;
+    const int ya = r0 + 2 * l;
+    const bool oka = l < FL && ya < g.M, okb = l < FL && ya + 1 < g.M;
+    va[i] = oka ? src[(size_t)ya * g.P + k] : make_float2(0.f, 0.f);
+    vb[i] = okb ? src[(size_t)(ya + 1) * g.P + k] : make_float2(0.f, 0.f);
+  }
   load_tw(tw, tw_g, N);
-  const float2* src = B + ((size_t)db * g.M + zp) * (size_t)N * g.P;
-  // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k])
-  for (int l = warp; l < FL; l += NT / 32) {
-    const int ya = r0 + 2 * l, yb = ya + 1;
-    const float2* rowa = src + (size_t)(ya + g.off) * g.P;
-    const float2* rowb = src + (size_t)(yb + g.off) * g.P;
-    for (int k = lane; k < g.NH; k += 32) {
-      const float2 a = ya < g.M ? rowa[k] : make_float2(0.f, 0.f);
-      const float2 c = yb < g.M ? rowb[k] : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NLD; i++) {
+    const int e = tid + NT * i, l = e / NHC, k = e - l * NHC;
+    if (l < FL) {
+      const float2 a = va[i], c = vb[i];
       s[k * LW + l] = make_float2(a.x - c.y, a.y + c.x);
       if (k && 2 * k != N) s[(N - k) * LW + l] = make_float2(a.x + c.y, c.x - a.y);
     }
@@ -392,6 +400,7 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom 
     const int l = r >> 1, im = r & 1;
     float* row = dst + ((size_t)yp * 3 + d) * g.FP;
     const float* sp = reinterpret_cast<const float*>(s) + im;
+#pragma unroll 4
     for (int x = lane; x < g.M; x += 32) row[x] = sp[((x + g.off) * LW + l) * 2];
   }
 }

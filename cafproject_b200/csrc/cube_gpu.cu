@@ -18,6 +18,7 @@
 #include "../../include/cube_gpu.h"
 #include "cube_kernels.cuh"
 #include "cube_fft.cuh"
+#include "cube_particles.cuh"
 
 using namespace cube;
 
@@ -87,7 +88,7 @@ struct cube_handle {
   long long* tile_count = nullptr;
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
-  float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f;
+  float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
   // fine mesh (cube_fft.cuh)
   int batch = 1;
   const FftPlan* plan = nullptr; FftGeom fg = {};
@@ -131,6 +132,7 @@ static int scan_counts(cube_handle* h, const int* in, long long n, long long* ou
   k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum); CKL();
   k_scan_bsums<<<1, 1024, 0, h->st>>>(h->bsum, nb); CKL();
   k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out); CKL();
+  CK(cudaMemcpyAsync(out + n, h->bsum + nb, sizeof(long long), cudaMemcpyDeviceToDevice, h->st));  // sentinel = total
   h->launches += 3;
   return 0;
 }
@@ -216,14 +218,15 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->key, cap));
   CK(dmalloc(&h->rhoc_p, g.ncell_p)); CK(dmalloc(&h->rhoc_p2, g.ncell_p));
   CK(dmalloc(&h->vfield_p, 3 * g.ncell_p)); CK(dmalloc(&h->vfield_p2, 3 * g.ncell_p));
-  CK(dmalloc(&h->cstart_p, g.ncell_p)); CK(dmalloc(&h->cstart_p2, g.ncell_p));
+  CK(dmalloc(&h->cstart_p, g.ncell_p + 1)); CK(dmalloc(&h->cstart_p2, g.ncell_p + 1));  // + sentinel = nplocal
   CK(dmalloc(&h->rhoc_e, g.ncell_e)); CK(dmalloc(&h->cstart_e, g.ncell_e)); CK(dmalloc(&h->vfield_e, 3 * g.ncell_e));
   h->nscan_blocks = (int)((g.ncell_p + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
   CK(dmalloc(&h->stat_partial, 3 * (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 3));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
-  CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536));
+  CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
+  k_build_enc<<<128, 256, 0, h->st>>>(h->enc); CKL();
   CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
   // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
   const int ntile = g.nnt * g.nnt * g.nnt;
@@ -291,7 +294,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r};
   for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
@@ -457,6 +460,7 @@ static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, floa
   return 0;
 }
 
+// leaves force_f of the nb tiles in h->F and the per-tile f2_max_fine in h->f2max[0..nb)
 static int fine_mesh(cube_handle* h, int tile0, int nb) {
   FftGeom f = h->fg;
   f.nbatch = nb;
@@ -487,21 +491,18 @@ static int fine_mesh(cube_handle* h, int tile0, int nb) {
     PhaseTimer pt(h, PH_IFFTX);
     pl.x_inv<<<dim3((f.M + 31) / 32, f.M, 3 * nb), T, smem_x, h->st>>>(f, h->Bk, h->F, h->tw); CKL();
   }
-  h->launches += 5;
+  {
+    PhaseTimer pt(h, PH_FMAX);
+    CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
+    k_f2max_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, h->f2max); CKL();
+  }
+  h->launches += 6;
   return 0;
 }
 
-static int fine_f2max(cube_handle* h, int nb, float* out /*host, nb*/) {
-  PhaseTimer pt(h, PH_FMAX);
-  CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
-  dim3 grid(592, nb);
-  k_f2max_rows<<<grid, 256, 0, h->st>>>(h->fg, h->F, h->f2max); CKL();
-  h->launches++;
-  CK(cudaMemcpyAsync(out, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
-  return 0;
-}
-
-static int coarse_mesh(cube_handle* h, bool through_force) {
+// coarse mesh (pm.f90:127-189): deposit -> r2c -> i kern_c -> 3 c2r -> force_c with halo.  Leaves the kick prefix
+// force_c*a_mid*dt/6/pi in h->fc, f2_max_coarse in h->f2max[batch]; raw (optional, device) gets force_c itself.
+static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw) {
   const Geom& g = h->g;
   {
     PhaseTimer pt(h, PH_CDEP);
@@ -515,8 +516,8 @@ static int coarse_mesh(cube_handle* h, bool through_force) {
   const float scale = 1.0f / ((float)g.nc * g.nn[0]) / ((float)g.nc * g.nn[1]) / ((float)g.nc * g.nn[2]);
   k_green<<<nblk(h->cnk, 256), 256, 0, h->st>>>(h->cnk, 1, (const float2*)h->r3, h->kern_c, scale, (float2*)h->cforce); CKL();
   CF(cufftExecC2R(h->cplan_c2r, (cufftComplex*)h->cforce, h->cforce));
-  const long long m = g.nc + 2;
-  k_force_c_assemble<<<nblk(m * m * m, 256), 256, 0, h->st>>>(g, h->cforce, h->fc); CKL();
+  CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
+  k_force_c_finish<<<1184, 256, 0, h->st>>>(g, h->cforce, a_mid, dt, h->fc, raw, h->f2max + h->batch); CKL();
   h->launches += 2;
   return 0;
 }
@@ -535,25 +536,22 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   for (int t0 = 0; t0 < ntile; t0 += h->batch) {
     const int nb = std::min(h->batch, ntile - t0);
     if (fine_mesh(h, t0, nb)) return 1;
-    if (fine_f2max(h, nb, f2.data() + t0)) return 1;
+    CK(cudaMemcpyAsync(f2.data() + t0, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
     PhaseTimer pt(h, PH_FKICK);
-    dim3 grid(nblk(nt3, 128), nb);
-    k_fine_kick<<<grid, 128, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->F, h->dvlut, S_new, a_mid, dt); CKL();
+    dim3 grid(nblk(nt3, PC_CELLS), nb);
+    k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new, a_mid, dt); CKL();
     h->launches++;
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
   if (build_dvlut(h, h->sigma_vi)) return 1;
-  if (coarse_mesh(h, true)) return 1;
-  const long long m = g.nc + 2;
+  if (coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   float f2c = 0; unsigned long long vb = 0;
   {
     PhaseTimer pt(h, PH_CKICK);
-    CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
     CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
-    k_f2max_aos<<<592, 256, 0, h->st>>>(m * m * m, h->fc, h->f2max + h->batch); CKL();
-    k_coarse_kick<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->fc, h->dvlut,
-                                                         vscale(h->sigma_vi), a_mid, dt, h->vmax_bits); CKL();
-    h->launches += 2;
+    k_coarse_kick_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->dvlut, h->enc,
+                                                                  vscale(h->sigma_vi), h->vmax_bits); CKL();
+    h->launches++;
     CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -647,9 +645,11 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   k_force_from_ref<<<nblk(n, 256), 256, 0, h->st>>>((int)m, h->fg.FP, tmp, h->F); CKL();
   if (build_dvlut(h, sigma_vi)) return 1;
   float f2 = 0;
-  if (fine_f2max(h, 1, &f2)) return 1;
-  dim3 grid(nblk(nt3, 128), 1);
-  k_fine_kick<<<grid, 128, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->F, h->dvlut, vscale(sigma_vi_new), a_mid, dt); CKL();
+  CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned), h->st));
+  { FftGeom f1 = h->fg; f1.nbatch = 1; k_f2max_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, h->f2max); CKL(); }
+  CK(cudaMemcpyAsync(&f2, h->f2max, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  dim3 grid(nblk(nt3, PC_CELLS), 1);
+  k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new), a_mid, dt); CKL();
   CK(cudaStreamSynchronize(h->st));
   cudaFree(tmp);
   if (f2_max) *f2_max = f2;
@@ -659,7 +659,7 @@ extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
   const Geom& g = h->g;
-  if (coarse_mesh(h, false)) return 1;
+  if (coarse_mesh(h, false, 0.f, 0.f, nullptr)) return 1;
   CK(cudaMemcpy2DAsync(r3, sizeof(float) * g.nc, h->r3, sizeof(float) * (g.nc + 2), sizeof(float) * g.nc, (size_t)g.nc * g.nc,
                        cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -668,10 +668,12 @@ extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
 extern "C" int cube_gpu_coarse_force(cube_handle* h, float* force_c) {
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
-  if (coarse_mesh(h, true)) return 1;
   const long long m = h->g.nc + 2;
-  CK(cudaMemcpyAsync(force_c, h->fc, sizeof(float) * 3 * m * m * m, cudaMemcpyDeviceToHost, h->st));
+  float* raw = nullptr; CK(dmalloc(&raw, 3 * m * m * m));
+  if (coarse_mesh(h, true, 0.f, 0.f, raw)) { cudaFree(raw); return 1; }
+  CK(cudaMemcpyAsync(force_c, raw, sizeof(float) * 3 * m * m * m, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
+  cudaFree(raw);
   return 0;
 }
 extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, float a_mid, float dt, float sigma_vi, float* vmax,
@@ -684,9 +686,9 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   if (build_dvlut(h, sigma_vi)) return 1;
   CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
-  k_f2max_aos<<<592, 256, 0, h->st>>>(m * m * m, h->fc, h->f2max + h->batch); CKL();
-  k_coarse_kick<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->fc, h->dvlut,
-                                                       vscale(sigma_vi), a_mid, dt, h->vmax_bits); CKL();
+  k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
+  k_coarse_kick_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->dvlut, h->enc,
+                                                                vscale(sigma_vi), h->vmax_bits); CKL();
   float f2c = 0; unsigned long long vb = 0;
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));

@@ -250,3 +250,19 @@ def test_multi_image_oracle_equals_single_image(co, tables):
     O2.update_particle(F32(0), F32(1.0))
     assert O2.nplocal(0) + O2.nplocal(1) == n
     O2.close()
+
+
+def test_fma_division_by_constants():
+    """cube_common.cuh::div_const_rn: q0=RN(a*rc), e=a-c*q0 (FMA), q=RN(q0+e*rc) equals the IEEE quotient a/c for c=6 and
+    c=pi_f on every mantissa -- the kick prefix F*a_mid*dt/6/pi (pm.f90:104) keeps the reference's two roundings."""
+    pi_f = F32(4) * np.arctan(F32(1), dtype=F32)
+    for c in (F32(6.0), pi_f):
+        rc = F32(1) / c
+        for lo in (0.5, 1.0, 2.0, 4.0):
+            a = (np.arange(0, 2 ** 23, dtype=np.uint32) + np.float32(lo).view(np.uint32)).view(np.float32)
+            q0 = (a * rc).astype(np.float32)
+            e64 = a.astype(np.float64) - np.float64(c) * q0.astype(np.float64)
+            e = e64.astype(np.float32)
+            assert np.all(e.astype(np.float64) == e64)          # the residual is exact in f32
+            q = (q0.astype(np.float64) + e.astype(np.float64) * np.float64(rc)).astype(np.float32)
+            assert np.array_equal(q, a / c)
