@@ -283,6 +283,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CF(cufftPlanMany(&h->cplan_c2r, 3, n, cembed, 1, (int)h->cnk, rembed, 1, (int)h->cvol, CUFFT_C2R, 3));
     CF(cufftSetStream(h->cplan_r2c, h->st)); CF(cufftSetStream(h->cplan_c2r, h->st));
   }
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_coarse_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM));
   if (build_kernels(h, fk_table, ck_table)) { return 1; }
   *out = h;
   return 0;
@@ -453,9 +455,9 @@ static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, floa
   const Geom& g = h->g;
   PhaseTimer pt(h, PH_FDEP);
   const int nc4 = w.n / 4;
-  const int nbx = (nc4 + DB_X - 1) / DB_X, nby = (nc4 + DB_Y - 1) / DB_Y, nbz = (nc4 + DB_Z - 1) / DB_Z;
+  const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y, nbz = (nc4 + FB_Z - 1) / FB_Z;
   dim3 grid(nbx * nby * nbz, nb);
-  k_fine_deposit<<<grid, DB_T, 0, h->st>>>(g, w, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
+  k_fine_deposit<<<grid, FD_T, FD_SMEM, h->st>>>(g, w, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
   h->launches++;
   return 0;
 }
@@ -506,7 +508,8 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
   const Geom& g = h->g;
   {
     PhaseTimer pt(h, PH_CDEP);
-    k_coarse_deposit<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3); CKL();
+    const int cbx = (g.nt + CB_X - 1) / CB_X, cby = (g.nt + CB_Y - 1) / CB_Y, cbz = (g.nt + CB_Z - 1) / CB_Z;
+    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3); CKL();
     h->launches++;
   }
   if (!through_force) return 0;

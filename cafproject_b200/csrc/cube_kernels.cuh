@@ -291,7 +291,6 @@ __global__ void __launch_bounds__(1024) k_reduce3(const double* __restrict__ par
 // =============================================================================================
 // fine mesh (pm.f90:44-118)
 // =============================================================================================
-constexpr int DB_X = 8, DB_Y = 4, DB_Z = 4, DB_T = DB_X * DB_Y * DB_Z;  // deposit brick (coarse cells)
 
 // tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution, rounded to f32 (pm.f90:54)
 __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
@@ -302,75 +301,86 @@ __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
 // 0-based fine index f0 (a multiple of 4) and spans n cells per dim; rows have pitch ld, tiles stride vol.
 struct DepWin { int f0, n; long long ld, vol; };
 
-// One thread per OUTPUT coarse cell of the window: it owns that cell's 4x4x4 fine cells (private accumulators in
-// shared memory, bank = thread id) and walks the (up to) eight source coarse cells that can reach them, in the
-// reference's k,j,i order.  Every fine cell of the window is written exactly once, so rho needs no zero-fill and
-// no atomics, and the sums are bit-identical to the reference's sequential scatter loop (pm.f90:44-72).
-__global__ void __launch_bounds__(DB_T) k_fine_deposit(Geom g, DepWin w, int tile0, const short* __restrict__ xp,
-                                                       const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                       float mass_p, float* __restrict__ rho /*[batch][n][n][ld]*/) {
-  __shared__ float acc[64 * DB_T];
+// One thread per SOURCE coarse cell: it walks its particles once, in storage order, and adds their eight CIC
+// weights into a private 5x5x5 block of shared-memory accumulators (its own 4^3 fine cells plus the +1 spill planes,
+// pm.f90:54-68).  A CTA covers a brick of FB_X x FB_Y x FB_Z output coarse cells plus the low-side neighbour layer
+// whose spill lands in the brick; afterwards every fine cell of the brick is the sum of the (up to eight) blocks that
+// reach it, taken in the reference's k,j,i source order.  No atomics, every fine cell of the window written exactly
+// once (no zero-fill), run-to-run deterministic.  The summation is grouped per source cell, so rho equals the
+// reference's sequential scatter to round-off (~1e-7 relative), not bit for bit.
+constexpr int FB_X = 8, FB_Y = 4, FB_Z = 4;
+constexpr int FS_X = FB_X + 1, FS_Y = FB_Y + 1, FS_Z = FB_Z + 1, FS_N = FS_X * FS_Y * FS_Z;  // 225 source cells
+constexpr int FD_T = 256;
+constexpr int FD_SMEM = 125 * FS_N * (int)sizeof(float);
+
+__global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int tile0, const short* __restrict__ xp,
+                                                         const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
+                                                         float mass_p, float* __restrict__ rho /*[batch][n][n][ld]*/) {
+  extern __shared__ float acc[];  // [125 = (a*5+b)*5+c][FS_N]
   const int t = threadIdx.x;
   const int tile = tile0 + blockIdx.y;
   const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
   const int nc4 = w.n / 4, c0 = w.f0 / 4;
-  const int nbx = (nc4 + DB_X - 1) / DB_X, nby = (nc4 + DB_Y - 1) / DB_Y;
+  const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y;
   const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
-  const int cx = t % DB_X, cy = (t / DB_X) % DB_Y, cz = t / (DB_X * DB_Y);
-  // tile-local Fortran index of my output cell (1-ncb .. nt+ncb inside the extended tile)
-  const int i = c0 + bx * DB_X + cx + 1 - NCB, j = c0 + by * DB_Y + cy + 1 - NCB, k = c0 + bz * DB_Z + cz + 1 - NCB;
+  for (int e = t; e < 125 * FS_N; e += FD_T) acc[e] = 0.f;
+  __syncthreads();
+  if (t < FS_N) {
+    const int sx = t % FS_X, sy = (t / FS_X) % FS_Y, sz = t / (FS_X * FS_Y);
+    // tile-local Fortran index of my source cell (sx = 0 is the low-side neighbour layer)
+    const int si = c0 + bx * FB_X + sx - NCB, sj = c0 + by * FB_Y + sy - NCB, sk = c0 + bz * FB_Z + sz - NCB;
+    const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
+    if (si >= lo && si <= hi && sj >= lo && sj <= hi && sk >= lo && sk <= hi) {
+      const long long e = ext_index(g, tx * g.nt - 1 + si, ty * g.nt - 1 + sj, tz * g.nt - 1 + sk);
+      const int n = rhoc_e[e];
+      const long long s = cstart_e[e];
+      float* my = acc + t;
+      for (int l = 0; l < n; l++) {
+        const Code3 c = load_code3(xp, s + l);
+        int i1, j1, k1; float ax[2], ay[2], az[2];
+        cic_split(fine_tempx(si, c.x), i1, ax[0], ax[1]);
+        cic_split(fine_tempx(sj, c.y), j1, ay[0], ay[1]);
+        cic_split(fine_tempx(sk, c.z), k1, az[0], az[1]);
+        const int fa = i1 - (4 * (si - 1) + 1), fb = j1 - (4 * (sj - 1) + 1), fc = k1 - (4 * (sk - 1) + 1);  // 0..3 (4 on an f32 tie)
 #pragma unroll
-  for (int q = 0; q < 64; q++) acc[q * DB_T + t] = 0.f;
-  const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
-  {
-    const int X0 = tx * g.nt - 1, Y0 = ty * g.nt - 1, Z0 = tz * g.nt - 1;  // image-local = X0 + Fortran local
-    for (int sk = k - 1; sk <= k; sk++) {
-      if (sk < lo || sk > hi) continue;
-      for (int sj = j - 1; sj <= j; sj++) {
-        if (sj < lo || sj > hi) continue;
-        for (int si = i - 1; si <= i; si++) {
-          if (si < lo || si > hi) continue;
-          const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
-          const int n = rhoc_e[e];
-          if (n == 0) continue;
-          const long long s = cstart_e[e];
-          // conservative early reject: a lower neighbour only reaches me from its top quarter
-          const unsigned rx = si < i ? 0xB000u : 0u, ry = sj < j ? 0xB000u : 0u, rz = sk < k ? 0xB000u : 0u;
-          for (int l = 0; l < n; l++) {
-            Code3 c = load_code3(xp, s + l);
-            if ((unsigned short)c.x < rx || (unsigned short)c.y < ry || (unsigned short)c.z < rz) continue;
-            int i1, j1, k1; float ax1, ax2, ay1, ay2, az1, az2;
-            cic_split(fine_tempx(si, c.x), i1, ax1, ax2);
-            cic_split(fine_tempx(sj, c.y), j1, ay1, ay2);
-            cic_split(fine_tempx(sk, c.z), k1, az1, az2);
-            // fine index (without nfb) relative to my first fine cell 4(i-1)+1
-            const int fa = i1 - (4 * (i - 1) + 1), fb = j1 - (4 * (j - 1) + 1), fc = k1 - (4 * (k - 1) + 1);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
-              const int a = fa + qa, b = fb + qb, cc = fc + qc;
-              if ((unsigned)a < 4u && (unsigned)b < 4u && (unsigned)cc < 4u) {
-                // dx(1)*dx(2)*dx(3)*mass_p, left to right (pm.f90:61-68)
-                float wgt = __fmul_rn(__fmul_rn(__fmul_rn(qa ? ax2 : ax1, qb ? ay2 : ay1), qc ? az2 : az1), mass_p);
-                float* p = &acc[((cc * 4 + b) * 4 + a) * DB_T + t];
-                *p = __fadd_rn(*p, wgt);
-              }
-            }
+        for (int q = 0; q < 8; q++) {
+          const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
+          const int a = fa + qa, b = fb + qb, cc = fc + qc;
+          if (a <= 4 && b <= 4 && cc <= 4) {  // index 5 only occurs with weight exactly 0
+            const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:61-68
+            float* p = my + ((a * 5 + b) * 5 + cc) * FS_N;
+            *p = __fadd_rn(*p, wgt);
           }
         }
       }
     }
   }
   __syncthreads();
-  // write the brick's fine region, one 32-float row per warp iteration
-  const int lane = t & 31, wp = t >> 5, nw = DB_T >> 5;
+  // gather: one 32-float row (8 coarse cells x 4) per warp iteration
+  const int lane = t & 31, wp = t >> 5;
   float* out = rho + (long long)blockIdx.y * w.vol;
-  for (int row = wp; row < 16 * DB_Y * DB_Z; row += nw) {
-    const int fy = row % (4 * DB_Y), fz = row / (4 * DB_Y);
-    const int ocx = lane >> 2, a = lane & 3, ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
-    const int gx = (bx * DB_X + ocx) * 4 + a, gy = (by * DB_Y + ocy) * 4 + b, gz = (bz * DB_Z + ocz) * 4 + cc;
-    if (gx < w.n && gy < w.n && gz < w.n)
-      out[((long long)gz * w.n + gy) * w.ld + gx] = acc[((cc * 4 + b) * 4 + a) * DB_T + ((ocz * DB_Y + ocy) * DB_X + ocx)];
+  const int ocx = lane >> 2, a = lane & 3;
+  const int gx = (bx * FB_X + ocx) * 4 + a;
+  for (int row = wp; row < 16 * FB_Y * FB_Z; row += FD_T / 32) {
+    const int fy = row % (4 * FB_Y), fz = row / (4 * FB_Y);
+    const int ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
+    const int gy = (by * FB_Y + ocy) * 4 + b, gz = (bz * FB_Z + ocz) * 4 + cc;
+    float v = 0.f;
+#pragma unroll
+    for (int dz = 1; dz >= 0; dz--) {      // sources in k, j, i order: the lower neighbour first
+      if (dz && cc) continue;
+#pragma unroll
+      for (int dy = 1; dy >= 0; dy--) {
+        if (dy && b) continue;
+#pragma unroll
+        for (int dx = 1; dx >= 0; dx--) {
+          if (dx && a) continue;
+          const int S = ((ocz + 1 - dz) * FS_Y + (ocy + 1 - dy)) * FS_X + (ocx + 1 - dx);
+          v = __fadd_rn(v, acc[(((a + 4 * dx) * 5 + (b + 4 * dy)) * 5 + (cc + 4 * dz)) * FS_N + S]);
+        }
+      }
+    }
+    if (gx < w.n && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = v;
   }
 }
 
@@ -449,42 +459,67 @@ __device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
   return __double2float_rn(__dsub_rn(__dadd_rn((double)cell0, xp_frac(xp)), 0.5));
 }
 
-// one thread per physical coarse cell: gathers from the 27 surrounding source cells in the tile's
-// frame, in k,j,i order => identical summation order to the r3t scatter loop
-__global__ void __launch_bounds__(128) k_coarse_deposit(Geom g, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
-                                                        const long long* __restrict__ cstart_e, float mass_p,
-                                                        float* __restrict__ r3 /*[nc][nc][nc+2]*/) {
-  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (L >= g.ncell_p) return;
-  int tx, ty, tz, i, j, k;
-  phys_decompose(g, L, tx, ty, tz, i, j, k);
+// Coarse CIC deposit (pm.f90:130-163).  Same scheme as the fine deposit: one thread per SOURCE cell adds its
+// particles into a private 3x3x3 block of accumulators (targets cell-1..cell+1 of the tile's r3t), a CTA covers a
+// brick of CB_X x CB_Y x CB_Z target cells plus one source layer on every side (tile frame, like r3t(-1:nt+2)),
+// and every target is the sum of its 27 blocks in k,j,i source order.  Deterministic, no atomics.
+constexpr int CB_X = 8, CB_Y = 8, CB_Z = 4, CD_T = CB_X * CB_Y * CB_Z;
+constexpr int CS_X = CB_X + 2, CS_Y = CB_Y + 2, CS_Z = CB_Z + 2, CS_N = CS_X * CS_Y * CS_Z;  // 600 source cells
+constexpr int CD_SMEM = 27 * CS_N * (int)sizeof(float);
+
+__global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
+                                                         const long long* __restrict__ cstart_e, float mass_p,
+                                                         float* __restrict__ r3 /*[nc][nc][nc+2]*/) {
+  extern __shared__ float acc[];  // [27 = (rz*3+ry)*3+rx][CS_N]
+  const int t = threadIdx.x;
+  const int tile = blockIdx.y;
+  const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
+  const int nbx = (g.nt + CB_X - 1) / CB_X, nby = (g.nt + CB_Y - 1) / CB_Y;
+  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
   const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
-  float acc = 0.f;
-  const int ti = i + 1, tj = j + 1, tk = k + 1;  // my r3t index (Fortran)
-  for (int sk = k - 1; sk <= k + 1; sk++)
-    for (int sj = j - 1; sj <= j + 1; sj++)
-      for (int si = i - 1; si <= i + 1; si++) {
-        const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
-        const int n = rhoc_e[e];
-        if (n == 0) continue;
-        const long long s = cstart_e[e];
-        for (int l = 0; l < n; l++) {
-          Code3 c = load_code3(xp, s + l);
-          int i1, j1, k1; float ax1, ax2, ay1, ay2, az1, az2;
-          cic_split(coarse_tempx(si, c.x), i1, ax1, ax2);  // si is 0-based = Fortran cell - 1
-          const int da = ti - i1;
-          if ((unsigned)da > 1u) continue;
-          cic_split(coarse_tempx(sj, c.y), j1, ay1, ay2);
-          const int db = tj - j1;
-          if ((unsigned)db > 1u) continue;
-          cic_split(coarse_tempx(sk, c.z), k1, az1, az2);
-          const int dc = tk - k1;
-          if ((unsigned)dc > 1u) continue;
-          float w = __fmul_rn(__fmul_rn(__fmul_rn(da ? ax2 : ax1, db ? ay2 : ay1), dc ? az2 : az1), mass_p);
-          acc = __fadd_rn(acc, w);
-        }
+  for (int e = t; e < 27 * CS_N; e += CD_T) acc[e] = 0.f;
+  __syncthreads();
+  for (int sidx = t; sidx < CS_N; sidx += CD_T) {
+    const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
+    const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;  // 0-based tile-local, -1..nt
+    if (si > g.nt || sj > g.nt || sk > g.nt) continue;
+    const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
+    const int n = rhoc_e[e];
+    const long long s = cstart_e[e];
+    float* my = acc + sidx;
+    for (int l = 0; l < n; l++) {
+      const Code3 c = load_code3(xp, s + l);
+      int i1, j1, k1; float ax[2], ay[2], az[2];
+      cic_split(coarse_tempx(si, c.x), i1, ax[0], ax[1]);  // i1 = Fortran r3t index of the lower target = si or si+1
+      cic_split(coarse_tempx(sj, c.y), j1, ay[0], ay[1]);
+      cic_split(coarse_tempx(sk, c.z), k1, az[0], az[1]);
+      const int ra = i1 - si, rb = j1 - sj, rc = k1 - sk;  // 0 or 1
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
+        const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:147-154
+        float* p = my + (((rc + qc) * 3 + (rb + qb)) * 3 + (ra + qa)) * CS_N;
+        *p = __fadd_rn(*p, wgt);
       }
-  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * (g.nc + 2) + (X0 + i)] = acc;
+    }
+  }
+  __syncthreads();
+  const int ox = t % CB_X, oy = (t / CB_X) % CB_Y, oz = t / (CB_X * CB_Y);
+  const int i = bx * CB_X + ox, j = by * CB_Y + oy, k = bz * CB_Z + oz;
+  if (i >= g.nt || j >= g.nt || k >= g.nt) return;
+  float v = 0.f;
+#pragma unroll
+  for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        // source S = T + d holds my value at relative index r = T - (S - 1) = 1 - d ; Fortran r3t index of T is T0+1,
+        // block index 0 <-> target S0 (Fortran), so r = (T0 + 1) - S0 = 1 - d
+        const int S = ((oz + 1 + dz) * CS_Y + (oy + 1 + dy)) * CS_X + (ox + 1 + dx);
+        v = __fadd_rn(v, acc[(((1 - dz) * 3 + (1 - dy)) * 3 + (1 - dx)) * CS_N + S]);
+      }
+  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * (g.nc + 2) + (X0 + i)] = v;
 }
 
 // force_c(3,0:nc+1,0:nc+1,0:nc+1) from the three inverse transforms + periodic 1-cell halo

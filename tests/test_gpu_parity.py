@@ -2,7 +2,7 @@
 
 Parity is unpinned by the reference (no golden vectors upstream); the oracle restates it line by line.
 Gates: integer codes / counts bit-exact; densities and forces <= 1e-5 norm-relative
-(in fact the densities are bit-exact because the deposit kernels keep the reference's summation order).
+(the deposits are deterministic and atomics-free but group the sum per source cell: equal to ~1e-7).
 """
 import numpy as np
 import pytest
@@ -47,13 +47,18 @@ def test_kernels(setup, tables):
     assert norm_rel(G.kern_c(), O.kern_c) < 1e-5
 
 
-def test_fine_density_bit_exact(setup):
+def test_fine_density(setup):
+    """The GPU deposit groups the sum per source coarse cell (deterministic, atomics-free) instead of the reference's
+    particle-by-particle scatter: equal to round-off, far inside the 1e-5 gate; the total mass matches."""
     O, G, _, _ = setup
     for t in [(1, 1, 1), (2, 1, 2), (2, 2, 2)]:
         ro = O.fine_density(0, *t)
         rg = G.fine_density(*t)
         assert abs(float(rg[:, :, :O.nfe].sum(dtype=np.float64)) - float(ro[:, :, :O.nfe].sum(dtype=np.float64))) < 1e-3
-        assert np.array_equal(ro[:, :, :O.nfe], rg[:, :, :O.nfe]), t
+        assert norm_rel(rg[:, :, :O.nfe], ro[:, :, :O.nfe]) < 1e-6, t
+        assert np.array_equal(rg[:, :, :O.nfe] == 0, ro[:, :, :O.nfe] == 0)      # same support
+        rg2 = G.fine_density(*t)
+        assert np.array_equal(rg, rg2)                                              # run-to-run deterministic
 
 
 def test_fine_force(setup):
@@ -64,9 +69,12 @@ def test_fine_force(setup):
         assert norm_rel(fg, fo) < 1e-5, t
 
 
-def test_coarse_density_bit_exact(setup):
+def test_coarse_density(setup):
     O, G, _, _ = setup
-    assert np.array_equal(O.coarse_density(), G.coarse_density())
+    ro, rg = O.coarse_density(), G.coarse_density()
+    assert norm_rel(rg, ro) < 1e-6
+    assert abs(float(rg.sum(dtype=np.float64)) - float(ro.sum(dtype=np.float64))) < 1e-6 * float(ro.sum(dtype=np.float64))
+    assert np.array_equal(rg, G.coarse_density())                                   # run-to-run deterministic
 
 
 def test_coarse_force(setup):
