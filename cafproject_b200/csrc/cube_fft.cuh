@@ -288,32 +288,53 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_y(FftGeom g, f
 
 // ---------------------------------------------------------------------------------------------
 // z forward + Green multiply + z inverse for the three force components.
-// A[b][z][ky][kx] -> B[d][b][z'][ky][kx];  kern[d][kz][ky][kx] real (already scaled by 1/N^3).
-// out = i*K*c  (pm.f90:79-80: re' = -im*K, im' = re*K).   grid = (P/16, N); loops over the batch.
+// A[b][z][ky][kx] -> B[d][b][z'][ky][kx];  kern[d][kz][ky][kx] real, multiplied by `scale` (1/N^3) on load.
+// out = i*K*c  (pm.f90:79-80: re' = -im*K, im' = re*K).   grid = (P/16, N); the CTA loops over the batch with the
+// next tile's 16 lines prefetched (cp.async, 16-byte copies) into the other half of a double buffer while the
+// current tile is transformed.  K is kept in shared memory for kz <= N/2 only: K_d(N-kz) = +-K_d(kz) (odd in its
+// own axis, even in the others: kernel_f.f90:32-38 mirrors the table that way).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
 template <int R1, int R2>
-__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
-                                                                         const float* __restrict__ kern, float scale,
-                                                                         const float2* __restrict__ tw_g) {
-  constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2);
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 : 1)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
+                                                                            const float* __restrict__ kern, float scale,
+                                                                            const float2* __restrict__ tw_g) {
+  constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2), NHZ = N / 2 + 1;
   extern __shared__ float2 smem[];
-  float2* s = smem;                                         // [N][16]
-  float2* tw = smem + N * LW;                               // [N]
-  float* ks = reinterpret_cast<float*>(smem + N * LW + N);  // [3][N][16]
+  float2* sbuf = smem;                                          // [2][N][16]
+  float2* tw = smem + 2 * N * LW;                               // [N]
+  float* ks = reinterpret_cast<float*>(smem + 2 * N * LW + N);  // [3][NHZ][16]
   const int tid = threadIdx.x, line = tid % FL, idx = tid / FL;
-  const int kx = blockIdx.x * FL + line, ky = blockIdx.y;
+  const int kx0 = blockIdx.x * FL, kx = kx0 + line, ky = blockIdx.y;
   const bool act = kx < g.NH;
-  load_tw(tw, tw_g, N);
-  for (int q = idx; q < 3 * N; q += NT / FL) ks[q * FL + line] = act ? kern[((size_t)q * N + ky) * g.P + kx] * scale : 0.f;
   const size_t plane = (size_t)N * g.P;
   const size_t colo = (size_t)ky * g.P + kx;
-  for (int b = 0; b < g.nbatch; b++) {
-    const float2* src = A + (size_t)b * N * plane + colo;
-    __syncthreads();  // previous iteration's readers of s are done (also orders the ks/tw fill)
-    if (act) {
-#pragma unroll 4
-      for (int n = idx; n < N; n += NT / FL) s[n * LW + line] = src[(size_t)n * plane];
+  // prefetch: thread -> (n, pair of lines); rows of A are 16-byte aligned (P and kx0 are multiples of 16)
+  auto prefetch = [&](int b, float2* dst) {
+    const float2* src = A + (size_t)b * N * plane + (size_t)ky * g.P + kx0;
+    for (int e = tid; e < N * (FL / 2); e += NT) {
+      const int n = e / (FL / 2), pr = e - n * (FL / 2);
+      if (kx0 + 2 * pr < g.NH) cp_async16(dst + n * LW + 2 * pr, src + (size_t)n * plane + 2 * pr);
     }
+    cp_async_commit();
+  };
+  prefetch(0, sbuf);
+  load_tw(tw, tw_g, N);
+  for (int q = idx; q < 3 * NHZ; q += NT / FL) {
+    const int d = q / NHZ, kz = q - d * NHZ;
+    ks[q * FL + line] = act ? kern[((size_t)(d * N + kz) * N + ky) * g.P + kx] * scale : 0.f;
+  }
+  for (int b = 0; b < g.nbatch; b++) {
+    float2* s = sbuf + (b & 1) * N * LW;
+    __syncthreads();  // the other buffer's readers (tile b-1) are done; also orders the ks/tw fill
+    if (b + 1 < g.nbatch) { prefetch(b + 1, sbuf + ((b + 1) & 1) * N * LW); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
     if (act) fft_step_a<R1, R2, -1, LW>(s, tw, line, idx);
     __syncthreads();
@@ -326,7 +347,10 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_z_green(FftGeo
         float2 w[R2];
 #pragma unroll
         for (int k2 = 0; k2 < R2; k2++) {
-          const float K = ks[(d * N + idx + R1 * k2) * FL + line];
+          const int kz = idx + R1 * k2;
+          const int kf = kz < NHZ ? kz : N - kz;
+          float K = ks[(d * NHZ + kf) * FL + line];
+          if (d == 2 && kz >= NHZ) K = -K;
           w[k2] = make_float2(-X[k2].y * K, X[k2].x * K);
         }
         ifft_step_a<R1, R2, LW>(w, s, tw, line, idx);

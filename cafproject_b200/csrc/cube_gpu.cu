@@ -264,12 +264,13 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaMemcpyAsync(h->tw, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
     const int smem_x = (N * (FL + 1) + N) * (int)sizeof(float2), smem_y = (N * FL + N) * (int)sizeof(float2);
-    const int smem_z = smem_y + 3 * N * FL * (int)sizeof(float);
+    const int smem_z = (2 * N * FL + N) * (int)sizeof(float2) + 3 * (N / 2 + 1) * FL * (int)sizeof(float);
     CK(cudaFuncSetAttribute((const void*)h->plan->x_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
     CK(cudaFuncSetAttribute((const void*)h->plan->x_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
+    CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   // coarse mesh
   h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
@@ -469,7 +470,7 @@ static int fine_mesh(cube_handle* h, int tile0, int nb) {
   const FftPlan& pl = *h->plan;
   const int N = f.N, T = pl.threads();
   const size_t smem_x = (size_t)(N * (FL + 1) + N) * sizeof(float2), smem_y = (size_t)(N * FL + N) * sizeof(float2);
-  const size_t smem_z = smem_y + (size_t)3 * N * FL * sizeof(float);
+  const size_t smem_z = (size_t)(2 * N * FL + N) * sizeof(float2) + (size_t)3 * (N / 2 + 1) * FL * sizeof(float);
   DepWin w{8, N, N, (long long)h->rho_n};
   if (fine_deposit(h, tile0, nb, w, h->rho)) return 1;
   {
