@@ -281,6 +281,7 @@ def main():
             t = torch.tensor([sec], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); sec = float(t.item())
         e2e = {"value": world * npart * n_e2e / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * sec / n_e2e, "steps": n_e2e}
+    radius = G.query("drift_radius")
     G.close()
 
     cpu = None
@@ -293,7 +294,7 @@ def main():
                 "dtype": "f32 mesh / f64 particle update / int16 codes", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roof, "phases_ms_per_step": phases, "cpu_baseline": cpu,
-                "particles_per_gpu": int(npart)}
+                "particles_per_gpu": int(npart), "drift_radius": radius}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -85,6 +85,7 @@ struct cube_handle {
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
+  unsigned* rank = nullptr;
   long long* tile_count = nullptr;
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
@@ -107,7 +108,7 @@ struct cube_handle {
   // profiling
   cudaEvent_t tev[2] = {};
   bool prof = false; cudaEvent_t ev[2 * PH_N] = {}; float phase_ms[PH_N] = {}; long long launches = 0;
-  float last_f2max_fine = 0;
+  float last_f2max_fine = 0; int last_radius = 0;
 };
 
 struct PhaseTimer {  // CUBEnu-style phase bracket (pm.f90:35,195,...) with CUDA events on the launch stream
@@ -222,7 +223,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->rhoc_e, g.ncell_e)); CK(dmalloc(&h->cstart_e, g.ncell_e)); CK(dmalloc(&h->vfield_e, 3 * g.ncell_e));
   h->nscan_blocks = (int)((g.ncell_p + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
-  CK(dmalloc(&h->stat_partial, 3 * (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 3));
+  CK(dmalloc(&h->stat_partial, 2 * (long long)nblk(g.ncell_p, PC_CELLS) + (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 3));
+  CK(dmalloc(&h->rank, cap));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
   CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
@@ -296,7 +298,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
-                  h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->tile_count, h->maxoff, h->f2max,
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
                   h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r};
@@ -390,9 +392,10 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemsetAsync(h->maxoff, 0, sizeof(int), h->st));
   int maxoff = 0;
+  const unsigned nchunk = nblk(g.ncell_p, PC_CELLS);
   {
     PhaseTimer pt(h, PH_KEY);
-    k_drift_key<<<nblk(g.ncell_p, 128), 128, 0, h->st>>>(g, h->xp, h->vp, h->rhoc_p, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->maxoff); CKL();
+    k_drift_key_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff); CKL();
     h->launches++;
     CK(cudaMemcpyAsync(&maxoff, h->maxoff, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -406,12 +409,14 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   }
   if (maxoff > NCB) return fail("cube_gpu_update_x: a particle moves %d coarse cells in one step (> ncb=%d): outside the tile buffer", maxoff, NCB);
   const int r = maxoff;
+  h->last_radius = r;
   const unsigned nb = nblk(g.ncell_p, 128);
   {
     PhaseTimer pt(h, PH_COUNT);
-    k_drift_gather<false><<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, S,
-                                                h->rhoc_p2, h->vfield_p2, nullptr, nullptr, nullptr, nullptr); CKL();
-    h->launches++;
+    k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
+                                        h->vfield_p2, h->rank, h->stat_partial); CKL();
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
+    h->launches += 2;
   }
   {
     PhaseTimer pt(h, PH_SCAN);
@@ -424,10 +429,11 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", tot, h->np_image_max, h->p.rank + 1);
   {
     PhaseTimer pt(h, PH_PLACE);
-    k_drift_gather<true><<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, S,
-                                               h->rhoc_p2, h->vfield_p2, h->cstart_p2, h->xp2, h->vp2, h->stat_partial); CKL();
-    k_reduce3<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, h->stat3); CKL();
-    h->launches += 2;
+    k_drift_place_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2, h->dvlut, h->enc,
+                                               dt_mid, S, h->xp2, h->vp2, h->stat_partial); CKL();
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 0, h->stat3); CKL();
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 1, h->stat3 + 2); CKL();
+    h->launches += 3;
   }
   double st[3];
   CK(cudaMemcpyAsync(st, h->stat3, sizeof st, cudaMemcpyDeviceToHost, h->st));
@@ -584,6 +590,7 @@ extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   if (w == "nft") return h->g.nft;
   if (w == "nt") return h->g.nt;
   if (w == "fine_batch") return h->batch;
+  if (w == "drift_radius") return h->last_radius;
   if (w == "nfft") return h->fg.N;
   if (w == "nfft_pitch") return h->fg.P;
   if (w == "kernel_launches") return h->launches;

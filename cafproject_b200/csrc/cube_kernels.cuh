@@ -125,150 +125,6 @@ __global__ void k_build_dvlut(const float* __restrict__ tanlut, double S, double
   if (u < 65536) dvlut[u] = (double)tanlut[u] / S;
 }
 
-// =============================================================================================
-// drift (update_particle.f90)
-// =============================================================================================
-constexpr double TIE_EPS = 1e-9;
-
-// destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
-__device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
-  double xq = __dadd_rn((double)(cell1 - 1), xp_frac(xp));
-  double dx = __dmul_rn(__dmul_rn(dt_mid, v), 0.25);  // (dt_mid*vreal)/ncell, ncell=4: exact scaling
-  double s = __dadd_rn(xq, dx);
-  double c = ceil(s);
-  tie = tie || (c - s < TIE_EPS) || (s - (c - 1.0) < TIE_EPS);
-  return (int)c;
-}
-
-// pass 0: one thread per storage-owning cell; key = destination offset of every particle
-__global__ void __launch_bounds__(128) k_drift_key(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                   const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
-                                                   const float* __restrict__ vfield_p, const double* __restrict__ dvlut,
-                                                   double dt_mid, unsigned short* __restrict__ key, int* __restrict__ maxoff) {
-  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int m = 0;
-  if (L < g.ncell_p) {
-    int tx, ty, tz, i, j, k;
-    phys_decompose(g, L, tx, ty, tz, i, j, k);
-    const int n = rhoc_p[L];
-    const long long s = cstart_p[L];
-    const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
-    for (int l = 0; l < n; l++) {
-      Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
-      bool tie = false;
-      int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
-      int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
-      int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
-      m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
-      ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
-      key[s + l] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
-    }
-  }
-  m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
-}
-
-// pass 1 (PLACE=false): count + vfield_new chain;  pass 2 (PLACE=true): rank + write + statistics.
-// One thread per destination cell; sources are visited in the reference's traversal order.
-template <bool PLACE>
-__global__ void __launch_bounds__(128) k_drift_gather(
-    Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp, const unsigned short* __restrict__ key,
-    const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
-    const double* __restrict__ dvlut, double dt_mid, double S, int* __restrict__ rhoc_new, float* __restrict__ vfield_new,
-    const long long* __restrict__ cstart_new, short* __restrict__ xp_new, short* __restrict__ vp_new,
-    double* __restrict__ stat_partial) {
-  const double weight_v = (double)0.1f;  // update_particle.f90:10
-  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double st_tot = 0, st_c = 0, st_res = 0;
-  if (L < g.ncell_p) {
-    int tx, ty, tz, i, j, k;
-    phys_decompose(g, L, tx, ty, tz, i, j, k);
-    const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
-    float vfn0, vfn1, vfn2;
-    int cnt = 0;
-    long long pos = 0;
-    if (!PLACE) {
-      long long e = ext_index(g, X0 + i, Y0 + j, Z0 + k);
-      vfn0 = (float)__dmul_rn((double)vfield_e[3 * e], weight_v);  // :27
-      vfn1 = (float)__dmul_rn((double)vfield_e[3 * e + 1], weight_v);
-      vfn2 = (float)__dmul_rn((double)vfield_e[3 * e + 2], weight_v);
-    } else {
-      vfn0 = vfield_new[3 * L]; vfn1 = vfield_new[3 * L + 1]; vfn2 = vfield_new[3 * L + 2];
-      pos = cstart_new[L];
-      st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
-    }
-    for (int sk = k - r; sk <= k + r; sk++)
-      for (int sj = j - r; sj <= j + r; sj++)
-        for (int si = i - r; si <= i + r; si++) {
-          const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
-          const int n = rhoc_e[e];
-          if (n == 0) continue;
-          const long long s = cstart_e[e];
-          const unsigned want = key_pack(i - si, j - sj, k - sk);
-          const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
-          for (int l = 0; l < n; l++) {
-            const unsigned kk = key[s + l];
-            if (!(kk & KEY_FLAG) && kk != want) continue;
-            Code3 vc = load_code3(vp, s + l);
-            const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], vf0);
-            const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], vf1);
-            const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], vf2);
-            Code3 xc;
-            if (PLACE || (kk & KEY_FLAG)) xc = load_code3(xp, s + l);
-            if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
-              bool t = false;
-              if (drift_dest(si + 1, xc.x, v0, dt_mid, t) != i + 1) continue;
-              if (drift_dest(sj + 1, xc.y, v1, dt_mid, t) != j + 1) continue;
-              if (drift_dest(sk + 1, xc.z, v2, dt_mid, t) != k + 1) continue;
-            }
-            if (!PLACE) {
-              cnt++;
-              vfn0 = (float)__dadd_rn((double)vfn0, v0);  // :47, f32 store after each f64 add
-              vfn1 = (float)__dadd_rn((double)vfn1, v1);
-              vfn2 = (float)__dadd_rn((double)vfn2, v2);
-            } else {
-              // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
-              short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
-              short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
-              short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
-              short w0 = vp_encode(__dsub_rn(v0, (double)vfn0), S);  // :85-86
-              short w1 = vp_encode(__dsub_rn(v1, (double)vfn1), S);
-              short w2 = vp_encode(__dsub_rn(v2, (double)vfn2), S);
-              store_code3(xp_new, pos, x0, x1, x2);
-              store_code3(vp_new, pos, w0, w1, w2);
-              pos++;
-              // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
-              double a0 = dvlut[(unsigned short)w0], a1 = dvlut[(unsigned short)w1], a2 = dvlut[(unsigned short)w2];
-              st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-              a0 = __dadd_rn(a0, (double)vfn0); a1 = __dadd_rn(a1, (double)vfn1); a2 = __dadd_rn(a2, (double)vfn2);
-              st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-            }
-          }
-        }
-    if (!PLACE) {
-      const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
-      rhoc_new[L] = cnt;
-      vfield_new[3 * L] = (float)((double)vfn0 / den);
-      vfield_new[3 * L + 1] = (float)((double)vfn1 / den);
-      vfield_new[3 * L + 2] = (float)((double)vfn2 / den);
-    }
-  }
-  if (PLACE) {  // deterministic block reduction of the three sums
-    __shared__ double sm[3][4];
-    for (int o = 16; o; o >>= 1) {
-      st_tot += __shfl_down_sync(0xffffffffu, st_tot, o);
-      st_c += __shfl_down_sync(0xffffffffu, st_c, o);
-      st_res += __shfl_down_sync(0xffffffffu, st_res, o);
-    }
-    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = st_tot; sm[1][threadIdx.x >> 5] = st_c; sm[2][threadIdx.x >> 5] = st_res; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      double s = ((sm[threadIdx.x][0] + sm[threadIdx.x][1]) + sm[threadIdx.x][2]) + sm[threadIdx.x][3];
-      stat_partial[3 * (long long)blockIdx.x + threadIdx.x] = s;
-    }
-  }
-}
-
 // fixed-order final reduction of per-block partial sums (3 interleaved series)
 __global__ void __launch_bounds__(1024) k_reduce3(const double* __restrict__ part, long long nb, double* __restrict__ out) {
   __shared__ double sm[3][32];

@@ -181,4 +181,209 @@ __global__ void __launch_bounds__(256) k_force_c_prefix(long long n, float* __re
   best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
   if ((threadIdx.x & 31) == 0) atomicMax(f2max, __float_as_uint(best));
 }
+
+// =============================================================================================
+// drift (update_particle.f90) in three particle-parallel / cell-parallel passes
+//   A  k_drift_key_p    per particle : destination offset key (+ near-tie flag), max |offset|
+//   B  k_drift_count    per destination cell: visits its source cells in the reference's traversal order
+//                       (tile-local k,j,i, then storage order), counts, chains vfield_new (order-dependent f32
+//                       rounding, update_particle.f90:47), and writes every accepted particle's rank in its cell
+//   C  k_drift_place_p  per particle : pos = cstart_new[dest] + rank ; xp_new, vp_new, velocity statistics
+// Near-tie particles (flagged in A) are decided in B in the destination tile's frame, like the reference.
+// rank[p] = rank in the destination cell (20 bits) | destination offset (3 x 4 bits, biased by 8) << 20; A presets
+// 0xFFFFFFFF for flagged particles so that one no destination accepts is dropped, as the reference would.
+// (No atomics inside the gather loop: they make nvcc give up warp reconvergence -- 4x the instructions.)
+// =============================================================================================
+constexpr double TIE_EPS = 1e-9;
+constexpr unsigned RANK_LOST = 0xFFFFFFFFu;
+constexpr int RANK_BITS = 20;
+__device__ __forceinline__ unsigned off_pack12(int dx, int dy, int dz) { return (unsigned)(dx + 8) | ((unsigned)(dy + 8) << 4) | ((unsigned)(dz + 8) << 8); }
+
+// destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
+__device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
+  double xq = __dadd_rn((double)(cell1 - 1), xp_frac(xp));
+  double dx = __dmul_rn(__dmul_rn(dt_mid, v), 0.25);  // (dt_mid*vreal)/ncell, ncell=4: exact scaling
+  double s = __dadd_rn(xq, dx);
+  double c = ceil(s);
+  tie = tie || (c - s < TIE_EPS) || (s - (c - 1.0) < TIE_EPS);
+  return (int)c;
+}
+
+__global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                     const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
+                                                     const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
+                                                     unsigned* __restrict__ rank, int* __restrict__ maxoff) {
+  __shared__ int soff[PC_CELLS + 1];
+  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
+  const long long p0 = cstart_p[c0];
+  int m = 0;
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const long long L = c0 + chunk_find(soff, q);
+    const long long nt = g.nt, nt3 = nt * nt * nt;
+    const long long c = L % nt3;
+    const int i = (int)(c % nt), j = (int)((c / nt) % nt), k = (int)(c / (nt * nt));
+    const long long p = p0 + q;
+    const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
+    const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
+    bool tie = false;
+    int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
+    int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
+    int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
+    m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
+    ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
+    key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
+    if (tie) rank[p] = RANK_LOST;
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
+}
+
+// pass B: one thread per destination (physical) cell, file order
+__global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                    const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
+                                                    const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
+                                                    const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
+                                                    float* __restrict__ vfield_new, unsigned* __restrict__ rank,
+                                                    double* __restrict__ stc_partial) {
+  const double weight_v = (double)0.1f;  // update_particle.f90:10
+  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double st_c = 0;
+  if (L < g.ncell_p) {
+    int tx, ty, tz, i, j, k;
+    phys_decompose(g, L, tx, ty, tz, i, j, k);
+    const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
+    int cnt = 0;
+    const long long e0 = ext_index(g, X0 + i, Y0 + j, Z0 + k);
+    float vfn0 = (float)__dmul_rn((double)vfield_e[3 * e0], weight_v);  // :27
+    float vfn1 = (float)__dmul_rn((double)vfield_e[3 * e0 + 1], weight_v);
+    float vfn2 = (float)__dmul_rn((double)vfield_e[3 * e0 + 2], weight_v);
+    for (int sk = k - r; sk <= k + r; sk++)
+      for (int sj = j - r; sj <= j + r; sj++) {
+        long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
+        for (int si = i - r; si <= i + r; si++, e++) {
+          const int n = rhoc_e[e];
+          if (n == 0) continue;
+          const long long s = cstart_e[e];
+          const unsigned want = key_pack(i - si, j - sj, k - sk), o12 = off_pack12(i - si, j - sj, k - sk) << RANK_BITS;
+          const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
+          for (int l = 0; l < n; l++) {
+            const unsigned kk = key[s + l];
+            if (kk == want) {  // common case: one predictable branch, the body is straight-line code
+              const Code3 vc = load_code3(vp, s + l);
+              rank[s + l] = (unsigned)cnt | o12;
+              cnt++;
+              vfn0 = (float)__dadd_rn((double)vfn0, __dadd_rn(dvlut[(unsigned short)vc.x], vf0));  // :47, f32 store after each f64 add
+              vfn1 = (float)__dadd_rn((double)vfn1, __dadd_rn(dvlut[(unsigned short)vc.y], vf1));
+              vfn2 = (float)__dadd_rn((double)vfn2, __dadd_rn(dvlut[(unsigned short)vc.z], vf2));
+            } else if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
+              const Code3 vc = load_code3(vp, s + l), xc = load_code3(xp, s + l);
+              const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], vf0);
+              const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], vf1);
+              const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], vf2);
+              bool t = false;
+              const bool ok = (drift_dest(si + 1, xc.x, v0, dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, dt_mid, t) == j + 1) &
+                              (drift_dest(sk + 1, xc.z, v2, dt_mid, t) == k + 1);
+              if (ok) {
+                rank[s + l] = (unsigned)cnt | o12;
+                cnt++;
+                vfn0 = (float)__dadd_rn((double)vfn0, v0);
+                vfn1 = (float)__dadd_rn((double)vfn1, v1);
+                vfn2 = (float)__dadd_rn((double)vfn2, v2);
+              }
+            }
+          }
+        }
+      }
+    const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
+    rhoc_new[L] = cnt;
+    vfn0 = (float)((double)vfn0 / den); vfn1 = (float)((double)vfn1 / den); vfn2 = (float)((double)vfn2 / den);
+    vfield_new[3 * L] = vfn0; vfield_new[3 * L + 1] = vfn1; vfield_new[3 * L + 2] = vfn2;
+    st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
+  }
+  __shared__ double sm[4];
+  for (int o = 16; o; o >>= 1) st_c += __shfl_down_sync(0xffffffffu, st_c, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = st_c;
+  __syncthreads();
+  if (threadIdx.x == 0) stc_partial[blockIdx.x] = ((sm[0] + sm[1]) + sm[2]) + sm[3];
+}
+
+// one particle: new codes at slot `pos` of the re-sorted arrays + its terms of the velocity statistics
+__device__ __forceinline__ void drift_move(long long p, long long pos, const short* __restrict__ xp, const short* __restrict__ vp,
+                                           const float* __restrict__ vf_src, const float* __restrict__ vf_new,
+                                           const double* __restrict__ dvlut, const double* __restrict__ enc, double dt_mid, double S,
+                                           short* __restrict__ xp_new, short* __restrict__ vp_new, double& st_tot, double& st_res) {
+  const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
+  const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], (double)vf_src[0]);
+  const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], (double)vf_src[1]);
+  const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], (double)vf_src[2]);
+  // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
+  const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
+  const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
+  const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
+  const float n0 = vf_new[0], n1 = vf_new[1], n2 = vf_new[2];
+  const short w0 = vp_encode_lut(__dsub_rn(v0, (double)n0), S, enc);  // :85-86
+  const short w1 = vp_encode_lut(__dsub_rn(v1, (double)n1), S, enc);
+  const short w2 = vp_encode_lut(__dsub_rn(v2, (double)n2), S, enc);
+  store_code3(xp_new, pos, x0, x1, x2);
+  store_code3(vp_new, pos, w0, w1, w2);
+  // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
+  double a0 = dvlut[(unsigned short)w0], a1 = dvlut[(unsigned short)w1], a2 = dvlut[(unsigned short)w2];
+  st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+  a0 = __dadd_rn(a0, (double)n0); a1 = __dadd_rn(a1, (double)n1); a2 = __dadd_rn(a2, (double)n2);
+  st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+}
+
+__device__ __forceinline__ void block_sum2(double a, double b, double* __restrict__ out2) {  // fixed-order block reduction
+  __shared__ double sm[2][PC_T / 32];
+  for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = a; sm[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0;
+    for (int w = 0; w < PC_T / 32; w++) t += sm[threadIdx.x][w];
+    out2[threadIdx.x] = t;
+  }
+}
+
+// pass C: one thread per particle; single image: destinations wrap periodically
+__global__ void __launch_bounds__(PC_T) k_drift_place_p(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                       const unsigned* __restrict__ rank, const long long* __restrict__ cstart_p,
+                                                       const float* __restrict__ vfield_p, const long long* __restrict__ cstart_new,
+                                                       const float* __restrict__ vfield_new, const double* __restrict__ dvlut,
+                                                       const double* __restrict__ enc, double dt_mid, double S, short* __restrict__ xp_new,
+                                                       short* __restrict__ vp_new, double* __restrict__ stat_partial) {
+  __shared__ int soff[PC_CELLS + 1];
+  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
+  const long long p0 = cstart_p[c0];
+  double st_tot = 0, st_res = 0;
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const long long p = p0 + q;
+    const unsigned rk = rank[p];
+    if (rk == RANK_LOST) continue;
+    const long long L = c0 + chunk_find(soff, q);
+    int tx, ty, tz, i, j, k;
+    phys_decompose(g, L, tx, ty, tz, i, j, k);
+    const unsigned o = rk >> RANK_BITS;
+    int X = tx * g.nt + i + (int)(o & 15u) - 8, Y = ty * g.nt + j + (int)((o >> 4) & 15u) - 8, Z = tz * g.nt + k + (int)((o >> 8) & 15u) - 8;
+    X = (X + g.nc) % g.nc; Y = (Y + g.nc) % g.nc; Z = (Z + g.nc) % g.nc;  // nn_d == 1: the neighbour image is this image
+    const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
+    drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_p + 3 * L, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
+               vp_new, st_tot, st_res);
+  }
+  block_sum2(st_tot, st_res, stat_partial + 2 * (long long)blockIdx.x);
+}
+
+// fixed-order final reduction of n partial sums laid out with stride `stride`, component `comp`
+__global__ void __launch_bounds__(1024) k_reduce_strided(const double* __restrict__ part, long long n, int stride, int comp, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double s = 0;
+  for (long long b = threadIdx.x; b < n; b += blockDim.x) s += part[b * stride + comp];
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 32; w++) t += sm[w]; *out = t; }
+}
+
 }  // namespace cube
