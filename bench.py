@@ -45,40 +45,79 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), sampled in-process through NVML
+    (nvidia_ml_py) every 20 ms so that even a sub-second timed region gets samples; falls back to one nvidia-smi query."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device=0):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.stop_flag, self.thread, self.nv = device, [], False, None, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device])
+            except Exception:
+                pass
+        return self.device
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.hd = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hd, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.hd, nv.NVML_CLOCK_SM))
+        try:
+            rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.hd))
+        except Exception:
+            rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.hd))
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(self.hd) / 1000.0
+        except Exception:
+            pw = None
+        self.rows.append((sm, rs, pw))
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        if self.nv is None:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["sampled once after the timed region (NVML unavailable)"], "samples": 1}
             except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join()
+        if not self.rows:
+            try:
+                self._sample()
+            except Exception:
+                pass
+        reasons = set()
+        for _, rs, _ in self.rows:
+            for name, bit in self.BITS.items():
+                if rs & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        pw = [r[2] for r in self.rows if r[2] is not None]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(pw)) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------
