@@ -186,7 +186,14 @@ def workload_config(args, world):
                         % (2 * args.nc, world, args.nc, args.nnt, nt, 4 * nt + 48),
             "step": "update_particle+buffer_density+buffer_x+particle_mesh+buffer_v (cafcube.f90:27-31)",
             "l2": "state and meshes (>1.5 GB) exceed the 126 MB L2; no flush needed",
-            "parallelism": "1 image" if world == 1 else "%d independent periodic images, one per GPU (ghost exchange over NCCL not built yet)" % world}
+            "parallelism": "1 image" if world == 1 else
+                           "%d images on a %dx%dx%d image grid, one per GPU; ghost-cell/particle exchange, distributed coarse FFT and scalar "
+                           "reductions over NCCL (global box = the tiling of one image's ICs)" % ((world,) + tuple(_grid(world)))}
+
+
+def _grid(world):
+    from cafproject_b200.cube import image_grid
+    return image_grid(world)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -212,7 +219,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cafproject_b200.cube import CubeGPU, host_tanf_lut
+    from cafproject_b200.cube import CubeGPU, host_tanf_lut, image_grid
+    from cafproject_b200.dist import shared_nccl_id
     from cafproject_b200.synthetic_ic import make_ic
 
     if not torch.cuda.is_available():
@@ -222,12 +230,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fk, ck = tables()
     nc, nnt = args.nc, args.nnt
-    states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=1000 * 2 + rank, device="cuda")
+    # every image starts from the same periodic ICs: the global box is their tiling (continuous across image boundaries,
+    # identical work per GPU = weak scaling)
+    states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=2000, device="cuda")
     torch.cuda.empty_cache()
     st = states[0]
     npart = st["xp"].shape[0]
-    G = CubeGPU(nc, nnt, fk, ck, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut())
-    G.particle_initialization(st, sig)
+    nccl_id = shared_nccl_id(device="cuda") if world > 1 else None
+    G = CubeGPU(nc, nnt, fk, ck, nn=image_grid(world), rank=rank, np_nc=2, device=local_rank, fine_batch=args.fine_batch,
+                tanf_lut=host_tanf_lut(), nccl_id=nccl_id)
+    G.particle_initialization(st, sig, npglobal=world * npart)
     G.buffer_density(); G.buffer_x(); G.buffer_v()
     # fixed small time step so that every timed step does the same work (dt from the first PM limits)
     dt, a_mid = np.float32(0.5), np.float32(0.0205)
@@ -302,18 +314,24 @@ def main():
     e2e = None
     if not args.no_e2e:
         cur, sig_cur = G.checkpoint()
-        pin = {k: torch.from_numpy(v).pin_memory() for k, v in cur.items()}
+        cap = int(1.25 * cur["xp"].shape[0]) + 1024      # nplocal of an image changes from step to step when nn > 1
+        pin = {k: (torch.empty((cap, 3), dtype=torch.int16).pin_memory() if k in ("xp", "vp") else torch.from_numpy(v).pin_memory())
+               for k, v in cur.items()}
         host = {k: v.numpy() for k, v in pin.items()}
+        n0 = cur["xp"].shape[0]
+        host["xp"][:n0] = cur["xp"]; host["vp"][:n0] = cur["vp"]
+        inp = dict(host, xp=host["xp"][:n0], vp=host["vp"][:n0])
         n_e2e = max(2, min(args.steps, 3))
-        h2d = sum(v.nbytes for v in host.values()); d2h = 0
+        h2d = d2h = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            G.particle_initialization(host, sig_cur, npglobal=npart)
+            G.particle_initialization(inp, sig_cur, npglobal=world * npart)
             G.buffer_density(); G.buffer_x(); G.buffer_v()
             one_step(dt)
-            out, sig_cur = G.checkpoint(out=host)   # result lands in the same pinned buffers = next step's input
-            d2h = sum(v.nbytes for v in out.values())
+            h2d = sum(v.nbytes for v in inp.values())
+            inp, sig_cur = G.checkpoint(out=host)   # result lands in the same pinned buffers = next step's input
+            d2h = sum(v.nbytes for v in inp.values())
         barrier()
         sec = time.perf_counter() - t0
         if world > 1:

@@ -48,6 +48,11 @@ __host__ __device__ inline long long ext_index(const Geom& g, int x, int y, int 
   return ((long long)(z + NCB) * g.ne + (y + NCB)) * g.ne + (x + NCB);
 }
 
+// true if extended-grid cell (x,y,z) is owned by another image (a real ghost), false if it aliases this image
+__host__ __device__ inline bool ext_is_remote(const Geom& g, int x, int y, int z) {
+  return ((x < 0 || x >= g.nc) && g.nn[0] > 1) || ((y < 0 || y >= g.nc) && g.nn[1] > 1) || ((z < 0 || z >= g.nc) && g.nn[2] > 1);
+}
+
 // ---- codes -----------------------------------------------------------------------------------
 // int(xp+ishift,izipx)+rshift == u + 0.5 with u the raw 16-bit pattern (parameters.f90:14-15)
 __device__ __forceinline__ double xp_frac(short xp) {  // (u+0.5)*x_resolution, exact

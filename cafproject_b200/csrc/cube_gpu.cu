@@ -19,6 +19,11 @@
 #include "cube_kernels.cuh"
 #include "cube_fft.cuh"
 #include "cube_particles.cuh"
+#include "cube_comm.cuh"
+#include "cube_exchange.cuh"
+#include "cube_coarse.cuh"
+
+#include <memory>
 
 using namespace cube;
 
@@ -104,7 +109,26 @@ struct cube_handle {
   long long cvol = 0, cnk = 0;
   float* r3 = nullptr; float* cforce = nullptr; float* kern_c = nullptr; float* fc = nullptr;
   cufftHandle cplan_r2c = 0, cplan_c2r = 0;
-  // host pinned scalars
+  // ---- more than one image (cube_comm.cuh, cube_exchange.cuh, cube_coarse.cuh) ----
+  int nimg = 1;
+  std::unique_ptr<Comm> comm;
+  ExPlan ex;
+  int *gcell_ext = nullptr, *scell_L = nullptr, *gcnt = nullptr, *scnt = nullptr;
+  long long *gstart = nullptr, *sstart = nullptr, *dir_cell0 = nullptr, *dir_bounds = nullptr;
+  HaloRec *hsend = nullptr, *hrecv = nullptr;
+  short* psend = nullptr; long long sendcap = 0;
+  std::vector<long long> gbound, sbound;  // host copies of the message offsets [ndir+1]
+  long long nghost = 0;
+  double* stat_partial_g = nullptr;
+  CoarseGeom cg = {};
+  float *stageA = nullptr, *slabR = nullptr, *kernT = nullptr, *sendF = nullptr, *recvF = nullptr;
+  float2 *slabC = nullptr, *packT = nullptr, *T = nullptr, *T3 = nullptr;
+  cufftHandle p2d_r2c = 0, p2d_c2r = 0, pz = 0;
+  struct FTarget { int rank, icx, icy; std::vector<int> zloc; long long off; int* d_zloc; };
+  struct FSource { int rank; long long off, nplanes; };
+  std::vector<FTarget> ftargets;   // images that need planes of my z-slab (interior + halo)
+  std::vector<FSource> fsources;   // slab owners my force_c planes come from
+  long long *zzoff = nullptr, *zzcs = nullptr;
   // profiling
   cudaEvent_t tev[2] = {};
   bool prof = false; cudaEvent_t ev[2 * PH_N] = {}; float phase_ms[PH_N] = {}; long long launches = 0;
@@ -148,6 +172,212 @@ static int build_dvlut(cube_handle* h, float sigma) {
 
 extern "C" const char* cube_gpu_last_error(void) { return g_err.c_str(); }
 
+extern "C" int cube_gpu_nccl_unique_id(void* id128) {
+  if (!id128) return fail("null argument");
+  NcclApi& a = nccl_api();
+  if (!a.load()) return fail("cube_gpu_nccl_unique_id: %s", a.err.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = a.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail("ncclGetUniqueId: %s", a.GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+
+
+// parameters.f90:178-203 (geometry) generalised to an nn[0] x nn[1] x nn[2] image grid
+static void fill_geom(const cube_params* p, Geom& g) {
+  for (int d = 0; d < 3; d++) { g.nn[d] = p->nn[d]; }
+  g.ic[0] = p->rank % p->nn[0]; g.ic[1] = (p->rank / p->nn[0]) % p->nn[1]; g.ic[2] = p->rank / (p->nn[0] * p->nn[1]);
+  g.nnt = p->nnt; g.nc = p->nc; g.nt = p->nc / p->nnt;
+  g.nte = g.nt + 2 * NCB; g.nft = g.nt * NCELL; g.nfe = g.nft + 2 * NFB; g.ne = g.nc + 2 * NCB;
+  g.ncell_p = (long long)g.nc * g.nc * g.nc; g.ncell_e = (long long)g.ne * g.ne * g.ne;
+}
+static void fill_coarse_geom(const Geom& g, CoarseGeom& c) {
+  c.R = g.nn[0] * g.nn[1] * g.nn[2]; c.nc = g.nc;
+  c.Gx = g.nc * g.nn[0]; c.Gy = g.nc * g.nn[1]; c.Gz = g.nc * g.nn[2]; c.KX = c.Gx / 2 + 1;
+  c.grp = g.nn[0] * g.nn[1]; c.grp0 = g.ic[2] * c.grp;
+  c.sz = c.Gz / c.R; c.nyl = c.Gy / c.R;
+}
+// last hop of the inverse coarse transform: planes zz = -1..nc (halo included) of image m live on slab owner Z/sz
+struct FPlane { int rank; std::vector<int> zz; };
+static void force_plane_lists(const Geom& g, const CoarseGeom& c, int my_rank, std::vector<FPlane>& targets, std::vector<FPlane>& sources) {
+  targets.clear(); sources.clear();
+  for (int m = 0; m < c.R; m++) {  // what image m needs from my slab (stored as my local plane index)
+    const int mz = m / (g.nn[0] * g.nn[1]);
+    FPlane t; t.rank = m;
+    for (int zz = -1; zz <= g.nc; zz++) {
+      const int Z = ((mz * g.nc + zz) % c.Gz + c.Gz) % c.Gz;
+      if (Z / c.sz == my_rank) t.zz.push_back(Z - my_rank * c.sz);
+    }
+    if (!t.zz.empty()) targets.push_back(t);
+  }
+  for (int q = 0; q < c.R; q++) {  // where my own planes come from (stored as zz)
+    FPlane sr; sr.rank = q;
+    for (int zz = -1; zz <= g.nc; zz++) {
+      const int Z = ((g.ic[2] * g.nc + zz) % c.Gz + c.Gz) % c.Gz;
+      if (Z / c.sz == q) sr.zz.push_back(zz);
+    }
+    if (!sr.zz.empty()) sources.push_back(sr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// more than one image: exchange plan, distributed coarse FFT
+// ---------------------------------------------------------------------------------------------
+static int comm_fail(cube_handle* h) {
+  h->comm->abort_group();
+  return fail("image %d: %s", h->p.rank + 1, h->comm->err.c_str());
+}
+#define CC(call) do { if ((call)) return comm_fail(h); } while (0)
+
+static int init_exchange(cube_handle* h) {
+  const Geom& g = h->g;
+  build_exchange_plan(g, h->p.rank, h->ex, true);
+  const long long ng = h->ex.ng;
+  const int nd = (int)h->ex.dirs.size();
+  if (ng == 0) return 0;
+  CK(dmalloc(&h->gcell_ext, ng)); CK(dmalloc(&h->scell_L, ng)); CK(dmalloc(&h->gcnt, ng)); CK(dmalloc(&h->scnt, ng));
+  CK(dmalloc(&h->gstart, ng + 1)); CK(dmalloc(&h->sstart, ng + 1));
+  CK(dmalloc(&h->hsend, ng)); CK(dmalloc(&h->hrecv, ng));
+  CK(dmalloc(&h->dir_cell0, nd + 1)); CK(dmalloc(&h->dir_bounds, 2 * (nd + 1)));
+  CK(cudaMemcpyAsync(h->gcell_ext, h->ex.gcell_ext.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->scell_L, h->ex.scell_L.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, h->st));
+  std::vector<long long> c0(nd + 1);
+  for (int i = 0; i < nd; i++) c0[i] = h->ex.dirs[i].cell0;
+  c0[nd] = ng;
+  CK(cudaMemcpyAsync(h->dir_cell0, c0.data(), sizeof(long long) * (nd + 1), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  h->ex.gcell_ext.clear(); h->ex.gcell_ext.shrink_to_fit(); h->ex.scell_L.clear(); h->ex.scell_L.shrink_to_fit();
+  h->gbound.assign(nd + 1, 0); h->sbound.assign(nd + 1, 0);
+  // message buffer for the particles I send: mean occupancy of the send cells with the image_buffer margin, x2
+  const double mean = (double)h->p.np_nc * h->p.np_nc * h->p.np_nc;
+  h->sendcap = (long long)((double)ng * mean * (double)h->p.image_buffer * 2.0) + 4096;
+  CK(dmalloc(&h->psend, 3 * h->sendcap));
+  CK(dmalloc(&h->stat_partial_g, 2 * (long long)nblk(ng, PC_CELLS) + 2));
+  return 0;
+}
+
+static int init_coarse_dist(cube_handle* h) {
+  const Geom& g = h->g;
+  CoarseGeom& c = h->cg;
+  fill_coarse_geom(g, c);
+  if (c.Gz % c.R || c.Gy % c.R) return fail("cube_gpu_init: nc=%d must be a multiple of nnx*nny=%d and of nnx*nnz=%d for the distributed coarse FFT", g.nc, g.nn[0] * g.nn[1], g.nn[0] * g.nn[2]);
+  const long long slab = (long long)c.sz * c.Gy * c.Gx, slabk = (long long)c.sz * c.Gy * c.KX, nk = (long long)c.Gz * c.nyl * c.KX;
+  CK(dmalloc(&h->stageA, slab)); CK(dmalloc(&h->slabR, 3 * slab)); CK(dmalloc(&h->slabC, 3 * slabk)); CK(dmalloc(&h->packT, 3 * slabk));
+  CK(dmalloc(&h->T, nk)); CK(dmalloc(&h->T3, 3 * nk)); CK(dmalloc(&h->kernT, 3 * nk));
+  {
+    int n2[2] = {c.Gy, c.Gx};
+    CF(cufftPlanMany(&h->p2d_r2c, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, c.sz));
+    CF(cufftPlanMany(&h->p2d_c2r, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, 3 * c.sz));
+    int n1[1] = {c.Gz};
+    const int lines = c.nyl * c.KX;
+    CF(cufftPlanMany(&h->pz, 1, n1, n1, lines, 1, n1, lines, 1, CUFFT_C2C, lines));
+    CF(cufftSetStream(h->p2d_r2c, h->st)); CF(cufftSetStream(h->p2d_c2r, h->st)); CF(cufftSetStream(h->pz, h->st));
+  }
+  const int m2 = g.nc + 2;
+  std::vector<FPlane> targets, sources;
+  force_plane_lists(g, c, h->p.rank, targets, sources);
+  long long off = 0;
+  for (const FPlane& fp : targets) {
+    cube_handle::FTarget t; t.rank = fp.rank; t.icx = fp.rank % g.nn[0]; t.icy = (fp.rank / g.nn[0]) % g.nn[1]; t.off = off; t.d_zloc = nullptr;
+    t.zloc = fp.zz;
+    CK(dmalloc(&t.d_zloc, (long long)t.zloc.size()));
+    CK(cudaMemcpyAsync(t.d_zloc, t.zloc.data(), sizeof(int) * t.zloc.size(), cudaMemcpyHostToDevice, h->st));
+    off += 3LL * (long long)t.zloc.size() * m2 * m2;
+    h->ftargets.push_back(t);
+  }
+  CK(dmalloc(&h->sendF, off));
+  std::vector<long long> zzoff(m2), zzcs(m2);
+  off = 0;
+  for (const FPlane& fp : sources) {
+    cube_handle::FSource sr; sr.rank = fp.rank; sr.off = off; sr.nplanes = (long long)fp.zz.size();
+    for (size_t i = 0; i < fp.zz.size(); i++) { zzoff[fp.zz[i] + 1] = off + (long long)i * m2 * m2; zzcs[fp.zz[i] + 1] = sr.nplanes * m2 * m2; }
+    off += 3LL * sr.nplanes * m2 * m2;
+    h->fsources.push_back(sr);
+  }
+  CK(dmalloc(&h->recvF, off));
+  CK(dmalloc(&h->zzoff, m2)); CK(dmalloc(&h->zzcs, m2));
+  CK(cudaMemcpyAsync(h->zzoff, zzoff.data(), sizeof(long long) * m2, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->zzcs, zzcs.data(), sizeof(long long) * m2, cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+// forward transform of this image's block in[nc][nc][nc] (unpadded) -> h->T[kz][kyl][kx]
+static int coarse_forward(cube_handle* h, const float* in) {
+  const CoarseGeom& c = h->cg;
+  const Geom& g = h->g;
+  Comm* cm = h->comm.get();
+  const size_t blk = (size_t)c.sz * g.nc * g.nc;
+  CC(cm->begin(h->st));
+  for (int j = 0; j < c.grp; j++) CC(cm->send(in + (size_t)j * blk, blk * sizeof(float), c.grp0 + j));
+  for (int j = 0; j < c.grp; j++) CC(cm->recv(h->stageA + (size_t)j * blk, blk * sizeof(float), c.grp0 + j));
+  CC(cm->end());
+  k_slab_assemble<<<1184, 256, 0, h->st>>>(c, g.nn[0], h->stageA, h->slabR); CKL();
+  CF(cufftExecR2C(h->p2d_r2c, h->slabR, (cufftComplex*)h->slabC));
+  k_pack_T<<<1184, 256, 0, h->st>>>(c, h->slabC, h->packT); CKL();
+  const size_t seg = (size_t)c.sz * c.nyl * c.KX;
+  CC(cm->begin(h->st));
+  for (int q = 0; q < c.R; q++) CC(cm->send(h->packT + (size_t)q * seg, seg * sizeof(float2), q));
+  for (int q = 0; q < c.R; q++) CC(cm->recv(h->T + (size_t)q * seg, seg * sizeof(float2), q));
+  CC(cm->end());
+  CF(cufftExecC2C(h->pz, (cufftComplex*)h->T, (cufftComplex*)h->T, CUFFT_FORWARD));
+  h->launches += 2;
+  return 0;
+}
+
+// T -> i*kern_c*T/(Gx Gy Gz) -> three inverse transforms -> force planes with halo in h->recvF
+static int coarse_backward3(cube_handle* h) {
+  const CoarseGeom& c = h->cg;
+  const Geom& g = h->g;
+  Comm* cm = h->comm.get();
+  const long long nk = (long long)c.Gz * c.nyl * c.KX;
+  const float scale = 1.0f / ((float)g.nc * g.nn[0]) / ((float)g.nc * g.nn[1]) / ((float)g.nc * g.nn[2]);
+  k_green_T<<<nblk(nk, 256), 256, 0, h->st>>>(nk, h->T, h->kernT, scale, h->T3); CKL();
+  for (int d = 0; d < 3; d++) CF(cufftExecC2C(h->pz, (cufftComplex*)(h->T3 + d * nk), (cufftComplex*)(h->T3 + d * nk), CUFFT_INVERSE));
+  const size_t seg = (size_t)c.sz * c.nyl * c.KX;
+  CC(cm->begin(h->st));
+  for (int q = 0; q < c.R; q++)
+    for (int d = 0; d < 3; d++) CC(cm->send(h->T3 + (size_t)d * nk + (size_t)q * seg, seg * sizeof(float2), q));
+  for (int q = 0; q < c.R; q++)
+    for (int d = 0; d < 3; d++) CC(cm->recv(h->packT + ((size_t)q * 3 + d) * seg, seg * sizeof(float2), q));
+  CC(cm->end());
+  k_unpack_T<<<1184, 256, 0, h->st>>>(c, h->packT, h->slabC); CKL();
+  CF(cufftExecC2R(h->p2d_c2r, (cufftComplex*)h->slabC, h->slabR));
+  const int m2 = g.nc + 2;
+  for (auto& t : h->ftargets) {
+    k_pack_F<<<592, 256, 0, h->st>>>(c, t.icx, t.icy, (int)t.zloc.size(), t.d_zloc, h->slabR, h->sendF + t.off); CKL();
+    h->launches++;
+  }
+  CC(cm->begin(h->st));
+  for (auto& t : h->ftargets) CC(cm->send(h->sendF + t.off, 3 * t.zloc.size() * (size_t)m2 * m2 * sizeof(float), t.rank));
+  for (auto& sr : h->fsources) CC(cm->recv(h->recvF + sr.off, 3 * (size_t)sr.nplanes * m2 * m2 * sizeof(float), sr.rank));
+  CC(cm->end());
+  h->launches += 2;
+  return 0;
+}
+
+// kernel_c.f90:16-117 on the global lattice, k-space in the transposed layout
+static int build_kernel_c_dist(cube_handle* h, const float* d_ck) {
+  const Geom& g = h->g;
+  const CoarseGeom& c = h->cg;
+  const long long n = (long long)g.nc * g.nc * g.nc, nk = (long long)c.Gz * c.nyl * c.KX;
+  float* blk = h->r3;  // [nc]^3 scratch
+  const int ox0 = g.ic[0] * g.nc, oy0 = g.ic[1] * g.nc, oz0 = g.ic[2] * g.nc;
+  for (int d = 0; d < 3; d++) {
+    k_kernc_fill_dist<<<nblk(n, 256), 256, 0, h->st>>>(c, ox0, oy0, oz0, d_ck, d, 1, blk); CKL();
+    if (coarse_forward(h, blk)) return 1;
+    k_take_imag_scaled<<<nblk(nk, 256), 256, 0, h->st>>>(nk, h->T, h->kernT + d * nk); CKL();
+    k_kernc_fill_dist<<<nblk(n, 256), 256, 0, h->st>>>(c, ox0, oy0, oz0, d_ck, d, 0, blk); CKL();
+    if (coarse_forward(h, blk)) return 1;
+    k_kernc_lrck_T<<<nblk(nk, 256), 256, 0, h->st>>>(c, h->p.rank, d, h->T, h->kernT + d * nk); CKL();
+  }
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int build_kernels(cube_handle* h, const float* fk_table, const float* ck_table) {
   const Geom& g = h->g;
@@ -171,6 +401,11 @@ static int build_kernels(cube_handle* h, const float* fk_table, const float* ck_
     CK(cudaStreamSynchronize(h->st));
     cufftDestroy(pl); cudaFree(tmp);
   }
+  if (h->nimg > 1) {
+    const int rc = build_kernel_c_dist(h, d_ck);
+    cudaFree(d_fk); cudaFree(d_ck);
+    return rc;
+  }
   // kernel_c.f90:16-117 (single image: the coarse lattice is this image's nc^3)
   float* pure = h->cforce;  // scratch [cvol]
   for (int d = 0; d < 3; d++) {
@@ -191,8 +426,10 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   if (!p || !fk_table || !ck_table || !tanf_lut || !out) return fail("cube_gpu_init: null argument");
   if (p->izipx != 2 || p->izipv != 2) return fail("zip format incompatable: only izipx=izipv=2 is built (got %d,%d)", p->izipx, p->izipv);
   if (p->ncell != NCELL || p->ncb != NCB) return fail("cube_gpu_init: ncell must be 4 and ncb 6");
-  if (p->nn[0] * p->nn[1] * p->nn[2] != 1 || nccl_unique_id)
-    return fail("cube_gpu_init: multi-image runs (nn>1) are not available in this build");
+  const int nimg = p->nn[0] * p->nn[1] * p->nn[2];
+  if (p->nn[0] < 1 || p->nn[1] < 1 || p->nn[2] < 1 || p->rank < 0 || p->rank >= nimg) return fail("cube_gpu_init: bad image grid / rank");
+  if (nimg > 1 && !nccl_unique_id && p->local_group <= 0)
+    return fail("cube_gpu_init: %d images need either an ncclUniqueId (one process per GPU) or local_group > 0 (all images are threads of this process)", nimg);
   if (p->nnt < 1 || p->nc % p->nnt) return fail("cube_gpu_init: nc must be a multiple of nnt");
   if (p->nc / p->nnt < 12 || p->nc < 24) return fail("cube_gpu_init: need nc>=24 and nt>=12 (parameters.f90:23-24)");
   int ndev = 0;
@@ -200,12 +437,9 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(cudaSetDevice(p->device));
   cube_handle* h = new cube_handle();
   h->p = *p;
+  h->nimg = nimg;
   Geom& g = h->g;
-  for (int d = 0; d < 3; d++) { g.nn[d] = p->nn[d]; }
-  g.ic[0] = p->rank % p->nn[0]; g.ic[1] = (p->rank / p->nn[0]) % p->nn[1]; g.ic[2] = p->rank / (p->nn[0] * p->nn[1]);
-  g.nnt = p->nnt; g.nc = p->nc; g.nt = p->nc / p->nnt;
-  g.nte = g.nt + 2 * NCB; g.nft = g.nt * NCELL; g.nfe = g.nft + 2 * NFB; g.ne = g.nc + 2 * NCB;
-  g.ncell_p = (long long)g.nc * g.nc * g.nc; g.ncell_e = (long long)g.ne * g.ne * g.ne;
+  fill_geom(p, g);
   // variables.f90:7-9 (real(4) arithmetic)
   long long np_image = (long long)g.nc * p->np_nc; np_image = np_image * np_image * np_image;
   float r = ((float)g.nte * 1.f) / (float)g.nt, r3 = r * r * r;
@@ -221,9 +455,21 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->vfield_p, 3 * g.ncell_p)); CK(dmalloc(&h->vfield_p2, 3 * g.ncell_p));
   CK(dmalloc(&h->cstart_p, g.ncell_p + 1)); CK(dmalloc(&h->cstart_p2, g.ncell_p + 1));  // + sentinel = nplocal
   CK(dmalloc(&h->rhoc_e, g.ncell_e)); CK(dmalloc(&h->cstart_e, g.ncell_e)); CK(dmalloc(&h->vfield_e, 3 * g.ncell_e));
-  h->nscan_blocks = (int)((g.ncell_p + SCAN_B - 1) / SCAN_B);
+  if (nimg > 1) {
+    if (nccl_unique_id) {
+      auto c = std::make_unique<NcclComm>();
+      if (c->init(p->rank, nimg, nccl_unique_id)) return fail("cube_gpu_init: %s", c->err.c_str());
+      h->comm = std::move(c);
+    } else {
+      auto c = std::make_unique<LocalComm>();
+      if (c->init(p->rank, nimg, p->local_group)) return fail("cube_gpu_init: %s", c->err.c_str());
+      h->comm = std::move(c);
+    }
+    if (init_exchange(h)) return 1;
+  }
+  h->nscan_blocks = (int)((std::max(g.ncell_p, h->ex.ng) + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
-  CK(dmalloc(&h->stat_partial, 2 * (long long)nblk(g.ncell_p, PC_CELLS) + (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 3));
+  CK(dmalloc(&h->stat_partial, 2 * (long long)nblk(g.ncell_p, PC_CELLS) + (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 8));
   CK(dmalloc(&h->rank, cap));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
@@ -277,9 +523,12 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   // coarse mesh
   h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
   h->cnk = (long long)g.nc * g.nc * (g.nc / 2 + 1);
-  CK(dmalloc(&h->r3, h->cvol)); CK(dmalloc(&h->cforce, 3 * h->cvol)); CK(dmalloc(&h->kern_c, 3 * h->cnk));
+  CK(dmalloc(&h->r3, h->cvol));
   CK(dmalloc(&h->fc, 3LL * (g.nc + 2) * (g.nc + 2) * (g.nc + 2)));
-  {
+  if (nimg > 1) {
+    if (init_coarse_dist(h)) return 1;
+  } else {
+    CK(dmalloc(&h->cforce, 3 * h->cvol)); CK(dmalloc(&h->kern_c, 3 * h->cnk));
     int n[3] = {g.nc, g.nc, g.nc};
     int rembed[3] = {g.nc, g.nc, g.nc + 2}, cembed[3] = {g.nc, g.nc, g.nc / 2 + 1};
     CF(cufftPlanMany(&h->cplan_r2c, 3, n, rembed, 1, (int)h->cvol, cembed, 1, (int)h->cnk, CUFFT_R2C, 1));
@@ -301,7 +550,12 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
                   h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
-  cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r};
+  void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
+                   h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
+  for (void* q : mptrs) if (q) cudaFree(q);
+  for (auto& t : h->ftargets) if (t.d_zloc) cudaFree(t.d_zloc);
+  h->comm.reset();
+  cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r, h->p2d_r2c, h->p2d_c2r, h->pz};
   for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
   for (int i = 0; i < 2 * PH_N; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   cudaStreamDestroy(h->st);
@@ -323,7 +577,7 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
   CK(cudaMemcpyAsync(h->vfield_p, vfield_phys, sizeof(float) * 3 * g.ncell_p, cudaMemcpyHostToDevice, h->st));
   if (scan_counts(h, h->rhoc_p, g.ncell_p, h->cstart_p)) return 1;
   long long tot = 0;
-  CK(cudaMemcpyAsync(&tot, h->bsum + h->nscan_blocks, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&tot, h->cstart_p + g.ncell_p, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   if (tot != nplocal) return fail("cube_gpu_upload: sum(rhoc)=%lld differs from nplocal=%lld", tot, (long long)nplocal);
   h->nplocal = nplocal; h->npglobal = npglobal;
@@ -350,29 +604,92 @@ extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32
   return 0;
 }
 
+// rhoc + vfield ghost layers from the other images (buffer_density.f90:11-68), message offsets of the particle exchange
+static int exchange_density(cube_handle* h, int* status) {
+  const long long ng = h->ex.ng;
+  const int nd = (int)h->ex.dirs.size();
+  Comm* cm = h->comm.get();
+  k_halo_pack<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->scell_L, h->rhoc_p, h->vfield_p, h->hsend, h->scnt); CKL();
+  CC(cm->begin(h->st));
+  for (const ExDir& d : h->ex.dirs) CC(cm->send(h->hsend + d.cell0, (size_t)d.ncell * sizeof(HaloRec), d.dst_rank));
+  for (const ExDir& d : h->ex.dirs) CC(cm->recv(h->hrecv + d.cell0, (size_t)d.ncell * sizeof(HaloRec), d.src_rank));
+  CC(cm->end());
+  k_halo_unpack<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->gcell_ext, h->hrecv, h->rhoc_e, h->vfield_e, h->gcnt); CKL();
+  if (scan_counts(h, h->gcnt, ng, h->gstart)) return 1;
+  if (scan_counts(h, h->scnt, ng, h->sstart)) return 1;
+  k_ghost_cstart<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->gcell_ext, h->gstart, h->nplocal, h->cstart_e); CKL();
+  k_dir_bounds<<<1, 64, 0, h->st>>>(nd, h->dir_cell0, h->gstart, h->sstart, h->dir_bounds); CKL();
+  h->launches += 4;
+  std::vector<long long> b(2 * (nd + 1));
+  CK(cudaMemcpyAsync(b.data(), h->dir_bounds, sizeof(long long) * b.size(), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  for (int i = 0; i <= nd; i++) { h->gbound[i] = b[i]; h->sbound[i] = b[nd + 1 + i]; }
+  h->nghost = h->gbound[nd];
+  if (h->nplocal + h->nghost > h->np_image_max || h->sbound[nd] > h->sendcap) *status = 1;
+  return 0;
+}
+
+// ghost particles (buffer_x.f90 for xp, buffer_v.f90 for vp): received behind the physical particles
+static int exchange_particles(cube_handle* h, short* arr) {
+  const long long ng = h->ex.ng;
+  const int nd = (int)h->ex.dirs.size();
+  Comm* cm = h->comm.get();
+  k_particle_pack<<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, arr, h->psend); CKL();
+  h->launches++;
+  CC(cm->begin(h->st));
+  for (int i = 0; i < nd; i++) {
+    const size_t n = (size_t)(h->sbound[i + 1] - h->sbound[i]);
+    if (n) CC(cm->send(h->psend + 3 * h->sbound[i], n * 3 * sizeof(short), h->ex.dirs[i].dst_rank));
+  }
+  for (int i = 0; i < nd; i++) {
+    const size_t n = (size_t)(h->gbound[i + 1] - h->gbound[i]);
+    if (n) CC(cm->recv(arr + 3 * (h->nplocal + h->gbound[i]), n * 3 * sizeof(short), h->ex.dirs[i].src_rank));
+  }
+  CC(cm->end());
+  return 0;
+}
+
 extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_v, float* overhead_image) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   const Geom& g = h->g;
-  (void)do_x; (void)do_v;  // single image: ghost particles alias the periodic image, nothing to copy
+  const bool multi = h->nimg > 1;
   if (do_density) {
     PhaseTimer pt(h, PH_BUFFER);
+    int status = 0;
     k_build_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g, h->rhoc_p, h->cstart_p, h->vfield_p, h->rhoc_e, h->cstart_e, h->vfield_e); CKL();
+    if (multi && exchange_density(h, &status)) return 1;
     k_tile_counts<<<g.nnt * g.nnt * g.nnt, 256, 0, h->st>>>(g, h->rhoc_e, h->tile_count); CKL();
     h->launches += 2;
-    h->buffered = true;
-  }
-  if (overhead_image) {
     // overhead_image=sum(rhoc)/np_image_max over the buffered rhoc of all tiles (buffer_density.f90:75)
     const int ntile = g.nnt * g.nnt * g.nnt;
     std::vector<long long> tc(ntile);
-    CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    if (multi || overhead_image) {
+      CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+    }
     long long s = 0; for (long long v : tc) s += v;
-    *overhead_image = (float)((double)s / (double)h->np_image_max);
-    if ((double)*overhead_image > 1.0)
-      return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", s, h->np_image_max, h->p.rank + 1);
+    float ovh = (float)((double)s / (double)h->np_image_max);
+    int bad_image = (double)ovh > 1.0 || status ? h->p.rank + 1 : 0;
+    long long bad_count = s;
+    if (multi) {  // overhead_image is the maximum over the images (buffer_density.f90:78-86); every image stops together
+      struct Rec { float ovh; int bad; long long s; } mine = {ovh, bad_image, s};
+      std::vector<Rec> all(h->nimg);
+      CC(h->comm->allgather_host(&mine, all.data(), sizeof(Rec), h->st));
+      bad_image = 0;
+      for (int m = 0; m < h->nimg; m++) {
+        ovh = std::max(ovh, all[m].ovh);
+        if (all[m].bad && !bad_image) { bad_image = all[m].bad; bad_count = all[m].s; }
+      }
+    }
+    if (overhead_image) *overhead_image = ovh;
+    if (bad_image)
+      return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", bad_count, h->np_image_max, bad_image);
+    h->buffered = true;
   }
+  // one image: ghost particles alias the periodic image, nothing to copy
+  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp)) return 1; }
+  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp)) return 1; }
   return 0;
 }
 
@@ -383,6 +700,8 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("cube_gpu_update_x: state is not buffered (call cube_gpu_buffer first, cafcube.f90:17-19)");
   const Geom& g = h->g;
+  const bool multi = h->nimg > 1;
+  const long long ng = h->ex.ng;
   const float dt_mid_f = (dt_old + dt) / 2;  // update_particle.f90:16
   const double dt_mid = (double)dt_mid_f, S = vscale(h->sigma_vi);
   if (build_dvlut(h, h->sigma_vi)) return 1;
@@ -392,57 +711,106 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemsetAsync(h->maxoff, 0, sizeof(int), h->st));
   int maxoff = 0;
-  const unsigned nchunk = nblk(g.ncell_p, PC_CELLS);
+  const unsigned nchunk = nblk(g.ncell_p, PC_CELLS), nchunk_g = nblk(ng, PC_CELLS);
   {
     PhaseTimer pt(h, PH_KEY);
     k_drift_key_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff); CKL();
     h->launches++;
+    if (multi && ng) {
+      k_drift_key_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->vfield_e, h->dvlut, dt_mid, h->key,
+                                                 h->rank, h->maxoff); CKL();
+      h->launches++;
+    }
     CK(cudaMemcpyAsync(&maxoff, h->maxoff, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
   }
+  // local failures are agreed on by all images before anyone returns (the reference `stop`s every image)
+  int status = 0; std::string msg;
   float ovh = 0;
   for (int t = 0; t < ntile; t++) {
     ovh = std::max(ovh, (float)tc[t] / (float)h->np_tile_max);
-    if (tc[t] > h->np_tile_max)
-      return fail("error: too many particles in this tile+buffer: %lld > %lld on image %d tile %d %d %d; please set tile_buffer larger",
-                  tc[t], h->np_tile_max, h->p.rank + 1, t % g.nnt + 1, (t / g.nnt) % g.nnt + 1, t / (g.nnt * g.nnt) + 1);
+    if (tc[t] > h->np_tile_max && !status) {
+      status = 1;
+      char buf[512];
+      snprintf(buf, sizeof buf, "error: too many particles in this tile+buffer: %lld > %lld on image %d tile %d %d %d; please set tile_buffer larger",
+               tc[t], h->np_tile_max, h->p.rank + 1, t % g.nnt + 1, (t / g.nnt) % g.nnt + 1, t / (g.nnt * g.nnt) + 1);
+      msg = buf;
+    }
   }
-  if (maxoff > NCB) return fail("cube_gpu_update_x: a particle moves %d coarse cells in one step (> ncb=%d): outside the tile buffer", maxoff, NCB);
-  const int r = maxoff;
-  h->last_radius = r;
-  const unsigned nb = nblk(g.ncell_p, 128);
-  {
-    PhaseTimer pt(h, PH_COUNT);
-    k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
-                                        h->vfield_p2, h->rank, h->stat_partial); CKL();
-    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
-    h->launches += 2;
-  }
-  {
-    PhaseTimer pt(h, PH_SCAN);
-    if (scan_counts(h, h->rhoc_p2, g.ncell_p, h->cstart_p2)) return 1;
+  if (maxoff > NCB && !status) {
+    status = 2;
+    char buf[256];
+    snprintf(buf, sizeof buf, "cube_gpu_update_x: a particle of image %d moves %d coarse cells in one step (> ncb=%d): outside the tile buffer", h->p.rank + 1, maxoff, NCB);
+    msg = buf;
   }
   long long tot = 0;
-  CK(cudaMemcpyAsync(&tot, h->bsum + h->nscan_blocks, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
-  if (tot > h->np_image_max)
-    return fail("error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", tot, h->np_image_max, h->p.rank + 1);
-  {
+  double st[3] = {0, 0, 0};
+  if (!status) {
+    const int r = maxoff;
+    h->last_radius = r;
+    const unsigned nb = nblk(g.ncell_p, 128);
+    {
+      PhaseTimer pt(h, PH_COUNT);
+      k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
+                                          h->vfield_p2, h->rank, h->stat_partial); CKL();
+      k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
+      h->launches += 2;
+    }
+    {
+      PhaseTimer pt(h, PH_SCAN);
+      if (scan_counts(h, h->rhoc_p2, g.ncell_p, h->cstart_p2)) return 1;
+    }
+    CK(cudaMemcpyAsync(&tot, h->cstart_p2 + g.ncell_p, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (tot > h->np_image_max) {
+      status = 3;
+      char buf[256];
+      snprintf(buf, sizeof buf, "error: too many particles in this image+buffer: %lld > %lld on image %d; please set image_buffer larger", tot, h->np_image_max, h->p.rank + 1);
+      msg = buf;
+    }
+  }
+  if (!status) {
     PhaseTimer pt(h, PH_PLACE);
     k_drift_place_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2, h->dvlut, h->enc,
                                                dt_mid, S, h->xp2, h->vp2, h->stat_partial); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 0, h->stat3); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 1, h->stat3 + 2); CKL();
     h->launches += 3;
+    double stg[2] = {0, 0};
+    if (multi && ng) {
+      k_drift_place_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->rank, h->vfield_e, h->cstart_p2,
+                                                   h->vfield_p2, h->dvlut, h->enc, dt_mid, S, h->xp2, h->vp2, h->stat_partial_g); CKL();
+      k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial_g, (long long)nchunk_g, 2, 0, h->stat3 + 3); CKL();
+      k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial_g, (long long)nchunk_g, 2, 1, h->stat3 + 4); CKL();
+      h->launches += 3;
+      CK(cudaMemcpyAsync(stg, h->stat3 + 3, sizeof stg, cudaMemcpyDeviceToHost, h->st));
+    }
+    CK(cudaMemcpyAsync(st, h->stat3, sizeof st, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    st[0] += stg[0]; st[2] += stg[1];
   }
-  double st[3];
-  CK(cudaMemcpyAsync(st, h->stat3, sizeof st, cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
+  long long npsum = tot;
+  if (multi) {  // co_sum / co_max of update_particle.f90:154-166,186-193 in image order
+    struct Rec { double st[3]; long long np; float ovh; int status; } mine = {{st[0], st[1], st[2]}, tot, ovh, status};
+    std::vector<Rec> all(h->nimg);
+    CC(h->comm->allgather_host(&mine, all.data(), sizeof(Rec), h->st));
+    int bad = -1;
+    st[0] = all[0].st[0]; st[1] = all[0].st[1]; st[2] = all[0].st[2]; npsum = all[0].np; ovh = all[0].ovh;
+    if (all[0].status) bad = 0;
+    for (int m = 1; m < h->nimg; m++) {
+      st[0] += all[m].st[0]; st[1] += all[m].st[1]; st[2] += all[m].st[2]; npsum += all[m].np; ovh = std::max(ovh, all[m].ovh);
+      if (all[m].status && bad < 0) bad = m;
+    }
+    if (bad >= 0 && !status) return fail("update_particle stopped: image %d reported an error (status %d)", bad + 1, all[bad].status);
+  }
+  if (status) return fail("%s", msg.c_str());
+  if (multi && npsum != h->npglobal)  // update_particle.f90:205-211
+    return fail("np check failed: sum(nplocal)=%lld differs from npglobal=%lld", npsum, h->npglobal);
   std::swap(h->xp, h->xp2); std::swap(h->vp, h->vp2);
   std::swap(h->rhoc_p, h->rhoc_p2); std::swap(h->vfield_p, h->vfield_p2); std::swap(h->cstart_p, h->cstart_p2);
   h->nplocal = tot;
   h->buffered = false;
-  // update_particle.f90:170-175 (single image: no co_sum)
+  // update_particle.f90:170-175
   const double nglob = (double)h->npglobal;
   const double sv = std::sqrt(st[0] / nglob);
   const double svc = std::sqrt(st[1] / (double)g.nc / (double)g.nc / (double)g.nc / (double)g.nn[0] / (double)g.nn[1] / (double)g.nn[2]);
@@ -513,20 +881,29 @@ static int fine_mesh(cube_handle* h, int tile0, int nb) {
 // force_c*a_mid*dt/6/pi in h->fc, f2_max_coarse in h->f2max[batch]; raw (optional, device) gets force_c itself.
 static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw) {
   const Geom& g = h->g;
+  const bool multi = h->nimg > 1;
   {
     PhaseTimer pt(h, PH_CDEP);
     const int cbx = (g.nt + CB_X - 1) / CB_X, cby = (g.nt + CB_Y - 1) / CB_Y, cbz = (g.nt + CB_Z - 1) / CB_Z;
-    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3); CKL();
+    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3,
+                                                                                            multi ? g.nc : g.nc + 2); CKL();
     h->launches++;
   }
   if (!through_force) return 0;
   PhaseTimer pt(h, PH_CFFT);
+  CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
+  if (multi) {  // distributed transform (cube_coarse.cuh) replacing pencil_fft.f90 + the halo GETs of pm.f90:182-189
+    if (coarse_forward(h, h->r3)) return 1;
+    if (coarse_backward3(h)) return 1;
+    k_force_c_finish_dist<<<1184, 256, 0, h->st>>>(g.nc, h->recvF, h->zzoff, h->zzcs, a_mid, dt, h->fc, raw, h->f2max + h->batch); CKL();
+    h->launches++;
+    return 0;
+  }
   CF(cufftExecR2C(h->cplan_r2c, h->r3, (cufftComplex*)h->r3));
   // rxyz = i*kern_c*crho_c ; r3=r3/ng_global^3 (pm.f90:172-175, pencil_fft.f90:58)
   const float scale = 1.0f / ((float)g.nc * g.nn[0]) / ((float)g.nc * g.nn[1]) / ((float)g.nc * g.nn[2]);
   k_green<<<nblk(h->cnk, 256), 256, 0, h->st>>>(h->cnk, 1, (const float2*)h->r3, h->kern_c, scale, (float2*)h->cforce); CKL();
   CF(cufftExecC2R(h->cplan_c2r, (cufftComplex*)h->cforce, h->cforce));
-  CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
   k_force_c_finish<<<1184, 256, 0, h->st>>>(g, h->cforce, a_mid, dt, h->fc, raw, h->f2max + h->batch); CKL();
   h->launches += 2;
   return 0;
@@ -569,12 +946,19 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   double vmd; memcpy(&vmd, &vb, sizeof vmd);
   const float vmax = (float)vmd;  // f32 <- max(f32, f64) is monotone, so one final rounding is the same
   float f2f = 0; for (float v : f2) f2f = std::max(f2f, v);
+  float vmax_all = vmax;
+  if (h->nimg > 1) {  // pm.f90:239-244: every image takes the minimum of every image's dt = the dt of the maxima
+    struct Rec { float f2f, f2c, vmax; } mine = {f2f, f2c, vmax};
+    std::vector<Rec> all(h->nimg);
+    CC(h->comm->allgather_host(&mine, all.data(), sizeof(Rec), h->st));
+    for (int m = 0; m < h->nimg; m++) { f2f = std::max(f2f, all[m].f2f); f2c = std::max(f2c, all[m].f2c); vmax_all = std::max(vmax_all, all[m].vmax); }
+  }
   h->last_f2max_fine = f2f;
   // pm.f90:233-236, all f32
   const float GG = 1.0f / 6.0f / PI_F;
   if (dt_fine) *dt_fine = sqrtf(1.0f / (sqrtf(f2f) * a_mid * GG));
   if (dt_coarse) *dt_coarse = sqrtf((float)NCELL / (sqrtf(f2c) * a_mid * GG));
-  if (dt_vmax) *dt_vmax = 0.9f * 20 / vmax;
+  if (dt_vmax) *dt_vmax = 0.9f * 20 / vmax_all;
   if (vmax_out) *vmax_out = vmax;
   return 0;
 }
@@ -606,6 +990,7 @@ extern "C" int cube_gpu_get_kern_f(cube_handle* h, float* out) {
 }
 extern "C" int cube_gpu_get_kern_c(cube_handle* h, float* out) {
   CK(cudaSetDevice(h->p.device));
+  if (h->nimg > 1) return fail("cube_gpu_get_kern_c: single-image diagnostic (the distributed kern_c lives in the transposed k-space layout)");
   CK(cudaMemcpy(out, h->kern_c, sizeof(float) * 3 * h->cnk, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -671,7 +1056,7 @@ extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
   if (!h->buffered) return fail("state is not buffered");
   const Geom& g = h->g;
   if (coarse_mesh(h, false, 0.f, 0.f, nullptr)) return 1;
-  CK(cudaMemcpy2DAsync(r3, sizeof(float) * g.nc, h->r3, sizeof(float) * (g.nc + 2), sizeof(float) * g.nc, (size_t)g.nc * g.nc,
+  CK(cudaMemcpy2DAsync(r3, sizeof(float) * g.nc, h->r3, sizeof(float) * (h->nimg > 1 ? g.nc : g.nc + 2), sizeof(float) * g.nc, (size_t)g.nc * g.nc,
                        cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   return 0;
@@ -709,6 +1094,32 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   if (f2_max) *f2_max = f2c;
   return 0;
 }
+// message plan of one image (host only, no device needed): rows of 8 int64
+//   {0, rx, ry, rz, src_rank, dst_rank, ncell, cell0}   ghost direction (halo cells; particle messages follow the same pairs)
+//   {1, rank, nplanes, 0...}                            force_c planes I send to `rank` (last hop of the coarse inverse)
+//   {2, rank, nplanes, 0...}                            force_c planes I receive from `rank`
+//   {3, R, Gx, Gy, Gz, sz, nyl, grp0}                   coarse transform geometry
+extern "C" int cube_gpu_exchange_plan(const cube_params* p, int64_t* out, int cap_rows) {
+  if (!p || !out) return -1;
+  const int nimg = p->nn[0] * p->nn[1] * p->nn[2];
+  if (p->nn[0] < 1 || p->nn[1] < 1 || p->nn[2] < 1 || p->rank < 0 || p->rank >= nimg || p->nnt < 1 || p->nc % p->nnt) return -1;
+  Geom g; fill_geom(p, g);
+  ExPlan P; build_exchange_plan(g, p->rank, P, false);
+  CoarseGeom c; fill_coarse_geom(g, c);
+  std::vector<FPlane> targets, sources;
+  if (nimg > 1 && c.Gz % c.R == 0 && c.Gy % c.R == 0) force_plane_lists(g, c, p->rank, targets, sources);
+  int n = 0;
+  auto row = [&](long long a0, long long a1, long long a2, long long a3, long long a4, long long a5, long long a6, long long a7) {
+    if (n < cap_rows) { int64_t* r = out + 8 * n; r[0] = a0; r[1] = a1; r[2] = a2; r[3] = a3; r[4] = a4; r[5] = a5; r[6] = a6; r[7] = a7; }
+    n++;
+  };
+  for (const ExDir& d : P.dirs) row(0, d.r[0], d.r[1], d.r[2], d.src_rank, d.dst_rank, d.ncell, d.cell0);
+  for (const FPlane& t : targets) row(1, t.rank, (long long)t.zz.size(), 0, 0, 0, 0, 0);
+  for (const FPlane& t : sources) row(2, t.rank, (long long)t.zz.size(), 0, 0, 0, 0, 0);
+  row(3, c.R, c.Gx, c.Gy, c.Gz, c.sz, c.nyl, c.grp0);
+  return n;
+}
+
 extern "C" int cube_gpu_phase_count(void) { return PH_N; }
 extern "C" const char* cube_gpu_phase_name(int i) { return (i >= 0 && i < PH_N) ? kPhaseNames[i] : ""; }
 extern "C" int cube_gpu_phase_times(cube_handle* h, float* ms) {

@@ -94,6 +94,7 @@ __global__ void k_build_ext(Geom g, const int* __restrict__ rhoc_p, const long l
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.ncell_e) return;
   int x = (int)(e % g.ne) - NCB, y = (int)((e / g.ne) % g.ne) - NCB, z = (int)(e / ((long long)g.ne * g.ne)) - NCB;
+  if (ext_is_remote(g, x, y, z)) return;  // owned by another image: filled by the halo exchange (cube_exchange.cuh)
   // nn_d == 1: neighbour image is this image (inx=ipx=icx), parameters.f90:189-194
   int xw = (x + g.nc) % g.nc, yw = (y + g.nc) % g.nc, zw = (z + g.nc) % g.nc;
   long long L = phys_index(g, xw / g.nt, yw / g.nt, zw / g.nt, xw % g.nt, yw % g.nt, zw % g.nt);
@@ -325,7 +326,7 @@ constexpr int CD_SMEM = 27 * CS_N * (int)sizeof(float);
 
 __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
                                                          const long long* __restrict__ cstart_e, float mass_p,
-                                                         float* __restrict__ r3 /*[nc][nc][nc+2]*/) {
+                                                         float* __restrict__ r3 /*[nc][nc][ld]*/, int ld) {
   extern __shared__ float acc[];  // [27 = (rz*3+ry)*3+rx][CS_N]
   const int t = threadIdx.x;
   const int tile = blockIdx.y;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __
         const int S = ((oz + 1 + dz) * CS_Y + (oy + 1 + dy)) * CS_X + (ox + 1 + dx);
         v = __fadd_rn(v, acc[(((1 - dz) * 3 + (1 - dy)) * 3 + (1 - dx)) * CS_N + S]);
       }
-  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * (g.nc + 2) + (X0 + i)] = v;
+  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * ld + (X0 + i)] = v;
 }
 
 // force_c(3,0:nc+1,0:nc+1,0:nc+1) from the three inverse transforms + periodic 1-cell halo

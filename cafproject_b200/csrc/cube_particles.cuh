@@ -233,7 +233,38 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
     m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
-    if (tie) rank[p] = RANK_LOST;
+    rank[p] = RANK_LOST;  // pass B overwrites it for the one destination cell of this image that accepts the particle
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
+}
+
+// pass A for the ghost particles received from other images (cube_exchange.cuh): cells in message order,
+// gstart = exclusive prefix of their counts (+ sentinel), particles at base + gstart[.]
+__global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
+                                                     long long base, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                     const float* __restrict__ vfield_e, const double* __restrict__ dvlut, double dt_mid,
+                                                     unsigned short* __restrict__ key, unsigned* __restrict__ rank, int* __restrict__ maxoff) {
+  __shared__ int soff[PC_CELLS + 1];
+  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  const int np = chunk_setup(gstart, c0, ng, soff);
+  const long long p0 = base + gstart[c0];
+  int m = 0;
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const long long e = gcell_ext[c0 + chunk_find(soff, q)];
+    const int i = (int)(e % g.ne) - NCB, j = (int)((e / g.ne) % g.ne) - NCB, k = (int)(e / ((long long)g.ne * g.ne)) - NCB;
+    const long long p = p0 + q;
+    const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
+    const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
+    bool tie = false;
+    int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
+    int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
+    int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
+    // a ghost can only enter from at most ncb cells away; its owner image checks the full offset of the same particle
+    m = max(m, min(NCB, max(abs(ox), max(abs(oy), abs(oz)))));
+    ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
+    key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
+    rank[p] = RANK_LOST;
   }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
@@ -367,9 +398,41 @@ __global__ void __launch_bounds__(PC_T) k_drift_place_p(Geom g, const short* __r
     phys_decompose(g, L, tx, ty, tz, i, j, k);
     const unsigned o = rk >> RANK_BITS;
     int X = tx * g.nt + i + (int)(o & 15u) - 8, Y = ty * g.nt + j + (int)((o >> 4) & 15u) - 8, Z = tz * g.nt + k + (int)((o >> 8) & 15u) - 8;
-    X = (X + g.nc) % g.nc; Y = (Y + g.nc) % g.nc; Z = (Z + g.nc) % g.nc;  // nn_d == 1: the neighbour image is this image
+    // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: an accepted particle stays inside
+    if (g.nn[0] == 1) X = (X + g.nc) % g.nc;
+    if (g.nn[1] == 1) Y = (Y + g.nc) % g.nc;
+    if (g.nn[2] == 1) Z = (Z + g.nc) % g.nc;
+    if ((unsigned)X >= (unsigned)g.nc || (unsigned)Y >= (unsigned)g.nc || (unsigned)Z >= (unsigned)g.nc) continue;
     const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
     drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_p + 3 * L, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
+               vp_new, st_tot, st_res);
+  }
+  block_sum2(st_tot, st_res, stat_partial + 2 * (long long)blockIdx.x);
+}
+
+// pass C for the ghost particles that enter this image
+__global__ void __launch_bounds__(PC_T) k_drift_place_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
+                                                       long long base, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                       const unsigned* __restrict__ rank, const float* __restrict__ vfield_e,
+                                                       const long long* __restrict__ cstart_new, const float* __restrict__ vfield_new,
+                                                       const double* __restrict__ dvlut, const double* __restrict__ enc, double dt_mid, double S,
+                                                       short* __restrict__ xp_new, short* __restrict__ vp_new, double* __restrict__ stat_partial) {
+  __shared__ int soff[PC_CELLS + 1];
+  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  const int np = chunk_setup(gstart, c0, ng, soff);
+  const long long p0 = base + gstart[c0];
+  double st_tot = 0, st_res = 0;
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const long long p = p0 + q;
+    const unsigned rk = rank[p];
+    if (rk == RANK_LOST) continue;
+    const long long e = gcell_ext[c0 + chunk_find(soff, q)];
+    const unsigned o = rk >> RANK_BITS;
+    const int X = (int)(e % g.ne) - NCB + (int)(o & 15u) - 8, Y = (int)((e / g.ne) % g.ne) - NCB + (int)((o >> 4) & 15u) - 8,
+              Z = (int)(e / ((long long)g.ne * g.ne)) - NCB + (int)((o >> 8) & 15u) - 8;
+    if ((unsigned)X >= (unsigned)g.nc || (unsigned)Y >= (unsigned)g.nc || (unsigned)Z >= (unsigned)g.nc) continue;  // cannot happen for an accepted particle
+    const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
+    drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_e + 3 * e, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
                vp_new, st_tot, st_res);
   }
   block_sum2(st_tot, st_res, stat_partial + 2 * (long long)blockIdx.x);

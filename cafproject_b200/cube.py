@@ -26,7 +26,7 @@ class CubeParams(C.Structure):
     _fields_ = [("nn", C.c_int32 * 3), ("rank", C.c_int32), ("nnt", C.c_int32), ("nc", C.c_int32),
                 ("ncell", C.c_int32), ("ncb", C.c_int32), ("izipx", C.c_int32), ("izipv", C.c_int32),
                 ("np_nc", C.c_int32), ("image_buffer", C.c_float), ("tile_buffer", C.c_float),
-                ("device", C.c_int32), ("fine_batch", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("device", C.c_int32), ("fine_batch", C.c_int32), ("local_group", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class CubeGPUError(RuntimeError):
@@ -70,6 +70,8 @@ def load_library():
     L.cube_gpu_phase_times.argtypes = [vp, vp]
     L.cube_gpu_set_profiling.argtypes = [vp, i32]
     L.cube_gpu_timer.argtypes = [vp, i32, C.POINTER(f32)]
+    L.cube_gpu_nccl_unique_id.argtypes = [vp]
+    L.cube_gpu_exchange_plan.argtypes = [C.POINTER(CubeParams), vp, i32]
     _lib = L
     return L
 
@@ -80,8 +82,43 @@ ABI_SYMBOLS = [
     "cube_gpu_download", "cube_gpu_finalize", "cube_gpu_last_error", "cube_gpu_query", "cube_gpu_get_kern_f",
     "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
-    "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer",
+    "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
+    "cube_gpu_exchange_plan",
 ]
+
+
+def exchange_plan(nn, rank, nc, nnt):
+    """Message plan of image ``rank`` on the image grid ``nn`` (host only; see include/cube_gpu.h)."""
+    L = load_library()
+    p = CubeParams()
+    p.nn[:] = tuple(int(v) for v in nn)
+    p.rank, p.nnt, p.nc, p.ncell, p.ncb, p.izipx, p.izipv = rank, nnt, nc, 4, 6, 2, 2
+    out = np.zeros((128, 8), np.int64)
+    n = L.cube_gpu_exchange_plan(C.byref(p), out.ctypes.data, 128)
+    if n < 0:
+        raise CubeGPUError("bad parameters")
+    rows = out[:n]
+    return dict(ghost=[tuple(int(v) for v in r[1:]) for r in rows if r[0] == 0],
+                force_send=[(int(r[1]), int(r[2])) for r in rows if r[0] == 1],
+                force_recv=[(int(r[1]), int(r[2])) for r in rows if r[0] == 2],
+                coarse=[tuple(int(v) for v in r[1:]) for r in rows if r[0] == 3][0])
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId made by the library's own NCCL (image 1 calls this and broadcasts it)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.cube_gpu_nccl_unique_id(buf) != 0:
+        raise CubeGPUError(L.cube_gpu_last_error().decode())
+    return buf.raw
+
+
+def image_grid(n: int):
+    """Image grid (nnx,nny,nnz) used for n = 1, 2, 4, 8 GPUs: 1x1x1, 2x1x1, 2x2x1, 2x2x2 (the reference only has nn^3)."""
+    grids = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+    if n not in grids:
+        raise ValueError("supported image counts: 1, 2, 4, 8")
+    return grids[n]
 
 
 def host_tanf_lut() -> np.ndarray:
@@ -103,7 +140,10 @@ class CubeGPU:
     """One image of a CUBE run on one B200.  Mirrors the step subroutines of CUBE/main."""
 
     def __init__(self, nc, nnt, fk_table, ck_table, nn=(1, 1, 1), rank=0, np_nc=2, image_buffer=1.5, tile_buffer=2.5,
-                 device=0, fine_batch=0, tanf_lut=None):
+                 device=0, fine_batch=0, tanf_lut=None, nccl_id=None, local_group=0):
+        """``nn``: image grid; ``rank``: this image (0-based, x fastest).  More than one image needs either ``nccl_id``
+        (one process per GPU; the 128 bytes of :func:`nccl_unique_id` broadcast from image 1) or ``local_group`` > 0
+        (every image is a host thread of this process, e.g. several images per GPU)."""
         L = load_library()
         self.L = L
         nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
@@ -112,6 +152,7 @@ class CubeGPU:
         p.rank, p.nnt, p.nc, p.ncell, p.ncb = rank, nnt, nc, 4, 6
         p.izipx = p.izipv = 2
         p.np_nc, p.image_buffer, p.tile_buffer, p.device, p.fine_batch = np_nc, image_buffer, tile_buffer, device, fine_batch
+        p.local_group = int(local_group)
         self.params = p
         self.nn, self.nc, self.nnt, self.nt = nn, nc, nnt, nc // nnt
         self.nft = 4 * self.nt
@@ -123,7 +164,8 @@ class CubeGPU:
         assert lut.shape == (65536,)
         h = C.c_void_p()
         self.h = None
-        self._ck(L.cube_gpu_init(C.byref(p), _p(fk), _p(ck), _p(lut), None, C.byref(h)))
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
+        self._ck(L.cube_gpu_init(C.byref(p), _p(fk), _p(ck), _p(lut), idbuf, C.byref(h)))
         self.h = h
         self.nplocal = 0
         self.sigma_vi = F32(0)

@@ -44,7 +44,9 @@ typedef struct cube_params {
   float tile_buffer;    /* parameters.f90:60 */
   int32_t device;       /* CUDA device ordinal */
   int32_t fine_batch;   /* tiles per batched fine-mesh FFT, 0 = choose automatically */
-  int32_t reserved[4];
+  int32_t local_group;  /* 0: one process per image (NCCL when nn>1); k>0: all images of the run are host threads of THIS
+                           process and share in-process group k (several images per GPU, `-fcoarray=single`-style runs) */
+  int32_t reserved[3];
 } cube_params;
 
 typedef struct cube_handle cube_handle;
@@ -58,6 +60,12 @@ typedef struct cube_handle cube_handle;
  *   nccl_unique_id  NULL for a single image; otherwise the 128-byte ncclUniqueId shared by all images. */
 int cube_gpu_init(const cube_params *p, const float *fk_table, const float *ck_table, const float *tanf_lut,
                   const void *nccl_unique_id, cube_handle **h);
+
+/* Replaces the coarray runtime's bootstrap (cafcube.f90:6-14, `sync all`): image 1 calls this and broadcasts the 128
+ * bytes to every image (coarray assignment, MPI_Bcast, torch.distributed...), which pass them to cube_gpu_init.
+ * The image grid is nn[0] x nn[1] x nn[2] (the reference hard-wires nn^3, parameters.f90:181-183); image
+ * rank = icx-1 + nn[0]*((icy-1) + nn[1]*(icz-1)) as in parameters.f90:200-203. */
+int cube_gpu_nccl_unique_id(void *id128);
 
 /* particle_initialization.f90:11-72: take the disjoint state (file order). mass_p = nf_global^3/npglobal. */
 int cube_gpu_upload(cube_handle *h, const int16_t *xp, const int16_t *vp, const int32_t *rhoc_phys,
@@ -105,6 +113,12 @@ int cube_gpu_coarse_force(cube_handle *h, float *force_c);
 /* coarse kick with a caller-supplied force_c  pm.f90:192-228 */
 int cube_gpu_coarse_kick_with(cube_handle *h, const float *force_c, float a_mid, float dt, float sigma_vi,
                               float *vmax, float *f2_max);
+/* message plan of one image, host only (no device needed): rows of 8 int64, returns the row count (-1 = bad params)
+ *   {0, rx, ry, rz, src_rank, dst_rank, ncell, cell0}  ghost direction: I receive my ghost box from src_rank and send
+ *                                                      the opposite physical box to dst_rank (buffer_density/x/v)
+ *   {1, rank, nplanes, ...} / {2, rank, nplanes, ...}  force_c planes sent to / received from `rank` (pm.f90:176-189)
+ *   {3, R, Gx, Gy, Gz, sz, nyl, grp0}                  distributed coarse FFT geometry (replaces pencil_fft.f90) */
+int cube_gpu_exchange_plan(const cube_params *p, int64_t *out, int cap_rows);
 /* per-phase device times (ms) of the last update_x / particle_mesh, CUBEnu-style phase brackets
  * (CUBEnu/work/main/pm.f90:35,195,268,299,388): names returned via cube_gpu_phase_name(i) */
 int cube_gpu_phase_count(void);
