@@ -216,6 +216,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # library chatter (e.g. NCCL's version banner) must not share stdout with the one JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -352,7 +355,8 @@ def main():
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roof, "phases_ms_per_step": phases, "cpu_baseline": cpu,
                 "particles_per_gpu": int(npart), "drift_radius": radius}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
