@@ -299,8 +299,10 @@ def main():
            "fine_fft_x": ntile * (4 * N ** 3 + 8 * N * N * NH), "fine_fft_y": ntile * 16 * N * N * NH,
            "fine_fft_z_green": ntile * (8 * N * N * NH + 24 * M * N * NH) + 12 * N * N * NH,
            "fine_ifft_y": ntile * 3 * (8 * M * N * NH + 8 * M * M * NH), "fine_ifft_x": ntile * 3 * (8 * M * M * NH + 4 * M ** 3),
-           "fine_f2max": ntile * 12 * M ** 3, "fine_kick": 18 * npart + 12 * ntile * M ** 3,
+           "fine_f2max": ntile * 12 * M ** 3, "fine_fft_xy": ntile * (4 * N ** 3 + 8 * N * N * NH),
+           "fine_ifft_yx_f2max": ntile * 3 * (8 * M * N * NH + 4 * M ** 3), "fine_kick": 18 * npart + 12 * ntile * M ** 3,
            "coarse_deposit": 6 * npart + 4 * nc ** 3, "coarse_fft_green": 50 * nc ** 3, "coarse_kick": 18 * npart + 12 * nc ** 3}
+    phases = {k: v for k, v in phases.items() if v > 0}
     launches_per_step = {k: (ntile + batch - 1) // batch if k.startswith("fine") else 1 for k in phases}
     dom = max(phases, key=lambda k: phases[k])
     peak, which = measured_peak()

@@ -79,13 +79,15 @@ __global__ void __launch_bounds__(256) k_halo_pack(long long ng, const int* __re
   scnt[s] = r.rho;
 }
 __global__ void __launch_bounds__(256) k_halo_unpack(long long ng, const int* __restrict__ gcell_ext, const HaloRec* __restrict__ in,
-                                                     int* __restrict__ rhoc_e, float* __restrict__ vfield_e, int* __restrict__ gcnt) {
+                                                     int* __restrict__ rhoc_e, float* __restrict__ vfield_e, int* __restrict__ gcnt,
+                                                     int* __restrict__ sid_e, long long ncell_p) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= ng) return;
   const long long e = gcell_ext[q];
   const HaloRec r = in[q];
   rhoc_e[e] = r.rho; vfield_e[3 * e] = r.v[0]; vfield_e[3 * e + 1] = r.v[1]; vfield_e[3 * e + 2] = r.v[2];
   gcnt[q] = r.rho;
+  sid_e[e] = (int)(ncell_p + q);
 }
 // ghost cells point into the received segment behind the physical particles
 __global__ void __launch_bounds__(256) k_ghost_cstart(long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,

@@ -20,6 +20,7 @@
 // N = R1*R2, each thread doing one R-point DFT in registers with compile-time twiddles.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <type_traits>
 #include "cube_common.cuh"
 
@@ -373,10 +374,14 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
 // ---------------------------------------------------------------------------------------------
 // x inverse (c2r): B[d][b][z'][y][kx] -> F[b][z'][y'][d][x'] (x' = M kept points, pitch FP).
 // One CTA = 32 kept rows (16 complex lines) of one component.  grid = (ceil(M/32), M, 3*nbatch)
+// With `prefix` the value stored is force_f*a_mid*dt/6/pi, the per-node prefix of every kick term (pm.f90:104), so that
+// the kick does not redo it for each of its 8 corners x 3 components.
+// (Measured alternatives, profiles/r01e_fused_fft.md: looping the three components inside one CTA, or a (1,1,3) cluster
+//  that takes f2_max through distributed shared memory, both lose more occupancy than the separate f2_max pass costs.)
 // ---------------------------------------------------------------------------------------------
 template <int R1, int R2>
 __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
-                                                                       const float2* __restrict__ tw_g) {
+                                                                       const float2* __restrict__ tw_g, float a_mid, float dt, int prefix) {
   constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
   constexpr int NHC = N / 2 + 1, NLD = (FL * NHC + NT - 1) / NT;  // loads per thread
   extern __shared__ float2 smem[];
@@ -424,8 +429,13 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom 
     const int l = r >> 1, im = r & 1;
     float* row = dst + ((size_t)yp * 3 + d) * g.FP;
     const float* sp = reinterpret_cast<const float*>(s) + im;
+    if (prefix) {
 #pragma unroll 4
-    for (int x = lane; x < g.M; x += 32) row[x] = sp[((x + g.off) * LW + l) * 2];
+      for (int x = lane; x < g.M; x += 32) row[x] = kick_prefix(sp[((x + g.off) * LW + l) * 2], a_mid, dt);
+    } else {
+#pragma unroll 4
+      for (int x = lane; x < g.M; x += 32) row[x] = sp[((x + g.off) * LW + l) * 2];
+    }
   }
 }
 
@@ -445,6 +455,15 @@ __global__ void __launch_bounds__(256) k_f2max_rows(FftGeom g, const float* __re
   }
   best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
   if (lane == 0) atomicMax(&f2max[b], __float_as_uint(best));
+}
+
+// F <- F*a_mid*dt/6/pi in place (diagnostic path: a caller-supplied force_f goes through the same kick as the step's)
+__global__ void __launch_bounds__(256) k_prefix_rows(FftGeom g, float* __restrict__ F, float a_mid, float dt) {
+  const size_t nrow = (size_t)g.M * g.M * 3;
+  float* base = F + (size_t)blockIdx.y * nrow * g.FP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (size_t r = (size_t)blockIdx.x * nw + warp; r < nrow; r += (size_t)gridDim.x * nw)
+    for (int x = lane; x < g.M; x += 32) base[r * g.FP + x] = kick_prefix(base[r * g.FP + x], a_mid, dt);
 }
 
 }  // namespace cube

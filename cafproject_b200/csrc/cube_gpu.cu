@@ -18,6 +18,7 @@
 #include "../../include/cube_gpu.h"
 #include "cube_kernels.cuh"
 #include "cube_fft.cuh"
+#include "cube_fft2d.cuh"
 #include "cube_particles.cuh"
 #include "cube_comm.cuh"
 #include "cube_exchange.cuh"
@@ -47,10 +48,10 @@ static int fail(const char* fmt, ...) {
 #define CKL() CK(cudaGetLastError())
 
 enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFTX, PH_FFTY, PH_FFTZ, PH_IFFTY, PH_IFFTX, PH_FMAX, PH_FKICK,
-             PH_CDEP, PH_CFFT, PH_CKICK, PH_N };
+             PH_CDEP, PH_CFFT, PH_CKICK, PH_FFTXY, PH_IFFTYX, PH_N };
 static const char* kPhaseNames[PH_N] = {"drift_key", "drift_count", "drift_scan", "drift_place", "buffer", "fine_deposit",
                                         "fine_fft_x", "fine_fft_y", "fine_fft_z_green", "fine_ifft_y", "fine_ifft_x", "fine_f2max",
-                                        "fine_kick", "coarse_deposit", "coarse_fft_green", "coarse_kick"};
+                                        "fine_kick", "coarse_deposit", "coarse_fft_green", "coarse_kick", "fine_fft_xy", "fine_ifft_yx_f2max"};
 
 // one instantiation of the hand-written fine-mesh FFT kernels per supported transform length N = R1*R2
 struct FftPlan {
@@ -59,12 +60,17 @@ struct FftPlan {
   void (*y_fwd)(FftGeom, float2*, const float2*);
   void (*y_inv)(FftGeom, float2*, const float2*);
   void (*z_green)(FftGeom, const float2*, float2*, const float*, float, const float2*);
-  void (*x_inv)(FftGeom, const float2*, float*, const float2*);
+  void (*x_inv)(FftGeom, const float2*, float*, const float2*, float, float, int);
+  // plane-fused cluster kernels (cube_fft2d.cuh); used when their shared memory fits one SM
+  void (*xy_fwd)(FftGeom, const float*, float2*, const float2*);
+  void (*yx_inv)(FftGeom, const float2*, float*, unsigned*, const float2*);
+  size_t smem2d;
   int N() const { return R1 * R2; }
   int threads() const { return FL * (R1 > R2 ? R1 : R2); }
 };
 template <int R1, int R2> static FftPlan make_plan() {
-  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv<R1, R2>};
+  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv<R1, R2>,
+          k_fft_xy_fwd<R1, R2>, k_fft_yx_inv<R1, R2>, Fft2dCfg<R1, R2>::SMEM};
 }
 // N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
 static const FftPlan kPlans[] = {make_plan<8, 10>(), make_plan<8, 12>(), make_plan<8, 16>(), make_plan<10, 16>(), make_plan<12, 16>(),
@@ -87,6 +93,7 @@ struct cube_handle {
   long long *cstart_p = nullptr, *cstart_p2 = nullptr;
   // extended image grid
   int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
+  int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
@@ -97,6 +104,7 @@ struct cube_handle {
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
   // fine mesh (cube_fft.cuh)
   int batch = 1;
+  bool fused2d = false;
   const FftPlan* plan = nullptr; FftGeom fg = {};
   size_t rho_n = 0, A_n = 0, B_n = 0, F_n = 0;  // elements per tile
   float* rho = nullptr;      // [batch][N][N][N]            (aliases the head of Bk: dead before Bk is written)
@@ -467,6 +475,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     }
     if (init_exchange(h)) return 1;
   }
+  CK(dmalloc(&h->sid_e, g.ncell_e)); CK(dmalloc(&h->mask_e, g.ncell_e)); CK(dmalloc(&h->mask_s, g.ncell_p + h->ex.ng));
   h->nscan_blocks = (int)((std::max(g.ncell_p, h->ex.ng) + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
   CK(dmalloc(&h->stat_partial, 2 * (long long)nblk(g.ncell_p, PC_CELLS) + (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 8));
@@ -519,6 +528,16 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int smem_max = 0;
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    // measured on B200 (profiles/r01e_fused_fft.md): with one 288-thread CTA per SM the plane-fused kernels cannot hide
+    // their own phase latencies (xy 13.0 ms vs 6.7 ms, yx 28.1 ms vs 17.4 ms for the line kernels at cfg 2), so they are
+    // opt-in until they are warp-specialised
+    h->fused2d = h->plan->smem2d <= (size_t)smem_max && getenv("CUBE_GPU_FUSED_FFT") != nullptr;
+    if (h->fused2d) {
+      CK(cudaFuncSetAttribute((const void*)h->plan->xy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->smem2d));
+      CK(cudaFuncSetAttribute((const void*)h->plan->yx_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->smem2d));
+    }
   }
   // coarse mesh
   h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
@@ -547,7 +566,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
-                  h->rhoc_e, h->cstart_e, h->vfield_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
                   h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
@@ -614,7 +633,7 @@ static int exchange_density(cube_handle* h, int* status) {
   for (const ExDir& d : h->ex.dirs) CC(cm->send(h->hsend + d.cell0, (size_t)d.ncell * sizeof(HaloRec), d.dst_rank));
   for (const ExDir& d : h->ex.dirs) CC(cm->recv(h->hrecv + d.cell0, (size_t)d.ncell * sizeof(HaloRec), d.src_rank));
   CC(cm->end());
-  k_halo_unpack<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->gcell_ext, h->hrecv, h->rhoc_e, h->vfield_e, h->gcnt); CKL();
+  k_halo_unpack<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->gcell_ext, h->hrecv, h->rhoc_e, h->vfield_e, h->gcnt, h->sid_e, h->g.ncell_p); CKL();
   if (scan_counts(h, h->gcnt, ng, h->gstart)) return 1;
   if (scan_counts(h, h->scnt, ng, h->sstart)) return 1;
   k_ghost_cstart<<<nblk(ng, 256), 256, 0, h->st>>>(ng, h->gcell_ext, h->gstart, h->nplocal, h->cstart_e); CKL();
@@ -657,9 +676,10 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
   if (do_density) {
     PhaseTimer pt(h, PH_BUFFER);
     int status = 0;
-    k_build_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g, h->rhoc_p, h->cstart_p, h->vfield_p, h->rhoc_e, h->cstart_e, h->vfield_e); CKL();
+    k_build_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g, h->rhoc_p, h->cstart_p, h->vfield_p, h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e); CKL();
     if (multi && exchange_density(h, &status)) return 1;
-    k_tile_counts<<<g.nnt * g.nnt * g.nnt, 256, 0, h->st>>>(g, h->rhoc_e, h->tile_count); CKL();
+    CK(cudaMemsetAsync(h->tile_count, 0, sizeof(long long) * g.nnt * g.nnt * g.nnt, h->st));
+    k_tile_counts<<<dim3(32, g.nnt * g.nnt * g.nnt), 256, 0, h->st>>>(g, h->rhoc_e, (unsigned long long*)h->tile_count); CKL();
     h->launches += 2;
     // overhead_image=sum(rhoc)/np_image_max over the buffered rhoc of all tiles (buffer_density.f90:75)
     const int ntile = g.nnt * g.nnt * g.nnt;
@@ -714,13 +734,15 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   const unsigned nchunk = nblk(g.ncell_p, PC_CELLS), nchunk_g = nblk(ng, PC_CELLS);
   {
     PhaseTimer pt(h, PH_KEY);
-    k_drift_key_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff); CKL();
+    k_drift_key_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff, h->mask_s); CKL();
     h->launches++;
     if (multi && ng) {
       k_drift_key_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->vfield_e, h->dvlut, dt_mid, h->key,
-                                                 h->rank, h->maxoff); CKL();
+                                                 h->rank, h->maxoff, h->mask_s + g.ncell_p); CKL();
       h->launches++;
     }
+    k_mask_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g.ncell_e, h->sid_e, h->mask_s, h->mask_e); CKL();
+    h->launches++;
     CK(cudaMemcpyAsync(&maxoff, h->maxoff, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
   }
@@ -752,7 +774,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     {
       PhaseTimer pt(h, PH_COUNT);
       k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
-                                          h->vfield_p2, h->rank, h->stat_partial); CKL();
+                                          h->vfield_p2, h->rank, h->stat_partial, h->mask_e); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
       h->launches += 2;
     }
@@ -837,8 +859,9 @@ static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, floa
   return 0;
 }
 
-// leaves force_f of the nb tiles in h->F and the per-tile f2_max_fine in h->f2max[0..nb)
-static int fine_mesh(cube_handle* h, int tile0, int nb) {
+// leaves force_f of the nb tiles in h->F (multiplied by the kick prefix a_mid*dt/6/pi when `prefix`) and the per-tile
+// f2_max_fine in h->f2max[0..nb)
+static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid, float dt) {
   FftGeom f = h->fg;
   f.nbatch = nb;
   const FftPlan& pl = *h->plan;
@@ -847,6 +870,29 @@ static int fine_mesh(cube_handle* h, int tile0, int nb) {
   const size_t smem_z = (size_t)(2 * N * FL + N) * sizeof(float2) + (size_t)3 * (N / 2 + 1) * FL * sizeof(float);
   DepWin w{8, N, N, (long long)h->rho_n};
   if (fine_deposit(h, tile0, nb, w, h->rho)) return 1;
+  if (h->fused2d) {  // plane-fused passes (cube_fft2d.cuh): k-space makes one HBM trip per plane on each side of the z pass
+    {
+      PhaseTimer pt(h, PH_FFTXY);
+      pl.xy_fwd<<<dim3(2, N, nb), T, pl.smem2d, h->st>>>(f, h->rho, h->Ak, h->tw); CKL();
+    }
+    {
+      PhaseTimer pt(h, PH_FFTZ);
+      const float scale = 1.0f / ((float)N * (float)N * (float)N);
+      pl.z_green<<<dim3(f.P / FL, N), T, smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
+    }
+    {
+      PhaseTimer pt(h, PH_IFFTYX);
+      CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
+      pl.yx_inv<<<dim3(2, f.M, nb), T, pl.smem2d, h->st>>>(f, h->Bk, h->F, h->f2max, h->tw); CKL();
+      if (prefix) {  // same contract as the line kernels: prefixed mesh, f2_max over the prefixed values
+        k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, a_mid, dt); CKL();
+        CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
+        k_f2max_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, h->f2max); CKL();
+      }
+    }
+    h->launches += 4;
+    return 0;
+  }
   {
     PhaseTimer pt(h, PH_FFTX);
     pl.x_fwd<<<dim3((N + 31) / 32, N, nb), T, smem_x, h->st>>>(f, h->rho, h->Ak, h->tw); CKL();
@@ -866,7 +912,7 @@ static int fine_mesh(cube_handle* h, int tile0, int nb) {
   }
   {
     PhaseTimer pt(h, PH_IFFTX);
-    pl.x_inv<<<dim3((f.M + 31) / 32, f.M, 3 * nb), T, smem_x, h->st>>>(f, h->Bk, h->F, h->tw); CKL();
+    pl.x_inv<<<dim3((f.M + 31) / 32, f.M, 3 * nb), T, smem_x, h->st>>>(f, h->Bk, h->F, h->tw, a_mid, dt, prefix ? 1 : 0); CKL();
   }
   {
     PhaseTimer pt(h, PH_FMAX);
@@ -920,13 +966,24 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   if (build_dvlut(h, h->sigma_vi)) return 1;
   const double S_new = vscale(h->sigma_vi_new);
   std::vector<float> f2(ntile, 0.f);
+  // The x inverse stores force_f*a_mid*dt/6/pi (the kick's per-node prefix, pm.f90:104); f2_max_fine is then taken over
+  // the prefixed mesh and scaled back by the square of the same f32 factor: equal to maxval(sum(force_f**2,1)) (pm.f90:85)
+  // to 3e-7 relative, below the difference between any two FFT implementations.  A degenerate factor (dt = 0) takes
+  // the unfused route: raw forces, exact f2_max, separate prefix pass.
+  const float pscale = ((1.0f * a_mid) * dt) / 6.0f / PI_F;
+  const bool pre_in_fft = pscale > 1e-12f && pscale < 1e12f;
   for (int t0 = 0; t0 < ntile; t0 += h->batch) {
     const int nb = std::min(h->batch, ntile - t0);
-    if (fine_mesh(h, t0, nb)) return 1;
+    if (fine_mesh(h, t0, nb, pre_in_fft, a_mid, dt)) return 1;
     CK(cudaMemcpyAsync(f2.data() + t0, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
+    if (!pre_in_fft) {
+      FftGeom fb = h->fg; fb.nbatch = nb;
+      k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(fb, h->F, a_mid, dt); CKL();
+      h->launches++;
+    }
     PhaseTimer pt(h, PH_FKICK);
     dim3 grid(nblk(nt3, PC_CELLS), nb);
-    k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new, a_mid, dt); CKL();
+    k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
     h->launches++;
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
@@ -946,6 +1003,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   double vmd; memcpy(&vmd, &vb, sizeof vmd);
   const float vmax = (float)vmd;  // f32 <- max(f32, f64) is monotone, so one final rounding is the same
   float f2f = 0; for (float v : f2) f2f = std::max(f2f, v);
+  if (pre_in_fft) f2f = f2f / pscale / pscale;
   float vmax_all = vmax;
   if (h->nimg > 1) {  // pm.f90:239-244: every image takes the minimum of every image's dt = the dt of the maxima
     struct Rec { float f2f, f2c, vmax; } mine = {f2f, f2c, vmax};
@@ -978,6 +1036,7 @@ extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   if (w == "nfft") return h->fg.N;
   if (w == "nfft_pitch") return h->fg.P;
   if (w == "kernel_launches") return h->launches;
+  if (w == "fused_fft") return h->fused2d ? 1 : 0;
   if (w == "nplocal") return h->nplocal;
   return -1;
 }
@@ -1020,7 +1079,7 @@ extern "C" int cube_gpu_fine_force(cube_handle* h, int itx, int ity, int itz, fl
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
-  if (fine_mesh(h, t, 1)) return 1;
+  if (fine_mesh(h, t, 1, false, 0.f, 0.f)) return 1;
   const long long m = h->fg.M, n = m * m * m;
   float* tmp = nullptr; CK(dmalloc(&tmp, 3 * n));
   k_force_to_ref<<<nblk(n, 256), 256, 0, h->st>>>((int)m, h->fg.FP, h->F, tmp); CKL();
@@ -1042,10 +1101,12 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   if (build_dvlut(h, sigma_vi)) return 1;
   float f2 = 0;
   CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned), h->st));
-  { FftGeom f1 = h->fg; f1.nbatch = 1; k_f2max_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, h->f2max); CKL(); }
+  FftGeom f1 = h->fg; f1.nbatch = 1;
+  k_f2max_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, h->f2max); CKL();
   CK(cudaMemcpyAsync(&f2, h->f2max, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   dim3 grid(nblk(nt3, PC_CELLS), 1);
-  k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new), a_mid, dt); CKL();
+  k_prefix_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, a_mid, dt); CKL();
+  k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new)); CKL();
   CK(cudaStreamSynchronize(h->st));
   cudaFree(tmp);
   if (f2_max) *f2_max = f2;

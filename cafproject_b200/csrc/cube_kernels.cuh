@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_final(const int* __restrict__ i
 // =============================================================================================
 __global__ void k_build_ext(Geom g, const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
                             const float* __restrict__ vfield_p, int* __restrict__ rhoc_e, long long* __restrict__ cstart_e,
-                            float* __restrict__ vfield_e) {
+                            float* __restrict__ vfield_e, int* __restrict__ sid_e) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.ncell_e) return;
   int x = (int)(e % g.ne) - NCB, y = (int)((e / g.ne) % g.ne) - NCB, z = (int)(e / ((long long)g.ne * g.ne)) - NCB;
@@ -99,25 +99,29 @@ __global__ void k_build_ext(Geom g, const int* __restrict__ rhoc_p, const long l
   int xw = (x + g.nc) % g.nc, yw = (y + g.nc) % g.nc, zw = (z + g.nc) % g.nc;
   long long L = phys_index(g, xw / g.nt, yw / g.nt, zw / g.nt, xw % g.nt, yw % g.nt, zw % g.nt);
   rhoc_e[e] = rhoc_p[L];
+  sid_e[e] = (int)L;
   cstart_e[e] = cstart_p[L];
   vfield_e[3 * e + 0] = vfield_p[3 * L + 0];
   vfield_e[3 * e + 1] = vfield_p[3 * L + 1];
   vfield_e[3 * e + 2] = vfield_p[3 * L + 2];
 }
 
-// particles in each tile's extended region (cume(nt+2ncb,...) of update_particle.f90:60)
-__global__ void k_tile_counts(Geom g, const int* __restrict__ rhoc_e, long long* __restrict__ tile_count) {
+// particles in each tile's extended region (cume(nt+2ncb,...) of update_particle.f90:60); grid = (splits, tiles),
+// tile_count zeroed by the caller (integer atomics: order-independent)
+__global__ void __launch_bounds__(256) k_tile_counts(Geom g, const int* __restrict__ rhoc_e, unsigned long long* __restrict__ tile_count) {
   __shared__ long long sm[33];
-  int t = blockIdx.x;
-  int tx = t % g.nnt, ty = (t / g.nnt) % g.nnt, tz = t / (g.nnt * g.nnt);
-  long long n = (long long)g.nte * g.nte * g.nte, s = 0;
-  for (long long q = threadIdx.x; q < n; q += blockDim.x) {
-    int i = (int)(q % g.nte), j = (int)((q / g.nte) % g.nte), k = (int)(q / ((long long)g.nte * g.nte));
-    s += rhoc_e[ext_index(g, tx * g.nt + i - NCB, ty * g.nt + j - NCB, tz * g.nt + k - NCB)];
+  const int t = blockIdx.y;
+  const int tx = t % g.nnt, ty = (t / g.nnt) % g.nnt, tz = t / (g.nnt * g.nnt);
+  const long long nrow = (long long)g.nte * g.nte;
+  long long s = 0;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrow; row += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int j = (int)(row % g.nte), k = (int)(row / g.nte);
+    const int* r = rhoc_e + ext_index(g, tx * g.nt - NCB, ty * g.nt + j - NCB, tz * g.nt + k - NCB);
+    for (int i = threadIdx.x & 31; i < g.nte; i += 32) s += r[i];
   }
   long long tot;
   block_exclusive_scan(s, sm, tot);
-  if (threadIdx.x == 0) tile_count[t] = tot;
+  if (threadIdx.x == 0 && tot) atomicAdd(&tile_count[t], (unsigned long long)tot);
 }
 
 // dv table: dble(tan((pi*real(vp))/real(nvbin-1))) / (sqrt(pi/2)/(sigma_vi*vrel_boost))
@@ -149,9 +153,11 @@ __global__ void __launch_bounds__(1024) k_reduce3(const double* __restrict__ par
 // fine mesh (pm.f90:44-118)
 // =============================================================================================
 
-// tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution, rounded to f32 (pm.f90:54)
+// tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution, rounded to f32 (pm.f90:54).
+// = (2K+1)/2^15 with K = 65536*(cell-1) + u an integer: the f64 expression is exact, so its f32 rounding equals the
+// round-to-nearest int->float conversion of 2K+1 scaled by a power of two (no f64 instructions)
 __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
-  return __double2float_rn((double)(4 * (cell1 - 1)) + ((double)(unsigned short)xp + 0.5) * 0x1p-14);
+  return __int2float_rn(2 * (65536 * (cell1 - 1) + (int)(unsigned short)xp) + 1) * 0x1p-15f;
 }
 
 // Output window of the fine deposit on the reference's padded tile grid rho_f(1:nfe): the window starts at
@@ -161,10 +167,11 @@ struct DepWin { int f0, n; long long ld, vol; };
 // One thread per SOURCE coarse cell: it walks its particles once, in storage order, and adds their eight CIC
 // weights into a private 5x5x5 block of shared-memory accumulators (its own 4^3 fine cells plus the +1 spill planes,
 // pm.f90:54-68).  A CTA covers a brick of FB_X x FB_Y x FB_Z output coarse cells plus the low-side neighbour layer
-// whose spill lands in the brick; afterwards every fine cell of the brick is the sum of the (up to eight) blocks that
-// reach it, taken in the reference's k,j,i source order.  No atomics, every fine cell of the window written exactly
-// once (no zero-fill), run-to-run deterministic.  The summation is grouped per source cell, so rho equals the
-// reference's sequential scatter to round-off (~1e-7 relative), not bit for bit.
+// whose spill lands in the brick.  The spill planes are then handed to the +x, +y, +z neighbour blocks in three
+// barrier-separated sweeps (every accumulator has exactly one writer per sweep; edges and corners travel transitively,
+// like the reference's x,y,z buffer syncs), after which every fine cell of the brick is one accumulator.  No atomics,
+// every fine cell of the window written exactly once (no zero-fill), run-to-run deterministic.  The summation is
+// grouped per source cell, so rho equals the reference's sequential scatter to round-off (~1e-7 relative), not bit for bit.
 constexpr int FB_X = 8, FB_Y = 4, FB_Z = 4;
 constexpr int FS_X = FB_X + 1, FS_Y = FB_Y + 1, FS_Z = FB_Z + 1, FS_N = FS_X * FS_Y * FS_Z;  // 225 source cells
 constexpr int FD_T = 256;
@@ -180,40 +187,67 @@ __global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int 
   const int nc4 = w.n / 4, c0 = w.f0 / 4;
   const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y;
   const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
-  for (int e = t; e < 125 * FS_N; e += FD_T) acc[e] = 0.f;
+  // my source cell: its particle run is fetched before the accumulators are cleared (the loads overlap the clearing)
+  const int sx = t % FS_X, sy = (t / FS_X) % FS_Y, sz = t / (FS_X * FS_Y);
+  // tile-local Fortran index of my source cell (sx = 0 is the low-side neighbour layer)
+  const int si = c0 + bx * FB_X + sx - NCB, sj = c0 + by * FB_Y + sy - NCB, sk = c0 + bz * FB_Z + sz - NCB;
+  const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
+  int n = 0; long long s = 0;
+  if (t < FS_N && si >= lo && si <= hi && sj >= lo && sj <= hi && sk >= lo && sk <= hi) {
+    const long long e = ext_index(g, tx * g.nt - 1 + si, ty * g.nt - 1 + sj, tz * g.nt - 1 + sk);
+    n = rhoc_e[e];
+    s = cstart_e[e];
+  }
+  {
+    float4* a4 = reinterpret_cast<float4*>(acc);
+    for (int e = t; e < 125 * FS_N / 4 + 1; e += FD_T)
+      if (e < 125 * FS_N / 4) a4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t == 0) acc[125 * FS_N - 1] = 0.f;  // 28125 = 4*7031 + 1
+  }
   __syncthreads();
-  if (t < FS_N) {
-    const int sx = t % FS_X, sy = (t / FS_X) % FS_Y, sz = t / (FS_X * FS_Y);
-    // tile-local Fortran index of my source cell (sx = 0 is the low-side neighbour layer)
-    const int si = c0 + bx * FB_X + sx - NCB, sj = c0 + by * FB_Y + sy - NCB, sk = c0 + bz * FB_Z + sz - NCB;
-    const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
-    if (si >= lo && si <= hi && sj >= lo && sj <= hi && sk >= lo && sk <= hi) {
-      const long long e = ext_index(g, tx * g.nt - 1 + si, ty * g.nt - 1 + sj, tz * g.nt - 1 + sk);
-      const int n = rhoc_e[e];
-      const long long s = cstart_e[e];
-      float* my = acc + t;
-      for (int l = 0; l < n; l++) {
-        const Code3 c = load_code3(xp, s + l);
-        int i1, j1, k1; float ax[2], ay[2], az[2];
-        cic_split(fine_tempx(si, c.x), i1, ax[0], ax[1]);
-        cic_split(fine_tempx(sj, c.y), j1, ay[0], ay[1]);
-        cic_split(fine_tempx(sk, c.z), k1, az[0], az[1]);
-        const int fa = i1 - (4 * (si - 1) + 1), fb = j1 - (4 * (sj - 1) + 1), fc = k1 - (4 * (sk - 1) + 1);  // 0..3 (4 on an f32 tie)
+  if (n) {
+    float* my = acc + t;
+    Code3 c = load_code3(xp, s);
+    for (int l = 0; l < n; l++) {
+      const Code3 cur = c;
+      if (l + 1 < n) c = load_code3(xp, s + l + 1);  // next particle in flight while this one is spread
+      int i1, j1, k1; float ax[2], ay[2], az[2];
+      cic_split(fine_tempx(si, cur.x), i1, ax[0], ax[1]);
+      cic_split(fine_tempx(sj, cur.y), j1, ay[0], ay[1]);
+      cic_split(fine_tempx(sk, cur.z), k1, az[0], az[1]);
+      const int fa = i1 - (4 * (si - 1) + 1), fb = j1 - (4 * (sj - 1) + 1), fc = k1 - (4 * (sk - 1) + 1);  // 0..3 (4 on an f32 tie)
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
-          const int a = fa + qa, b = fb + qb, cc = fc + qc;
-          if (a <= 4 && b <= 4 && cc <= 4) {  // index 5 only occurs with weight exactly 0
-            const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:61-68
-            float* p = my + ((a * 5 + b) * 5 + cc) * FS_N;
-            *p = __fadd_rn(*p, wgt);
-          }
+      for (int q = 0; q < 8; q++) {
+        const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
+        const int a = fa + qa, b = fb + qb, cc = fc + qc;
+        if (a <= 4 && b <= 4 && cc <= 4) {  // index 5 only occurs with weight exactly 0
+          const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:61-68
+          float* p = my + ((a * 5 + b) * 5 + cc) * FS_N;
+          *p = __fadd_rn(*p, wgt);
         }
       }
     }
   }
   __syncthreads();
-  // gather: one 32-float row (8 coarse cells x 4) per warp iteration
+  // spill planes -> neighbour blocks.  Work items are (entry, source) pairs with the source index fastest: conflict-free.
+  for (int e = t; e < 25 * FS_N; e += FD_T) {  // +x: (4,b,c) of S -> (0,b,c) of S+1
+    const int S = e % FS_N, bc = e / FS_N;
+    if (S % FS_X != FS_X - 1) acc[bc * FS_N + S + 1] = __fadd_rn(acc[bc * FS_N + S + 1], acc[(100 + bc) * FS_N + S]);
+  }
+  __syncthreads();
+  for (int e = t; e < 20 * FS_N; e += FD_T) {  // +y: (a,4,c) of S -> (a,0,c) of S+FS_X, a = 0..3
+    const int S = e % FS_N, ac = e / FS_N, a = ac / 5, c = ac - 5 * a;
+    if ((S / FS_X) % FS_Y != FS_Y - 1)
+      acc[(a * 25 + c) * FS_N + S + FS_X] = __fadd_rn(acc[(a * 25 + c) * FS_N + S + FS_X], acc[(a * 25 + 20 + c) * FS_N + S]);
+  }
+  __syncthreads();
+  for (int e = t; e < 16 * FS_N; e += FD_T) {  // +z: (a,b,4) of S -> (a,b,0) of S+FS_X*FS_Y, a,b = 0..3
+    const int S = e % FS_N, ab = e / FS_N, a = ab >> 2, b = ab & 3;
+    if (S / (FS_X * FS_Y) != FS_Z - 1)
+      acc[(a * 25 + b * 5) * FS_N + S + FS_X * FS_Y] = __fadd_rn(acc[(a * 25 + b * 5) * FS_N + S + FS_X * FS_Y], acc[(a * 25 + b * 5 + 4) * FS_N + S]);
+  }
+  __syncthreads();
+  // write-out: one 32-float row (8 coarse cells x 4) per warp iteration
   const int lane = t & 31, wp = t >> 5;
   float* out = rho + (long long)blockIdx.y * w.vol;
   const int ocx = lane >> 2, a = lane & 3;
@@ -222,22 +256,8 @@ __global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int 
     const int fy = row % (4 * FB_Y), fz = row / (4 * FB_Y);
     const int ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
     const int gy = (by * FB_Y + ocy) * 4 + b, gz = (bz * FB_Z + ocz) * 4 + cc;
-    float v = 0.f;
-#pragma unroll
-    for (int dz = 1; dz >= 0; dz--) {      // sources in k, j, i order: the lower neighbour first
-      if (dz && cc) continue;
-#pragma unroll
-      for (int dy = 1; dy >= 0; dy--) {
-        if (dy && b) continue;
-#pragma unroll
-        for (int dx = 1; dx >= 0; dx--) {
-          if (dx && a) continue;
-          const int S = ((ocz + 1 - dz) * FS_Y + (ocy + 1 - dy)) * FS_X + (ocx + 1 - dx);
-          v = __fadd_rn(v, acc[(((a + 4 * dx) * 5 + (b + 4 * dy)) * 5 + (cc + 4 * dz)) * FS_N + S]);
-        }
-      }
-    }
-    if (gx < w.n && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = v;
+    const int S = ((ocz + 1) * FS_Y + (ocy + 1)) * FS_X + (ocx + 1);
+    if (gx < w.n && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = acc[((a * 5 + b) * 5 + cc) * FS_N + S];
   }
 }
 
@@ -311,9 +331,10 @@ __global__ void k_force_from_ref(int M, int FP, const float* __restrict__ in, fl
 // =============================================================================================
 // coarse mesh (pm.f90:127-228)
 // =============================================================================================
-// tempx=((/i,j,k/)-1)+(...)*x_resolution-0.5 -> f32 (pm.f90:142); cell0 = Fortran index - 1
+// tempx=((/i,j,k/)-1)+(...)*x_resolution-0.5 -> f32 (pm.f90:142); cell0 = Fortran index - 1.
+// = (2K+1)/2^17 with K = 65536*cell0 + u - 32768 (every f64 step of the reference expression is exact)
 __device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
-  return __double2float_rn(__dsub_rn(__dadd_rn((double)cell0, xp_frac(xp)), 0.5));
+  return __int2float_rn(2 * (65536 * cell0 + (int)(unsigned short)xp - 32768) + 1) * 0x1p-17f;
 }
 
 // Coarse CIC deposit (pm.f90:130-163).  Same scheme as the fine deposit: one thread per SOURCE cell adds its

@@ -31,6 +31,21 @@ __device__ __forceinline__ int chunk_find(const int* soff, int q) {
   return lo;
 }
 
+// tile and tile-local coordinates of the CTA's cells, worked out once per cell (the integer divisions of phys_decompose
+// cost more than the rest of a particle's index arithmetic when they are redone per particle)
+struct CellPos { short tx, ty, tz, i, j, k; };
+__device__ __forceinline__ void chunk_cells(const Geom& g, long long c0, long long ncell, CellPos* sp) {
+  for (int t = threadIdx.x; t < PC_CELLS; t += blockDim.x) {
+    CellPos q = {0, 0, 0, 0, 0, 0};
+    if (c0 + t < ncell) {
+      int tx, ty, tz, i, j, k;
+      phys_decompose(g, c0 + t, tx, ty, tz, i, j, k);
+      q.tx = (short)tx; q.ty = (short)ty; q.tz = (short)tz; q.i = (short)i; q.j = (short)j; q.k = (short)k;
+    }
+    sp[t] = q;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // velocity encode without atan:  code = nint(65535*atan(X)/pi_f) is a monotone step function of X = S*v; the
 // table holds, for c = 0..32767, the smallest double X with code(X) >= c+1, found at start-up by bisection on
@@ -56,30 +71,35 @@ __device__ __forceinline__ short vp_encode_lut(double v, double S, const double*
   const double a = fabs(X);
   int c = __float2int_rn(atanf((float)a) * (65535.0f / PI_F));
   c = min(max(c, 0), 32767);
-  while (c < 32767 && a >= __ldg(B + c)) c++;
-  while (c > 0 && a < __ldg(B + c - 1)) c--;
+  // the f32 guess is within one code of the answer: fetch both neighbouring thresholds at once (two independent loads
+  // instead of a chain of dependent ones); the loops only run on if the guess was farther off
+  const double t0 = __ldg(B + c), tm = __ldg(B + max(c - 1, 0));
+  if (c < 32767 && a >= t0) { c++; while (c < 32767 && a >= __ldg(B + c)) c++; }
+  else if (c > 0 && a < tm) { c--; while (c > 0 && a < __ldg(B + c - 1)) c--; }
   return (short)(X < 0.0 ? -c : c);
 }
 
 // ---------------------------------------------------------------------------------------------
 // fine kick (pm.f90:88-118) for the tiles [tile0, tile0+nb): grid = (chunks per tile, nb)
-// F[b][z'][y'][d][x'] = force_f on the M kept points
+// G[b][z'][y'][d][x'] = force_f*a_mid*dt/6/pi (the per-node prefix of every kick term, applied once per mesh node in
+// the epilogue of the x inverse, cube_fft.cuh) on the M kept points
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, int FP, const short* __restrict__ xp, short* __restrict__ vp,
                                                      const long long* __restrict__ cstart_p, const float* __restrict__ G,
-                                                     const double* __restrict__ dvlut, const double* __restrict__ enc, double S_new,
-                                                     float a_mid, float dt) {
+                                                     const double* __restrict__ dvlut, const double* __restrict__ enc, double S_new) {
   __shared__ int soff[PC_CELLS + 1];
+  __shared__ CellPos spos[PC_CELLS];
   const long long nt3 = (long long)g.nt * g.nt * g.nt;
   const int b = blockIdx.y;
   const long long tbase = (long long)(tile0 + b) * nt3;
   const long long c0 = tbase + (long long)blockIdx.x * PC_CELLS;
+  chunk_cells(g, c0, tbase + nt3, spos);
   const int np = chunk_setup(cstart_p, c0, tbase + nt3, soff);
   const long long p0 = cstart_p[c0];
   const float* Gb = G + (long long)b * M * M * 3 * FP;
   for (int q = threadIdx.x; q < np; q += PC_T) {
-    const long long c = (long long)blockIdx.x * PC_CELLS + chunk_find(soff, q);
-    const int i = (int)(c % g.nt) + 1, j = (int)((c / g.nt) % g.nt) + 1, k = (int)(c / ((long long)g.nt * g.nt)) + 1;
+    const CellPos cp = spos[chunk_find(soff, q)];
+    const int i = cp.i + 1, j = cp.j + 1, k = cp.k + 1;
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
     int i1, j1, k1; float ax[2], ay[2], az[2];
@@ -94,8 +114,6 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
       const float* f = Gb + ((long long)(k1 + qz[t]) * M + (j1 + qy[t])) * 3 * FP + (i1 + qx[t]);
       f0[t] = __ldg(f); f1[t] = __ldg(f + FP); f2[t] = __ldg(f + 2 * FP);
     }
-#pragma unroll
-    for (int t = 0; t < 8; t++) { f0[t] = kick_prefix(f0[t], a_mid, dt); f1[t] = kick_prefix(f1[t], a_mid, dt); f2[t] = kick_prefix(f2[t], a_mid, dt); }
 #pragma unroll
     for (int t = 0; t < 8; t++) {
       const float wx = ax[qx[t]], wy = ay[qy[t]], wz = az[qz[t]];
@@ -115,16 +133,18 @@ __global__ void __launch_bounds__(PC_T) k_coarse_kick_p(Geom g, const short* __r
                                                        const float* __restrict__ Gc, const double* __restrict__ dvlut,
                                                        const double* __restrict__ enc, double S, unsigned long long* __restrict__ vmax_bits) {
   __shared__ int soff[PC_CELLS + 1];
+  __shared__ CellPos spos[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  chunk_cells(g, c0, g.ncell_p, spos);
   const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
   const long long p0 = cstart_p[c0];
   const int m = g.nc + 2;
   double vm = 0.0;
   for (int q = threadIdx.x; q < np; q += PC_T) {
-    const long long L = c0 + chunk_find(soff, q);
-    int tx, ty, tz, i, j, k;
-    phys_decompose(g, L, tx, ty, tz, i, j, k);
-    const int X = tx * g.nt + i, Y = ty * g.nt + j, Z = tz * g.nt + k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
+    const int cl = chunk_find(soff, q);
+    const long long L = c0 + cl;
+    const CellPos cp = spos[cl];
+    const int X = cp.tx * g.nt + cp.i, Y = cp.ty * g.nt + cp.j, Z = cp.tz * g.nt + cp.k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
     int i1, j1, k1; float ax[2], ay[2], az[2];
@@ -199,6 +219,16 @@ constexpr unsigned RANK_LOST = 0xFFFFFFFFu;
 constexpr int RANK_BITS = 20;
 __device__ __forceinline__ unsigned off_pack12(int dx, int dy, int dz) { return (unsigned)(dx + 8) | ((unsigned)(dy + 8) << 4) | ((unsigned)(dz + 8) << 8); }
 
+// per-source-cell summary of pass A: bit (dx+1)+3(dy+1)+9(dz+1) = "some particle of this cell moves by (dx,dy,dz)",
+// bit 27 = "some particle moves farther than one cell or sits on a cell boundary (near-tie)".  Pass B only walks the
+// particles of a source cell when the bit of the offset it is looking for (or bit 27) is set: at small time steps
+// almost every particle stays in its cell, so 26 of the 27 source cells of a destination are skipped unread.
+constexpr unsigned MASK_FAR = 1u << 27;
+__device__ __forceinline__ unsigned offset_bit(int dx, int dy, int dz) { return 1u << ((dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)); }
+__device__ __forceinline__ unsigned mover_bit(int ox, int oy, int oz, bool tie) {
+  return (tie || max(abs(ox), max(abs(oy), abs(oz))) > 1) ? MASK_FAR : offset_bit(ox, oy, oz);
+}
+
 // destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
 __device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
   double xq = __dadd_rn((double)(cell1 - 1), xp_frac(xp));
@@ -212,17 +242,20 @@ __device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double 
 __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
                                                      const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
                                                      const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
-                                                     unsigned* __restrict__ rank, int* __restrict__ maxoff) {
+                                                     unsigned* __restrict__ rank, int* __restrict__ maxoff, unsigned* __restrict__ mask_s) {
   __shared__ int soff[PC_CELLS + 1];
+  __shared__ unsigned smask[PC_CELLS];
+  __shared__ CellPos spos[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  if (threadIdx.x < PC_CELLS) smask[threadIdx.x] = 0u;
+  chunk_cells(g, c0, g.ncell_p, spos);
   const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
   const long long p0 = cstart_p[c0];
   int m = 0;
   for (int q = threadIdx.x; q < np; q += PC_T) {
-    const long long L = c0 + chunk_find(soff, q);
-    const long long nt = g.nt, nt3 = nt * nt * nt;
-    const long long c = L % nt3;
-    const int i = (int)(c % nt), j = (int)((c / nt) % nt), k = (int)(c / (nt * nt));
+    const int cl = chunk_find(soff, q);
+    const long long L = c0 + cl;
+    const int i = spos[cl].i, j = spos[cl].j, k = spos[cl].k;
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
     const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
@@ -231,12 +264,15 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
     int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
     int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
     m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
+    atomicOr(&smask[cl], mover_bit(ox, oy, oz, tie));
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
     rank[p] = RANK_LOST;  // pass B overwrites it for the one destination cell of this image that accepts the particle
   }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
+  __syncthreads();
+  if (threadIdx.x < PC_CELLS && c0 + threadIdx.x < g.ncell_p) mask_s[c0 + threadIdx.x] = smask[threadIdx.x];
 }
 
 // pass A for the ghost particles received from other images (cube_exchange.cuh): cells in message order,
@@ -244,14 +280,18 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
 __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
                                                      long long base, const short* __restrict__ xp, const short* __restrict__ vp,
                                                      const float* __restrict__ vfield_e, const double* __restrict__ dvlut, double dt_mid,
-                                                     unsigned short* __restrict__ key, unsigned* __restrict__ rank, int* __restrict__ maxoff) {
+                                                     unsigned short* __restrict__ key, unsigned* __restrict__ rank, int* __restrict__ maxoff,
+                                                     unsigned* __restrict__ mask_g) {
   __shared__ int soff[PC_CELLS + 1];
+  __shared__ unsigned smask[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  if (threadIdx.x < PC_CELLS) smask[threadIdx.x] = 0u;
   const int np = chunk_setup(gstart, c0, ng, soff);
   const long long p0 = base + gstart[c0];
   int m = 0;
   for (int q = threadIdx.x; q < np; q += PC_T) {
-    const long long e = gcell_ext[c0 + chunk_find(soff, q)];
+    const int cl = chunk_find(soff, q);
+    const long long e = gcell_ext[c0 + cl];
     const int i = (int)(e % g.ne) - NCB, j = (int)((e / g.ne) % g.ne) - NCB, k = (int)(e / ((long long)g.ne * g.ne)) - NCB;
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
@@ -262,12 +302,22 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, cons
     int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
     // a ghost can only enter from at most ncb cells away; its owner image checks the full offset of the same particle
     m = max(m, min(NCB, max(abs(ox), max(abs(oy), abs(oz)))));
+    atomicOr(&smask[cl], mover_bit(ox, oy, oz, tie));
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
     rank[p] = RANK_LOST;
   }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
+  __syncthreads();
+  if (threadIdx.x < PC_CELLS && c0 + threadIdx.x < ng) mask_g[c0 + threadIdx.x] = smask[threadIdx.x];
+}
+
+// source-cell summaries on the extended grid: sid_e[e] = file-order index of an aliased cell, ncell_p + q of ghost cell q
+__global__ void __launch_bounds__(256) k_mask_ext(long long ncell_e, const int* __restrict__ sid_e, const unsigned* __restrict__ mask_s,
+                                                  unsigned* __restrict__ mask_e) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ncell_e) mask_e[e] = mask_s[sid_e[e]];
 }
 
 // pass B: one thread per destination (physical) cell, file order
@@ -276,7 +326,7 @@ __global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short*
                                                     const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
                                                     const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
                                                     float* __restrict__ vfield_new, unsigned* __restrict__ rank,
-                                                    double* __restrict__ stc_partial) {
+                                                    double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e) {
   const double weight_v = (double)0.1f;  // update_particle.f90:10
   long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double st_c = 0;
@@ -293,8 +343,10 @@ __global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short*
       for (int sj = j - r; sj <= j + r; sj++) {
         long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
         for (int si = i - r; si <= i + r; si++, e++) {
+          const int ddx = i - si, ddy = j - sj, ddz = k - sk;
+          const unsigned need = (max(abs(ddx), max(abs(ddy), abs(ddz))) <= 1 ? offset_bit(ddx, ddy, ddz) : 0u) | MASK_FAR;
+          if (!(mask_e[e] & need)) continue;  // nobody in this source cell comes my way
           const int n = rhoc_e[e];
-          if (n == 0) continue;
           const long long s = cstart_e[e];
           const unsigned want = key_pack(i - si, j - sj, k - sk), o12 = off_pack12(i - si, j - sj, k - sk) << RANK_BITS;
           const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
@@ -385,25 +437,33 @@ __global__ void __launch_bounds__(PC_T) k_drift_place_p(Geom g, const short* __r
                                                        const double* __restrict__ enc, double dt_mid, double S, short* __restrict__ xp_new,
                                                        short* __restrict__ vp_new, double* __restrict__ stat_partial) {
   __shared__ int soff[PC_CELLS + 1];
+  __shared__ CellPos spos[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  chunk_cells(g, c0, g.ncell_p, spos);
   const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
   const long long p0 = cstart_p[c0];
+  const int nt = g.nt, nnt = g.nnt;
   double st_tot = 0, st_res = 0;
   for (int q = threadIdx.x; q < np; q += PC_T) {
     const long long p = p0 + q;
     const unsigned rk = rank[p];
     if (rk == RANK_LOST) continue;
-    const long long L = c0 + chunk_find(soff, q);
-    int tx, ty, tz, i, j, k;
-    phys_decompose(g, L, tx, ty, tz, i, j, k);
+    const int cl = chunk_find(soff, q);
+    const long long L = c0 + cl;
+    const CellPos cp = spos[cl];
     const unsigned o = rk >> RANK_BITS;
-    int X = tx * g.nt + i + (int)(o & 15u) - 8, Y = ty * g.nt + j + (int)((o >> 4) & 15u) - 8, Z = tz * g.nt + k + (int)((o >> 8) & 15u) - 8;
+    // destination = source + offset (|offset| <= ncb < nt): at most one tile step per dimension, no divisions
+    int i = cp.i + (int)(o & 15u) - 8, j = cp.j + (int)((o >> 4) & 15u) - 8, k = cp.k + (int)((o >> 8) & 15u) - 8;
+    int tx = cp.tx, ty = cp.ty, tz = cp.tz;
+    if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
+    if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
+    if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
     // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: an accepted particle stays inside
-    if (g.nn[0] == 1) X = (X + g.nc) % g.nc;
-    if (g.nn[1] == 1) Y = (Y + g.nc) % g.nc;
-    if (g.nn[2] == 1) Z = (Z + g.nc) % g.nc;
-    if ((unsigned)X >= (unsigned)g.nc || (unsigned)Y >= (unsigned)g.nc || (unsigned)Z >= (unsigned)g.nc) continue;
-    const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
+    if (g.nn[0] == 1) tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
+    if (g.nn[1] == 1) ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
+    if (g.nn[2] == 1) tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
+    if ((unsigned)tx >= (unsigned)nnt || (unsigned)ty >= (unsigned)nnt || (unsigned)tz >= (unsigned)nnt) continue;
+    const long long D = phys_index(g, tx, ty, tz, i, j, k);
     drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_p + 3 * L, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
                vp_new, st_tot, st_res);
   }
