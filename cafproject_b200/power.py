@@ -1,0 +1,83 @@
+"""CIC density contrast and (cross) power spectrum of checkpoints: CUBE/utilities/cicpower.f90:70-140 and
+CUBE/utilities/powerspectrum.f90:21-108 (``linear_kbin``), for all images of a run at once.  Analysis utility ("next"
+row f1 of SURVEY.md sec. 8): NumPy, sized for the parity tests' grids; used for the z=0 P(k) gate.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+
+def cic_delta(states, nn, nc, nnt, ng_per_nc=4):
+    """Density contrast ``delta_N`` on the global grid ``ng_global = ng_per_nc*nc*nn`` from the disjoint states
+    (``states[m] = dict(xp int16 (n,3), rhoc (nnt,nnt,nnt,nt,nt,nt))``, image order x fastest).  numpy ``[z][y][x]``."""
+    nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
+    nt = nc // nnt
+    G = [ng_per_nc * nc * n for n in nn]
+    rho = np.zeros(G[2] * G[1] * G[0], np.float64)
+    for m, st in enumerate(states):
+        ic = (m % nn[0], (m // nn[0]) % nn[1], m // (nn[0] * nn[1]))
+        cnt = np.asarray(st["rhoc"]).reshape(-1).astype(np.int64)
+        L = np.repeat(np.arange(cnt.size, dtype=np.int64), cnt)            # file-order cell of every particle
+        nt3 = nt ** 3
+        t, c = L // nt3, L % nt3
+        cell = [(t % nnt) * nt + c % nt, ((t // nnt) % nnt) * nt + (c // nt) % nt, (t // (nnt * nnt)) * nt + c // (nt * nt)]
+        u = np.asarray(st["xp"]).astype(np.int64) & 0xFFFF                 # int(xp+ishift,izipx)+rshift = u + 0.5
+        idx, w = [], []
+        for d in range(3):
+            pos = (cell[d] + ic[d] * nc + (u[:, d] + 0.5) / 65536.0) * ng_per_nc - 0.5     # cicpower.f90:84-85, global
+            i1 = np.floor(pos).astype(np.int64)
+            dx1 = (i1 + 1) - pos
+            idx.append((np.mod(i1, G[d]), np.mod(i1 + 1, G[d])))
+            w.append((dx1, 1.0 - dx1))
+        for qz in (0, 1):
+            for qy in (0, 1):
+                for qx in (0, 1):
+                    flat = (idx[2][qz] * G[1] + idx[1][qy]) * G[0] + idx[0][qx]
+                    rho += np.bincount(flat, weights=w[0][qx] * w[1][qy] * w[2][qz], minlength=rho.size)
+    rho = rho.reshape(G[2], G[1], G[0])
+    return (rho / rho.mean() - 1.0).astype(F32)                            # cicpower.f90:140
+
+
+def cross_power(d1, d2, box):
+    """``xi(10,nbin)`` of powerspectrum.f90:47-108 for two density contrasts on the same (cubic) grid: rows
+    0 count, 1 k [h/Mpc], 2 Delta^2_11, 3 Delta^2_22, 4 Delta^2_12, 5-6 kernels, 7 r, 8 b, 9 reco power."""
+    n = d1.shape[0]
+    assert d1.shape == d2.shape == (n, n, n)
+    nyq = n // 2
+    nbin = int(round(nyq * np.sqrt(3.0)))
+    c1, c2 = np.fft.rfftn(d1.astype(np.float64)), np.fft.rfftn(d2.astype(np.float64))
+    kf = np.mod(np.arange(n) + nyq, n) - nyq                                # mod((/ig,jg,kg/)+nyquest-1,ng_global)-nyquest
+    kx = np.arange(nyq + 1, dtype=np.float64)[None, None, :]
+    ky = kf.astype(np.float64)[None, :, None]
+    kz = kf.astype(np.float64)[:, None, None]
+    kr = np.sqrt(kx ** 2 + ky ** 2 + kz ** 2)
+    keep = np.ones(kr.shape, bool)
+    ig = np.arange(nyq + 1)[None, None, :]; jg = np.arange(n)[None, :, None]; kg = np.arange(n)[:, None, None]
+    edge = (ig == 0) | (ig == nyq)
+    keep &= ~((ig == 0) & (jg == 0) & (kg == 0))                            # powerspectrum.f90:56-58
+    keep &= ~(edge & (jg > nyq))
+    keep &= ~(edge & ((jg == 0) | (jg == nyq)) & (kg > nyq))
+    sinc = np.sinc(kx / n) * np.sinc(ky / n) * np.sinc(kz / n)              # np.sinc(x) = sin(pi x)/(pi x)
+    ibin = np.rint(kr).astype(np.int64)                                      # linear_kbin: ibin=nint(kr)
+    norm = 4 * np.pi * kr ** 3 / float(n) ** 6 / sinc ** 4
+    sel = keep & (ibin >= 1) & (ibin <= nbin)
+    b = ibin[sel] - 1
+    xi = np.zeros((10, nbin))
+    xi[0] = np.bincount(b, minlength=nbin)
+    xi[1] = np.bincount(b, weights=kr[sel], minlength=nbin)
+    xi[2] = np.bincount(b, weights=(c1 * np.conj(c1)).real[sel] * norm[sel], minlength=nbin)
+    xi[3] = np.bincount(b, weights=(c2 * np.conj(c2)).real[sel] * norm[sel], minlength=nbin)
+    xi[4] = np.bincount(b, weights=(c1 * np.conj(c2)).real[sel] * norm[sel], minlength=nbin)
+    xi[5] = np.bincount(b, weights=(1 / sinc ** 2)[sel], minlength=nbin)
+    xi[6] = np.bincount(b, weights=(1 / sinc ** 4)[sel], minlength=nbin)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cnt = xi[0]
+        xi[1] = xi[1] / cnt * (2 * np.pi) / box
+        for r in (2, 3, 4, 5, 6):
+            xi[r] = xi[r] / cnt
+        xi[7] = xi[4] / np.sqrt(xi[2] * xi[3])
+        xi[8] = np.sqrt(xi[3] / xi[2])
+        xi[9] = xi[7] ** 4 / xi[8] ** 2 * xi[3]
+    return xi
