@@ -96,10 +96,16 @@ __device__ __forceinline__ float div_const_rn(float a, float c, float rc) {
   const float e = __fmaf_rn(-c, q0, a);
   return __fmaf_rn(e, rc, q0);
 }
-// F*a_mid*dt/6/pi in the reference's order (pm.f90:104): the per-node prefix of every kick term
+// F*a_mid*dt/6/pi in the reference's order (pm.f90:104): the per-node prefix of every kick term.  One range test covers
+// both divisions: with |t| in [1e-28, 1e28] (or 0) t/6 is still inside div_const_rn's verified range.
 __device__ __forceinline__ float kick_prefix(float F, float a_mid, float dt) {
   const float t = __fmul_rn(__fmul_rn(F, a_mid), dt);
-  return div_const_rn(div_const_rn(t, 6.0f, 1.0f / 6.0f), PI_F, 1.0f / PI_F);
+  const float aa = fabsf(t);
+  if (aa != 0.f && (aa < 1e-28f || aa > 1e28f)) return __fdiv_rn(__fdiv_rn(t, 6.0f), PI_F);
+  const float q0 = __fmul_rn(t, 1.0f / 6.0f);
+  const float q = __fmaf_rn(__fmaf_rn(-6.0f, q0, t), 1.0f / 6.0f, q0);
+  const float r0 = __fmul_rn(q, 1.0f / PI_F);
+  return __fmaf_rn(__fmaf_rn(-PI_F, r0, q), 1.0f / PI_F, r0);
 }
 __device__ __forceinline__ float kick_weight(float G, float wx, float wy, float wz) {
   return __fmul_rn(__fmul_rn(__fmul_rn(G, wx), wy), wz);

@@ -80,6 +80,7 @@ struct cube_handle {
   cube_params p;
   Geom g;
   cudaStream_t st = nullptr;
+  cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false;  // cube_gpu_download_async
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
@@ -454,6 +455,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   h->np_image_max = (long long)((float)np_image * r3 * p->image_buffer);
   h->np_tile_max = (long long)((float)(np_image / ((long long)g.nnt * g.nnt * g.nnt)) * r3 * p->tile_buffer);
   CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
   CK(cudaEventCreate(&h->tev[0])); CK(cudaEventCreate(&h->tev[1]));
   const long long cap = h->np_image_max;
@@ -577,6 +580,8 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cufftHandle plans[] = {h->cplan_r2c, h->cplan_c2r, h->p2d_r2c, h->p2d_c2r, h->pz};
   for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
   for (int i = 0; i < 2 * PH_N; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
+  for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -608,11 +613,27 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
   return 0;
 }
 
+// Start copying xp and/or vp (whichever is not NULL) of the current disjoint state to the host on a second stream, behind
+// everything already queued; returns at once.  Lets the checkpoint's device->host traffic overlap the rest of the step
+// (e.g. xp right after update_x: particle_mesh does not change positions).  cube_gpu_download waits for it.
+extern "C" int cube_gpu_download_async(cube_handle* h, int16_t* xp, int16_t* vp) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaEventRecord(h->ev_copy[0], h->st));
+  CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
+  if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
+  if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
+  CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
+  h->copy_pending = true;
+  return 0;
+}
+
 extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32_t* rhoc_phys, float* vfield_phys,
                                  int64_t* nplocal, float* sigma_vi) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   const Geom& g = h->g;
+  if (h->copy_pending) { CK(cudaEventSynchronize(h->ev_copy[1])); h->copy_pending = false; }
   if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   if (rhoc_phys) CK(cudaMemcpyAsync(rhoc_phys, h->rhoc_p, sizeof(int) * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
@@ -719,6 +740,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("cube_gpu_update_x: state is not buffered (call cube_gpu_buffer first, cafcube.f90:17-19)");
+  if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // an asynchronous download still reads the particle arrays
   const Geom& g = h->g;
   const bool multi = h->nimg > 1;
   const long long ng = h->ex.ng;

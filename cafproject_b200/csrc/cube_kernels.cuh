@@ -229,35 +229,49 @@ __global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int 
     }
   }
   __syncthreads();
-  // spill planes -> neighbour blocks.  Work items are (entry, source) pairs with the source index fastest: conflict-free.
-  for (int e = t; e < 25 * FS_N; e += FD_T) {  // +x: (4,b,c) of S -> (0,b,c) of S+1
-    const int S = e % FS_N, bc = e / FS_N;
-    if (S % FS_X != FS_X - 1) acc[bc * FS_N + S + 1] = __fadd_rn(acc[bc * FS_N + S + 1], acc[(100 + bc) * FS_N + S]);
+  // spill planes -> neighbour blocks: thread t = source cell S hands its planes on, every offset a compile-time constant
+  // (4 instructions per accumulator); consecutive threads touch consecutive banks
+  if (t < FS_N) {
+    float* my = acc + t;
+    if (sx != FS_X - 1) {  // +x: (4,b,c) of S -> (0,b,c) of S+1
+#pragma unroll
+      for (int bc = 0; bc < 25; bc++) my[bc * FS_N + 1] = __fadd_rn(my[bc * FS_N + 1], my[(100 + bc) * FS_N]);
+    }
   }
   __syncthreads();
-  for (int e = t; e < 20 * FS_N; e += FD_T) {  // +y: (a,4,c) of S -> (a,0,c) of S+FS_X, a = 0..3
-    const int S = e % FS_N, ac = e / FS_N, a = ac / 5, c = ac - 5 * a;
-    if ((S / FS_X) % FS_Y != FS_Y - 1)
-      acc[(a * 25 + c) * FS_N + S + FS_X] = __fadd_rn(acc[(a * 25 + c) * FS_N + S + FS_X], acc[(a * 25 + 20 + c) * FS_N + S]);
+  if (t < FS_N && sy != FS_Y - 1) {  // +y: (a,4,c) of S -> (a,0,c) of S+FS_X, a = 0..3
+    float* my = acc + t;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int c = 0; c < 5; c++)
+        my[(a * 25 + c) * FS_N + FS_X] = __fadd_rn(my[(a * 25 + c) * FS_N + FS_X], my[(a * 25 + 20 + c) * FS_N]);
   }
   __syncthreads();
-  for (int e = t; e < 16 * FS_N; e += FD_T) {  // +z: (a,b,4) of S -> (a,b,0) of S+FS_X*FS_Y, a,b = 0..3
-    const int S = e % FS_N, ab = e / FS_N, a = ab >> 2, b = ab & 3;
-    if (S / (FS_X * FS_Y) != FS_Z - 1)
-      acc[(a * 25 + b * 5) * FS_N + S + FS_X * FS_Y] = __fadd_rn(acc[(a * 25 + b * 5) * FS_N + S + FS_X * FS_Y], acc[(a * 25 + b * 5 + 4) * FS_N + S]);
+  if (t < FS_N && sz != FS_Z - 1) {  // +z: (a,b,4) of S -> (a,b,0) of S+FS_X*FS_Y, a,b = 0..3
+    float* my = acc + t;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        my[(a * 25 + b * 5) * FS_N + FS_X * FS_Y] = __fadd_rn(my[(a * 25 + b * 5) * FS_N + FS_X * FS_Y], my[(a * 25 + b * 5 + 4) * FS_N]);
   }
   __syncthreads();
-  // write-out: one 32-float row (8 coarse cells x 4) per warp iteration
+  // write-out: one 32-float row (8 coarse cells x 4 fine cells) per warp and iteration; with 8 warps and 16 fine rows per
+  // z plane the row pattern of a warp is fixed, so all shared-memory offsets are compile-time constants
+  static_assert(FD_T == 256 && FB_X == 8 && FB_Y == 4 && FB_Z == 4, "write-out loop is unrolled for this brick");
   const int lane = t & 31, wp = t >> 5;
   float* out = rho + (long long)blockIdx.y * w.vol;
-  const int ocx = lane >> 2, a = lane & 3;
+  const int ocx = lane >> 2, a = lane & 3, b = wp & 3;
   const int gx = (bx * FB_X + ocx) * 4 + a;
-  for (int row = wp; row < 16 * FB_Y * FB_Z; row += FD_T / 32) {
-    const int fy = row % (4 * FB_Y), fz = row / (4 * FB_Y);
-    const int ocy = fy >> 2, b = fy & 3, ocz = fz >> 2, cc = fz & 3;
+  const float* src = acc + ((a * 5 + b) * 5) * FS_N + (FS_Y + (wp >> 2) + 1) * FS_X + (ocx + 1);  // ocz = 0, ocy = wp>>2, cc = 0
+  const bool okx = gx < w.n;
+#pragma unroll
+  for (int it = 0; it < 32; it++) {  // row = wp + 8*it: fy = wp + 8*(it&1), fz = it>>1
+    const int ocy = (wp >> 2) + 2 * (it & 1), cc = (it >> 1) & 3, ocz = it >> 3;
     const int gy = (by * FB_Y + ocy) * 4 + b, gz = (bz * FB_Z + ocz) * 4 + cc;
-    const int S = ((ocz + 1) * FS_Y + (ocy + 1)) * FS_X + (ocx + 1);
-    if (gx < w.n && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = acc[((a * 5 + b) * 5 + cc) * FS_N + S];
+    const float v = src[cc * FS_N + (ocz * FS_Y + 2 * (it & 1)) * FS_X];
+    if (okx && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = v;
   }
 }
 

@@ -53,6 +53,7 @@ def load_library():
     L.cube_gpu_particle_mesh.argtypes = [vp, f32, f32] + [C.POINTER(f32)] * 4
     L.cube_gpu_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(f32)]
     L.cube_gpu_finalize.argtypes = [vp]
+    L.cube_gpu_download_async.argtypes = [vp, vp, vp]
     L.cube_gpu_last_error.restype = C.c_char_p
     L.cube_gpu_query.restype = i64
     L.cube_gpu_query.argtypes = [vp, C.c_char_p]
@@ -83,7 +84,7 @@ ABI_SYMBOLS = [
     "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
-    "cube_gpu_exchange_plan",
+    "cube_gpu_exchange_plan", "cube_gpu_download_async",
 ]
 
 
@@ -198,9 +199,10 @@ class CubeGPU:
         self.nplocal = n
         self.sigma_vi = F32(sigma_vi)
 
-    def checkpoint(self, out=None):
+    def checkpoint(self, out=None, skip=()):
         """Disjoint state back on the host (what checkpoint.f90 writes).  ``out`` may hold preallocated
-        (e.g. pinned) arrays xp, vp (capacity >= nplocal rows), rhoc, vfield."""
+        (e.g. pinned) arrays xp, vp (capacity >= nplocal rows), rhoc, vfield; names in ``skip`` were already streamed by
+        :meth:`checkpoint_begin` and are only waited for."""
         n = self.query("nplocal")
         shp = (self.nnt,) * 3 + (self.nt,) * 3
         if out is None:
@@ -208,11 +210,18 @@ class CubeGPU:
                        vfield=np.empty(shp + (3,), np.float32))
         assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n
         npl = C.c_int64(); sig = C.c_float()
-        self._ck(self.L.cube_gpu_download(self.h, _p(out["xp"]), _p(out["vp"]), _p(out["rhoc"]), _p(out["vfield"]),
-                                          C.byref(npl), C.byref(sig)))
+        self._ck(self.L.cube_gpu_download(self.h, None if "xp" in skip else _p(out["xp"]), None if "vp" in skip else _p(out["vp"]),
+                                          _p(out["rhoc"]), _p(out["vfield"]), C.byref(npl), C.byref(sig)))
         if out["xp"].shape[0] != n:
             out = dict(out, xp=out["xp"][:n], vp=out["vp"][:n])
         return out, F32(sig.value)
+
+    def checkpoint_begin(self, out, xp=True, vp=False):
+        """Start streaming xp and/or vp of the current disjoint state into ``out`` (page-locked arrays with capacity >=
+        nplocal rows) while later calls run; finish with ``checkpoint(out=out, skip=...)``."""
+        n = self.query("nplocal")
+        assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n
+        self._ck(self.L.cube_gpu_download_async(self.h, _p(out["xp"]) if xp else None, _p(out["vp"]) if vp else None))
 
     # ---- step subroutines -------------------------------------------------------------------
     def update_particle(self, dt_old, dt):

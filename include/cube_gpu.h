@@ -89,6 +89,12 @@ int cube_gpu_particle_mesh(cube_handle *h, float a_mid, float dt, float *dt_fine
 int cube_gpu_download(cube_handle *h, int16_t *xp, int16_t *vp, int32_t *rhoc_phys, float *vfield_phys,
                       int64_t *nplocal, float *sigma_vi);
 
+/* Streamed checkpoint: start the device->host copy of xp and/or vp (NULL = skip) of the current disjoint state behind the
+ * work already queued and return at once; cube_gpu_download (with NULL for what was streamed) waits for it.  Host buffers
+ * should be page-locked.  Typical use: xp right after cube_gpu_update_x -- particle_mesh does not move particles, so the
+ * position traffic of checkpoint.f90:43-50 overlaps the force computation. */
+int cube_gpu_download_async(cube_handle *h, int16_t *xp, int16_t *vp);
+
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);
 

@@ -156,3 +156,30 @@ def test_full_steps(tables):
             assert abs(float(pg[k]) - float(po[k])) <= 1e-4 * abs(float(po[k])), k
         ts.dt_fine, ts.dt_coarse, ts.dt_vmax = po["dt_fine"], po["dt_coarse"], po["dt_vmax"]
     G.close(); O.close()
+
+
+def test_streamed_checkpoint_equals_direct(tables):
+    """cube_gpu_download_async: positions streamed out right after update_particle (while particle_mesh runs) are the
+    positions a plain checkpoint returns at the end of the step."""
+    import torch
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=8, disp_rms=0.6)
+    G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC)
+    G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+    n = states[0]["xp"].shape[0]
+    pin = dict(xp=torch.zeros((n + 64, 3), dtype=torch.int16).pin_memory().numpy(), vp=torch.zeros((n + 64, 3), dtype=torch.int16).pin_memory().numpy(),
+               rhoc=np.empty((NNT,) * 3 + (NC // NNT,) * 3, np.int32), vfield=np.empty((NNT,) * 3 + (NC // NNT,) * 3 + (3,), np.float32))
+    dt, a_mid = np.float32(0.8), np.float32(0.021)
+    G.update_particle(np.float32(0), dt)
+    G.checkpoint_begin(pin, xp=True)
+    G.buffer_density(); G.buffer_x()
+    G.particle_mesh(a_mid, dt)
+    G.buffer_v()
+    streamed, _ = G.checkpoint(out=pin, skip=("xp",))
+    direct, _ = G.checkpoint()
+    for k in ("xp", "vp", "rhoc", "vfield"):
+        assert np.array_equal(streamed[k], direct[k]), k
+    G.update_particle(dt, dt)          # the next drift must not race the finished stream
+    G.close()
