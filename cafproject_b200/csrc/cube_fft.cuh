@@ -193,6 +193,17 @@ struct FftGeom {
   int nbatch;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ void load_tw(float2* tw_s, const float2* __restrict__ tw_g, int N) {
   for (int t = threadIdx.x; t < N; t += blockDim.x) tw_s[t] = tw_g[t];
 }
@@ -217,13 +228,15 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom 
     const int y = y0 + r;
     const int l = r >> 1, im = r & 1;
     float* dst = reinterpret_cast<float*>(s) + im;
-    if (y < N) {
+    if (y < N) {  // asynchronous copies: every load of the CTA is in flight at once (the pass was bound by global-load latency)
       const float* row = src + (size_t)y * N;
-      for (int x = lane; x < N; x += 32) dst[(x * LW + l) * 2] = row[x];
+      for (int x = lane; x < N; x += 32) cp_async4(&dst[(x * LW + l) * 2], row + x);
     } else {
       for (int x = lane; x < N; x += 32) dst[(x * LW + l) * 2] = 0.f;
     }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const int line = tid % FL, idx = tid / FL;
   fft_step_a<R1, R2, -1, LW>(s, tw, line, idx);
@@ -269,9 +282,15 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_y(FftGeom g, f
   load_tw(tw, tw_g, N);
   float2* base = A + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (size_t)N * g.P + kx;
   const bool act = kx < g.NH;
-  if (act) {
-#pragma unroll 4
-    for (int n = idx; n < N; n += NT / FL) s[n * LW + line] = base[(size_t)n * g.P];
+  {  // all N x 16 elements as 16-byte asynchronous copies issued at once (rows of A are 16-byte aligned: P, kx0 multiples of 16)
+    const int kx0 = blockIdx.x * FL;
+    const float2* src = base - line;
+    for (int e = tid; e < N * (FL / 2); e += NT) {
+      const int n = e / (FL / 2), pr = e - n * (FL / 2);
+      if (kx0 + 2 * pr < g.NH) cp_async16(s + n * LW + 2 * pr, src + (size_t)n * g.P + 2 * pr);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
   }
   __syncthreads();
   if (act) fft_step_a<R1, R2, DIR, LW>(s, tw, line, idx);
@@ -295,12 +314,6 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_y(FftGeom g, f
 // current tile is transformed.  K is kept in shared memory for kz <= N/2 only: K_d(N-kz) = +-K_d(kz) (odd in its
 // own axis, even in the others: kernel_f.f90:32-38 mirrors the table that way).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
 template <int R1, int R2>
 __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 : 1)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,

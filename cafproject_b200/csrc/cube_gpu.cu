@@ -103,6 +103,8 @@ struct cube_handle {
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
+  float *tanh = nullptr, *thrf = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
+  int nsm = 1;
   // fine mesh (cube_fft.cuh)
   int batch = 1;
   bool fused2d = false;
@@ -173,10 +175,17 @@ static int scan_counts(cube_handle* h, const int* in, long long n, long long* ou
 
 static int build_dvlut(cube_handle* h, float sigma) {
   if (h->lut_sigma == sigma) return 0;
-  k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, vscale(sigma), h->dvlut); CKL();
+  CK(cudaMemsetAsync(h->divok, 0xff, sizeof(int), h->st));  // cleared by the kernel if the FMA division misses t/S anywhere
+  k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, vscale(sigma), 1.0 / vscale(sigma), h->dvlut, h->divok); CKL();
   h->launches++;
   h->lut_sigma = sigma;
   return 0;
+}
+static VTab vtab(const cube_handle* h) { return VTab{h->tanh, h->thrf, h->enc, h->dvlut, h->divok, h->vt_hot}; }
+// one 1024-thread CTA per SM, fewer when there are not enough warp chunks
+static unsigned pw_grid(const cube_handle* h, long long ncells) {
+  const long long nwc = (ncells + WC - 1) / WC;
+  return (unsigned)std::max<long long>(1, std::min<long long>(h->nsm, (nwc + PW_W - 1) / PW_W));
 }
 
 extern "C" const char* cube_gpu_last_error(void) { return g_err.c_str(); }
@@ -481,13 +490,32 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->sid_e, g.ncell_e)); CK(dmalloc(&h->mask_e, g.ncell_e)); CK(dmalloc(&h->mask_s, g.ncell_p + h->ex.ng));
   h->nscan_blocks = (int)((std::max(g.ncell_p, h->ex.ng) + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
-  CK(dmalloc(&h->stat_partial, 2 * (long long)nblk(g.ncell_p, PC_CELLS) + (long long)nblk(g.ncell_p, 128))); CK(dmalloc(&h->stat3, 8));
+  CK(dmalloc(&h->stat_partial, std::max<long long>(2 * 4096 * PW_W, (long long)nblk(g.ncell_p, 128)))); CK(dmalloc(&h->stat3, 8));
   CK(dmalloc(&h->rank, cap));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
   CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
+  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->thrf, 32768)); CK(dmalloc(&h->divok, 1));
   k_build_enc<<<128, 256, 0, h->st>>>(h->enc); CKL();
+  k_build_thrf<<<128, 256, 0, h->st>>>(h->enc, h->thrf); CKL();
   CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+  {
+    // half table for shared memory: index = |code|.  tanf_lut is indexed by the code's 16-bit pattern, so -c sits at 65536-c.
+    // The host tanf must be odd for this (glibc's is); if it is not, hot = 0 sends every lookup to the full global tables.
+    std::vector<float> half(32772, 0.f);
+    bool odd = true;
+    for (int c = 0; c <= 32767; c++) half[c] = tanf_lut[c];
+    half[32768] = -tanf_lut[32768];
+    for (int c = 1; c <= 32767; c++) { const float neg = -tanf_lut[65536 - c]; if (memcmp(&neg, &tanf_lut[c], 4) != 0) { odd = false; break; } }
+    if (tanf_lut[0] != 0.f || std::signbit(tanf_lut[0])) odd = false;
+    h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? VT_HOT : 0;
+    CK(cudaMemcpyAsync(h->tanh, half.data(), 32772 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
+    h->nsm = prop.multiProcessorCount;
+    CK(cudaFuncSetAttribute((const void*)k_drift_place_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
+    CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
+  }
   // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
   const int ntile = g.nnt * g.nnt * g.nnt;
   {
@@ -570,7 +598,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->thrf, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -753,10 +781,10 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   CK(cudaMemcpyAsync(tc.data(), h->tile_count, sizeof(long long) * ntile, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemsetAsync(h->maxoff, 0, sizeof(int), h->st));
   int maxoff = 0;
-  const unsigned nchunk = nblk(g.ncell_p, PC_CELLS), nchunk_g = nblk(ng, PC_CELLS);
+  const unsigned npw = pw_grid(h, g.ncell_p), nchunk_g = nblk(ng, PC_CELLS);
   {
     PhaseTimer pt(h, PH_KEY);
-    k_drift_key_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff, h->mask_s); CKL();
+    k_drift_key_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff, h->mask_s); CKL();
     h->launches++;
     if (multi && ng) {
       k_drift_key_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->vfield_e, h->dvlut, dt_mid, h->key,
@@ -815,10 +843,10 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   }
   if (!status) {
     PhaseTimer pt(h, PH_PLACE);
-    k_drift_place_p<<<nchunk, PC_T, 0, h->st>>>(g, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2, h->dvlut, h->enc,
-                                               dt_mid, S, h->xp2, h->vp2, h->stat_partial); CKL();
-    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 0, h->stat3); CKL();
-    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)nchunk, 2, 1, h->stat3 + 2); CKL();
+    k_drift_place_w<<<npw, PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), S, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2,
+                                                       dt_mid, h->xp2, h->vp2, h->stat_partial); CKL();
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 0, h->stat3); CKL();
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 1, h->stat3 + 2); CKL();
     h->launches += 3;
     double stg[2] = {0, 0};
     if (multi && ng) {
@@ -1004,8 +1032,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
       h->launches++;
     }
     PhaseTimer pt(h, PH_FKICK);
-    dim3 grid(nblk(nt3, PC_CELLS), nb);
-    k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
+    k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
     h->launches++;
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
@@ -1015,8 +1042,8 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   {
     PhaseTimer pt(h, PH_CKICK);
     CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
-    k_coarse_kick_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->dvlut, h->enc,
-                                                                  vscale(h->sigma_vi), h->vmax_bits); CKL();
+    k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), vscale(h->sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
+                                                                         h->vmax_bits); CKL();
     h->launches++;
     CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
@@ -1126,9 +1153,8 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   FftGeom f1 = h->fg; f1.nbatch = 1;
   k_f2max_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, h->f2max); CKL();
   CK(cudaMemcpyAsync(&f2, h->f2max, sizeof(float), cudaMemcpyDeviceToHost, h->st));
-  dim3 grid(nblk(nt3, PC_CELLS), 1);
   k_prefix_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, a_mid, dt); CKL();
-  k_fine_kick_p<<<grid, PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new)); CKL();
+  k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), 1), PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new)); CKL();
   CK(cudaStreamSynchronize(h->st));
   cudaFree(tmp);
   if (f2_max) *f2_max = f2;
@@ -1166,8 +1192,8 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
   k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
-  k_coarse_kick_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->dvlut, h->enc,
-                                                                vscale(sigma_vi), h->vmax_bits); CKL();
+  k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), vscale(sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
+                                                                       h->vmax_bits); CKL();
   float f2c = 0; unsigned long long vb = 0;
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));

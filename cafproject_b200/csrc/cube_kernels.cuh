@@ -125,9 +125,16 @@ __global__ void __launch_bounds__(256) k_tile_counts(Geom g, const int* __restri
 }
 
 // dv table: dble(tan((pi*real(vp))/real(nvbin-1))) / (sqrt(pi/2)/(sigma_vi*vrel_boost))
-__global__ void k_build_dvlut(const float* __restrict__ tanlut, double S, double* __restrict__ dvlut) {
+// Also checks, entry by entry, that t/S equals its FMA form q0 = t*rS, q = fma(fma(-S,q0,t), rS, q0) (rS = 1/S): the
+// particle kernels then divide that way (cube_particles.cuh, v_decode); *divok is cleared on any mismatch.
+__global__ void k_build_dvlut(const float* __restrict__ tanlut, double S, double rS, double* __restrict__ dvlut, int* __restrict__ divok) {
   int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u < 65536) dvlut[u] = (double)tanlut[u] / S;
+  if (u >= 65536) return;
+  const double t = (double)tanlut[u], q = t / S;
+  dvlut[u] = q;
+  const double q0 = __dmul_rn(t, rS);
+  const double qf = __fma_rn(__fma_rn(-S, q0, t), rS, q0);
+  if (__double_as_longlong(qf) != __double_as_longlong(q)) atomicExch(divok, 0);
 }
 
 // fixed-order final reduction of per-block partial sums (3 interleaved series)
@@ -291,43 +298,6 @@ __global__ void __launch_bounds__(256) k_green(long long nk, int nbatch, const f
   }
 }
 
-// fine kick (pm.f90:88-118): one thread per physical coarse cell of the tile.
-// F[b][z'][y'][d][x'] holds force_f(d, nfb-1+x'+1, ...) on the M=nft+2 kept points, x' pitch FP.
-__global__ void __launch_bounds__(128) k_fine_kick(Geom g, int tile0, int M, int FP, const short* __restrict__ xp, short* __restrict__ vp,
-                                                   const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
-                                                   const float* __restrict__ F, const double* __restrict__ dvlut, double S_new,
-                                                   float a_mid, float dt) {
-  const long long nt3 = (long long)g.nt * g.nt * g.nt;
-  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nt3) return;
-  const int b = blockIdx.y;
-  const long long L = (long long)(tile0 + b) * nt3 + c;
-  const int n = rhoc_p[L];
-  if (n == 0) return;
-  const int i = (int)(c % g.nt) + 1, j = (int)((c / g.nt) % g.nt) + 1, k = (int)(c / ((long long)g.nt * g.nt)) + 1;
-  const long long s = cstart_p[L];
-  const float* Fb = F + (long long)b * M * M * 3 * FP;
-  for (int l = 0; l < n; l++) {
-    Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
-    int i1, j1, k1; float ax[2], ay[2], az[2];
-    cic_split(fine_tempx(i, xc.x), i1, ax[0], ax[1]);  // i1 = idx1 of pm.f90:96 = 0-based kept index
-    cic_split(fine_tempx(j, xc.y), j1, ay[0], ay[1]);
-    cic_split(fine_tempx(k, xc.z), k1, az[0], az[1]);
-    double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
-    // corner order of pm.f90:104-111
-    const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const float* f = Fb + ((long long)(k1 + qz[q]) * M + (j1 + qy[q])) * 3 * FP + (i1 + qx[q]);
-      const float wx = ax[qx[q]], wy = ay[qy[q]], wz = az[qz[q]];
-      v0 = __dadd_rn(v0, (double)kick_term(__ldg(f), a_mid, dt, wx, wy, wz));
-      v1 = __dadd_rn(v1, (double)kick_term(__ldg(f + FP), a_mid, dt, wx, wy, wz));
-      v2 = __dadd_rn(v2, (double)kick_term(__ldg(f + 2 * FP), a_mid, dt, wx, wy, wz));
-    }
-    store_code3(vp, s + l, vp_encode(v0, S_new), vp_encode(v1, S_new), vp_encode(v2, S_new));
-  }
-}
-
 // force_f(3,nft+2,nft+2,nft+2) [z][y][x][3] <-> F[z'][y'][d][x'] of batch slot 0 (diagnostics only)
 __global__ void k_force_to_ref(int M, int FP, const float* __restrict__ F, float* __restrict__ out) {
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,49 +404,6 @@ __global__ void __launch_bounds__(256) k_f2max_aos(long long n, const float* __r
   }
   best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
   if ((threadIdx.x & 31) == 0) atomicMax(f2max, __float_as_uint(best));
-}
-
-// coarse kick (pm.f90:196-228): one thread per physical coarse cell, image-local coordinates
-__global__ void __launch_bounds__(128) k_coarse_kick(Geom g, const short* __restrict__ xp, short* __restrict__ vp,
-                                                     const int* __restrict__ rhoc_p, const long long* __restrict__ cstart_p,
-                                                     const float* __restrict__ vfield_p, const float* __restrict__ fc,
-                                                     const double* __restrict__ dvlut, double S, float a_mid, float dt,
-                                                     unsigned long long* __restrict__ vmax_bits) {
-  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double vm = 0.0;
-  if (L < g.ncell_p) {
-    const int n = rhoc_p[L];
-    if (n) {
-      int tx, ty, tz, i, j, k;
-      phys_decompose(g, L, tx, ty, tz, i, j, k);
-      const int X = tx * g.nt + i, Y = ty * g.nt + j, Z = tz * g.nt + k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
-      const long long s = cstart_p[L];
-      const int m = g.nc + 2;
-      const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
-      for (int l = 0; l < n; l++) {
-        Code3 xc = load_code3(xp, s + l), vc = load_code3(vp, s + l);
-        int i1, j1, k1; float ax[2], ay[2], az[2];
-        cic_split(coarse_tempx(X, xc.x), i1, ax[0], ax[1]);
-        cic_split(coarse_tempx(Y, xc.y), j1, ay[0], ay[1]);
-        cic_split(coarse_tempx(Z, xc.z), k1, az[0], az[1]);
-        double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
-        const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const float* f = fc + 3 * (((long long)(k1 + qz[q]) * m + (j1 + qy[q])) * m + (i1 + qx[q]));
-          const float wx = ax[qx[q]], wy = ay[qy[q]], wz = az[qz[q]];
-          v0 = __dadd_rn(v0, (double)kick_term(__ldg(f), a_mid, dt, wx, wy, wz));
-          v1 = __dadd_rn(v1, (double)kick_term(__ldg(f + 1), a_mid, dt, wx, wy, wz));
-          v2 = __dadd_rn(v2, (double)kick_term(__ldg(f + 2), a_mid, dt, wx, wy, wz));
-        }
-        // vmax=max(vmax,maxval(vreal+vfield(:,i,j,k,...)))  (no abs, pm.f90:220)
-        vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));
-        store_code3(vp, s + l, vp_encode(v0, S), vp_encode(v1, S), vp_encode(v2, S));
-      }
-    }
-  }
-  for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(0xffffffffu, vm, o));
-  if ((threadIdx.x & 31) == 0 && vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
 }
 
 // =============================================================================================

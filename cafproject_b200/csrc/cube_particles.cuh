@@ -9,8 +9,8 @@
 
 namespace cube {
 
-constexpr int PC_CELLS = 128;  // file-order coarse cells per CTA
-constexpr int PC_T = 256;      // threads per CTA
+constexpr int PC_CELLS = 128;  // file-order coarse cells per CTA (ghost-particle kernels)
+constexpr int PC_T = 256;      // threads per CTA (ghost-particle kernels)
 
 // prefix offsets of the CTA's cells relative to its first particle; cstart has ncell+1 entries (sentinel = total)
 __device__ __forceinline__ int chunk_setup(const long long* __restrict__ cstart, long long c0, long long ncell, int* soff) {
@@ -29,21 +29,6 @@ __device__ __forceinline__ int chunk_find(const int* soff, int q) {
   for (int step = PC_CELLS / 2; step > 0; step >>= 1)
     if (soff[lo + step] <= q) lo += step;
   return lo;
-}
-
-// tile and tile-local coordinates of the CTA's cells, worked out once per cell (the integer divisions of phys_decompose
-// cost more than the rest of a particle's index arithmetic when they are redone per particle)
-struct CellPos { short tx, ty, tz, i, j, k; };
-__device__ __forceinline__ void chunk_cells(const Geom& g, long long c0, long long ncell, CellPos* sp) {
-  for (int t = threadIdx.x; t < PC_CELLS; t += blockDim.x) {
-    CellPos q = {0, 0, 0, 0, 0, 0};
-    if (c0 + t < ncell) {
-      int tx, ty, tz, i, j, k;
-      phys_decompose(g, c0 + t, tx, ty, tz, i, j, k);
-      q.tx = (short)tx; q.ty = (short)ty; q.tz = (short)tz; q.i = (short)i; q.j = (short)j; q.k = (short)k;
-    }
-    sp[t] = q;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,22 +50,154 @@ __global__ void k_build_enc(double* __restrict__ B) {
   }
   B[c] = __longlong_as_double((long long)hi);
 }
-// nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86)
-__device__ __forceinline__ short vp_encode_lut(double v, double S, const double* __restrict__ B) {
-  const double X = __dmul_rn(S, v);
-  const double a = fabs(X);
-  int c = __float2int_rn(atanf((float)a) * (65535.0f / PI_F));
-  c = min(max(c, 0), 32767);
+// the thresholds rounded DOWN to f32 (shared-memory copy of the encoder, see v_encode)
+__global__ void k_build_thrf(const double* __restrict__ B, float* __restrict__ Bf) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= 32767) Bf[c] = __double2float_rd(B[c]);
+}
+// code of a = |S*v| from a guess c that is at most a few codes off, with the exact thresholds
+__device__ __forceinline__ int enc_refine(double a, int c, const double* __restrict__ B) {
   // the f32 guess is within one code of the answer: fetch both neighbouring thresholds at once (two independent loads
   // instead of a chain of dependent ones); the loops only run on if the guess was farther off
   const double t0 = __ldg(B + c), tm = __ldg(B + max(c - 1, 0));
   if (c < 32767 && a >= t0) { c++; while (c < 32767 && a >= __ldg(B + c)) c++; }
   else if (c > 0 && a < tm) { c--; while (c > 0 && a < __ldg(B + c - 1)) c--; }
+  return c;
+}
+__device__ __forceinline__ int enc_guess(double a) {
+  return min(max(__float2int_rn(atanf((float)a) * (65535.0f / PI_F)), 0), 32767);
+}
+// nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86), tables in global memory
+__device__ __forceinline__ short vp_encode_lut(double v, double S, const double* __restrict__ B) {
+  const double X = __dmul_rn(S, v);
+  const double a = fabs(X);
+  const int c = enc_refine(a, enc_guess(a), B);
   return (short)(X < 0.0 ? -c : c);
+}
+
+// =============================================================================================
+// Velocity-code tables in SHARED memory.
+// The particle kernels were bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 77-90 % of peak,
+// profiles/r01h_ncu_full_cfg1.csv): every decode/encode gathered from the 512 KB f64 tables in global memory, ~23
+// wavefronts per warp-wide gather.  A random 4-byte gather from shared memory costs ~3.  So the drift's placement pass and
+// the coarse kick run one 1024-thread CTA per SM, keep the "hot" part of both tables in shared memory as f32 and stay
+// bit-identical (measured at cfg 2: place 5.4 -> 3.6 ms, coarse kick 4.5 -> 3.3 ms; the key pass and the fine kick, which
+// need the L1 cache that 221 KB of shared memory takes away, are faster in the small-CTA form and keep it):
+//   decode  dv = dble(tanf(pi*vp/N)) / S : s_tan[|vp|] is the host tanf table (odd: checked at init) for |vp| < VT_HOT,
+//           the f64 division is done as q0 = t*rS, q = fma(fma(-S,q0,t), rS, q0) with rS = 1/S, which k_build_dvlut
+//           checks against t/S for every table entry each time S changes (vt.divok; else a true division);
+//   encode  the exact f64 thresholds T[c] are compared through Tf[c] = T[c] rounded down to f32 and af = a rounded down:
+//           af > Tf => a >= T, af < Tf => a < T, af == Tf (probability ~1e-7) => the exact table in global memory;
+//   codes at or beyond VT_HOT (|v| > 4.8 sigma) use the global f64 tables.
+// A warp owns WC consecutive cells of the file order at a time (their particles are one contiguous run): warp-private
+// prefix offsets, no block barriers after the table fill.
+// =============================================================================================
+constexpr int VT_HOT = 24576;
+constexpr int WC = 32;         // cells per warp chunk
+constexpr int PW_T = 1024;     // threads per CTA
+constexpr int PW_W = PW_T / 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct VTab {
+  const float* tanh;    // [32769] host tanf of codes 0..32768 (tanh[32768] = -tanf(code -32768))
+  const float* thrf;    // [32768] encoder thresholds rounded down to f32
+  const double* thr;    // [32768] exact encoder thresholds
+  const double* dvlut;  // [65536] f64 decode table of the current S
+  const int* divok;     // != 0: the FMA division reproduces t/S for every table entry (current S)
+  int hot;              // VT_HOT, or 0 when the host tanf table is not odd (everything takes the global tables)
+};
+
+// tile and tile-local coordinates of a warp's cells, worked out once per cell
+struct CellPos { short tx, ty, tz, i, j, k, tile, pad; };
+struct WarpScratch { int soff[WC + 1]; unsigned mask[WC]; CellPos pos[WC]; };
+constexpr int PW_SMEM_FULL = 2 * VT_HOT * 4 + PW_W * (int)sizeof(WarpScratch);  // decode + encode
+
+__device__ __forceinline__ void fill_tab(float* dst, const float* __restrict__ src, int n) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+struct VDec { const float* s_tan; const double* dvlut; double S, rS; int hot, fast; };
+__device__ __forceinline__ VDec make_dec(const VTab& vt, const float* s_tan, double S) {
+  VDec d; d.s_tan = s_tan; d.dvlut = vt.dvlut; d.S = S; d.rS = 1.0 / S; d.hot = vt.hot; d.fast = *vt.divok;
+  return d;
+}
+__device__ __forceinline__ double v_decode(const VDec& d, short c) {
+  const int a = abs((int)c);
+  if (a < d.hot) {
+    const float t = d.s_tan[a];
+    const double td = (double)(c < 0 ? -t : t);
+    if (d.fast) { const double q0 = __dmul_rn(td, d.rS); return __fma_rn(__fma_rn(-d.S, q0, td), d.rS, q0); }
+    return __ddiv_rn(td, d.S);
+  }
+  return __ldg(d.dvlut + (unsigned short)c);
+}
+struct VEnc { const float* s_thr; const double* thr; double S; int hot; };
+__device__ __forceinline__ short v_encode(const VEnc& e, double v) {
+  const double X = __dmul_rn(e.S, v);
+  const double a = fabs(X);
+  int c = enc_guess(a);
+  bool done = false;
+  if (c < e.hot) {
+    const float af = __double2float_rd(a);
+    const float t0 = e.s_thr[c], tm = e.s_thr[max(c - 1, 0)];
+    if (af != t0 && (c == 0 || af != tm)) { c += (int)(af > t0) - (int)(c > 0 && af < tm); done = true; }
+  }
+  if (!done) c = enc_refine(a, c, e.thr);
+  return (short)(X < 0.0 ? -c : c);
+}
+
+// prefix offsets and coordinates of the warp's cells [c0, c0+WC) (clipped at cend); returns the number of particles,
+// p0 = index of the first one.  cstart[cend] must be readable (next cell's start or the sentinel).
+__device__ __forceinline__ int warp_chunk_setup(const Geom& g, const long long* __restrict__ cstart, long long c0, long long cend,
+                                                WarpScratch* ws, int lane, long long& p0) {
+  const long long c = c0 + lane < cend ? c0 + lane : cend;
+  const long long cs = cstart[c];
+  const long long ce = cstart[c0 + WC < cend ? c0 + WC : cend];
+  p0 = __shfl_sync(FULL, cs, 0);
+  __syncwarp();  // the previous chunk's readers are done
+  ws->soff[lane] = (int)(cs - p0);
+  if (lane == 0) ws->soff[WC] = (int)(ce - p0);
+  ws->mask[lane] = 0u;
+  CellPos q = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 + lane < cend) {
+    int tx, ty, tz, i, j, k;
+    phys_decompose(g, c0 + lane, tx, ty, tz, i, j, k);
+    q.tx = (short)tx; q.ty = (short)ty; q.tz = (short)tz; q.i = (short)i; q.j = (short)j; q.k = (short)k;
+    q.tile = (short)((tz * g.nnt + ty) * g.nnt + tx);
+  }
+  ws->pos[lane] = q;
+  __syncwarp();
+  return (int)(ce - p0);
+}
+// cell (0..WC-1) of particle q of the chunk: largest c with soff[c] <= q
+__device__ __forceinline__ int warp_chunk_find(const WarpScratch* ws, int q) {
+  int lo = 0;
+#pragma unroll
+  for (int step = WC / 2; step > 0; step >>= 1)
+    if (ws->soff[lo + step] <= q) lo += step;
+  return lo;
+}
+
+// tile and tile-local coordinates of the CTA's cells, worked out once per cell (the integer divisions of phys_decompose
+// cost more than the rest of a particle's index arithmetic when they are redone per particle)
+__device__ __forceinline__ void chunk_cells(const Geom& g, long long c0, long long ncell, CellPos* sp) {
+  for (int t = threadIdx.x; t < PC_CELLS; t += blockDim.x) {
+    CellPos q = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 + t < ncell) {
+      int tx, ty, tz, i, j, k;
+      phys_decompose(g, c0 + t, tx, ty, tz, i, j, k);
+      q.tx = (short)tx; q.ty = (short)ty; q.tz = (short)tz; q.i = (short)i; q.j = (short)j; q.k = (short)k;
+    }
+    sp[t] = q;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // fine kick (pm.f90:88-118) for the tiles [tile0, tile0+nb): grid = (chunks per tile, nb)
+// Stays on the small-CTA / global-table form: its 24 force gathers per particle live off the L1 cache, and the 221 KB of
+// shared-memory tables of the warp kernels leave 28 KB of L1 (measured: 10.8 ms against 5.2 ms at cfg 2).
 // G[b][z'][y'][d][x'] = force_f*a_mid*dt/6/pi (the per-node prefix of every kick term, applied once per mesh node in
 // the epilogue of the x inverse, cube_fft.cuh) on the M kept points
 // ---------------------------------------------------------------------------------------------
@@ -128,45 +245,51 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
 // ---------------------------------------------------------------------------------------------
 // coarse kick (pm.f90:196-228); Gc(3,0:nc+1,0:nc+1,0:nc+1) = kick_prefix(force_c), vmax over v+vfield (no abs)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PC_T) k_coarse_kick_p(Geom g, const short* __restrict__ xp, short* __restrict__ vp,
-                                                       const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
-                                                       const float* __restrict__ Gc, const double* __restrict__ dvlut,
-                                                       const double* __restrict__ enc, double S, unsigned long long* __restrict__ vmax_bits) {
-  __shared__ int soff[PC_CELLS + 1];
-  __shared__ CellPos spos[PC_CELLS];
-  const long long c0 = (long long)blockIdx.x * PC_CELLS;
-  chunk_cells(g, c0, g.ncell_p, spos);
-  const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
-  const long long p0 = cstart_p[c0];
+__global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, double S, const short* __restrict__ xp, short* __restrict__ vp,
+                                                          const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
+                                                          const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits) {
+  extern __shared__ __align__(16) unsigned char pw_smem[];
+  float* s_tan = reinterpret_cast<float*>(pw_smem);
+  float* s_thr = s_tan + VT_HOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + 2 * VT_HOT * 4) + warp;
+  if (vt.hot) { fill_tab(s_tan, vt.tanh, VT_HOT); fill_tab(s_thr, vt.thrf, VT_HOT); }
+  const VDec dec = make_dec(vt, s_tan, S);
+  const VEnc enc = {s_thr, vt.thr, S, vt.hot};
+  __syncthreads();
   const int m = g.nc + 2;
   double vm = 0.0;
-  for (int q = threadIdx.x; q < np; q += PC_T) {
-    const int cl = chunk_find(soff, q);
-    const long long L = c0 + cl;
-    const CellPos cp = spos[cl];
-    const int X = cp.tx * g.nt + cp.i, Y = cp.ty * g.nt + cp.j, Z = cp.tz * g.nt + cp.k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
-    const long long p = p0 + q;
-    const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
-    int i1, j1, k1; float ax[2], ay[2], az[2];
-    cic_split(coarse_tempx(X, xc.x), i1, ax[0], ax[1]);
-    cic_split(coarse_tempx(Y, xc.y), j1, ay[0], ay[1]);
-    cic_split(coarse_tempx(Z, xc.z), k1, az[0], az[1]);
-    double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
-    const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
+  for (long long c0 = ((long long)blockIdx.x * PW_W + warp) * WC; c0 < g.ncell_p; c0 += (long long)gridDim.x * PW_W * WC) {
+    long long p0;
+    const int np = warp_chunk_setup(g, cstart_p, c0, g.ncell_p, ws, lane, p0);
+    for (int q = lane; q < np; q += 32) {
+      const int cl = warp_chunk_find(ws, q);
+      const long long L = c0 + cl;
+      const CellPos cp = ws->pos[cl];
+      const int X = cp.tx * g.nt + cp.i, Y = cp.ty * g.nt + cp.j, Z = cp.tz * g.nt + cp.k;  // ((itx-1)*nt + (i-1)) of pm.f90:206
+      const long long p = p0 + q;
+      const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
+      int i1, j1, k1; float ax[2], ay[2], az[2];
+      cic_split(coarse_tempx(X, xc.x), i1, ax[0], ax[1]);
+      cic_split(coarse_tempx(Y, xc.y), j1, ay[0], ay[1]);
+      cic_split(coarse_tempx(Z, xc.z), k1, az[0], az[1]);
+      double v0 = v_decode(dec, vc.x), v1 = v_decode(dec, vc.y), v2 = v_decode(dec, vc.z);
+      const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const float* f = Gc + 3 * (((long long)(k1 + qz[t]) * m + (j1 + qy[t])) * m + (i1 + qx[t]));
-      const float wx = ax[qx[t]], wy = ay[qy[t]], wz = az[qz[t]];
-      v0 = __dadd_rn(v0, (double)kick_weight(__ldg(f), wx, wy, wz));
-      v1 = __dadd_rn(v1, (double)kick_weight(__ldg(f + 1), wx, wy, wz));
-      v2 = __dadd_rn(v2, (double)kick_weight(__ldg(f + 2), wx, wy, wz));
+      for (int t = 0; t < 8; t++) {
+        const float* f = Gc + 3 * (((long long)(k1 + qz[t]) * m + (j1 + qy[t])) * m + (i1 + qx[t]));
+        const float wx = ax[qx[t]], wy = ay[qy[t]], wz = az[qz[t]];
+        v0 = __dadd_rn(v0, (double)kick_weight(__ldg(f), wx, wy, wz));
+        v1 = __dadd_rn(v1, (double)kick_weight(__ldg(f + 1), wx, wy, wz));
+        v2 = __dadd_rn(v2, (double)kick_weight(__ldg(f + 2), wx, wy, wz));
+      }
+      const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
+      vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));  // pm.f90:220
+      store_code3(vp, p, v_encode(enc, v0), v_encode(enc, v1), v_encode(enc, v2));
     }
-    const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
-    vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));  // pm.f90:220
-    store_code3(vp, p, vp_encode_lut(v0, S, enc), vp_encode_lut(v1, S, enc), vp_encode_lut(v2, S, enc));
   }
-  for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(0xffffffffu, vm, o));
-  if ((threadIdx.x & 31) == 0 && vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
+  for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(FULL, vm, o));
+  if (lane == 0 && vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
 }
 
 // force_c(3,0:nc+1,...) from the three inverse transforms + periodic 1-cell halo (pm.f90:176-189, single image),
@@ -208,7 +331,7 @@ __global__ void __launch_bounds__(256) k_force_c_prefix(long long n, float* __re
 //   B  k_drift_count    per destination cell: visits its source cells in the reference's traversal order
 //                       (tile-local k,j,i, then storage order), counts, chains vfield_new (order-dependent f32
 //                       rounding, update_particle.f90:47), and writes every accepted particle's rank in its cell
-//   C  k_drift_place_p  per particle : pos = cstart_new[dest] + rank ; xp_new, vp_new, velocity statistics
+//   C  k_drift_place_w  per particle : pos = cstart_new[dest] + rank ; xp_new, vp_new, velocity statistics
 // Near-tie particles (flagged in A) are decided in B in the destination tile's frame, like the reference.
 // rank[p] = rank in the destination cell (20 bits) | destination offset (3 x 4 bits, biased by 8) << 20; A presets
 // 0xFFFFFFFF for flagged particles so that one no destination accepts is dropped, as the reference would.
@@ -429,45 +552,76 @@ __device__ __forceinline__ void block_sum2(double a, double b, double* __restric
   }
 }
 
-// pass C: one thread per particle; single image: destinations wrap periodically
-__global__ void __launch_bounds__(PC_T) k_drift_place_p(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                       const unsigned* __restrict__ rank, const long long* __restrict__ cstart_p,
-                                                       const float* __restrict__ vfield_p, const long long* __restrict__ cstart_new,
-                                                       const float* __restrict__ vfield_new, const double* __restrict__ dvlut,
-                                                       const double* __restrict__ enc, double dt_mid, double S, short* __restrict__ xp_new,
-                                                       short* __restrict__ vp_new, double* __restrict__ stat_partial) {
-  __shared__ int soff[PC_CELLS + 1];
-  __shared__ CellPos spos[PC_CELLS];
-  const long long c0 = (long long)blockIdx.x * PC_CELLS;
-  chunk_cells(g, c0, g.ncell_p, spos);
-  const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
-  const long long p0 = cstart_p[c0];
+// pass C: one thread per particle; single image: destinations wrap periodically.  stat_partial gets one (total, residual)
+// pair per warp of the launch (fixed order for a fixed grid).
+__global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, double S, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                          const unsigned* __restrict__ rank, const long long* __restrict__ cstart_p,
+                                                          const float* __restrict__ vfield_p, const long long* __restrict__ cstart_new,
+                                                          const float* __restrict__ vfield_new, double dt_mid, short* __restrict__ xp_new,
+                                                          short* __restrict__ vp_new, double* __restrict__ stat_partial) {
+  extern __shared__ __align__(16) unsigned char pw_smem[];
+  float* s_tan = reinterpret_cast<float*>(pw_smem);
+  float* s_thr = s_tan + VT_HOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + 2 * VT_HOT * 4) + warp;
+  if (vt.hot) { fill_tab(s_tan, vt.tanh, VT_HOT); fill_tab(s_thr, vt.thrf, VT_HOT); }
+  const VDec dec = make_dec(vt, s_tan, S);
+  const VEnc enc = {s_thr, vt.thr, S, vt.hot};
+  __syncthreads();
   const int nt = g.nt, nnt = g.nnt;
   double st_tot = 0, st_res = 0;
-  for (int q = threadIdx.x; q < np; q += PC_T) {
-    const long long p = p0 + q;
-    const unsigned rk = rank[p];
-    if (rk == RANK_LOST) continue;
-    const int cl = chunk_find(soff, q);
-    const long long L = c0 + cl;
-    const CellPos cp = spos[cl];
-    const unsigned o = rk >> RANK_BITS;
-    // destination = source + offset (|offset| <= ncb < nt): at most one tile step per dimension, no divisions
-    int i = cp.i + (int)(o & 15u) - 8, j = cp.j + (int)((o >> 4) & 15u) - 8, k = cp.k + (int)((o >> 8) & 15u) - 8;
-    int tx = cp.tx, ty = cp.ty, tz = cp.tz;
-    if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
-    if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
-    if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
-    // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: an accepted particle stays inside
-    if (g.nn[0] == 1) tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
-    if (g.nn[1] == 1) ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
-    if (g.nn[2] == 1) tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
-    if ((unsigned)tx >= (unsigned)nnt || (unsigned)ty >= (unsigned)nnt || (unsigned)tz >= (unsigned)nnt) continue;
-    const long long D = phys_index(g, tx, ty, tz, i, j, k);
-    drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_p + 3 * L, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
-               vp_new, st_tot, st_res);
+  for (long long c0 = ((long long)blockIdx.x * PW_W + warp) * WC; c0 < g.ncell_p; c0 += (long long)gridDim.x * PW_W * WC) {
+    long long p0;
+    const int np = warp_chunk_setup(g, cstart_p, c0, g.ncell_p, ws, lane, p0);
+    for (int q = lane; q < np; q += 32) {
+      const long long p = p0 + q;
+      const unsigned rk = rank[p];
+      const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);  // issued with the rank load: one memory latency, not two
+      if (rk == RANK_LOST) continue;
+      const int cl = warp_chunk_find(ws, q);
+      const long long L = c0 + cl;
+      const CellPos cp = ws->pos[cl];
+      const unsigned o = rk >> RANK_BITS;
+      // destination = source + offset (|offset| <= ncb < nt): at most one tile step per dimension, no divisions
+      int i = cp.i + (int)(o & 15u) - 8, j = cp.j + (int)((o >> 4) & 15u) - 8, k = cp.k + (int)((o >> 8) & 15u) - 8;
+      int tx = cp.tx, ty = cp.ty, tz = cp.tz;
+      if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
+      if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
+      if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
+      // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: an accepted particle stays inside
+      if (g.nn[0] == 1) tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
+      if (g.nn[1] == 1) ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
+      if (g.nn[2] == 1) tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
+      if ((unsigned)tx >= (unsigned)nnt || (unsigned)ty >= (unsigned)nnt || (unsigned)tz >= (unsigned)nnt) continue;
+      const long long D = phys_index(g, tx, ty, tz, i, j, k);
+      const long long pos = cstart_new[D] + (rk & ((1u << RANK_BITS) - 1));
+      const float* vf_src = vfield_p + 3 * L;
+      const float* vf_new = vfield_new + 3 * D;
+      const double v0 = __dadd_rn(v_decode(dec, vc.x), (double)vf_src[0]);
+      const double v1 = __dadd_rn(v_decode(dec, vc.y), (double)vf_src[1]);
+      const double v2 = __dadd_rn(v_decode(dec, vc.z), (double)vf_src[2]);
+      // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
+      const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
+      const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
+      const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
+      const float n0 = vf_new[0], n1 = vf_new[1], n2 = vf_new[2];
+      const short w0 = v_encode(enc, __dsub_rn(v0, (double)n0));  // :85-86
+      const short w1 = v_encode(enc, __dsub_rn(v1, (double)n1));
+      const short w2 = v_encode(enc, __dsub_rn(v2, (double)n2));
+      store_code3(xp_new, pos, x0, x1, x2);
+      store_code3(vp_new, pos, w0, w1, w2);
+      // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
+      double a0 = v_decode(dec, w0), a1 = v_decode(dec, w1), a2 = v_decode(dec, w2);
+      st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+      a0 = __dadd_rn(a0, (double)n0); a1 = __dadd_rn(a1, (double)n1); a2 = __dadd_rn(a2, (double)n2);
+      st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+    }
   }
-  block_sum2(st_tot, st_res, stat_partial + 2 * (long long)blockIdx.x);
+  for (int o = 16; o; o >>= 1) { st_tot += __shfl_down_sync(FULL, st_tot, o); st_res += __shfl_down_sync(FULL, st_res, o); }
+  if (lane == 0) {
+    stat_partial[2 * ((long long)blockIdx.x * PW_W + warp)] = st_tot;
+    stat_partial[2 * ((long long)blockIdx.x * PW_W + warp) + 1] = st_res;
+  }
 }
 
 // pass C for the ghost particles that enter this image
