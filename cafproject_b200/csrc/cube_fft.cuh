@@ -14,7 +14,7 @@
 //                                                              k_fft_y (in place)
 //   B   [d][b][z'][ky][kx]    complex, z' = M kept planes      k_fft_z_green: z forward, x i*K_d, z inverse, d=1..3
 //                                                              k_fft_y (inverse, in place, keeps M rows)
-//   F   [b][z'][y'][d][x']    real, x' pitch FP                k_fft_x_inv (c2r) -> read by the fine kick
+//   F   [b][z'][y'][d][x']    real, x' pitch FP                k_fft_x_inv3 (c2r, 3 components + f2_max) -> read by the fine kick
 // Every kernel moves 16 lines x N points through shared memory in the layout s[n][line] (line fastest):
 // a warp then touches 32 consecutive float2 per access (conflict-free) in both Cooley-Tukey steps
 // N = R1*R2, each thread doing one R-point DFT in registers with compile-time twiddles.
@@ -385,70 +385,107 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
 }
 
 // ---------------------------------------------------------------------------------------------
-// x inverse (c2r): B[d][b][z'][y][kx] -> F[b][z'][y'][d][x'] (x' = M kept points, pitch FP).
-// One CTA = 32 kept rows (16 complex lines) of one component.  grid = (ceil(M/32), M, 3*nbatch)
-// With `prefix` the value stored is force_f*a_mid*dt/6/pi, the per-node prefix of every kick term (pm.f90:104), so that
-// the kick does not redo it for each of its 8 corners x 3 components.
-// (Measured alternatives, profiles/r01e_fused_fft.md: looping the three components inside one CTA, or a (1,1,3) cluster
-//  that takes f2_max through distributed shared memory, both lose more occupancy than the separate f2_max pass costs.)
+// x inverse (c2r) of the THREE force components in one CTA + f2_max_fine (pm.f90:83-85).
+// B[d][b][z'][y][kx] -> F[b][z'][y'][d][x'].  One CTA = 16 kept rows x 3 components = 24 complex lines (two real rows per
+// complex line); grid = (ceil(M/16), M, nbatch), 24*max(R1,R2) threads.  Having the three components of a mesh node in
+// one CTA lets the epilogue take |force|^2 for f2_max_fine without another pass over F (the separate pass cost 1.9 ms at
+// cfg 2), and the epilogue reads a transposed copy T[line][x] of the result: one 8-byte shared load yields both rows of a
+// line, every global store is a full 128-byte row segment.  (The one-component-per-CTA kernel it replaces spent half of
+// its instructions in its epilogue and was issue-bound: ncu 82 % issue-active, profiles/r01h_ncu_full_cfg1.csv.)
+// The kick's per-node prefix a_mid*dt/6/pi (pm.f90:104) is folded into the Green multiply of k_fft_z_green by the caller,
+// so the values stored here are already what the kick gathers.
+// Work layout s[n*25 + (n/R2)*6 + line]: odd line pitch keeps the Hermitian unpack (lanes along k) conflict-free, the
+// +6 per R2 rows keeps step B's half-warps that straddle two idx values on disjoint banks.
 // ---------------------------------------------------------------------------------------------
+constexpr int X3L = 24, X3LW = 25, X3PAD = 6;
+template <int R1, int R2> struct X3Cfg {
+  static constexpr int N = R1 * R2, NT = X3L * (R1 > R2 ? R1 : R2);
+  static constexpr int WORK = N * X3LW + R1 * X3PAD, TP = N + 1, TRANS = X3L * TP;
+  static constexpr int BUF = WORK > TRANS ? WORK : TRANS;
+  static constexpr size_t SMEM = (size_t)(BUF + N) * sizeof(float2);
+};
 template <int R1, int R2>
-__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_inv(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
-                                                                       const float2* __restrict__ tw_g, float a_mid, float dt, int prefix) {
-  constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
-  constexpr int NHC = N / 2 + 1, NLD = (FL * NHC + NT - 1) / NT;  // loads per thread
+__global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
+                                                                     const float2* __restrict__ tw_g, unsigned* __restrict__ f2max) {
+  using C = X3Cfg<R1, R2>;
+  constexpr int N = C::N, NT = C::NT, NHC = N / 2 + 1, NLD = (X3L * NHC + NT - 1) / NT, TP = C::TP;
   extern __shared__ float2 smem[];
   float2* s = smem;
-  float2* tw = smem + N * LW;
+  float2* tw = smem + C::BUF;
+  __shared__ float wmax[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = blockIdx.x * 32, zp = blockIdx.y, db = blockIdx.z, d = db / g.nbatch, b = db - d * g.nbatch;
-  const float2* src = B + ((size_t)db * g.M + zp) * (size_t)N * g.P + (size_t)g.off * g.P;
+  const int r0 = blockIdx.x * 16, zp = blockIdx.y, b = blockIdx.z;
+  const size_t plane = (size_t)N * g.P;
   // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k]); all loads are issued before the first use
   float2 va[NLD], vb[NLD];
 #pragma unroll
   for (int i = 0; i < NLD; i++) {
-    const int e = tid + NT * i, l = e / NHC, k = e - l * NHC;
-    const int ya = r0 + 2 * l;
-    const bool oka = l < FL && ya < g.M, okb = l < FL && ya + 1 < g.M;
-    va[i] = oka ? src[(size_t)ya * g.P + k] : make_float2(0.f, 0.f);
-    vb[i] = okb ? src[(size_t)(ya + 1) * g.P + k] : make_float2(0.f, 0.f);
+    const int e = tid + NT * i, dl = e / NHC, k = e - dl * NHC;
+    const int d = dl >> 3, ya = r0 + 2 * (dl & 7);
+    const float2* src = B + (((size_t)d * g.nbatch + b) * g.M + zp) * plane + (size_t)(g.off + ya) * g.P + k;
+    const bool oka = dl < X3L && ya < g.M, okb = dl < X3L && ya + 1 < g.M;
+    va[i] = oka ? __ldg(src) : make_float2(0.f, 0.f);
+    vb[i] = okb ? __ldg(src + g.P) : make_float2(0.f, 0.f);
   }
   load_tw(tw, tw_g, N);
 #pragma unroll
   for (int i = 0; i < NLD; i++) {
-    const int e = tid + NT * i, l = e / NHC, k = e - l * NHC;
-    if (l < FL) {
+    const int e = tid + NT * i, dl = e / NHC, k = e - dl * NHC;
+    if (dl < X3L) {
       const float2 a = va[i], c = vb[i];
-      s[k * LW + l] = make_float2(a.x - c.y, a.y + c.x);
-      if (k && 2 * k != N) s[(N - k) * LW + l] = make_float2(a.x + c.y, c.x - a.y);
+      s[k * X3LW + (k / R2) * X3PAD + dl] = make_float2(a.x - c.y, a.y + c.x);
+      if (k && 2 * k != N) { const int m = N - k; s[m * X3LW + (m / R2) * X3PAD + dl] = make_float2(a.x + c.y, c.x - a.y); }
     }
   }
   __syncthreads();
-  const int line = tid % FL, idx = tid / FL;
-  fft_step_a<R1, R2, +1, LW>(s, tw, line, idx);
+  const int line = tid % X3L, idx = tid / X3L;
+  if (idx < R2) {  // R1-point DFTs over n1 for fixed n2 = idx, twiddle, back to the same slots
+    float2 v[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; n1++) v[n1] = s[(n1 * R2 + idx) * X3LW + n1 * X3PAD + line];
+    dft<R1, +1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; k1++) s[(k1 * R2 + idx) * X3LW + k1 * X3PAD + line] = k1 ? mul_tw<+1>(v[k1], tw[idx * k1]) : v[0];
+  }
   __syncthreads();
   float2 v[R2];
-  if (idx < R1) fft_step_b<R1, R2, +1, LW>(s, line, idx, v);
-  __syncthreads();
-  if (idx < R1) {
+  if (idx < R1) {  // R2-point DFT over n2 for fixed k1 = idx; v[k2] = x[k1 + R1*k2]
 #pragma unroll
-    for (int k2 = 0; k2 < R2; k2++) s[(idx + R1 * k2) * LW + line] = v[k2];
+    for (int n2 = 0; n2 < R2; n2++) v[n2] = s[(idx * R2 + n2) * X3LW + idx * X3PAD + line];
+    dft<R2, +1>(v);
   }
   __syncthreads();
+  if (idx < R1) {  // transposed: T[line][x], pitch N+1 (odd: the 16 lines of a half-warp land on 16 banks)
+#pragma unroll
+    for (int k2 = 0; k2 < R2; k2++) s[line * TP + idx + R1 * k2] = v[k2];
+  }
+  __syncthreads();
+  // epilogue: item = (row pair l, x); .x of T is row r0+2l, .y is row r0+2l+1
+  float best = 0.f;
   float* dst = F + (((size_t)b * g.M + zp) * g.M) * 3 * (size_t)g.FP;
-  for (int r = warp; r < 32; r += NT / 32) {
-    const int yp = r0 + r;
-    if (yp >= g.M) continue;
-    const int l = r >> 1, im = r & 1;
-    float* row = dst + ((size_t)yp * 3 + d) * g.FP;
-    const float* sp = reinterpret_cast<const float*>(s) + im;
-    if (prefix) {
-#pragma unroll 4
-      for (int x = lane; x < g.M; x += 32) row[x] = kick_prefix(sp[((x + g.off) * LW + l) * 2], a_mid, dt);
-    } else {
-#pragma unroll 4
-      for (int x = lane; x < g.M; x += 32) row[x] = sp[((x + g.off) * LW + l) * 2];
+  const int XW = (g.M + 31) & ~31;
+  for (int it = tid; it < 8 * XW; it += NT) {
+    const int l = it / XW, x = it - l * XW;
+    const int ya = r0 + 2 * l;
+    if (x < g.M && ya < g.M) {
+      const float2 f0 = s[l * TP + x + g.off], f1 = s[(8 + l) * TP + x + g.off], f2 = s[(16 + l) * TP + x + g.off];
+      float* row = dst + (size_t)ya * 3 * g.FP + x;
+      row[0] = f0.x; row[g.FP] = f1.x; row[2 * g.FP] = f2.x;
+      best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.x, f0.x), __fmul_rn(f1.x, f1.x)), __fmul_rn(f2.x, f2.x)));
+      if (ya + 1 < g.M) {
+        row += 3 * g.FP;
+        row[0] = f0.y; row[g.FP] = f1.y; row[2 * g.FP] = f2.y;
+        best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+      }
     }
+  }
+  best = __uint_as_float(__reduce_max_sync(__activemask(), __float_as_uint(best)));  // the last warp may be partial
+  if (lane == 0) wmax[warp] = best;
+  __syncthreads();
+  if (tid == 0) {
+    float m = 0.f;
+    for (int w = 0; w < (NT + 31) / 32; w++) m = fmaxf(m, wmax[w]);
+    if (__float_as_uint(m) > f2max[b]) atomicMax(&f2max[b], __float_as_uint(m));
   }
 }
 

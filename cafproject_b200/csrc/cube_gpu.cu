@@ -60,7 +60,8 @@ struct FftPlan {
   void (*y_fwd)(FftGeom, float2*, const float2*);
   void (*y_inv)(FftGeom, float2*, const float2*);
   void (*z_green)(FftGeom, const float2*, float2*, const float*, float, const float2*);
-  void (*x_inv)(FftGeom, const float2*, float*, const float2*, float, float, int);
+  void (*x_inv)(FftGeom, const float2*, float*, const float2*, unsigned*);
+  int x_inv_threads; size_t x_inv_smem;
   // plane-fused cluster kernels (cube_fft2d.cuh); used when their shared memory fits one SM
   void (*xy_fwd)(FftGeom, const float*, float2*, const float2*);
   void (*yx_inv)(FftGeom, const float2*, float*, unsigned*, const float2*);
@@ -69,8 +70,8 @@ struct FftPlan {
   int threads() const { return FL * (R1 > R2 ? R1 : R2); }
 };
 template <int R1, int R2> static FftPlan make_plan() {
-  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv<R1, R2>,
-          k_fft_xy_fwd<R1, R2>, k_fft_yx_inv<R1, R2>, Fft2dCfg<R1, R2>::SMEM};
+  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv3<R1, R2>,
+          X3Cfg<R1, R2>::NT, X3Cfg<R1, R2>::SMEM, k_fft_xy_fwd<R1, R2>, k_fft_yx_inv<R1, R2>, Fft2dCfg<R1, R2>::SMEM};
 }
 // N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
 static const FftPlan kPlans[] = {make_plan<8, 10>(), make_plan<8, 12>(), make_plan<8, 16>(), make_plan<10, 16>(), make_plan<12, 16>(),
@@ -554,7 +555,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     const int smem_x = (N * (FL + 1) + N) * (int)sizeof(float2), smem_y = (N * FL + N) * (int)sizeof(float2);
     const int smem_z = (2 * N * FL + N) * (int)sizeof(float2) + 3 * (N / 2 + 1) * FL * (int)sizeof(float);
     CK(cudaFuncSetAttribute((const void*)h->plan->x_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
-    CK(cudaFuncSetAttribute((const void*)h->plan->x_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
+    CK(cudaFuncSetAttribute((const void*)h->plan->x_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->x_inv_smem));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
@@ -953,7 +954,9 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
   }
   {
     PhaseTimer pt(h, PH_FFTZ);
-    const float scale = 1.0f / ((float)N * (float)N * (float)N);
+    // 1/N^3 (pm.f90:82) and, with `prefix`, the kick's per-node factor a_mid*dt/6/pi (pm.f90:104) ride on the Green multiply
+    float scale = 1.0f / ((float)N * (float)N * (float)N);
+    if (prefix) scale *= ((1.0f * a_mid) * dt) / 6.0f / PI_F;
     pl.z_green<<<dim3(f.P / FL, N), T, smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
   }
   {
@@ -961,15 +964,11 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
     pl.y_inv<<<dim3(f.P / FL, f.M, 3 * nb), T, smem_y, h->st>>>(f, h->Bk, h->tw); CKL();
   }
   {
-    PhaseTimer pt(h, PH_IFFTX);
-    pl.x_inv<<<dim3((f.M + 31) / 32, f.M, 3 * nb), T, smem_x, h->st>>>(f, h->Bk, h->F, h->tw, a_mid, dt, prefix ? 1 : 0); CKL();
-  }
-  {
-    PhaseTimer pt(h, PH_FMAX);
+    PhaseTimer pt(h, PH_IFFTX);  // x inverse of the three components + f2_max_fine
     CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
-    k_f2max_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, h->f2max); CKL();
+    pl.x_inv<<<dim3((f.M + 15) / 16, f.M, nb), pl.x_inv_threads, pl.x_inv_smem, h->st>>>(f, h->Bk, h->F, h->tw, h->f2max); CKL();
   }
-  h->launches += 6;
+  h->launches += 5;
   return 0;
 }
 
