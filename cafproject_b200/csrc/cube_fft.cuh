@@ -408,7 +408,7 @@ template <int R1, int R2>
 __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
                                                                      const float2* __restrict__ tw_g, unsigned* __restrict__ f2max) {
   using C = X3Cfg<R1, R2>;
-  constexpr int N = C::N, NT = C::NT, NHC = N / 2 + 1, NLD = (X3L * NHC + NT - 1) / NT, TP = C::TP;
+  constexpr int N = C::N, NT = C::NT, NHC = N / 2 + 1, TP = C::TP;
   extern __shared__ float2 smem[];
   float2* s = smem;
   float2* tw = smem + C::BUF;
@@ -416,25 +416,29 @@ __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.x * 16, zp = blockIdx.y, b = blockIdx.z;
   const size_t plane = (size_t)N * g.P;
-  // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k]); all loads are issued before the first use
-  float2 va[NLD], vb[NLD];
-#pragma unroll
-  for (int i = 0; i < NLD; i++) {
-    const int e = tid + NT * i, dl = e / NHC, k = e - dl * NHC;
-    const int d = dl >> 3, ya = r0 + 2 * (dl & 7);
-    const float2* src = B + (((size_t)d * g.nbatch + b) * g.M + zp) * plane + (size_t)(g.off + ya) * g.P + k;
-    const bool oka = dl < X3L && ya < g.M, okb = dl < X3L && ya + 1 < g.M;
-    va[i] = oka ? __ldg(src) : make_float2(0.f, 0.f);
-    vb[i] = okb ? __ldg(src + g.P) : make_float2(0.f, 0.f);
-  }
+  // Z[k] = Xa[k] + i Xb[k], Z[N-k] = conj(Xa[k]) + i conj(Xb[k]).  Thread -> (component grp, kx = kk [+ KQ]); it walks
+  // the 8 line pairs with constant pointer increments (no per-element index arithmetic), 16 loads in flight.
+  constexpr int KQ = NT / 3;
+  const int grp = tid / KQ, kk = tid - grp * KQ;
+  const int nrow = g.M - r0;  // kept rows left from r0 on (>= 1)
   load_tw(tw, tw_g, N);
+  for (int k = kk; k < NHC; k += KQ) {
+    const float2* src = B + (((size_t)grp * g.nbatch + b) * g.M + zp) * plane + (size_t)(g.off + r0) * g.P + k;
+    float2 va[8], vb[8];
 #pragma unroll
-  for (int i = 0; i < NLD; i++) {
-    const int e = tid + NT * i, dl = e / NHC, k = e - dl * NHC;
-    if (dl < X3L) {
-      const float2 a = va[i], c = vb[i];
-      s[k * X3LW + (k / R2) * X3PAD + dl] = make_float2(a.x - c.y, a.y + c.x);
-      if (k && 2 * k != N) { const int m = N - k; s[m * X3LW + (m / R2) * X3PAD + dl] = make_float2(a.x + c.y, c.x - a.y); }
+    for (int l = 0; l < 8; l++) {
+      va[l] = 2 * l < nrow ? __ldg(src + (size_t)(2 * l) * g.P) : make_float2(0.f, 0.f);
+      vb[l] = 2 * l + 1 < nrow ? __ldg(src + (size_t)(2 * l + 1) * g.P) : make_float2(0.f, 0.f);
+    }
+    float2* sk = s + k * X3LW + (k / R2) * X3PAD + grp * 8;
+    const int m = N - k;
+    float2* sm = s + m * X3LW + (m / R2) * X3PAD + grp * 8;
+    const bool mir = k && 2 * k != N;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      const float2 a = va[l], c = vb[l];
+      sk[l] = make_float2(a.x - c.y, a.y + c.x);
+      if (mir) sm[l] = make_float2(a.x + c.y, c.x - a.y);
     }
   }
   __syncthreads();
@@ -460,22 +464,24 @@ __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, 
     for (int k2 = 0; k2 < R2; k2++) s[line * TP + idx + R1 * k2] = v[k2];
   }
   __syncthreads();
-  // epilogue: item = (row pair l, x); .x of T is row r0+2l, .y is row r0+2l+1
+  // epilogue: thread -> (x = kk [+ KQ ...], row pairs l = grp, grp+3, grp+6); .x of T is row r0+2l, .y is row r0+2l+1
   float best = 0.f;
-  float* dst = F + (((size_t)b * g.M + zp) * g.M) * 3 * (size_t)g.FP;
-  const int XW = (g.M + 31) & ~31;
-  for (int it = tid; it < 8 * XW; it += NT) {
-    const int l = it / XW, x = it - l * XW;
-    const int ya = r0 + 2 * l;
-    if (x < g.M && ya < g.M) {
-      const float2 f0 = s[l * TP + x + g.off], f1 = s[(8 + l) * TP + x + g.off], f2 = s[(16 + l) * TP + x + g.off];
-      float* row = dst + (size_t)ya * 3 * g.FP + x;
-      row[0] = f0.x; row[g.FP] = f1.x; row[2 * g.FP] = f2.x;
-      best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.x, f0.x), __fmul_rn(f1.x, f1.x)), __fmul_rn(f2.x, f2.x)));
-      if (ya + 1 < g.M) {
-        row += 3 * g.FP;
-        row[0] = f0.y; row[g.FP] = f1.y; row[2 * g.FP] = f2.y;
-        best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+  float* dst = F + (((size_t)b * g.M + zp) * g.M + r0) * 3 * (size_t)g.FP;
+  const size_t rp = 3 * (size_t)g.FP;
+  for (int x = kk; x < g.M; x += KQ) {
+    const float2* t = s + x + g.off;
+#pragma unroll
+    for (int l = grp; l < 8; l += 3) {
+      if (2 * l < nrow) {
+        const float2 f0 = t[l * TP], f1 = t[(8 + l) * TP], f2 = t[(16 + l) * TP];
+        float* row = dst + (size_t)(2 * l) * rp + x;
+        row[0] = f0.x; row[g.FP] = f1.x; row[2 * g.FP] = f2.x;
+        best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.x, f0.x), __fmul_rn(f1.x, f1.x)), __fmul_rn(f2.x, f2.x)));
+        if (2 * l + 1 < nrow) {
+          row += rp;
+          row[0] = f0.y; row[g.FP] = f1.y; row[2 * g.FP] = f2.y;
+          best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+        }
       }
     }
   }

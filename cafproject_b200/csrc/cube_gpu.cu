@@ -104,7 +104,7 @@ struct cube_handle {
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
-  float *tanh = nullptr, *thrf = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
+  float* tanh = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
   int nsm = 1;
   // fine mesh (cube_fft.cuh)
   int batch = 1;
@@ -182,7 +182,7 @@ static int build_dvlut(cube_handle* h, float sigma) {
   h->lut_sigma = sigma;
   return 0;
 }
-static VTab vtab(const cube_handle* h) { return VTab{h->tanh, h->thrf, h->enc, h->dvlut, h->divok, h->vt_hot}; }
+static VTab vtab(const cube_handle* h) { return VTab{h->tanh, h->enc, h->dvlut, h->divok, h->vt_hot}; }
 // one 1024-thread CTA per SM, fewer when there are not enough warp chunks
 static unsigned pw_grid(const cube_handle* h, long long ncells) {
   const long long nwc = (ncells + WC - 1) / WC;
@@ -496,9 +496,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
   CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
-  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->thrf, 32768)); CK(dmalloc(&h->divok, 1));
+  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->divok, 1));
   k_build_enc<<<128, 256, 0, h->st>>>(h->enc); CKL();
-  k_build_thrf<<<128, 256, 0, h->st>>>(h->enc, h->thrf); CKL();
   CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
   {
     // half table for shared memory: index = |code|.  tanf_lut is indexed by the code's 16-bit pattern, so -c sits at 65536-c.
@@ -515,6 +514,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
     h->nsm = prop.multiProcessorCount;
     CK(cudaFuncSetAttribute((const void*)k_drift_place_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
+    CK(cudaFuncSetAttribute((const void*)k_selftest_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
     CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
   }
   // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
@@ -599,7 +599,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->thrf, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -824,8 +824,8 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     const unsigned nb = nblk(g.ncell_p, 128);
     {
       PhaseTimer pt(h, PH_COUNT);
-      k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
-                                          h->vfield_p2, h->rank, h->stat_partial, h->mask_e); CKL();
+      k_drift_count<<<nb, DC_T, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
+                                           h->vfield_p2, h->rank, h->stat_partial, h->mask_e, h->cstart_p); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
       h->launches += 2;
     }
@@ -1226,6 +1226,27 @@ extern "C" int cube_gpu_exchange_plan(const cube_params* p, int64_t* out, int ca
   for (const FPlane& t : sources) row(2, t.rank, (long long)t.zz.size(), 0, 0, 0, 0, 0);
   row(3, c.R, c.Gx, c.Gy, c.Gz, c.sz, c.nyl, c.grp0);
   return n;
+}
+
+// table-driven velocity code conversions against their defining formulas (see k_selftest_encode / k_selftest_decode)
+extern "C" int cube_gpu_selftest_codes(cube_handle* h, float sigma_vi, int64_t nsweep, int64_t* bad_encode, int64_t* bad_decode, int* fma_division) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  if (build_dvlut(h, sigma_vi)) return 1;
+  unsigned long long* cnt = nullptr; CK(dmalloc(&cnt, 2));
+  CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->st));
+  const long long n = 3LL * 32767 + std::max<long long>(0, nsweep);
+  k_selftest_encode<<<nblk(n, 256), 256, 0, h->st>>>(h->enc, std::max<long long>(0, nsweep), cnt); CKL();
+  k_selftest_decode<<<1, PW_T, PW_SMEM_FULL, h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
+  unsigned long long out[2] = {0, 0}; int ok = 0;
+  CK(cudaMemcpyAsync(out, cnt, sizeof out, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&ok, h->divok, sizeof ok, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(cnt);
+  if (bad_encode) *bad_encode = (int64_t)out[0];
+  if (bad_decode) *bad_decode = (int64_t)out[1];
+  if (fma_division) *fma_division = (ok != 0 && h->vt_hot) ? 1 : 0;
+  return 0;
 }
 
 extern "C" int cube_gpu_phase_count(void) { return PH_N; }

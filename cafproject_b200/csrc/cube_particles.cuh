@@ -50,28 +50,20 @@ __global__ void k_build_enc(double* __restrict__ B) {
   }
   B[c] = __longlong_as_double((long long)hi);
 }
-// the thresholds rounded DOWN to f32 (shared-memory copy of the encoder, see v_encode)
-__global__ void k_build_thrf(const double* __restrict__ B, float* __restrict__ Bf) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c <= 32767) Bf[c] = __double2float_rd(B[c]);
-}
-// code of a = |S*v| from a guess c that is at most a few codes off, with the exact thresholds
-__device__ __forceinline__ int enc_refine(double a, int c, const double* __restrict__ B) {
-  // the f32 guess is within one code of the answer: fetch both neighbouring thresholds at once (two independent loads
-  // instead of a chain of dependent ones); the loops only run on if the guess was farther off
-  const double t0 = __ldg(B + c), tm = __ldg(B + max(c - 1, 0));
-  if (c < 32767 && a >= t0) { c++; while (c < 32767 && a >= __ldg(B + c)) c++; }
-  else if (c > 0 && a < tm) { c--; while (c > 0 && a < __ldg(B + c - 1)) c--; }
-  return c;
-}
-__device__ __forceinline__ int enc_guess(double a) {
-  return min(max(__float2int_rn(atanf((float)a) * (65535.0f / PI_F)), 0), 32767);
-}
-// nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86), tables in global memory
+// nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86).
+// cr = 65535*atanf(a)/pi_f in f32 is within 0.01 of the exact real-valued code (atanf: 1 ulp, CUDA math API; the f32
+// roundings of a and of the product add < 0.005), and the code is its rounding to nearest: unless cr lies within 1/16 of a
+// half-integer that rounding is already decided; otherwise (1 encode in 8) the exact threshold T[c] between codes c and
+// c+1, c = floor(cr), decides it.  Same result as the formula for every input, 1/8 table load per encode instead of 2.
 __device__ __forceinline__ short vp_encode_lut(double v, double S, const double* __restrict__ B) {
   const double X = __dmul_rn(S, v);
   const double a = fabs(X);
-  const int c = enc_refine(a, enc_guess(a), B);
+  const float cr = atanf((float)a) * (65535.0f / PI_F);
+  const float fl = floorf(cr), fr = cr - fl;
+  int c = (int)fl;
+  if (fabsf(fr - 0.5f) <= 0.0625f) { c = min(c, 32767); c += (int)(a >= __ldg(B + c)); }
+  else c += (int)(fr > 0.5f);
+  c = min(c, 32767);
   return (short)(X < 0.0 ? -c : c);
 }
 
@@ -80,15 +72,14 @@ __device__ __forceinline__ short vp_encode_lut(double v, double S, const double*
 // The particle kernels were bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 77-90 % of peak,
 // profiles/r01h_ncu_full_cfg1.csv): every decode/encode gathered from the 512 KB f64 tables in global memory, ~23
 // wavefronts per warp-wide gather.  A random 4-byte gather from shared memory costs ~3.  So the drift's placement pass and
-// the coarse kick run one 1024-thread CTA per SM, keep the "hot" part of both tables in shared memory as f32 and stay
+// the coarse kick run one 1024-thread CTA per SM, keep the "hot" part of the decode table in shared memory as f32 and stay
 // bit-identical (measured at cfg 2: place 5.4 -> 3.6 ms, coarse kick 4.5 -> 3.3 ms; the key pass and the fine kick, which
-// need the L1 cache that 221 KB of shared memory takes away, are faster in the small-CTA form and keep it):
+// need the L1 cache that the shared-memory table takes away, are faster in the small-CTA form and keep it):
 //   decode  dv = dble(tanf(pi*vp/N)) / S : s_tan[|vp|] is the host tanf table (odd: checked at init) for |vp| < VT_HOT,
 //           the f64 division is done as q0 = t*rS, q = fma(fma(-S,q0,t), rS, q0) with rS = 1/S, which k_build_dvlut
 //           checks against t/S for every table entry each time S changes (vt.divok; else a true division);
-//   encode  the exact f64 thresholds T[c] are compared through Tf[c] = T[c] rounded down to f32 and af = a rounded down:
-//           af > Tf => a >= T, af < Tf => a < T, af == Tf (probability ~1e-7) => the exact table in global memory;
-//   codes at or beyond VT_HOT (|v| > 4.8 sigma) use the global f64 tables.
+//   encode  needs its table once in 8 calls (vp_encode_lut) and reads it from global memory;
+//   codes at or beyond VT_HOT (|v| > 4.8 sigma) use the global f64 decode table.
 // A warp owns WC consecutive cells of the file order at a time (their particles are one contiguous run): warp-private
 // prefix offsets, no block barriers after the table fill.
 // =============================================================================================
@@ -100,7 +91,6 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct VTab {
   const float* tanh;    // [32769] host tanf of codes 0..32768 (tanh[32768] = -tanf(code -32768))
-  const float* thrf;    // [32768] encoder thresholds rounded down to f32
   const double* thr;    // [32768] exact encoder thresholds
   const double* dvlut;  // [65536] f64 decode table of the current S
   const int* divok;     // != 0: the FMA division reproduces t/S for every table entry (current S)
@@ -110,7 +100,7 @@ struct VTab {
 // tile and tile-local coordinates of a warp's cells, worked out once per cell
 struct CellPos { short tx, ty, tz, i, j, k, tile, pad; };
 struct WarpScratch { int soff[WC + 1]; unsigned mask[WC]; CellPos pos[WC]; };
-constexpr int PW_SMEM_FULL = 2 * VT_HOT * 4 + PW_W * (int)sizeof(WarpScratch);  // decode + encode
+constexpr int PW_SMEM_FULL = VT_HOT * 4 + PW_W * (int)sizeof(WarpScratch);
 
 __device__ __forceinline__ void fill_tab(float* dst, const float* __restrict__ src, int n) {
   const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -133,21 +123,6 @@ __device__ __forceinline__ double v_decode(const VDec& d, short c) {
   }
   return __ldg(d.dvlut + (unsigned short)c);
 }
-struct VEnc { const float* s_thr; const double* thr; double S; int hot; };
-__device__ __forceinline__ short v_encode(const VEnc& e, double v) {
-  const double X = __dmul_rn(e.S, v);
-  const double a = fabs(X);
-  int c = enc_guess(a);
-  bool done = false;
-  if (c < e.hot) {
-    const float af = __double2float_rd(a);
-    const float t0 = e.s_thr[c], tm = e.s_thr[max(c - 1, 0)];
-    if (af != t0 && (c == 0 || af != tm)) { c += (int)(af > t0) - (int)(c > 0 && af < tm); done = true; }
-  }
-  if (!done) c = enc_refine(a, c, e.thr);
-  return (short)(X < 0.0 ? -c : c);
-}
-
 // prefix offsets and coordinates of the warp's cells [c0, c0+WC) (clipped at cend); returns the number of particles,
 // p0 = index of the first one.  cstart[cend] must be readable (next cell's start or the sentinel).
 __device__ __forceinline__ int warp_chunk_setup(const Geom& g, const long long* __restrict__ cstart, long long c0, long long cend,
@@ -192,6 +167,42 @@ __device__ __forceinline__ void chunk_cells(const Geom& g, long long c0, long lo
     }
     sp[t] = q;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test of the table-driven code conversions against their defining formulas (cube_gpu_selftest_codes):
+//   encode: vp_encode_lut(X, 1, T) vs vp_encode(X, 1) (cube_common.cuh: f64 atan formula) for X just below, at and just
+//           above every threshold, both signs, plus a geometric sweep of `nsweep` values over [1e-12, 1e8];
+//   decode: v_decode (shared-memory f32 table + FMA division) vs dvlut[] for all 65536 codes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_selftest_encode(const double* __restrict__ T, long long nsweep, unsigned long long* __restrict__ bad) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double X;
+  if (q < 3LL * 32767) {
+    const int c = (int)(q / 3), w = (int)(q % 3);
+    const long long bits = __double_as_longlong(T[c]);
+    X = __longlong_as_double(bits + (w - 1));
+  } else if (q < 3LL * 32767 + nsweep) {
+    const double f = (double)(q - 3LL * 32767) / (double)nsweep;
+    X = exp(-27.631021115928547 + f * 46.051701859880914);  // 1e-12 .. 1e8
+  } else return;
+  int n = 0;
+  if (vp_encode_lut(X, 1.0, T) != vp_encode(X, 1.0)) n++;
+  if (vp_encode_lut(-X, 1.0, T) != vp_encode(-X, 1.0)) n++;
+  if (n) atomicAdd(bad, (unsigned long long)n);
+}
+__global__ void __launch_bounds__(PW_T, 1) k_selftest_decode(VTab vt, double S, unsigned long long* __restrict__ bad) {
+  extern __shared__ __align__(16) unsigned char pw_smem[];
+  float* s_tan = reinterpret_cast<float*>(pw_smem);
+  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
+  const VDec dec = make_dec(vt, s_tan, S);
+  __syncthreads();
+  int n = 0;
+  for (int u = threadIdx.x; u < 65536; u += PW_T) {
+    const short c = (short)(unsigned short)u;
+    if (__double_as_longlong(v_decode(dec, c)) != __double_as_longlong(vt.dvlut[u])) n++;
+  }
+  if (n) atomicAdd(bad, (unsigned long long)n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -250,12 +261,10 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
                                                           const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
-  float* s_thr = s_tan + VT_HOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + 2 * VT_HOT * 4) + warp;
-  if (vt.hot) { fill_tab(s_tan, vt.tanh, VT_HOT); fill_tab(s_thr, vt.thrf, VT_HOT); }
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + VT_HOT * 4) + warp;
+  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
   const VDec dec = make_dec(vt, s_tan, S);
-  const VEnc enc = {s_thr, vt.thr, S, vt.hot};
   __syncthreads();
   const int m = g.nc + 2;
   double vm = 0.0;
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
       }
       const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
       vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));  // pm.f90:220
-      store_code3(vp, p, v_encode(enc, v0), v_encode(enc, v1), v_encode(enc, v2));
+      store_code3(vp, p, vp_encode_lut(v0, S, vt.thr), vp_encode_lut(v1, S, vt.thr), vp_encode_lut(v2, S, vt.thr));
     }
   }
   for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(FULL, vm, o));
@@ -443,15 +452,39 @@ __global__ void __launch_bounds__(256) k_mask_ext(long long ncell_e, const int* 
   if (e < ncell_e) mask_e[e] = mask_s[sid_e[e]];
 }
 
-// pass B: one thread per destination (physical) cell, file order
-__global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                    const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
-                                                    const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
-                                                    const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
-                                                    float* __restrict__ vfield_new, unsigned* __restrict__ rank,
-                                                    double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e) {
+// pass B: one thread per destination (physical) cell, file order.  The per-thread walk is a serial chain (the f32 rounding
+// of vfield_new after every add fixes the order), so its loads must be short: each warp first copies the keys and velocity
+// codes of its own 32 cells' particles (one contiguous run, coalesced) into shared memory; a source cell whose run lies
+// inside that copy -- the destination itself and its x neighbours, i.e. nearly everything at small time steps -- is then
+// walked out of shared memory instead of paying one global-memory latency per particle.
+constexpr int DC_T = 128, DC_CAP = 384;  // threads per CTA; staged particles per warp (12 KB per CTA: leaves the L1 its size)
+__global__ void __launch_bounds__(DC_T) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                     const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
+                                                     const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
+                                                     const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
+                                                     float* __restrict__ vfield_new, unsigned* __restrict__ rank,
+                                                     double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e,
+                                                     const long long* __restrict__ cstart_p) {
+  __shared__ unsigned short s_key[DC_T / 32][DC_CAP];
+  __shared__ short s_vp[DC_T / 32][3 * DC_CAP];
   const double weight_v = (double)0.1f;  // update_particle.f90:10
   long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long P0 = 0; int nst = 0;
+  {
+    const long long L0 = L - lane;
+    if (L0 < g.ncell_p) {
+      P0 = cstart_p[L0];
+      const long long P1 = cstart_p[L0 + 32 < g.ncell_p ? L0 + 32 : g.ncell_p];
+      nst = (int)(P1 - P0 < DC_CAP ? P1 - P0 : DC_CAP);
+      for (int q = lane; q < nst; q += 32) s_key[wid][q] = key[P0 + q];
+      const short* vsrc = vp + 3 * P0;
+      for (int q = lane; q < 3 * nst; q += 32) s_vp[wid][q] = __ldg(vsrc + q);
+    }
+    __syncwarp();
+  }
+  const unsigned short* kS = s_key[wid];
+  const short* vS = s_vp[wid];
   double st_c = 0;
   if (L < g.ncell_p) {
     int tx, ty, tz, i, j, k;
@@ -473,6 +506,37 @@ __global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short*
           const long long s = cstart_e[e];
           const unsigned want = key_pack(i - si, j - sj, k - sk), o12 = off_pack12(i - si, j - sj, k - sk) << RANK_BITS;
           const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
+          const long long so = s - P0;
+          if (so >= 0 && so + n <= nst) {  // the whole run is staged: same walk, keys and codes from shared memory
+            const int o = (int)so;
+            for (int l = 0; l < n; l++) {
+              const unsigned kk = kS[o + l];
+              if (kk == want) {
+                const short c0 = vS[3 * (o + l)], c1 = vS[3 * (o + l) + 1], c2 = vS[3 * (o + l) + 2];
+                rank[s + l] = (unsigned)cnt | o12;
+                cnt++;
+                vfn0 = (float)__dadd_rn((double)vfn0, __dadd_rn(dvlut[(unsigned short)c0], vf0));  // :47, f32 store after each f64 add
+                vfn1 = (float)__dadd_rn((double)vfn1, __dadd_rn(dvlut[(unsigned short)c1], vf1));
+                vfn2 = (float)__dadd_rn((double)vfn2, __dadd_rn(dvlut[(unsigned short)c2], vf2));
+              } else if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
+                const Code3 xc = load_code3(xp, s + l);
+                const double v0 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l)]], vf0);
+                const double v1 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l) + 1]], vf1);
+                const double v2 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l) + 2]], vf2);
+                bool t = false;
+                const bool ok = (drift_dest(si + 1, xc.x, v0, dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, dt_mid, t) == j + 1) &
+                                (drift_dest(sk + 1, xc.z, v2, dt_mid, t) == k + 1);
+                if (ok) {
+                  rank[s + l] = (unsigned)cnt | o12;
+                  cnt++;
+                  vfn0 = (float)__dadd_rn((double)vfn0, v0);
+                  vfn1 = (float)__dadd_rn((double)vfn1, v1);
+                  vfn2 = (float)__dadd_rn((double)vfn2, v2);
+                }
+              }
+            }
+            continue;
+          }
           for (int l = 0; l < n; l++) {
             const unsigned kk = key[s + l];
             if (kk == want) {  // common case: one predictable branch, the body is straight-line code
@@ -507,7 +571,7 @@ __global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short*
     vfield_new[3 * L] = vfn0; vfield_new[3 * L + 1] = vfn1; vfield_new[3 * L + 2] = vfn2;
     st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
   }
-  __shared__ double sm[4];
+  __shared__ double sm[DC_T / 32];
   for (int o = 16; o; o >>= 1) st_c += __shfl_down_sync(0xffffffffu, st_c, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = st_c;
   __syncthreads();
@@ -561,12 +625,10 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
                                                           short* __restrict__ vp_new, double* __restrict__ stat_partial) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
-  float* s_thr = s_tan + VT_HOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + 2 * VT_HOT * 4) + warp;
-  if (vt.hot) { fill_tab(s_tan, vt.tanh, VT_HOT); fill_tab(s_thr, vt.thrf, VT_HOT); }
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + VT_HOT * 4) + warp;
+  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
   const VDec dec = make_dec(vt, s_tan, S);
-  const VEnc enc = {s_thr, vt.thr, S, vt.hot};
   __syncthreads();
   const int nt = g.nt, nnt = g.nnt;
   double st_tot = 0, st_res = 0;
@@ -605,9 +667,9 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
       const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
       const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
       const float n0 = vf_new[0], n1 = vf_new[1], n2 = vf_new[2];
-      const short w0 = v_encode(enc, __dsub_rn(v0, (double)n0));  // :85-86
-      const short w1 = v_encode(enc, __dsub_rn(v1, (double)n1));
-      const short w2 = v_encode(enc, __dsub_rn(v2, (double)n2));
+      const short w0 = vp_encode_lut(__dsub_rn(v0, (double)n0), S, vt.thr);  // :85-86
+      const short w1 = vp_encode_lut(__dsub_rn(v1, (double)n1), S, vt.thr);
+      const short w2 = vp_encode_lut(__dsub_rn(v2, (double)n2), S, vt.thr);
       store_code3(xp_new, pos, x0, x1, x2);
       store_code3(vp_new, pos, w0, w1, w2);
       // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)

@@ -73,6 +73,7 @@ def load_library():
     L.cube_gpu_timer.argtypes = [vp, i32, C.POINTER(f32)]
     L.cube_gpu_nccl_unique_id.argtypes = [vp]
     L.cube_gpu_exchange_plan.argtypes = [C.POINTER(CubeParams), vp, i32]
+    L.cube_gpu_selftest_codes.argtypes = [vp, f32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     _lib = L
     return L
 
@@ -84,7 +85,7 @@ ABI_SYMBOLS = [
     "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
-    "cube_gpu_exchange_plan", "cube_gpu_download_async",
+    "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_selftest_codes",
 ]
 
 
@@ -189,6 +190,12 @@ class CubeGPU:
 
     def query(self, what):
         return int(self.L.cube_gpu_query(self.h, what.encode()))
+
+    def selftest_codes(self, sigma_vi, nsweep=1 << 22):
+        """(bad_encode, bad_decode, fma_division): table-driven code conversions vs their formulas (include/cube_gpu.h)."""
+        be, bd, ok = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        self._ck(self.L.cube_gpu_selftest_codes(self.h, F32(sigma_vi), int(nsweep), C.byref(be), C.byref(bd), C.byref(ok)))
+        return be.value, bd.value, ok.value
 
     # ---- particle_initialization / checkpoint ------------------------------------------------
     def particle_initialization(self, state, sigma_vi, npglobal=None):

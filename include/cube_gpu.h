@@ -119,6 +119,12 @@ int cube_gpu_coarse_force(cube_handle *h, float *force_c);
 /* coarse kick with a caller-supplied force_c  pm.f90:192-228 */
 int cube_gpu_coarse_kick_with(cube_handle *h, const float *force_c, float a_mid, float dt, float sigma_vi,
                               float *vmax, float *f2_max);
+/* self-test of the table-driven velocity-code conversions against their defining formulas (pm.f90:102,113): the encoder
+ * on both sides of every code threshold plus `nsweep` values over [1e-12,1e8], the shared-memory decoder on all 65536
+ * codes for this sigma_vi.  Returns the mismatch counts (0, 0 expected) and whether the FMA form of the division by S
+ * reproduced t/S for every table entry (else the kernels use a true division). */
+int cube_gpu_selftest_codes(cube_handle *h, float sigma_vi, int64_t nsweep, int64_t *bad_encode, int64_t *bad_decode,
+                            int *fma_division);
 /* message plan of one image, host only (no device needed): rows of 8 int64, returns the row count (-1 = bad params)
  *   {0, rx, ry, rz, src_rank, dst_rank, ncell, cell0}  ghost direction: I receive my ghost box from src_rank and send
  *                                                      the opposite physical box to dst_rank (buffer_density/x/v)

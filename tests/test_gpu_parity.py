@@ -37,6 +37,17 @@ def test_host_tanf_lut_matches_oracle():
     assert np.array_equal(host_tanf_lut().view(np.uint32), co.tanf_lut().view(np.uint32))
 
 
+def test_code_tables_match_their_formulas(setup):
+    """The table-driven encoder (1 threshold load in 8 calls) and the shared-memory decoder (f32 tanf table + FMA division)
+    must reproduce pm.f90:113 / pm.f90:102 for every input: both sides of every code threshold, a 4M-point sweep, all
+    65536 codes, for two sigma_vi."""
+    _, G, _, sig = setup
+    for s in (float(sig), 0.37 * float(sig)):
+        bad_enc, bad_dec, fma = G.selftest_codes(s)
+        assert bad_enc == 0 and bad_dec == 0
+        assert fma in (0, 1)
+
+
 def test_kernels(setup, tables):
     O, G, _, _ = setup
     from oracle import cube_oracle as co
