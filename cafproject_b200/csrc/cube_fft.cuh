@@ -422,23 +422,33 @@ __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, 
   const int grp = tid / KQ, kk = tid - grp * KQ;
   const int nrow = g.M - r0;  // kept rows left from r0 on (>= 1)
   load_tw(tw, tw_g, N);
+  const bool full = nrow >= 16;  // all but the last row block: no per-row predicates on the hot path
   for (int k = kk; k < NHC; k += KQ) {
     const float2* src = B + (((size_t)grp * g.nbatch + b) * g.M + zp) * plane + (size_t)(g.off + r0) * g.P + k;
     float2 va[8], vb[8];
+    if (full) {
 #pragma unroll
-    for (int l = 0; l < 8; l++) {
-      va[l] = 2 * l < nrow ? __ldg(src + (size_t)(2 * l) * g.P) : make_float2(0.f, 0.f);
-      vb[l] = 2 * l + 1 < nrow ? __ldg(src + (size_t)(2 * l + 1) * g.P) : make_float2(0.f, 0.f);
+      for (int l = 0; l < 8; l++) { va[l] = __ldg(src + (size_t)(2 * l) * g.P); vb[l] = __ldg(src + (size_t)(2 * l + 1) * g.P); }
+    } else {
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        va[l] = 2 * l < nrow ? __ldg(src + (size_t)(2 * l) * g.P) : make_float2(0.f, 0.f);
+        vb[l] = 2 * l + 1 < nrow ? __ldg(src + (size_t)(2 * l + 1) * g.P) : make_float2(0.f, 0.f);
+      }
     }
     float2* sk = s + k * X3LW + (k / R2) * X3PAD + grp * 8;
     const int m = N - k;
     float2* sm = s + m * X3LW + (m / R2) * X3PAD + grp * 8;
-    const bool mir = k && 2 * k != N;
+    if (k && 2 * k != N) {
 #pragma unroll
-    for (int l = 0; l < 8; l++) {
-      const float2 a = va[l], c = vb[l];
-      sk[l] = make_float2(a.x - c.y, a.y + c.x);
-      if (mir) sm[l] = make_float2(a.x + c.y, c.x - a.y);
+      for (int l = 0; l < 8; l++) {
+        const float2 a = va[l], c = vb[l];
+        sk[l] = make_float2(a.x - c.y, a.y + c.x);
+        sm[l] = make_float2(a.x + c.y, c.x - a.y);
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < 8; l++) sk[l] = make_float2(va[l].x - vb[l].y, va[l].y + vb[l].x);
     }
   }
   __syncthreads();
@@ -468,19 +478,30 @@ __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, 
   float best = 0.f;
   float* dst = F + (((size_t)b * g.M + zp) * g.M + r0) * 3 * (size_t)g.FP;
   const size_t rp = 3 * (size_t)g.FP;
+  const int fp = g.FP;
   for (int x = kk; x < g.M; x += KQ) {
     const float2* t = s + x + g.off;
+    if (full) {
 #pragma unroll
-    for (int l = grp; l < 8; l += 3) {
-      if (2 * l < nrow) {
+      for (int l = grp; l < 8; l += 3) {
         const float2 f0 = t[l * TP], f1 = t[(8 + l) * TP], f2 = t[(16 + l) * TP];
         float* row = dst + (size_t)(2 * l) * rp + x;
-        row[0] = f0.x; row[g.FP] = f1.x; row[2 * g.FP] = f2.x;
+        row[0] = f0.x; row[fp] = f1.x; row[2 * fp] = f2.x;
+        row[3 * fp] = f0.y; row[4 * fp] = f1.y; row[5 * fp] = f2.y;
         best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.x, f0.x), __fmul_rn(f1.x, f1.x)), __fmul_rn(f2.x, f2.x)));
-        if (2 * l + 1 < nrow) {
-          row += rp;
-          row[0] = f0.y; row[g.FP] = f1.y; row[2 * g.FP] = f2.y;
-          best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+        best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+      }
+    } else {
+      for (int l = grp; l < 8; l += 3) {
+        if (2 * l < nrow) {
+          const float2 f0 = t[l * TP], f1 = t[(8 + l) * TP], f2 = t[(16 + l) * TP];
+          float* row = dst + (size_t)(2 * l) * rp + x;
+          row[0] = f0.x; row[fp] = f1.x; row[2 * fp] = f2.x;
+          best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.x, f0.x), __fmul_rn(f1.x, f1.x)), __fmul_rn(f2.x, f2.x)));
+          if (2 * l + 1 < nrow) {
+            row[3 * fp] = f0.y; row[4 * fp] = f1.y; row[5 * fp] = f2.y;
+            best = fmaxf(best, __fadd_rn(__fadd_rn(__fmul_rn(f0.y, f0.y), __fmul_rn(f1.y, f1.y)), __fmul_rn(f2.y, f2.y)));
+          }
         }
       }
     }

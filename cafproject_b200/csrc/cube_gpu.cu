@@ -824,8 +824,8 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     const unsigned nb = nblk(g.ncell_p, 128);
     {
       PhaseTimer pt(h, PH_COUNT);
-      k_drift_count<<<nb, DC_T, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
-                                           h->vfield_p2, h->rank, h->stat_partial, h->mask_e, h->cstart_p); CKL();
+      k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
+                                          h->vfield_p2, h->rank, h->stat_partial, h->mask_e); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
       h->launches += 2;
     }

@@ -452,39 +452,18 @@ __global__ void __launch_bounds__(256) k_mask_ext(long long ncell_e, const int* 
   if (e < ncell_e) mask_e[e] = mask_s[sid_e[e]];
 }
 
-// pass B: one thread per destination (physical) cell, file order.  The per-thread walk is a serial chain (the f32 rounding
-// of vfield_new after every add fixes the order), so its loads must be short: each warp first copies the keys and velocity
-// codes of its own 32 cells' particles (one contiguous run, coalesced) into shared memory; a source cell whose run lies
-// inside that copy -- the destination itself and its x neighbours, i.e. nearly everything at small time steps -- is then
-// walked out of shared memory instead of paying one global-memory latency per particle.
-constexpr int DC_T = 128, DC_CAP = 384;  // threads per CTA; staged particles per warp (12 KB per CTA: leaves the L1 its size)
-__global__ void __launch_bounds__(DC_T) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                     const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
-                                                     const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
-                                                     const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
-                                                     float* __restrict__ vfield_new, unsigned* __restrict__ rank,
-                                                     double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e,
-                                                     const long long* __restrict__ cstart_p) {
-  __shared__ unsigned short s_key[DC_T / 32][DC_CAP];
-  __shared__ short s_vp[DC_T / 32][3 * DC_CAP];
+// (Measured and dropped, profiles/r01i_notes.md: staging the warp's own keys/codes or host-tanf values in shared memory and
+//  batching the 27 summary loads at radius 1 did not help -- 3.0 -> 3.0 / 3.4 ms.  ncu: 18 of 32 lanes active on average,
+//  25 inner iterations per warp: the cost is the divergence of per-cell particle counts and of the neighbour visits.)
+// pass B: one thread per destination (physical) cell, file order
+__global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                    const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
+                                                    const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
+                                                    const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
+                                                    float* __restrict__ vfield_new, unsigned* __restrict__ rank,
+                                                    double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e) {
   const double weight_v = (double)0.1f;  // update_particle.f90:10
   long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long P0 = 0; int nst = 0;
-  {
-    const long long L0 = L - lane;
-    if (L0 < g.ncell_p) {
-      P0 = cstart_p[L0];
-      const long long P1 = cstart_p[L0 + 32 < g.ncell_p ? L0 + 32 : g.ncell_p];
-      nst = (int)(P1 - P0 < DC_CAP ? P1 - P0 : DC_CAP);
-      for (int q = lane; q < nst; q += 32) s_key[wid][q] = key[P0 + q];
-      const short* vsrc = vp + 3 * P0;
-      for (int q = lane; q < 3 * nst; q += 32) s_vp[wid][q] = __ldg(vsrc + q);
-    }
-    __syncwarp();
-  }
-  const unsigned short* kS = s_key[wid];
-  const short* vS = s_vp[wid];
   double st_c = 0;
   if (L < g.ncell_p) {
     int tx, ty, tz, i, j, k;
@@ -506,37 +485,6 @@ __global__ void __launch_bounds__(DC_T) k_drift_count(Geom g, int r, const short
           const long long s = cstart_e[e];
           const unsigned want = key_pack(i - si, j - sj, k - sk), o12 = off_pack12(i - si, j - sj, k - sk) << RANK_BITS;
           const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
-          const long long so = s - P0;
-          if (so >= 0 && so + n <= nst) {  // the whole run is staged: same walk, keys and codes from shared memory
-            const int o = (int)so;
-            for (int l = 0; l < n; l++) {
-              const unsigned kk = kS[o + l];
-              if (kk == want) {
-                const short c0 = vS[3 * (o + l)], c1 = vS[3 * (o + l) + 1], c2 = vS[3 * (o + l) + 2];
-                rank[s + l] = (unsigned)cnt | o12;
-                cnt++;
-                vfn0 = (float)__dadd_rn((double)vfn0, __dadd_rn(dvlut[(unsigned short)c0], vf0));  // :47, f32 store after each f64 add
-                vfn1 = (float)__dadd_rn((double)vfn1, __dadd_rn(dvlut[(unsigned short)c1], vf1));
-                vfn2 = (float)__dadd_rn((double)vfn2, __dadd_rn(dvlut[(unsigned short)c2], vf2));
-              } else if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
-                const Code3 xc = load_code3(xp, s + l);
-                const double v0 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l)]], vf0);
-                const double v1 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l) + 1]], vf1);
-                const double v2 = __dadd_rn(dvlut[(unsigned short)vS[3 * (o + l) + 2]], vf2);
-                bool t = false;
-                const bool ok = (drift_dest(si + 1, xc.x, v0, dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, dt_mid, t) == j + 1) &
-                                (drift_dest(sk + 1, xc.z, v2, dt_mid, t) == k + 1);
-                if (ok) {
-                  rank[s + l] = (unsigned)cnt | o12;
-                  cnt++;
-                  vfn0 = (float)__dadd_rn((double)vfn0, v0);
-                  vfn1 = (float)__dadd_rn((double)vfn1, v1);
-                  vfn2 = (float)__dadd_rn((double)vfn2, v2);
-                }
-              }
-            }
-            continue;
-          }
           for (int l = 0; l < n; l++) {
             const unsigned kk = key[s + l];
             if (kk == want) {  // common case: one predictable branch, the body is straight-line code
@@ -571,7 +519,7 @@ __global__ void __launch_bounds__(DC_T) k_drift_count(Geom g, int r, const short
     vfield_new[3 * L] = vfn0; vfield_new[3 * L + 1] = vfn1; vfield_new[3 * L + 2] = vfn2;
     st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
   }
-  __shared__ double sm[DC_T / 32];
+  __shared__ double sm[4];
   for (int o = 16; o; o >>= 1) st_c += __shfl_down_sync(0xffffffffu, st_c, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = st_c;
   __syncthreads();
