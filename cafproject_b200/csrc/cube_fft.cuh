@@ -271,8 +271,8 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom 
 // DIR=+1: B (writes only the M kept rows y' -> row index y'+off stays in place), planes = M per (d,b).
 // grid = (P/16, planes, nslab) ; plane stride = N*P, slab stride = planes*N*P
 // ---------------------------------------------------------------------------------------------
-template <int R1, int R2, int DIR>
-__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_y(FftGeom g, float2* __restrict__ A, const float2* __restrict__ tw_g) {
+template <int R1, int R2, int DIR, int MINB = 0>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), MINB) k_fft_y(FftGeom g, float2* __restrict__ A, const float2* __restrict__ tw_g) {
   constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2);
   extern __shared__ float2 smem[];
   float2* s = smem;

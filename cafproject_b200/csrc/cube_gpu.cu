@@ -70,7 +70,8 @@ struct FftPlan {
   int threads() const { return FL * (R1 > R2 ? R1 : R2); }
 };
 template <int R1, int R2> static FftPlan make_plan() {
-  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1>, k_fft_z_green<R1, R2>, k_fft_x_inv3<R1, R2>,
+  return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1, (R1 * R2 <= 320 ? 4 : 0)>,
+          k_fft_z_green<R1, R2>, k_fft_x_inv3<R1, R2>,
           X3Cfg<R1, R2>::NT, X3Cfg<R1, R2>::SMEM, k_fft_xy_fwd<R1, R2>, k_fft_yx_inv<R1, R2>, Fft2dCfg<R1, R2>::SMEM};
 }
 // N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
@@ -558,8 +559,11 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaFuncSetAttribute((const void*)h->plan->x_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->x_inv_smem));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
     CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_y));
+    // the inverse y pass is register-capped for four CTAs per SM (measured 6.1 -> 5.5 ms at cfg 2; the forward pass does not gain)
+    CK(cudaFuncSetAttribute((const void*)h->plan->y_inv, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+
     int smem_max = 0;
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
     // measured on B200 (profiles/r01e_fused_fft.md): with one 288-thread CTA per SM the plane-fused kernels cannot hide
