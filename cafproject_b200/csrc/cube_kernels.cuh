@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int 
   }
 }
 
+// (Measured and dropped, profiles/r01i_notes.md: a particle-parallel form -- one thread per particle, 64-bit fixed-point
+//  accumulators for one 32x16x16 block per CTA, shared-memory integer atomics, order-independent and therefore just as
+//  deterministic -- runs at full lane efficiency but needs ~270 instructions per particle for search, bounds and two
+//  atomics per target: 6.5 ms against 6.2 ms for the per-cell walk at cfg 2.)
 // k-space: F_d = i * kern_d * rho_k (pm.f90:79-80), with the 1/nfe^3 of pm.f90:82 folded in.
 // One thread per k-space element, looping over the tiles of the batch so that kern is read once.
 __global__ void __launch_bounds__(256) k_green(long long nk, int nbatch, const float2* __restrict__ crho,
