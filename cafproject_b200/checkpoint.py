@@ -10,6 +10,10 @@ Little-endian stream binary, no record markers, one set per image under ``<opath
 =========  ==============================================  =======================
 
 File names follow parameters.f90:221-257: ``<z as f7.3, trimmed><name>_<image>.bin``.
+
+The CUBEnu variant of the same state (CUBEnu/work/main/checkpoint.f90:10-50, parameters.f90:136-160,
+basic_functions.fh:36-87) is written with ``convention="cubenu"``: a 224-byte header alone in ``info``, the counts in
+``np``, and the names ``<z>_<name>_<image>.bin`` with ``xp, vp, np, vc`` (``id`` for particle IDs).
 """
 from __future__ import annotations
 
@@ -27,37 +31,70 @@ HEADER_DTYPE = np.dtype(
 assert HEADER_DTYPE.itemsize == 168
 
 
+#: CUBEnu sim_header, CUBEnu/work/main/parameters.f90:136-160: 17 x int64 then 22 x float32 (224 bytes)
+HEADER_NU_DTYPE = np.dtype(
+    [(n, "<i8") for n in ("nplocal", "npglobal", "nplocal_nu", "npglobal_nu", "izipx", "izipv", "izipx_nu", "izipv_nu", "image",
+                          "nn", "nnt", "nt", "ncell", "ncb", "timestep", "cur_checkpoint", "cur_halofind")]
+    + [(n, "<f4") for n in ("a", "t", "tau", "dt_pp", "dt_fine", "dt_coarse", "dt_vmax", "dt_vmax_nu", "mass_p_cdm", "mass_p_nu",
+                            "box", "h0", "omega_m", "omega_l", "s8", "vsim2phys", "sigma_vres", "sigma_vi", "sigma_vi_nu", "z_i",
+                            "z_i_nu", "vz_max")]
+)
+assert HEADER_NU_DTYPE.itemsize == 224
+#: CUBE name -> CUBEnu name of the same content
+NU_NAMES = {"zip2": "info", "zip0": "xp", "zip1": "vp", "rhoc": "np", "vfield": "vc", "zipid": "id"}
+
+
 def z2str(z: float) -> str:
     """parameters.f90:213-219: write(str,'(f7.3)') z ; trim(adjustl(str))."""
     return ("%7.3f" % z).strip()
 
 
-def file_name(opath: str, z: float, image: int, zipname: str) -> str:
-    """parameters.f90:244-257 (image is 1-based)."""
+def file_name(opath: str, z: float, image: int, zipname: str, convention: str = "cube") -> str:
+    """parameters.f90:244-257 (image is 1-based); CUBEnu: basic_functions.fh:52-87 with the CUBEnu name of ``zipname``."""
+    if convention == "cubenu":
+        return os.path.join(opath, "image%d" % image, "%s_%s_%d.bin" % (z2str(z), NU_NAMES.get(zipname, zipname), image))
     return os.path.join(opath, "image%d" % image, "%s%s_%d.bin" % (z2str(z), zipname, image))
 
 
-def make_header(**kw) -> np.ndarray:
-    h = np.zeros((), HEADER_DTYPE)
+def make_header(convention: str = "cube", **kw) -> np.ndarray:
+    h = np.zeros((), HEADER_NU_DTYPE if convention == "cubenu" else HEADER_DTYPE)
     for k, v in kw.items():
         h[k] = v
     return h
 
 
-def write_checkpoint(opath: str, z: float, image: int, header: np.ndarray, state: dict) -> None:
+def write_checkpoint(opath: str, z: float, image: int, header: np.ndarray, state: dict, convention: str = "cube") -> None:
     """``state``: xp (n,3) i16, vp (n,3) i16, rhoc [tz][ty][tx][k][j][i] i32, vfield [...][3] f32."""
     os.makedirs(os.path.join(opath, "image%d" % image), exist_ok=True)
     header = header.copy()
     header["nplocal"] = state["xp"].shape[0]
-    with open(file_name(opath, z, image, "zip2"), "wb") as f:
-        f.write(header.tobytes())
-        f.write(np.ascontiguousarray(state["rhoc"], "<i4").tobytes())
-    np.ascontiguousarray(state["vfield"], "<f4").tofile(file_name(opath, z, image, "vfield"))
-    np.ascontiguousarray(state["xp"], "<i2").tofile(file_name(opath, z, image, "zip0"))
-    np.ascontiguousarray(state["vp"], "<i2").tofile(file_name(opath, z, image, "zip1"))
+    if convention == "cubenu":
+        if header.dtype != HEADER_NU_DTYPE:
+            raise ValueError("convention='cubenu' needs a HEADER_NU_DTYPE header (make_header('cubenu', ...))")
+        with open(file_name(opath, z, image, "zip2", convention), "wb") as f:
+            f.write(header.tobytes())
+        np.ascontiguousarray(state["rhoc"], "<i4").tofile(file_name(opath, z, image, "rhoc", convention))
+    else:
+        with open(file_name(opath, z, image, "zip2"), "wb") as f:
+            f.write(header.tobytes())
+            f.write(np.ascontiguousarray(state["rhoc"], "<i4").tobytes())
+    np.ascontiguousarray(state["vfield"], "<f4").tofile(file_name(opath, z, image, "vfield", convention))
+    np.ascontiguousarray(state["xp"], "<i2").tofile(file_name(opath, z, image, "zip0", convention))
+    np.ascontiguousarray(state["vp"], "<i2").tofile(file_name(opath, z, image, "zip1", convention))
 
 
-def read_checkpoint(opath: str, z: float, image: int):
+def read_checkpoint(opath: str, z: float, image: int, convention: str = "cube"):
+    if convention == "cubenu":
+        header = np.fromfile(file_name(opath, z, image, "zip2", convention), HEADER_NU_DTYPE)[0]
+        nnt, nt = int(header["nnt"]), int(header["nt"])
+        rhoc = np.fromfile(file_name(opath, z, image, "rhoc", convention), "<i4").reshape((nnt,) * 3 + (nt,) * 3)
+        if int(header["izipx"]) != 2 or int(header["izipv"]) != 2:
+            raise ValueError("zip format incompatable")
+        n = int(header["nplocal"])
+        vfield = np.fromfile(file_name(opath, z, image, "vfield", convention), "<f4").reshape(rhoc.shape + (3,))
+        xp = np.fromfile(file_name(opath, z, image, "zip0", convention), "<i2").reshape(n, 3)
+        vp = np.fromfile(file_name(opath, z, image, "zip1", convention), "<i2").reshape(n, 3)
+        return header, dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield)
     with open(file_name(opath, z, image, "zip2"), "rb") as f:
         header = np.frombuffer(f.read(HEADER_DTYPE.itemsize), HEADER_DTYPE)[0]
         nnt, nt = int(header["nnt"]), int(header["nt"])

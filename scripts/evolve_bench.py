@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Evolve the bench workload from z=49 towards z=0 with the product's own step loop (cafproject_b200.run.cafcube over the
+C ABI) and time the PM step along the way: the z=49 state is nearly uniform, load imbalance between cells, bricks and tiles
+only appears once the particles cluster.  One JSON line per redshift window on stdout.
+
+usage: python scripts/evolve_bench.py [--nc 256 --nnt 4 --z-end 0 --max-steps 2000 --window 25]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nc", type=int, default=256)
+    ap.add_argument("--nnt", type=int, default=4)
+    ap.add_argument("--z-end", type=float, default=0.0)
+    ap.add_argument("--max-steps", type=int, default=2000)
+    ap.add_argument("--window", type=int, default=25, help="steps per reported timing window")
+    ap.add_argument("--max-seconds", type=float, default=600.0)
+    args = ap.parse_args()
+    import torch
+    from cafproject_b200.cube import CubeGPU, host_tanf_lut
+    from cafproject_b200.synthetic_ic import make_ic
+    from cafproject_b200.timestep import Cosmology, TimeStepper
+
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+    fk, ck = np.load(os.path.join(g, "fk_table.npy")), np.load(os.path.join(g, "ck_table.npy"))
+    states, sig, info = make_ic(nn=1, nc=args.nc, nnt=args.nnt, np_nc=2, seed=2000, device="cuda")
+    torch.cuda.empty_cache()
+    st = states[0]
+    npart = st["xp"].shape[0]
+    G = CubeGPU(args.nc, args.nnt, fk, ck, np_nc=2, tanf_lut=host_tanf_lut())
+    G.particle_initialization(st, sig)
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    ts = TimeStepper(Cosmology(), [args.z_end])
+    t_start = time.perf_counter()
+    win = dict(n=0, ms=0.0, ovh=0.0, radius=0)
+    nstep = 0
+    while nstep < args.max_steps and time.perf_counter() - t_start < args.max_seconds:
+        dt_old, dt, a_mid = ts.step()
+        G.timer_start()
+        up = G.update_particle(dt_old, dt)
+        G.buffer_density(); G.buffer_x()
+        pm = G.particle_mesh(a_mid, dt)
+        G.buffer_v()
+        ms = G.timer_stop()
+        ts.limits(pm)
+        nstep += 1
+        assert up["nplocal"] == npart, "particle count changed: %d != %d" % (up["nplocal"], npart)
+        win["n"] += 1; win["ms"] += ms; win["ovh"] = max(win["ovh"], float(up["overhead_tile"])); win["radius"] = max(win["radius"], G.query("drift_radius"))
+        if win["n"] == args.window or ts.checkpoint_step:
+            z = 1.0 / float(ts.a) - 1.0
+            print(json.dumps(dict(step=nstep, z=round(z, 3), a=float(ts.a), dt=float(dt), ms_per_step=win["ms"] / win["n"],
+                                  particle_updates_per_s=npart / (win["ms"] / win["n"] * 1e-3), overhead_tile=win["ovh"],
+                                  drift_radius=win["radius"], sigma_vi=float(up["sigma_vi_new"]),
+                                  limits=dict(fine=float(pm["dt_fine"]), coarse=float(pm["dt_coarse"]), vmax=float(pm["dt_vmax"])))), flush=True)
+            win = dict(n=0, ms=0.0, ovh=0.0, radius=0)
+        if ts.checkpoint_step:
+            break
+    # phase split of the last state (profiling brackets synchronise, so outside the timed windows)
+    G.set_profiling(True)
+    for _ in range(2):
+        dt_old, dt, a_mid = ts.dt, ts.dt, ts.a_mid
+        G.update_particle(dt_old, dt); G.buffer_density(); G.buffer_x(); G.particle_mesh(a_mid, dt); G.buffer_v()
+    ph = {k: v / 2 for k, v in G.phase_times().items() if v > 0}
+    rc = G.checkpoint()[0]["rhoc"]
+    print(json.dumps(dict(final=True, steps=nstep, z=1.0 / float(ts.a) - 1.0, wall_s=time.perf_counter() - t_start, phases_ms=ph,
+                          rhoc_max=int(rc.max()), rhoc_mean=float(rc.mean()), empty_cell_fraction=float((rc == 0).mean()), nparticles=int(npart))), flush=True)
+    G.close()
+
+
+if __name__ == "__main__":
+    main()
