@@ -308,8 +308,17 @@ def main():
     peak, which = measured_peak()
     dom_ms_per_launch = phases[dom] / launches_per_step[dom]
     achieved = alg[dom] / launches_per_step[dom] / (dom_ms_per_launch * 1e-3) / 1e9
+    # DRAM traffic of the dominant phase per launch, from the committed ncu capture of this workload (profiles/traffic_cfg2.json,
+    # made by scripts/traffic_summary.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); null for other workloads
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_cfg2.json")
+    if (nc, nnt, world) == (256, 4, 1) and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj["phases"]:
+            traffic = tj["phases"][dom]["dram_bytes"] / launches_per_step[dom]
+            traffic_src = "profiles/traffic_cfg2.json (" + tj["source"] + ")"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "ms_per_launch": dom_ms_per_launch,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": dom_ms_per_launch,
                 "algorithmic_bytes_per_launch": alg[dom] / launches_per_step[dom]}
     bytes_step = 48 * npart + 42 * nfine + 82 * nc ** 3
     step_roof = {"bytes_step": bytes_step, "achieved": bytes_step / (ms_per_step * 1e-3) / 1e9,

@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -96,7 +97,7 @@ struct cube_handle {
   long long *cstart_p = nullptr, *cstart_p2 = nullptr;
   // extended image grid
   int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
-  int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
+  int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr; int* farblk = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
@@ -105,6 +106,8 @@ struct cube_handle {
   int* maxoff = nullptr; unsigned* f2max = nullptr; unsigned long long* vmax_bits = nullptr;
   // LUTs
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
+  // cells above these particle counts are processed by a whole warp instead of one thread (cube_kernels.cuh, cube_particles.cuh)
+  int heavy_deposit = 32, dense_deposit = 32, heavy_count = 64, count_minb = 8;
   float* tanh = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
   int nsm = 1;
   // fine mesh (cube_fft.cuh)
@@ -489,7 +492,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     }
     if (init_exchange(h)) return 1;
   }
-  CK(dmalloc(&h->sid_e, g.ncell_e)); CK(dmalloc(&h->mask_e, g.ncell_e)); CK(dmalloc(&h->mask_s, g.ncell_p + h->ex.ng));
+  CK(dmalloc(&h->sid_e, g.ncell_e)); CK(dmalloc(&h->mask_e, MASK_W * g.ncell_e)); CK(dmalloc(&h->mask_s, MASK_W * (g.ncell_p + h->ex.ng)));
+  CK(dmalloc(&h->farblk, (long long)farblk_dim(g) * farblk_dim(g) * farblk_dim(g)));
   h->nscan_blocks = (int)((std::max(g.ncell_p, h->ex.ng) + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
   CK(dmalloc(&h->stat_partial, std::max<long long>(2 * 4096 * PW_W, (long long)nblk(g.ncell_p, 128)))); CK(dmalloc(&h->stat3, 8));
@@ -510,6 +514,10 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     for (int c = 1; c <= 32767; c++) { const float neg = -tanf_lut[65536 - c]; if (memcmp(&neg, &tanf_lut[c], 4) != 0) { odd = false; break; } }
     if (tanf_lut[0] != 0.f || std::signbit(tanf_lut[0])) odd = false;
     h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? VT_HOT : 0;
+    if (const char* e = getenv("CUBE_GPU_HEAVY_DEPOSIT")) h->heavy_deposit = atoi(e);
+    if (const char* e = getenv("CUBE_GPU_HEAVY_COUNT")) h->heavy_count = atoi(e);
+    if (const char* e = getenv("CUBE_GPU_DENSE_DEPOSIT")) h->dense_deposit = atoi(e);
+    if (const char* e = getenv("CUBE_GPU_COUNT_MINB")) h->count_minb = atoi(e);
     CK(cudaMemcpyAsync(h->tanh, half.data(), 32772 * sizeof(float), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
@@ -602,7 +610,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
-                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
                   h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
@@ -793,10 +801,11 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     h->launches++;
     if (multi && ng) {
       k_drift_key_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->vfield_e, h->dvlut, dt_mid, h->key,
-                                                 h->rank, h->maxoff, h->mask_s + g.ncell_p); CKL();
+                                                 h->rank, h->maxoff, h->mask_s + MASK_W * g.ncell_p); CKL();
       h->launches++;
     }
-    k_mask_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g.ncell_e, h->sid_e, h->mask_s, h->mask_e); CKL();
+    CK(cudaMemsetAsync(h->farblk, 0, sizeof(int) * (size_t)farblk_dim(g) * farblk_dim(g) * farblk_dim(g), h->st));
+    k_mask_ext<<<nblk(g.ncell_e, 256), 256, 0, h->st>>>(g, h->sid_e, h->mask_s, h->rhoc_e, std::max(1, h->heavy_count / 4), h->mask_e, h->farblk); CKL();
     h->launches++;
     CK(cudaMemcpyAsync(&maxoff, h->maxoff, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -828,10 +837,13 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     const unsigned nb = nblk(g.ncell_p, 128);
     {
       PhaseTimer pt(h, PH_COUNT);
-      k_drift_count<<<nb, 128, 0, h->st>>>(g, r, h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, dt_mid, h->rhoc_p2,
-                                          h->vfield_p2, h->rank, h->stat_partial, h->mask_e); CKL();
+      const DriftCountArgs A{h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, h->mask_e, h->farblk, h->rank, dt_mid, r};
+      if (h->count_minb == 8) k_drift_count<8><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, h->rhoc_p2, h->vfield_p2);
+      else k_drift_count<5><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, h->rhoc_p2, h->vfield_p2);
+      CKL();
+      k_vfield_sq<<<nb, 128, 0, h->st>>>(g.ncell_p, h->vfield_p2, h->stat_partial); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
-      h->launches += 2;
+      h->launches += 3;
     }
     {
       PhaseTimer pt(h, PH_SCAN);
@@ -909,7 +921,7 @@ static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, floa
   const int nc4 = w.n / 4;
   const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y, nbz = (nc4 + FB_Z - 1) / FB_Z;
   dim3 grid(nbx * nby * nbz, nb);
-  k_fine_deposit<<<grid, FD_T, FD_SMEM, h->st>>>(g, w, tile0, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
+  k_fine_deposit<<<grid, FD_T, FD_SMEM, h->st>>>(g, w, tile0, h->dense_deposit, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
   h->launches++;
   return 0;
 }
@@ -984,7 +996,7 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
   {
     PhaseTimer pt(h, PH_CDEP);
     const int cbx = (g.nt + CB_X - 1) / CB_X, cby = (g.nt + CB_Y - 1) / CB_Y, cbz = (g.nt + CB_Z - 1) / CB_Z;
-    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3,
+    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->mass_p <= 16.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3,
                                                                                             multi ? g.nc : g.nc + 2); CKL();
     h->launches++;
   }

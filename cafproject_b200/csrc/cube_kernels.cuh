@@ -184,7 +184,82 @@ constexpr int FS_X = FB_X + 1, FS_Y = FB_Y + 1, FS_Z = FB_Z + 1, FS_N = FS_X * F
 constexpr int FD_T = 256;
 constexpr int FD_SMEM = 125 * FS_N * (int)sizeof(float);
 
-__global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int tile0, const short* __restrict__ xp,
+// Bricks that hold a crowded cell (more than `dense` particles; haloes at late times put 10^3-10^4 particles into one coarse
+// cell, where a per-cell walk leaves a warp waiting for its fullest lane) are deposited particle-parallel instead: one thread
+// per particle of the brick's 225 source cells, the brick's 32x16x16 fine cells as fixed-point accumulators in shared
+// memory (two 32-bit words per cell, split at bit 13, resolution 2^-24: finer than the f32 sum it replaces), native 32-bit integer atomics.
+// Integer addition is associative, so the result does not depend on the order in which the hardware serialises the atomics:
+// deterministic like the walk, equal to it to round-off.  (A 64-bit shared-memory atomic add compiles to a CAS loop on
+// sm_100a -- that form was measured and dropped, profiles/r01i_notes.md.)
+constexpr int FDN = (4 * FB_X) * (4 * FB_Y) * (4 * FB_Z);  // 8192 fine cells per brick
+__device__ __forceinline__ bool fine_deposit_dense(const Geom& g, unsigned* __restrict__ sm, const short* __restrict__ xp, int n, long long s,
+                                                   int si0, int sj0, int sk0, float mass_p, float* __restrict__ out, const DepWin& w,
+                                                   int bx, int by, int bz) {
+  // layout: lo[FDN] hi[FDN] pref[256+1] start[225] (8-byte aligned)
+  unsigned* lo = sm;
+  unsigned* hi = sm + FDN;
+  int* pref = reinterpret_cast<int*>(sm + 2 * FDN);
+  long long* start = reinterpret_cast<long long*>(sm + 2 * FDN + 260);
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  // exclusive prefix of the 225 counts (256 threads: warp scans + one pass over the 8 warp totals)
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  __shared__ int s_wsum[FD_T / 32];
+  if (lane == 31) s_wsum[wp] = incl;
+  if (t < FS_N) start[t] = s;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < FD_T / 32; q++) { const int v = s_wsum[q]; if (q < wp) woff += v; total += v; }
+  // a fine cell receives at most one term per particle of the brick: the low word (13 bits per term) holds 2^19 terms, the high
+  // word (mass_p 2^11 per term) 2^21/mass_p; a brick beyond that (never seen: 30x the fullest cell of a z=0 run) is left to the walk
+  if ((float)total > fminf(524288.f, 2097152.f / mass_p)) return false;
+  for (int e = t; e < 2 * FDN / 4; e += FD_T) reinterpret_cast<uint4*>(sm)[e] = make_uint4(0u, 0u, 0u, 0u);
+  pref[t] = woff + incl - n;
+  if (t == 0) pref[FD_T] = total;
+  __syncthreads();
+  const float scale = __fmul_rn(mass_p, 16777216.0f);  // weights in units of 2^-24 (mass_p < 2^8: a term fits 32 bits)
+  for (int q = t; q < total; q += FD_T) {
+    int c = 0;
+#pragma unroll
+    for (int step = 128; step > 0; step >>= 1)
+      if (pref[c + step] <= q) c += step;  // largest c with pref[c] <= q (empty cells share their successor's offset)
+    const long long p = start[c] + (q - pref[c]);
+    const int sx = c % FS_X, sy = (c / FS_X) % FS_Y, sz = c / (FS_X * FS_Y);
+    const Code3 cur = load_code3(xp, p);
+    int i1, j1, k1; float ax[2], ay[2], az[2];
+    cic_split(fine_tempx(si0 + sx, cur.x), i1, ax[0], ax[1]);
+    cic_split(fine_tempx(sj0 + sy, cur.y), j1, ay[0], ay[1]);
+    cic_split(fine_tempx(sk0 + sz, cur.z), k1, az[0], az[1]);
+    // brick-local fine index of the lower corner: source layer 0 is the low-side neighbour (only its +1 spill lands in the brick)
+    const int gx = i1 - (4 * (si0 + sx - 1) + 1) + 4 * (sx - 1), gy = j1 - (4 * (sj0 + sy - 1) + 1) + 4 * (sy - 1),
+              gz = k1 - (4 * (sk0 + sz - 1) + 1) + 4 * (sz - 1);
+#pragma unroll
+    for (int qq = 0; qq < 8; qq++) {
+      const int qa = qq & 1, qb = (qq >> 1) & 1, qc = qq >> 2;
+      const int X = gx + qa, Y = gy + qb, Z = gz + qc;
+      if ((unsigned)X < 4u * FB_X && (unsigned)Y < 4u * FB_Y && (unsigned)Z < 4u * FB_Z) {
+        const unsigned wf = __float2uint_rn(__fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), scale));
+        const int o = (Z * (4 * FB_Y) + Y) * (4 * FB_X) + X;
+        atomicAdd(lo + o, wf & 0x1fffu);
+        atomicAdd(hi + o, wf >> 13);
+      }
+    }
+  }
+  __syncthreads();
+  for (int o = t; o < FDN; o += FD_T) {  // one 32-float row per warp and iteration
+    const int X = o % (4 * FB_X), Y = (o / (4 * FB_X)) % (4 * FB_Y), Z = o / (16 * FB_X * FB_Y);
+    const int gx = bx * 4 * FB_X + X, gy = by * 4 * FB_Y + Y, gz = bz * 4 * FB_Z + Z;
+    if (gx < w.n && gy < w.n && gz < w.n) {
+      const unsigned long long v = ((unsigned long long)hi[o] << 13) + lo[o];
+      out[((long long)gz * w.n + gy) * w.ld + gx] = __fmul_rn(__ull2float_rn(v), 0x1p-24f);
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int tile0, int dense, const short* __restrict__ xp,
                                                          const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
                                                          float mass_p, float* __restrict__ rho /*[batch][n][n][ld]*/) {
   extern __shared__ float acc[];  // [125 = (a*5+b)*5+c][FS_N]
@@ -205,6 +280,10 @@ __global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int 
     n = rhoc_e[e];
     s = cstart_e[e];
   }
+  if (__syncthreads_or(n > dense) &&
+      fine_deposit_dense(g, reinterpret_cast<unsigned*>(acc), xp, n, s, c0 + bx * FB_X - NCB, c0 + by * FB_Y - NCB, c0 + bz * FB_Z - NCB, mass_p,
+                         rho + (long long)blockIdx.y * w.vol, w, bx, by, bz))
+    return;
   {
     float4* a4 = reinterpret_cast<float4*>(acc);
     for (int e = t; e < 125 * FS_N / 4 + 1; e += FD_T)
@@ -333,10 +412,43 @@ constexpr int CB_X = 8, CB_Y = 8, CB_Z = 4, CD_T = CB_X * CB_Y * CB_Z;
 constexpr int CS_X = CB_X + 2, CS_Y = CB_Y + 2, CS_Z = CB_Z + 2, CS_N = CS_X * CS_Y * CS_Z;  // 600 source cells
 constexpr int CD_SMEM = 27 * CS_N * (int)sizeof(float);
 
-__global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
+// Crowded source cells (more than `heavy` particles) are summed by a whole warp instead of their own thread (a warp would
+// wait for its fullest lane; haloes put 10^3-10^4 particles into a coarse cell at late times): lane = particle, the 27
+// products wx_a wy_b wz_c mass_p (a,b,c = target cell-1, cell, cell+1; a particle has two non-zero weights per dimension) are
+// taken in f32 like the reference's, converted to fixed point (2^-23) and added over the warp with the integer warp
+// reduction (REDUX); lane T keeps the 64-bit total of accumulator T.  Integer sums: independent of any order, deterministic.
+__device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my, const short* __restrict__ xp, long long s, int n, int si, int sj, int sk,
+                                                float mass_p, int lane) {
+  unsigned long long tot = 0;
+  const float scale = __fmul_rn(mass_p, 8388608.0f);
+  for (int base = 0; base < n; base += 32) {
+    float wx[3] = {0.f, 0.f, 0.f}, wy[3] = {0.f, 0.f, 0.f}, wz[3] = {0.f, 0.f, 0.f};
+    if (base + lane < n) {
+      const Code3 c = load_code3(xp, s + base + lane);
+      int i1, j1, k1; float d1, d2;
+      cic_split(coarse_tempx(si, c.x), i1, d1, d2);  // i1 = si or si+1: lower target = cell-1 or cell
+      if (i1 == si) { wx[0] = d1; wx[1] = d2; } else { wx[1] = d1; wx[2] = d2; }
+      cic_split(coarse_tempx(sj, c.y), j1, d1, d2);
+      if (j1 == sj) { wy[0] = d1; wy[1] = d2; } else { wy[1] = d1; wy[2] = d2; }
+      cic_split(coarse_tempx(sk, c.z), k1, d1, d2);
+      if (k1 == sk) { wz[0] = d1; wz[1] = d2; } else { wz[1] = d1; wz[2] = d2; }
+    }
+#pragma unroll
+    for (int T = 0; T < 27; T++) {
+      const unsigned wf = __float2uint_rn(__fmul_rn(__fmul_rn(__fmul_rn(wx[T % 3], wy[(T / 3) % 3]), wz[T / 9]), scale));
+      const unsigned sum = __reduce_add_sync(0xffffffffu, wf);  // 32 terms below 2^26 each (mass_p <= 8): no overflow
+      if (lane == T) tot += sum;
+    }
+  }
+  if (lane < 27) my[lane * CS_N] = __fmul_rn(__ull2float_rn(tot), 0x1p-23f);
+}
+
+__global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, int heavy, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
                                                          const long long* __restrict__ cstart_e, float mass_p,
                                                          float* __restrict__ r3 /*[nc][nc][ld]*/, int ld) {
   extern __shared__ float acc[];  // [27 = (rz*3+ry)*3+rx][CS_N]
+  constexpr int CS_W = (CS_N + 31) / 32;  // 19 words of "crowded" flags
+  __shared__ unsigned s_hm[CS_W + 8];
   const int t = threadIdx.x;
   const int tile = blockIdx.y;
   const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
@@ -344,6 +456,18 @@ __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __
   const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
   const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
   for (int e = t; e < 27 * CS_N; e += CD_T) acc[e] = 0.f;
+  static_assert(CD_T % 32 == 0, "whole warps walk the source cells (ballots below)");
+  for (int sb = 0; sb < CS_N; sb += CD_T) {  // sidx = sb + t; CD_T is a multiple of 32, so word (sb + t) / 32 belongs to my warp
+    const int sidx = sb + t;
+    int n = 0;
+    if (sidx < CS_N) {
+      const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
+      const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;
+      if (si <= g.nt && sj <= g.nt && sk <= g.nt) n = rhoc_e[ext_index(g, X0 + si, Y0 + sj, Z0 + sk)];
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, n > heavy);
+    if ((t & 31) == 0) s_hm[sidx >> 5] = hm;
+  }
   __syncthreads();
   for (int sidx = t; sidx < CS_N; sidx += CD_T) {
     const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
@@ -351,6 +475,7 @@ __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __
     if (si > g.nt || sj > g.nt || sk > g.nt) continue;
     const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
     const int n = rhoc_e[e];
+    if (n > heavy) continue;  // spread by a warp below
     const long long s = cstart_e[e];
     float* my = acc + sidx;
     for (int l = 0; l < n; l++) {
@@ -366,6 +491,22 @@ __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, const short* __
         const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:147-154
         float* p = my + (((rc + qc) * 3 + (rb + qb)) * 3 + (ra + qa)) * CS_N;
         *p = __fadd_rn(*p, wgt);
+      }
+    }
+  }
+  {  // crowded cells, dealt round-robin to the warps
+    const int lane = t & 31, wp = t >> 5;
+    int ord = 0;
+    for (int wd = 0; wd < CS_W; wd++) {
+      unsigned bits = s_hm[wd];
+      while (bits) {
+        const int sidx = wd * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if ((ord++ & (CD_T / 32 - 1)) != wp) continue;
+        const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
+        const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;
+        const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
+        coarse_sum_warp(acc + sidx, xp, cstart_e[e], rhoc_e[e], si, sj, sk, mass_p, lane);
       }
     }
   }

@@ -351,15 +351,52 @@ constexpr unsigned RANK_LOST = 0xFFFFFFFFu;
 constexpr int RANK_BITS = 20;
 __device__ __forceinline__ unsigned off_pack12(int dx, int dy, int dz) { return (unsigned)(dx + 8) | ((unsigned)(dy + 8) << 4) | ((unsigned)(dz + 8) << 8); }
 
-// per-source-cell summary of pass A: bit (dx+1)+3(dy+1)+9(dz+1) = "some particle of this cell moves by (dx,dy,dz)",
-// bit 27 = "some particle moves farther than one cell or sits on a cell boundary (near-tie)".  Pass B only walks the
-// particles of a source cell when the bit of the offset it is looking for (or bit 27) is set: at small time steps
-// almost every particle stays in its cell, so 26 of the 27 source cells of a destination are skipped unread.
-constexpr unsigned MASK_FAR = 1u << 27;
-__device__ __forceinline__ unsigned offset_bit(int dx, int dy, int dz) { return 1u << ((dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)); }
-__device__ __forceinline__ unsigned mover_bit(int ox, int oy, int oz, bool tie) {
-  return (tie || max(abs(ox), max(abs(oy), abs(oz))) > 1) ? MASK_FAR : offset_bit(ox, oy, oz);
+// per-source-cell summary of pass A, four words per cell: bit (dx+2)+5(dy+2)+25(dz+2) = "some particle of this cell moves by
+// (dx,dy,dz)" for offsets up to two cells, bit 125 = "some particle moves farther".  A particle that sits on a cell boundary
+// (near-tie: its destination is re-decided in the destination tile's frame and may come out one cell off) sets the bits of
+// all 27 offsets around its own.  Pass B only walks the particles of a source cell when the bit of the offset it is looking
+// for is set: at small time steps almost every particle stays in its cell, and inside a halo (10^3-10^4 particles per cell,
+// velocity dispersion of a cell per step) a destination still skips the source cells that send it nothing.
+constexpr int MASK_W = 4;
+constexpr int MASK_FAR_BIT = 125;
+__device__ __forceinline__ int offset_bit(int dx, int dy, int dz) { return (dx + 2) + 5 * (dy + 2) + 25 * (dz + 2); }
+// does the summary `m` (pointer to the cell's four words) announce movers by (dx,dy,dz)?
+__device__ __forceinline__ bool mask_hit(const unsigned* __restrict__ m, int dx, int dy, int dz) {
+  const int b = max(abs(dx), max(abs(dy), abs(dz))) <= 2 ? offset_bit(dx, dy, dz) : MASK_FAR_BIT;
+  return (m[b >> 5] >> (b & 31)) & 1u;
 }
+__device__ __forceinline__ void mask_set(unsigned* m, int ox, int oy, int oz, bool tie) {
+  if (!tie) {
+    const int b = max(abs(ox), max(abs(oy), abs(oz))) <= 2 ? offset_bit(ox, oy, oz) : MASK_FAR_BIT;
+    atomicOr(m + (b >> 5), 1u << (b & 31));
+    return;
+  }
+  for (int dz = -1; dz <= 1; dz++)
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        const int x = ox + dx, y = oy + dy, z = oz + dz;
+        const int b = max(abs(x), max(abs(y), abs(z))) <= 2 ? offset_bit(x, y, z) : MASK_FAR_BIT;
+        atomicOr(m + (b >> 5), 1u << (b & 31));
+      }
+}
+// the bits of the offsets within one cell, per word (everything else = "moves two cells or more")
+__host__ __device__ constexpr unsigned mask_inner_word(int w) {
+  unsigned v = 0;
+  for (int dz = -1; dz <= 1; dz++)
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        const int b = (dx + 2) + 5 * (dy + 2) + 25 * (dz + 2);
+        if ((b >> 5) == w) v |= 1u << (b & 31);
+      }
+  return v;
+}
+// Block flags: 4^3 blocks of the extended grid.  FLAG_FAR = the block holds a source cell with movers beyond one cell: a
+// destination whose (2r+1)^3 neighbourhood touches no such block only has to visit its 27 nearest source cells, whatever the
+// step radius r.  FLAG_CROWD = the block holds a cell with more than `crowd` particles: a destination with no such block
+// nearby cannot have many candidates and skips the candidate count that decides between the thread and the warp path.
+constexpr int FARB = 4;
+constexpr int FLAG_FAR = 1, FLAG_CROWD = 2;
+__host__ __device__ inline int farblk_dim(const Geom& g) { return (g.ne + FARB - 1) / FARB; }
 
 // destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
 __device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
@@ -376,10 +413,10 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
                                                      const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
                                                      unsigned* __restrict__ rank, int* __restrict__ maxoff, unsigned* __restrict__ mask_s) {
   __shared__ int soff[PC_CELLS + 1];
-  __shared__ unsigned smask[PC_CELLS];
+  __shared__ unsigned smask[PC_CELLS * MASK_W];
   __shared__ CellPos spos[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
-  if (threadIdx.x < PC_CELLS) smask[threadIdx.x] = 0u;
+  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T) smask[t] = 0u;
   chunk_cells(g, c0, g.ncell_p, spos);
   const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
   const long long p0 = cstart_p[c0];
@@ -396,7 +433,7 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
     int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
     int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
     m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
-    atomicOr(&smask[cl], mover_bit(ox, oy, oz, tie));
+    mask_set(smask + cl * MASK_W, ox, oy, oz, tie);
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
     rank[p] = RANK_LOST;  // pass B overwrites it for the one destination cell of this image that accepts the particle
@@ -404,7 +441,8 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __res
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
   __syncthreads();
-  if (threadIdx.x < PC_CELLS && c0 + threadIdx.x < g.ncell_p) mask_s[c0 + threadIdx.x] = smask[threadIdx.x];
+  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T)
+    if (c0 + t / MASK_W < g.ncell_p) mask_s[c0 * MASK_W + t] = smask[t];
 }
 
 // pass A for the ghost particles received from other images (cube_exchange.cuh): cells in message order,
@@ -415,9 +453,9 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, cons
                                                      unsigned short* __restrict__ key, unsigned* __restrict__ rank, int* __restrict__ maxoff,
                                                      unsigned* __restrict__ mask_g) {
   __shared__ int soff[PC_CELLS + 1];
-  __shared__ unsigned smask[PC_CELLS];
+  __shared__ unsigned smask[PC_CELLS * MASK_W];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
-  if (threadIdx.x < PC_CELLS) smask[threadIdx.x] = 0u;
+  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T) smask[t] = 0u;
   const int np = chunk_setup(gstart, c0, ng, soff);
   const long long p0 = base + gstart[c0];
   int m = 0;
@@ -434,7 +472,7 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, cons
     int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
     // a ghost can only enter from at most ncb cells away; its owner image checks the full offset of the same particle
     m = max(m, min(NCB, max(abs(ox), max(abs(oy), abs(oz)))));
-    atomicOr(&smask[cl], mover_bit(ox, oy, oz, tie));
+    mask_set(smask + cl * MASK_W, ox, oy, oz, tie);
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
     rank[p] = RANK_LOST;
@@ -442,82 +480,190 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, cons
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
   __syncthreads();
-  if (threadIdx.x < PC_CELLS && c0 + threadIdx.x < ng) mask_g[c0 + threadIdx.x] = smask[threadIdx.x];
+  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T)
+    if (c0 + t / MASK_W < ng) mask_g[c0 * MASK_W + t] = smask[t];
 }
 
-// source-cell summaries on the extended grid: sid_e[e] = file-order index of an aliased cell, ncell_p + q of ghost cell q
-__global__ void __launch_bounds__(256) k_mask_ext(long long ncell_e, const int* __restrict__ sid_e, const unsigned* __restrict__ mask_s,
-                                                  unsigned* __restrict__ mask_e) {
+// source-cell summaries on the extended grid: sid_e[e] = file-order index of an aliased cell, ncell_p + q of ghost cell q;
+// also sets the block flags (farblk zeroed by the caller)
+__global__ void __launch_bounds__(256) k_mask_ext(Geom g, const int* __restrict__ sid_e, const unsigned* __restrict__ mask_s,
+                                                  const int* __restrict__ rhoc_e, int crowd, unsigned* __restrict__ mask_e, int* __restrict__ farblk) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < ncell_e) mask_e[e] = mask_s[sid_e[e]];
+  if (e >= g.ncell_e) return;
+  const uint4 m = reinterpret_cast<const uint4*>(mask_s)[sid_e[e]];
+  reinterpret_cast<uint4*>(mask_e)[e] = m;
+  int f = ((m.x & ~mask_inner_word(0)) | (m.y & ~mask_inner_word(1)) | (m.z & ~mask_inner_word(2)) | (m.w & ~mask_inner_word(3))) ? FLAG_FAR : 0;
+  if (rhoc_e[e] > crowd) f |= FLAG_CROWD;
+  if (f) {
+    const int nb = farblk_dim(g);
+    const int x = (int)(e % g.ne), y = (int)((e / g.ne) % g.ne), z = (int)(e / ((long long)g.ne * g.ne));
+    atomicOr(&farblk[((z / FARB) * nb + y / FARB) * nb + x / FARB], f);
+  }
+}
+// flags of the blocks touched by the (2r+1)^3 neighbourhood of the destination at extended-grid coordinates (x,y,z)
+// (0-based, ghost layers included)
+__device__ __forceinline__ int dest_flags(const Geom& g, const int* __restrict__ farblk, int r, int x, int y, int z) {
+  const int nb = farblk_dim(g);
+  int f = 0;
+  for (int bz = (z - r) / FARB; bz <= (z + r) / FARB; bz++)
+    for (int by = (y - r) / FARB; by <= (y + r) / FARB; by++)
+      for (int bx = (x - r) / FARB; bx <= (x + r) / FARB; bx++) f |= farblk[(bz * nb + by) * nb + bx];
+  return f;
 }
 
 // (Measured and dropped, profiles/r01i_notes.md: staging the warp's own keys/codes or host-tanf values in shared memory and
 //  batching the 27 summary loads at radius 1 did not help -- 3.0 -> 3.0 / 3.4 ms.  ncu: 18 of 32 lanes active on average,
 //  25 inner iterations per warp: the cost is the divergence of per-cell particle counts and of the neighbour visits.)
-// pass B: one thread per destination (physical) cell, file order
-__global__ void __launch_bounds__(128) k_drift_count(Geom g, int r, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                    const unsigned short* __restrict__ key, const int* __restrict__ rhoc_e,
-                                                    const long long* __restrict__ cstart_e, const float* __restrict__ vfield_e,
-                                                    const double* __restrict__ dvlut, double dt_mid, int* __restrict__ rhoc_new,
-                                                    float* __restrict__ vfield_new, unsigned* __restrict__ rank,
-                                                    double* __restrict__ stc_partial, const unsigned* __restrict__ mask_e) {
+struct DriftCountArgs {
+  const short* xp; const short* vp; const unsigned short* key; const int* rhoc_e; const long long* cstart_e; const float* vfield_e;
+  const double* dvlut; const unsigned* mask_e; const int* farblk; unsigned* rank; double dt_mid; int r;
+};
+// one candidate particle of source cell (si,sj,sk) for destination (i,j,k): accepted? and its velocity
+__device__ __forceinline__ bool drift_accept(const DriftCountArgs& A, long long p, unsigned want, int si, int sj, int sk, int i, int j, int k,
+                                             double vf0, double vf1, double vf2, double& v0, double& v1, double& v2) {
+  const unsigned kk = A.key[p];
+  if (kk == want) {  // common case: one predictable branch, the body is straight-line code
+    const Code3 vc = load_code3(A.vp, p);
+    v0 = __dadd_rn(A.dvlut[(unsigned short)vc.x], vf0); v1 = __dadd_rn(A.dvlut[(unsigned short)vc.y], vf1); v2 = __dadd_rn(A.dvlut[(unsigned short)vc.z], vf2);
+    return true;
+  }
+  if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
+    const Code3 vc = load_code3(A.vp, p), xc = load_code3(A.xp, p);
+    v0 = __dadd_rn(A.dvlut[(unsigned short)vc.x], vf0); v1 = __dadd_rn(A.dvlut[(unsigned short)vc.y], vf1); v2 = __dadd_rn(A.dvlut[(unsigned short)vc.z], vf2);
+    bool t = false;
+    return (drift_dest(si + 1, xc.x, v0, A.dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, A.dt_mid, t) == j + 1) &
+           (drift_dest(sk + 1, xc.z, v2, A.dt_mid, t) == k + 1);
+  }
+  return false;
+}
+
+// pass B: one thread per destination (physical) cell, file order.  A destination with more than `heavy` candidate particles
+// (everything in the source cells whose summary says somebody may come its way) is not walked by its thread -- a warp would
+// wait for its fullest lane, and at late times haloes put 10^3-10^4 particles into one coarse cell -- but by a whole warp:
+// 32 candidates are tested at once, ranks come from a ballot prefix, and only the vfield_new chain (f32 rounding after every
+// add, update_particle.f90:47) stays serial, fed by shuffles in storage order.  Same traversal order, same results.
+constexpr int DC_T = 128;
+template <int MINB>
+__global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountArgs A, int heavy, int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
   const double weight_v = (double)0.1f;  // update_particle.f90:10
-  long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double st_c = 0;
+  __shared__ unsigned s_hm[DC_T / 32];
+  const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool crowded = false;
   if (L < g.ncell_p) {
     int tx, ty, tz, i, j, k;
     phys_decompose(g, L, tx, ty, tz, i, j, k);
     const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
-    int cnt = 0;
-    const long long e0 = ext_index(g, X0 + i, Y0 + j, Z0 + k);
-    float vfn0 = (float)__dmul_rn((double)vfield_e[3 * e0], weight_v);  // :27
-    float vfn1 = (float)__dmul_rn((double)vfield_e[3 * e0 + 1], weight_v);
-    float vfn2 = (float)__dmul_rn((double)vfield_e[3 * e0 + 2], weight_v);
+    const int flags = dest_flags(g, A.farblk, A.r, X0 + i + NCB, Y0 + j + NCB, Z0 + k + NCB);
+    const int r = (flags & FLAG_FAR) ? A.r : min(A.r, 1);
+    // candidates (only counted when a crowded cell is near)
+    int cand = 0;
+    if (flags & FLAG_CROWD)
     for (int sk = k - r; sk <= k + r; sk++)
       for (int sj = j - r; sj <= j + r; sj++) {
         long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
         for (int si = i - r; si <= i + r; si++, e++) {
           const int ddx = i - si, ddy = j - sj, ddz = k - sk;
-          const unsigned need = (max(abs(ddx), max(abs(ddy), abs(ddz))) <= 1 ? offset_bit(ddx, ddy, ddz) : 0u) | MASK_FAR;
-          if (!(mask_e[e] & need)) continue;  // nobody in this source cell comes my way
-          const int n = rhoc_e[e];
-          const long long s = cstart_e[e];
-          const unsigned want = key_pack(i - si, j - sj, k - sk), o12 = off_pack12(i - si, j - sj, k - sk) << RANK_BITS;
-          const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
-          for (int l = 0; l < n; l++) {
-            const unsigned kk = key[s + l];
-            if (kk == want) {  // common case: one predictable branch, the body is straight-line code
-              const Code3 vc = load_code3(vp, s + l);
-              rank[s + l] = (unsigned)cnt | o12;
-              cnt++;
-              vfn0 = (float)__dadd_rn((double)vfn0, __dadd_rn(dvlut[(unsigned short)vc.x], vf0));  // :47, f32 store after each f64 add
-              vfn1 = (float)__dadd_rn((double)vfn1, __dadd_rn(dvlut[(unsigned short)vc.y], vf1));
-              vfn2 = (float)__dadd_rn((double)vfn2, __dadd_rn(dvlut[(unsigned short)vc.z], vf2));
-            } else if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
-              const Code3 vc = load_code3(vp, s + l), xc = load_code3(xp, s + l);
-              const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], vf0);
-              const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], vf1);
-              const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], vf2);
-              bool t = false;
-              const bool ok = (drift_dest(si + 1, xc.x, v0, dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, dt_mid, t) == j + 1) &
-                              (drift_dest(sk + 1, xc.z, v2, dt_mid, t) == k + 1);
-              if (ok) {
-                rank[s + l] = (unsigned)cnt | o12;
+          if (mask_hit(A.mask_e + MASK_W * e, ddx, ddy, ddz)) cand += A.rhoc_e[e];
+        }
+      }
+    crowded = cand > heavy;
+    if (!crowded) {
+      int cnt = 0;
+      const long long e0 = ext_index(g, X0 + i, Y0 + j, Z0 + k);
+      float vfn0 = (float)__dmul_rn((double)A.vfield_e[3 * e0], weight_v);  // :27
+      float vfn1 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 1], weight_v);
+      float vfn2 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 2], weight_v);
+      for (int sk = k - r; sk <= k + r; sk++)
+        for (int sj = j - r; sj <= j + r; sj++) {
+          long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
+          for (int si = i - r; si <= i + r; si++, e++) {
+            const int ddx = i - si, ddy = j - sj, ddz = k - sk;
+            if (!mask_hit(A.mask_e + MASK_W * e, ddx, ddy, ddz)) continue;  // nobody in this source cell comes my way
+            const int n = A.rhoc_e[e];
+            const long long s = A.cstart_e[e];
+            const unsigned want = key_pack(ddx, ddy, ddz), o12 = off_pack12(ddx, ddy, ddz) << RANK_BITS;
+            const double vf0 = A.vfield_e[3 * e], vf1 = A.vfield_e[3 * e + 1], vf2 = A.vfield_e[3 * e + 2];
+            for (int l = 0; l < n; l++) {
+              double v0, v1, v2;
+              if (drift_accept(A, s + l, want, si, sj, sk, i, j, k, vf0, vf1, vf2, v0, v1, v2)) {
+                A.rank[s + l] = (unsigned)cnt | o12;
                 cnt++;
-                vfn0 = (float)__dadd_rn((double)vfn0, v0);
+                vfn0 = (float)__dadd_rn((double)vfn0, v0);  // :47, f32 store after each f64 add
                 vfn1 = (float)__dadd_rn((double)vfn1, v1);
                 vfn2 = (float)__dadd_rn((double)vfn2, v2);
               }
             }
           }
         }
+      const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
+      rhoc_new[L] = cnt;
+      vfield_new[3 * L] = (float)((double)vfn0 / den); vfield_new[3 * L + 1] = (float)((double)vfn1 / den); vfield_new[3 * L + 2] = (float)((double)vfn2 / den);
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  {
+    const unsigned hm = __ballot_sync(FULL, crowded);
+    if (lane == 0) s_hm[wp] = hm;
+  }
+  __syncthreads();
+  int ord = 0;
+  for (int wd = 0; wd < DC_T / 32; wd++) {
+    unsigned bits = s_hm[wd];
+    while (bits) {
+      const long long D = (long long)blockIdx.x * blockDim.x + wd * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      if ((ord++ & (DC_T / 32 - 1)) != wp) continue;
+      int tx, ty, tz, i, j, k;
+      phys_decompose(g, D, tx, ty, tz, i, j, k);
+      const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
+      const int r = (dest_flags(g, A.farblk, A.r, X0 + i + NCB, Y0 + j + NCB, Z0 + k + NCB) & FLAG_FAR) ? A.r : min(A.r, 1);
+      int cnt = 0;
+      const long long e0 = ext_index(g, X0 + i, Y0 + j, Z0 + k);
+      float vfn0 = (float)__dmul_rn((double)A.vfield_e[3 * e0], weight_v);
+      float vfn1 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 1], weight_v);
+      float vfn2 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 2], weight_v);
+      for (int sk = k - r; sk <= k + r; sk++)
+        for (int sj = j - r; sj <= j + r; sj++) {
+          long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
+          for (int si = i - r; si <= i + r; si++, e++) {
+            const int ddx = i - si, ddy = j - sj, ddz = k - sk;
+            if (!mask_hit(A.mask_e + MASK_W * e, ddx, ddy, ddz)) continue;
+            const int n = A.rhoc_e[e];
+            const long long s = A.cstart_e[e];
+            const unsigned want = key_pack(ddx, ddy, ddz), o12 = off_pack12(ddx, ddy, ddz) << RANK_BITS;
+            const double vf0 = A.vfield_e[3 * e], vf1 = A.vfield_e[3 * e + 1], vf2 = A.vfield_e[3 * e + 2];
+            for (int base = 0; base < n; base += 32) {
+              double v0 = 0, v1 = 0, v2 = 0;
+              const bool acc = base + lane < n && drift_accept(A, s + base + lane, want, si, sj, sk, i, j, k, vf0, vf1, vf2, v0, v1, v2);
+              unsigned b = __ballot_sync(FULL, acc);
+              if (acc) A.rank[s + base + lane] = (unsigned)(cnt + __popc(b & ((1u << lane) - 1u))) | o12;
+              cnt += __popc(b);
+              while (b) {  // the chain, every lane the same
+                const int src = __ffs(b) - 1;
+                b &= b - 1;
+                vfn0 = (float)__dadd_rn((double)vfn0, __shfl_sync(FULL, v0, src));
+                vfn1 = (float)__dadd_rn((double)vfn1, __shfl_sync(FULL, v1, src));
+                vfn2 = (float)__dadd_rn((double)vfn2, __shfl_sync(FULL, v2, src));
+              }
+            }
+          }
+        }
+    
+      if (lane == 0) {
+        const double den = __dadd_rn((double)cnt, weight_v);
+        rhoc_new[D] = cnt;
+        vfield_new[3 * D] = (float)((double)vfn0 / den); vfield_new[3 * D + 1] = (float)((double)vfn1 / den); vfield_new[3 * D + 2] = (float)((double)vfn2 / den);
       }
-    const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
-    rhoc_new[L] = cnt;
-    vfn0 = (float)((double)vfn0 / den); vfn1 = (float)((double)vfn1 / den); vfn2 = (float)((double)vfn2 / den);
-    vfield_new[3 * L] = vfn0; vfield_new[3 * L + 1] = vfn1; vfield_new[3 * L + 2] = vfn2;
-    st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(vfn0, vfn0), __fmul_rn(vfn1, vfn1)), __fmul_rn(vfn2, vfn2));
+    }
+  }
+}
+// sum over the cells of vfield_new^2 (std_vsim_c, update_particle.f90:133-136): one partial per 128 cells, fixed order
+__global__ void __launch_bounds__(128) k_vfield_sq(long long ncell, const float* __restrict__ vfield_new, double* __restrict__ stc_partial) {
+  const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double st_c = 0;
+  if (L < ncell) {
+    const float a = vfield_new[3 * L], b = vfield_new[3 * L + 1], c = vfield_new[3 * L + 2];
+    st_c = (double)__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
   }
   __shared__ double sm[4];
   for (int o = 16; o; o >>= 1) st_c += __shfl_down_sync(0xffffffffu, st_c, o);

@@ -37,6 +37,61 @@ def vfactor(a, omega_m=0.32, omega_l=0.68):
     return a ** 2 * H
 
 
+def pack_states(xs, vels, nn, nc, nnt):
+    """Particles at global positions ``xs[d]`` (coarse cells, any real; wrapped periodically) with velocities ``vels[d]``
+    (f64 torch vectors) -> ``(states, sigma_vi)`` in CUBE's cell-ordered integer format, one state per image."""
+    nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
+    nt = nc // nnt
+    dev = xs[0].device
+    ncg = [nc * n for n in nn]
+    cells, codes = [], []
+    for d in range(3):
+        x = torch.remainder(xs[d].double(), float(ncg[d]))
+        c = torch.floor(x).clamp_(0, ncg[d] - 1)
+        u = torch.floor((x - c) * 65536.0).clamp_(0, 65535).to(torch.int64)
+        cells.append(c.to(torch.int64))
+        codes.append(u)
+    vels = [v.double() for v in vels]
+    # linear key: image (x fastest), tile (x fastest), k, j, i
+    img = [cells[d] // nc for d in range(3)]
+    loc = [cells[d] % nc for d in range(3)]
+    til = [loc[d] // nt for d in range(3)]
+    cel = [loc[d] % nt for d in range(3)]
+    m = img[0] + nn[0] * (img[1] + nn[1] * img[2])
+    t = til[0] + nnt * (til[1] + nnt * til[2])
+    cc = cel[0] + nt * (cel[1] + nt * cel[2])
+    ncell_img = nc ** 3
+    key = (m * (nnt ** 3) + t) * (nt ** 3) + cc
+    del img, loc, til, cel, m, t, cc, cells
+    nimg = nn[0] * nn[1] * nn[2]
+    order = torch.argsort(key, stable=True)
+    key_s = key[order]
+    counts = torch.bincount(key_s, minlength=nimg * ncell_img)
+    v_s = torch.stack([v[order] for v in vels], 1)          # (N,3) f64
+    u_s = torch.stack([c[order] for c in codes], 1)
+    del vels, codes, key
+    vsum = torch.zeros((nimg * ncell_img, 3), dtype=torch.float64, device=dev)
+    vsum.index_add_(0, key_s, v_s)
+    vfield = (vsum / counts.clamp(min=1)[:, None].double()).float()
+    res = v_s - vfield[key_s].double()
+    sigma_vi = np.float32(math.sqrt(float((res ** 2).sum(1).mean())) / math.sqrt(3.0))
+    S = float(np.float64(np.sqrt(np.float32(PI_F / 2), dtype=np.float32)) / (np.float64(sigma_vi) * 2.5))
+    vp = torch.round(65535.0 * torch.atan(S * res) / PI_F).clamp_(-32767, 32767).to(torch.int16)
+    xp = u_s.to(torch.int32)
+    xp = torch.where(xp >= 32768, xp - 65536, xp).to(torch.int16)
+    bounds = torch.cumsum(counts.view(nimg, -1).sum(1), 0).cpu().numpy()
+    starts = np.concatenate([[0], bounds[:-1]])
+    states = []
+    counts_c = counts.view(nimg, nnt, nnt, nnt, nt, nt, nt).to(torch.int32).cpu().numpy()
+    vfield_c = vfield.view(nimg, nnt, nnt, nnt, nt, nt, nt, 3).cpu().numpy()
+    xp_c = xp.cpu().numpy(); vp_c = vp.cpu().numpy()
+    for mi in range(nimg):
+        s, e = int(starts[mi]), int(bounds[mi])
+        states.append(dict(xp=np.ascontiguousarray(xp_c[s:e]), vp=np.ascontiguousarray(vp_c[s:e]),
+                           rhoc=np.ascontiguousarray(counts_c[mi]), vfield=np.ascontiguousarray(vfield_c[mi])))
+    return states, sigma_vi
+
+
 def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_image=200.0, z_i=49.0,
             n_s=0.9619, h=0.67, omega_m=0.32, device="cpu", velocity_boost=1.0):
     """Return ``(states, sigma_vi, info)``; ``states[m]`` = dict(xp, vp, rhoc, vfield) numpy arrays in
@@ -76,57 +131,44 @@ def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_i
     a = 1.0 / (1.0 + z_i)
     vf = vfactor(a, omega_m, 1 - omega_m) * velocity_boost
     # positions in coarse cells (global), float64
-    ncg = [nc * n for n in nn]
     idx = [torch.arange(npd[d], device=dev, dtype=torch.float64) for d in range(3)]
     q = [idx[d] / np_nc + 0.5 / ncell for d in range(3)]
     qb = (q[0][None, None, :], q[1][None, :, None], q[2][:, None, None])
-    cells, codes, vels = [], [], []
-    for d in range(3):
-        x = (qb[d] + psi[d].double() * (scale / ncell)).reshape(-1)
-        x = torch.remainder(x, float(ncg[d]))
-        c = torch.floor(x).clamp_(0, ncg[d] - 1)
-        u = torch.floor((x - c) * 65536.0).clamp_(0, 65535).to(torch.int64)
-        cells.append(c.to(torch.int64))
-        codes.append(u)
-        vels.append((psi[d].double() * (scale * vf)).reshape(-1))
+    xs = [(qb[d] + psi[d].double() * (scale / ncell)).reshape(-1) for d in range(3)]
+    vels = [(psi[d].double() * (scale * vf)).reshape(-1) for d in range(3)]
     del psi
-    # linear key: image (x fastest), tile (x fastest), k, j, i
-    img = [cells[d] // nc for d in range(3)]
-    loc = [cells[d] % nc for d in range(3)]
-    til = [loc[d] // nt for d in range(3)]
-    cel = [loc[d] % nt for d in range(3)]
-    m = img[0] + nn[0] * (img[1] + nn[1] * img[2])
-    t = til[0] + nnt * (til[1] + nnt * til[2])
-    cc = cel[0] + nt * (cel[1] + nt * cel[2])
-    ncell_img = nc ** 3
-    key = (m * (nnt ** 3) + t) * (nt ** 3) + cc
-    del img, loc, til, cel, m, t, cc, cells
-    nimg = nn[0] * nn[1] * nn[2]
-    order = torch.argsort(key, stable=True)
-    key_s = key[order]
-    counts = torch.bincount(key_s, minlength=nimg * ncell_img)
-    v_s = torch.stack([v[order] for v in vels], 1)          # (N,3) f64
-    u_s = torch.stack([c[order] for c in codes], 1)
-    del vels, codes, key
-    vsum = torch.zeros((nimg * ncell_img, 3), dtype=torch.float64, device=dev)
-    vsum.index_add_(0, key_s, v_s)
-    vfield = (vsum / counts.clamp(min=1)[:, None].double()).float()
-    res = v_s - vfield[key_s].double()
-    sigma_vi = np.float32(math.sqrt(float((res ** 2).sum(1).mean())) / math.sqrt(3.0))
-    S = float(np.float64(np.sqrt(np.float32(PI_F / 2), dtype=np.float32)) / (np.float64(sigma_vi) * 2.5))
-    vp = torch.round(65535.0 * torch.atan(S * res) / PI_F).clamp_(-32767, 32767).to(torch.int16)
-    xp = u_s.to(torch.int32)
-    xp = torch.where(xp >= 32768, xp - 65536, xp).to(torch.int16)
-    bounds = torch.cumsum(counts.view(nimg, -1).sum(1), 0).cpu().numpy()
-    starts = np.concatenate([[0], bounds[:-1]])
-    states = []
-    counts_c = counts.view(nimg, nnt, nnt, nnt, nt, nt, nt).to(torch.int32).cpu().numpy()
-    vfield_c = vfield.view(nimg, nnt, nnt, nnt, nt, nt, nt, 3).cpu().numpy()
-    xp_c = xp.cpu().numpy(); vp_c = vp.cpu().numpy()
-    for mi in range(nimg):
-        s, e = int(starts[mi]), int(bounds[mi])
-        states.append(dict(xp=np.ascontiguousarray(xp_c[s:e]), vp=np.ascontiguousarray(vp_c[s:e]),
-                           rhoc=np.ascontiguousarray(counts_c[mi]), vfield=np.ascontiguousarray(vfield_c[mi])))
-    info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, a=a, vf=vf, npglobal=int(xp_c.shape[0]), seed=seed,
+    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt)
+    npglobal = sum(int(st["xp"].shape[0]) for st in states)
+    info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, a=a, vf=vf, npglobal=npglobal, seed=seed,
                 disp_rms=disp_rms)
+    return states, sigma_vi, info
+
+
+def make_clustered_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, nblob=6, blob_fraction=0.5, blob_sigma=0.35, v_rms=0.3,
+                      device="cpu"):
+    """A late-time-like state for the tests of the crowded-cell paths: ``blob_fraction`` of the ``(np_nc nc)^3`` particles per
+    image sit in ``nblob`` Gaussian clumps per image (``blob_sigma`` coarse cells wide, so single coarse cells hold hundreds
+    of particles, next to empty ones), the rest are uniform; velocities = a per-clump bulk flow + Gaussian dispersion
+    ``v_rms``.  Returns ``(states, sigma_vi, info)`` like ``make_ic``."""
+    nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    nimg = nn[0] * nn[1] * nn[2]
+    ntot = (np_nc * nc) ** 3 * nimg
+    nb = int(ntot * blob_fraction)
+    L = [float(nc * n) for n in nn]
+    which = torch.randint(0, nblob * nimg, (nb,), generator=gen, device=dev)
+    xs, vels = [], []
+    for d in range(3):
+        centre = torch.rand(nblob * nimg, generator=gen, device=dev, dtype=torch.float64) * L[d]
+        bulk = torch.randn(nblob * nimg, generator=gen, device=dev, dtype=torch.float64) * v_rms
+        xb = centre[which] + torch.randn(nb, generator=gen, device=dev, dtype=torch.float64) * blob_sigma
+        xu = torch.rand(ntot - nb, generator=gen, device=dev, dtype=torch.float64) * L[d]
+        xs.append(torch.cat([xb, xu]))
+        v = torch.randn(ntot, generator=gen, device=dev, dtype=torch.float64) * v_rms
+        v[:nb] += bulk[which]
+        vels.append(v)
+    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt)
+    info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, npglobal=ntot, seed=seed, rhoc_max=max(int(st["rhoc"].max()) for st in states))
     return states, sigma_vi, info

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--max-steps", type=int, default=2000)
     ap.add_argument("--window", type=int, default=25, help="steps per reported timing window")
     ap.add_argument("--max-seconds", type=float, default=600.0)
+    ap.add_argument("--sweep", default="", help='";"-separated environment settings ("A=1,B=2;A=3") re-timed on the final state')
     args = ap.parse_args()
     import torch
     from cafproject_b200.cube import CubeGPU, host_tanf_lut
@@ -70,10 +71,35 @@ def main():
         dt_old, dt, a_mid = ts.dt, ts.dt, ts.a_mid
         G.update_particle(dt_old, dt); G.buffer_density(); G.buffer_x(); G.particle_mesh(a_mid, dt); G.buffer_v()
     ph = {k: v / 2 for k, v in G.phase_times().items() if v > 0}
-    rc = G.checkpoint()[0]["rhoc"]
+    final_state, final_sig = G.checkpoint()
+    rc = final_state["rhoc"]
+    edges = [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 1 << 30]
+    flat = rc.reshape(-1).astype(np.int64)
+    hist = {("%d-%d" % (lo, hi - 1)): dict(cells=int(((flat >= lo) & (flat < hi)).sum()), particles=int(flat[(flat >= lo) & (flat < hi)].sum()))
+            for lo, hi in zip(edges[:-1], edges[1:])}
+    print(json.dumps(dict(rhoc_histogram=hist)), flush=True)
     print(json.dumps(dict(final=True, steps=nstep, z=1.0 / float(ts.a) - 1.0, wall_s=time.perf_counter() - t_start, phases_ms=ph,
                           rhoc_max=int(rc.max()), rhoc_mean=float(rc.mean()), empty_cell_fraction=float((rc == 0).mean()), nparticles=int(npart))), flush=True)
     G.close()
+    # the same final state under other settings of the library's environment switches (read at init)
+    dts = (ts.dt, ts.a_mid)
+    for setting in [x for x in args.sweep.split(";") if x]:
+        for kv in setting.split(","):
+            k, v = kv.split("=")
+            os.environ[k] = v
+        G = CubeGPU(args.nc, args.nnt, fk, ck, np_nc=2, tanf_lut=host_tanf_lut())
+        G.particle_initialization(final_state, final_sig)
+        G.buffer_density(); G.buffer_x(); G.buffer_v()
+        G.set_profiling(True)
+        ph = None
+        for it in range(3):
+            G.update_particle(dts[0], dts[0]); G.buffer_density(); G.buffer_x(); G.particle_mesh(dts[1], dts[0]); G.buffer_v()
+            if it == 0:
+                G.phase_times()    # discard the first (warm-up) step
+        ph = {k: v / 2 for k, v in G.phase_times().items() if v > 0}
+        print(json.dumps(dict(sweep=setting, ms_per_step=sum(ph.values()),
+                              phases_ms={k: round(ph[k], 3) for k in ("drift_count", "fine_deposit", "coarse_deposit", "drift_place", "coarse_kick") if k in ph})), flush=True)
+        G.close()
 
 
 if __name__ == "__main__":

@@ -97,6 +97,10 @@ def test_coarse_force(setup):
 def test_drift_then_kicks_bit_exact(setup):
     """update_particle -> buffers -> both kicks with the ORACLE's forces: every code must match."""
     O, G, _, sig = setup
+    _check_drift_then_kicks(O, G)
+
+
+def _check_drift_then_kicks(O, G):
     dt_old, dt, a_mid = np.float32(0.0), np.float32(1.0), np.float32(0.021)
     uo = O.update_particle(dt_old, dt)
     ug = G.update_particle(dt_old, dt)
@@ -128,6 +132,81 @@ def test_drift_then_kicks_bit_exact(setup):
     sg, _ = G.checkpoint()
     assert np.array_equal(physical(O, "xp"), sg["xp"])
     assert np.array_equal(physical(O, "vp"), sg["vp"])
+
+
+@pytest.fixture(scope="module")
+def clustered(tables):
+    """A late-time-like state (half of the particles in a few clumps: coarse cells with 10^2-10^4 particles next to empty
+    ones) so that the crowded-cell warp paths of the deposits and of the drift count run at their default thresholds."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_clustered_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    states, sig, info = make_clustered_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=21, nblob=5, blob_sigma=0.5)
+    assert info["rhoc_max"] > 1000
+    O = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+    G.particle_initialization(states[0], sig)
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    yield O, G, states, sig
+    G.close(); O.close()
+
+
+def test_clustered_densities(clustered):
+    """Crowded bricks are deposited in fixed point (integer atomics / warp reductions, resolution 2^-24 resp. 2^-23): equal to
+    the reference's f32 scatter to round-off, and run-to-run deterministic."""
+    O, G, _, _ = clustered
+    for t in [(1, 1, 1), (2, 1, 2)]:
+        ro, rg = O.fine_density(0, *t), G.fine_density(*t)
+        # 1e-5 = the stated gate: here it is the reference's sequential f32 sum (10^3-10^4 terms per fine cell) that carries the round-off
+        assert norm_rel(rg[:, :, :O.nfe], ro[:, :, :O.nfe]) < 1e-5, t
+        assert not np.any(rg[:, :, :O.nfe][ro[:, :, :O.nfe] == 0])                 # nothing outside the reference's support
+        assert abs(float(rg[:, :, :O.nfe].sum(dtype=np.float64)) - float(ro[:, :, :O.nfe].sum(dtype=np.float64))) < 1e-6 * float(ro.sum(dtype=np.float64))
+        assert np.array_equal(rg, G.fine_density(*t))
+    ro, rg = O.coarse_density(), G.coarse_density()
+    assert norm_rel(rg, ro) < 1e-5
+    assert abs(float(rg.sum(dtype=np.float64)) - float(ro.sum(dtype=np.float64))) < 1e-6 * float(ro.sum(dtype=np.float64))
+    assert np.array_equal(rg, G.coarse_density())
+
+
+def test_clustered_drift_then_kicks_bit_exact(clustered):
+    O, G, _, _ = clustered
+    _check_drift_then_kicks(O, G)
+
+
+def test_crowded_cell_paths_equal_the_walk(tables, monkeypatch):
+    """Thresholds of the crowded-cell paths.  The warp path of the drift count adds the vfield_new terms in the same order as
+    the per-thread walk: counts, vfield and codes are bit-identical whatever the thresholds.  The fixed-point deposits
+    (dense bricks of the fine deposit, crowded cells of the coarse deposit) are equal to the walk to round-off."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_clustered_ic
+    fk, ck = tables
+    states, sig, _ = make_clustered_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=22, nblob=4, blob_sigma=0.6)
+    BIG = "1000000000"
+    outs = []
+    for heavy, dense, minb in ((BIG, BIG, "5"), ("2", BIG, "5"), ("2", "2", "8")):
+        monkeypatch.setenv("CUBE_GPU_HEAVY_DEPOSIT", heavy)
+        monkeypatch.setenv("CUBE_GPU_HEAVY_COUNT", heavy)
+        monkeypatch.setenv("CUBE_GPU_DENSE_DEPOSIT", dense)
+        monkeypatch.setenv("CUBE_GPU_COUNT_MINB", minb)
+        G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC)
+        G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+        rf, rc = G.fine_density(2, 1, 1), G.coarse_density()
+        assert np.array_equal(rf, G.fine_density(2, 1, 1)) and np.array_equal(rc, G.coarse_density())   # deterministic
+        u = G.update_particle(np.float32(0.3), np.float32(1.0))
+        st, _ = G.checkpoint()
+        outs.append((rf, rc, u, st))
+        G.close()
+    (rf0, rc0, u0, s0), (rf1, rc1, u1, s1), (rf2, rc2, u2, s2) = outs
+    assert np.array_equal(rf0, rf1)                                        # no dense brick in either
+    assert norm_rel(rc1, rc0) < 1e-5 and norm_rel(rf2, rf0) < 1e-5 and norm_rel(rc2, rc0) < 1e-5
+    for sa, ua in ((s1, u1), (s2, u2)):
+        for k in ("xp", "vp", "rhoc"):
+            assert np.array_equal(s0[k], sa[k]), k
+        assert np.array_equal(s0["vfield"].view(np.uint32), sa["vfield"].view(np.uint32))
+        assert u0["sigma_vi_new"] == ua["sigma_vi_new"] and u0["std_vsim_c"] == ua["std_vsim_c"]
 
 
 def test_full_steps(tables):
