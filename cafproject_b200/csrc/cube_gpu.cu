@@ -84,6 +84,7 @@ struct cube_handle {
   Geom g;
   cudaStream_t st = nullptr;
   cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false;  // cube_gpu_download_async
+  cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
@@ -470,6 +471,9 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   h->np_tile_max = (long long)((float)(np_image / ((long long)g.nnt * g.nnt * g.nnt)) * r3 * p->tile_buffer);
   CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->st_coarse, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;
   CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
   CK(cudaEventCreate(&h->tev[0])); CK(cudaEventCreate(&h->tev[1]));
@@ -622,6 +626,9 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   for (cufftHandle pl : plans) if (pl) cufftDestroy(pl);
   for (int i = 0; i < 2 * PH_N; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
+  if (h->st_coarse) { cudaStreamSynchronize(h->st_coarse); cudaStreamDestroy(h->st_coarse); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
@@ -988,6 +995,13 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
   return 0;
 }
 
+// the stream the coarse-mesh cuFFT plans execute on
+static int set_coarse_streams(cube_handle* h, cudaStream_t st) {
+  if (h->nimg > 1) { CF(cufftSetStream(h->p2d_r2c, st)); CF(cufftSetStream(h->p2d_c2r, st)); CF(cufftSetStream(h->pz, st)); }
+  else { CF(cufftSetStream(h->cplan_r2c, st)); CF(cufftSetStream(h->cplan_c2r, st)); }
+  return 0;
+}
+
 // coarse mesh (pm.f90:127-189): deposit -> r2c -> i kern_c -> 3 c2r -> force_c with halo.  Leaves the kick prefix
 // force_c*a_mid*dt/6/pi in h->fc, f2_max_coarse in h->f2max[batch]; raw (optional, device) gets force_c itself.
 static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw) {
@@ -1037,6 +1051,20 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   // the unfused route: raw forces, exact f2_max, separate prefix pass.
   const float pscale = ((1.0f * a_mid) * dt) / 6.0f / PI_F;
   const bool pre_in_fft = pscale > 1e-12f && pscale < 1e12f;
+  // The coarse mesh only needs the positions: it runs on a second stream under the fine mesh (its small FFTs and, with several
+  // images, its all-to-all exchanges then cost nothing).  Phase profiling keeps everything on one stream, in the reference's order.
+  const bool overlap = h->overlap_coarse && !h->prof;
+  if (overlap) {
+    cudaStream_t main_st = h->st;
+    CK(cudaEventRecord(h->ev_fork, main_st));
+    CK(cudaStreamWaitEvent(h->st_coarse, h->ev_fork, 0));
+    h->st = h->st_coarse;
+    int rc = set_coarse_streams(h, h->st_coarse);
+    if (!rc) rc = coarse_mesh(h, true, a_mid, dt, nullptr);
+    h->st = main_st;
+    if (set_coarse_streams(h, main_st) || rc) return 1;
+    CK(cudaEventRecord(h->ev_join, h->st_coarse));
+  }
   for (int t0 = 0; t0 < ntile; t0 += h->batch) {
     const int nb = std::min(h->batch, ntile - t0);
     if (fine_mesh(h, t0, nb, pre_in_fft, a_mid, dt)) return 1;
@@ -1052,7 +1080,8 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
   if (build_dvlut(h, h->sigma_vi)) return 1;
-  if (coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
+  if (overlap) { CK(cudaStreamWaitEvent(h->st, h->ev_join, 0)); }
+  else if (coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   float f2c = 0; unsigned long long vb = 0;
   {
     PhaseTimer pt(h, PH_CKICK);
