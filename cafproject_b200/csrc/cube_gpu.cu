@@ -98,7 +98,7 @@ struct cube_handle {
   long long *cstart_p = nullptr, *cstart_p2 = nullptr;
   // extended image grid
   int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
-  int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr; int* farblk = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
+  int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr; int* farblk = nullptr; float* csum = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
@@ -517,7 +517,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     half[32768] = -tanf_lut[32768];
     for (int c = 1; c <= 32767; c++) { const float neg = -tanf_lut[65536 - c]; if (memcmp(&neg, &tanf_lut[c], 4) != 0) { odd = false; break; } }
     if (tanf_lut[0] != 0.f || std::signbit(tanf_lut[0])) odd = false;
-    h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? VT_HOT : 0;
+    h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? VT_ALL : 0;
+    if (const char* e = getenv("CUBE_GPU_VT_HOT")) { if (h->vt_hot) h->vt_hot = std::min(VT_ALL, std::max(4, atoi(e) & ~3)); }
     if (const char* e = getenv("CUBE_GPU_HEAVY_DEPOSIT")) h->heavy_deposit = atoi(e);
     if (const char* e = getenv("CUBE_GPU_HEAVY_COUNT")) h->heavy_count = atoi(e);
     if (const char* e = getenv("CUBE_GPU_DENSE_DEPOSIT")) h->dense_deposit = atoi(e);
@@ -526,9 +527,9 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaStreamSynchronize(h->st));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
     h->nsm = prop.multiProcessorCount;
-    CK(cudaFuncSetAttribute((const void*)k_drift_place_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
-    CK(cudaFuncSetAttribute((const void*)k_selftest_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
-    CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_FULL));
+    CK(cudaFuncSetAttribute((const void*)k_drift_place_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+    CK(cudaFuncSetAttribute((const void*)k_selftest_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+    CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
   }
   // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
   const int ntile = g.nnt * g.nnt * g.nnt;
@@ -543,6 +544,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     h->F_n = (size_t)f.M * f.M * 3 * f.FP;
     if (h->rho_n * sizeof(float) > h->B_n * sizeof(float2)) return fail("cube_gpu_init: internal: rho does not fit its alias");
   }
+  CK(dmalloc(&h->csum, 27LL * (g.nc + 2) * (g.nc + 2) * (g.nc + 2)));  // partial sums of the coarse deposit (cube_kernels.cuh)
   int batch = p->fine_batch;
   {
     const size_t per = h->A_n * sizeof(float2) + h->B_n * sizeof(float2) + h->F_n * sizeof(float);
@@ -603,7 +605,6 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CF(cufftSetStream(h->cplan_r2c, h->st)); CF(cufftSetStream(h->cplan_c2r, h->st));
   }
   CK(cudaFuncSetAttribute((const void*)k_fine_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_coarse_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM));
   if (build_kernels(h, fk_table, ck_table)) { return 1; }
   *out = h;
   return 0;
@@ -614,7 +615,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
-                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
                   h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
@@ -867,7 +868,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   }
   if (!status) {
     PhaseTimer pt(h, PH_PLACE);
-    k_drift_place_w<<<npw, PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), S, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2,
+    k_drift_place_w<<<npw, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), S, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2,
                                                        dt_mid, h->xp2, h->vp2, h->stat_partial); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 0, h->stat3); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 1, h->stat3 + 2); CKL();
@@ -1009,10 +1010,11 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
   const bool multi = h->nimg > 1;
   {
     PhaseTimer pt(h, PH_CDEP);
-    const int cbx = (g.nt + CB_X - 1) / CB_X, cby = (g.nt + CB_Y - 1) / CB_Y, cbz = (g.nt + CB_Z - 1) / CB_Z;
-    k_coarse_deposit<<<dim3(cbx * cby * cbz, g.nnt * g.nnt * g.nnt), CD_T, CD_SMEM, h->st>>>(g, h->mass_p <= 16.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, h->r3,
-                                                                                            multi ? g.nc : g.nc + 2); CKL();
-    h->launches++;
+    const long long nbox = (long long)(g.nc + 2) * (g.nc + 2) * (g.nc + 2);
+    k_coarse_cell_sums<<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, h->mass_p <= 16.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */,
+                                                            h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum); CKL();
+    k_coarse_gather27<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, nbox, h->csum, h->r3, multi ? g.nc : g.nc + 2); CKL();
+    h->launches += 2;
   }
   if (!through_force) return 0;
   PhaseTimer pt(h, PH_CFFT);
@@ -1086,7 +1088,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   {
     PhaseTimer pt(h, PH_CKICK);
     CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
-    k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), vscale(h->sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
+    k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(h->sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
                                                                          h->vmax_bits); CKL();
     h->launches++;
     CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
@@ -1236,7 +1238,7 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
   k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
-  k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, PW_SMEM_FULL, h->st>>>(g, vtab(h), vscale(sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
+  k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
                                                                        h->vmax_bits); CKL();
   float f2c = 0; unsigned long long vb = 0;
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
@@ -1282,7 +1284,7 @@ extern "C" int cube_gpu_selftest_codes(cube_handle* h, float sigma_vi, int64_t n
   CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->st));
   const long long n = 3LL * 32767 + std::max<long long>(0, nsweep);
   k_selftest_encode<<<nblk(n, 256), 256, 0, h->st>>>(h->enc, std::max<long long>(0, nsweep), cnt); CKL();
-  k_selftest_decode<<<1, PW_T, PW_SMEM_FULL, h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
+  k_selftest_decode<<<1, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
   unsigned long long out[2] = {0, 0}; int ok = 0;
   CK(cudaMemcpyAsync(out, cnt, sizeof out, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&ok, h->divok, sizeof ok, cudaMemcpyDeviceToHost, h->st));

@@ -404,20 +404,21 @@ __device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
   return __int2float_rn(2 * (65536 * cell0 + (int)(unsigned short)xp - 32768) + 1) * 0x1p-17f;
 }
 
-// Coarse CIC deposit (pm.f90:130-163).  Same scheme as the fine deposit: one thread per SOURCE cell adds its
-// particles into a private 3x3x3 block of accumulators (targets cell-1..cell+1 of the tile's r3t), a CTA covers a
-// brick of CB_X x CB_Y x CB_Z target cells plus one source layer on every side (tile frame, like r3t(-1:nt+2)),
-// and every target is the sum of its 27 blocks in k,j,i source order.  Deterministic, no atomics.
-constexpr int CB_X = 8, CB_Y = 8, CB_Z = 4, CD_T = CB_X * CB_Y * CB_Z;
-constexpr int CS_X = CB_X + 2, CS_Y = CB_Y + 2, CS_Z = CB_Z + 2, CS_N = CS_X * CS_Y * CS_Z;  // 600 source cells
-constexpr int CD_SMEM = 27 * CS_N * (int)sizeof(float);
-
-// Crowded source cells (more than `heavy` particles) are summed by a whole warp instead of their own thread (a warp would
-// wait for its fullest lane; haloes put 10^3-10^4 particles into a coarse cell at late times): lane = particle, the 27
-// products wx_a wy_b wz_c mass_p (a,b,c = target cell-1, cell, cell+1; a particle has two non-zero weights per dimension) are
-// taken in f32 like the reference's, converted to fixed point (2^-23) and added over the warp with the integer warp
-// reduction (REDUX); lane T keeps the 64-bit total of accumulator T.  Integer sums: independent of any order, deterministic.
-__device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my, const short* __restrict__ xp, long long s, int n, int si, int sj, int sk,
+// Coarse CIC deposit (pm.f90:130-163) in two passes over the image, no atomics, deterministic:
+//   k_coarse_cell_sums   every source cell of the image and of its one-cell rim (extended-grid cells -1..nc per dimension; a rim
+//                        cell aliases the periodic image or holds received ghosts) adds its particles, in storage order, into its
+//                        27 partial sums S[T][cell], T = target cell-1..cell+1 per dimension -- once per source cell;
+//   k_coarse_gather27    every target cell is the sum of the 27 partial sums aimed at it, in the reference's k, j, i source order.
+// (The one-kernel form this replaces kept the partial sums in shared memory per 8x8x4 brick and had to redo the source layer
+// around every brick: 2.3 visits per particle.)  The weights only depend on the position inside the cell -- every f32 step of
+// pm.f90:142-146 is exact for tile-local indices -- so the source cells need no tile frame.
+// Crowded source cells (more than `heavy` particles; a warp would wait for its fullest lane, and haloes put 10^3-10^4 particles
+// into a coarse cell at late times) are summed by a whole warp instead of their own thread: lane = particle, the 27 products
+// wx_a wy_b wz_c mass_p (a particle has two non-zero weights per dimension) are taken in f32 like the reference's, converted to
+// fixed point (2^-23) and added over the warp with the integer warp reduction (REDUX); lane T keeps the 64-bit total of
+// accumulator T.  Integer sums: independent of any order, deterministic.
+constexpr int CD_T = 256;
+__device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my /*[27] stride CD_T*/, const short* __restrict__ xp, long long s, int n,
                                                 float mass_p, int lane) {
   unsigned long long tot = 0;
   const float scale = __fmul_rn(mass_p, 8388608.0f);
@@ -426,12 +427,12 @@ __device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my, const sh
     if (base + lane < n) {
       const Code3 c = load_code3(xp, s + base + lane);
       int i1, j1, k1; float d1, d2;
-      cic_split(coarse_tempx(si, c.x), i1, d1, d2);  // i1 = si or si+1: lower target = cell-1 or cell
-      if (i1 == si) { wx[0] = d1; wx[1] = d2; } else { wx[1] = d1; wx[2] = d2; }
-      cic_split(coarse_tempx(sj, c.y), j1, d1, d2);
-      if (j1 == sj) { wy[0] = d1; wy[1] = d2; } else { wy[1] = d1; wy[2] = d2; }
-      cic_split(coarse_tempx(sk, c.z), k1, d1, d2);
-      if (k1 == sk) { wz[0] = d1; wz[1] = d2; } else { wz[1] = d1; wz[2] = d2; }
+      cic_split(coarse_tempx(1, c.x), i1, d1, d2);  // i1 = 1 or 2: lower target = cell-1 or cell
+      if (i1 == 1) { wx[0] = d1; wx[1] = d2; } else { wx[1] = d1; wx[2] = d2; }
+      cic_split(coarse_tempx(1, c.y), j1, d1, d2);
+      if (j1 == 1) { wy[0] = d1; wy[1] = d2; } else { wy[1] = d1; wy[2] = d2; }
+      cic_split(coarse_tempx(1, c.z), k1, d1, d2);
+      if (k1 == 1) { wz[0] = d1; wz[1] = d2; } else { wz[1] = d1; wz[2] = d2; }
     }
 #pragma unroll
     for (int T = 0; T < 27; T++) {
@@ -440,80 +441,77 @@ __device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my, const sh
       if (lane == T) tot += sum;
     }
   }
-  if (lane < 27) my[lane * CS_N] = __fmul_rn(__ull2float_rn(tot), 0x1p-23f);
+  if (lane < 27) my[lane * CD_T] = __fmul_rn(__ull2float_rn(tot), 0x1p-23f);
 }
 
-__global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, int heavy, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
-                                                         const long long* __restrict__ cstart_e, float mass_p,
-                                                         float* __restrict__ r3 /*[nc][nc][ld]*/, int ld) {
-  extern __shared__ float acc[];  // [27 = (rz*3+ry)*3+rx][CS_N]
-  constexpr int CS_W = (CS_N + 31) / 32;  // 19 words of "crowded" flags
-  __shared__ unsigned s_hm[CS_W + 8];
-  const int t = threadIdx.x;
-  const int tile = blockIdx.y;
-  const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
-  const int nbx = (g.nt + CB_X - 1) / CB_X, nby = (g.nt + CB_Y - 1) / CB_Y;
-  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
-  const int X0 = tx * g.nt, Y0 = ty * g.nt, Z0 = tz * g.nt;
-  for (int e = t; e < 27 * CS_N; e += CD_T) acc[e] = 0.f;
-  static_assert(CD_T % 32 == 0, "whole warps walk the source cells (ballots below)");
-  for (int sb = 0; sb < CS_N; sb += CD_T) {  // sidx = sb + t; CD_T is a multiple of 32, so word (sb + t) / 32 belongs to my warp
-    const int sidx = sb + t;
-    int n = 0;
-    if (sidx < CS_N) {
-      const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
-      const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;
-      if (si <= g.nt && sj <= g.nt && sk <= g.nt) n = rhoc_e[ext_index(g, X0 + si, Y0 + sj, Z0 + sk)];
-    }
+// S[T][nbox], box cell b = ((z+1)*(nc+2) + (y+1))*(nc+2) + (x+1), x,y,z = -1..nc
+__global__ void __launch_bounds__(CD_T) k_coarse_cell_sums(Geom g, int heavy, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
+                                                           const long long* __restrict__ cstart_e, float mass_p, long long nbox,
+                                                           float* __restrict__ S) {
+  __shared__ float acc[27 * CD_T];  // [T][thread]: a thread's 27 sums sit in one bank
+  __shared__ unsigned s_hm[CD_T / 32];
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  const long long b = (long long)blockIdx.x * CD_T + t;
+  const int m = g.nc + 2;
+  int n = 0;
+  long long s = 0;
+  if (b < nbox) {
+    const long long e = ext_index(g, (int)(b % m) - 1, (int)((b / m) % m) - 1, (int)(b / ((long long)m * m)) - 1);
+    n = rhoc_e[e];
+    s = cstart_e[e];
+  }
+#pragma unroll
+  for (int T = 0; T < 27; T++) acc[T * CD_T + t] = 0.f;
+  {
     const unsigned hm = __ballot_sync(0xffffffffu, n > heavy);
-    if ((t & 31) == 0) s_hm[sidx >> 5] = hm;
+    if (lane == 0) s_hm[wp] = hm;
   }
   __syncthreads();
-  for (int sidx = t; sidx < CS_N; sidx += CD_T) {
-    const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
-    const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;  // 0-based tile-local, -1..nt
-    if (si > g.nt || sj > g.nt || sk > g.nt) continue;
-    const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
-    const int n = rhoc_e[e];
-    if (n > heavy) continue;  // spread by a warp below
-    const long long s = cstart_e[e];
-    float* my = acc + sidx;
+  if (n <= heavy) {
+    float* my = acc + t;
     for (int l = 0; l < n; l++) {
       const Code3 c = load_code3(xp, s + l);
       int i1, j1, k1; float ax[2], ay[2], az[2];
-      cic_split(coarse_tempx(si, c.x), i1, ax[0], ax[1]);  // i1 = Fortran r3t index of the lower target = si or si+1
-      cic_split(coarse_tempx(sj, c.y), j1, ay[0], ay[1]);
-      cic_split(coarse_tempx(sk, c.z), k1, az[0], az[1]);
-      const int ra = i1 - si, rb = j1 - sj, rc = k1 - sk;  // 0 or 1
+      cic_split(coarse_tempx(1, c.x), i1, ax[0], ax[1]);  // lower target: i1 - 1 = 0 (cell-1) or 1 (cell)
+      cic_split(coarse_tempx(1, c.y), j1, ay[0], ay[1]);
+      cic_split(coarse_tempx(1, c.z), k1, az[0], az[1]);
+      const int ra = i1 - 1, rb = j1 - 1, rc = k1 - 1;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
         const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:147-154
-        float* p = my + (((rc + qc) * 3 + (rb + qb)) * 3 + (ra + qa)) * CS_N;
+        float* p = my + (((rc + qc) * 3 + (rb + qb)) * 3 + (ra + qa)) * CD_T;
         *p = __fadd_rn(*p, wgt);
       }
     }
   }
   {  // crowded cells, dealt round-robin to the warps
-    const int lane = t & 31, wp = t >> 5;
     int ord = 0;
-    for (int wd = 0; wd < CS_W; wd++) {
+    for (int wd = 0; wd < CD_T / 32; wd++) {
       unsigned bits = s_hm[wd];
       while (bits) {
-        const int sidx = wd * 32 + __ffs(bits) - 1;
+        const int th = wd * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
         if ((ord++ & (CD_T / 32 - 1)) != wp) continue;
-        const int sx = sidx % CS_X, sy = (sidx / CS_X) % CS_Y, sz = sidx / (CS_X * CS_Y);
-        const int si = bx * CB_X + sx - 1, sj = by * CB_Y + sy - 1, sk = bz * CB_Z + sz - 1;
-        const long long e = ext_index(g, X0 + si, Y0 + sj, Z0 + sk);
-        coarse_sum_warp(acc + sidx, xp, cstart_e[e], rhoc_e[e], si, sj, sk, mass_p, lane);
+        const long long bh = (long long)blockIdx.x * CD_T + th;
+        const long long e = ext_index(g, (int)(bh % m) - 1, (int)((bh / m) % m) - 1, (int)(bh / ((long long)m * m)) - 1);
+        coarse_sum_warp(acc + th, xp, cstart_e[e], rhoc_e[e], mass_p, lane);
       }
     }
   }
   __syncthreads();
-  const int ox = t % CB_X, oy = (t / CB_X) % CB_Y, oz = t / (CB_X * CB_Y);
-  const int i = bx * CB_X + ox, j = by * CB_Y + oy, k = bz * CB_Z + oz;
-  if (i >= g.nt || j >= g.nt || k >= g.nt) return;
+  if (b < nbox) {
+#pragma unroll
+    for (int T = 0; T < 27; T++) S[T * nbox + b] = acc[T * CD_T + t];
+  }
+}
+
+// r3(X,Y,Z) = sum over the 27 source cells (X+dx, Y+dy, Z+dz), in k, j, i order, of the partial sum each aims at this target
+__global__ void __launch_bounds__(256) k_coarse_gather27(Geom g, long long nbox, const float* __restrict__ S, float* __restrict__ r3 /*[nc][nc][ld]*/, int ld) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.ncell_p) return;
+  const int X = (int)(q % g.nc), Y = (int)((q / g.nc) % g.nc), Z = (int)(q / ((long long)g.nc * g.nc));
+  const int m = g.nc + 2;
   float v = 0.f;
 #pragma unroll
   for (int dz = -1; dz <= 1; dz++)
@@ -521,12 +519,11 @@ __global__ void __launch_bounds__(CD_T) k_coarse_deposit(Geom g, int heavy, cons
     for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
       for (int dx = -1; dx <= 1; dx++) {
-        // source S = T + d holds my value at relative index r = T - (S - 1) = 1 - d ; Fortran r3t index of T is T0+1,
-        // block index 0 <-> target S0 (Fortran), so r = (T0 + 1) - S0 = 1 - d
-        const int S = ((oz + 1 + dz) * CS_Y + (oy + 1 + dy)) * CS_X + (ox + 1 + dx);
-        v = __fadd_rn(v, acc[(((1 - dz) * 3 + (1 - dy)) * 3 + (1 - dx)) * CS_N + S]);
+        // source S = target + d holds this target at relative index 1 - d
+        const long long b = ((long long)(Z + dz + 1) * m + (Y + dy + 1)) * m + (X + dx + 1);
+        v = __fadd_rn(v, S[(((1 - dz) * 3 + (1 - dy)) * 3 + (1 - dx)) * nbox + b]);
       }
-  r3[((long long)(Z0 + k) * g.nc + (Y0 + j)) * ld + (X0 + i)] = v;
+  r3[((long long)Z * g.nc + Y) * ld + X] = v;
 }
 
 // force_c(3,0:nc+1,0:nc+1,0:nc+1) from the three inverse transforms + periodic 1-cell halo

@@ -83,7 +83,9 @@ __device__ __forceinline__ short vp_encode_lut(double v, double S, const double*
 // A warp owns WC consecutive cells of the file order at a time (their particles are one contiguous run): warp-private
 // prefix offsets, no block barriers after the table fill.
 // =============================================================================================
-constexpr int VT_HOT = 24576;
+constexpr int VT_HOT = 24576;   // |code| < VT_HOT = 4.8 sigma: the part of the half table the kernels were first given
+constexpr int VT_ALL = 32768;   // the whole half table, the default: the velocity distribution of a clustered state has long tails
+                                // (z = 0 state of cfg 2: place 7.28 -> 6.78 ms, coarse kick 5.11 -> 4.99; z = 49: no change)
 constexpr int WC = 32;         // cells per warp chunk
 constexpr int PW_T = 1024;     // threads per CTA
 constexpr int PW_W = PW_T / 32;
@@ -101,6 +103,8 @@ struct VTab {
 struct CellPos { short tx, ty, tz, i, j, k, tile, pad; };
 struct WarpScratch { int soff[WC + 1]; unsigned mask[WC]; CellPos pos[WC]; };
 constexpr int PW_SMEM_FULL = VT_HOT * 4 + PW_W * (int)sizeof(WarpScratch);
+constexpr int PW_SMEM_MAX = VT_ALL * 4 + PW_W * (int)sizeof(WarpScratch);
+__host__ __device__ inline int pw_smem_bytes(int hot) { return hot * 4 + PW_W * (int)sizeof(WarpScratch); }
 
 __device__ __forceinline__ void fill_tab(float* dst, const float* __restrict__ src, int n) {
   const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) k_selftest_encode(const double* __restric
 __global__ void __launch_bounds__(PW_T, 1) k_selftest_decode(VTab vt, double S, unsigned long long* __restrict__ bad) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
-  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
+  if (vt.hot) fill_tab(s_tan, vt.tanh, vt.hot);
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
   int n = 0;
@@ -262,8 +266,8 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + VT_HOT * 4) + warp;
-  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + vt.hot * 4) + warp;
+  if (vt.hot) fill_tab(s_tan, vt.tanh, vt.hot);
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
   const int m = g.nc + 2;
@@ -720,8 +724,8 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + VT_HOT * 4) + warp;
-  if (vt.hot) fill_tab(s_tan, vt.tanh, VT_HOT);
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(pw_smem + vt.hot * 4) + warp;
+  if (vt.hot) fill_tab(s_tan, vt.tanh, vt.hot);
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
   const int nt = g.nt, nnt = g.nnt;
