@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nc", type=int, default=256)
+    ap.add_argument("--ic-tile", type=int, default=1, help="build the image by replicating an (nc/R)^3 image R times per dimension")
     ap.add_argument("--nnt", type=int, default=4)
     ap.add_argument("--fine-batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -235,7 +236,12 @@ def main():
     nc, nnt = args.nc, args.nnt
     # every image starts from the same periodic ICs: the global box is their tiling (continuous across image boundaries,
     # identical work per GPU = weak scaling)
-    states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=2000, device="cuda")
+    if args.ic_tile > 1:    # HBM-sized images: a smaller periodic image replicated (the field generator's temporaries would not fit)
+        from cafproject_b200.synthetic_ic import tile_state
+        states, sig, info = make_ic(nn=1, nc=nc // args.ic_tile, nnt=nnt // args.ic_tile, np_nc=2, seed=2000, device="cuda")
+        states = [tile_state(states[0], nnt // args.ic_tile, args.ic_tile)]
+    else:
+        states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=2000, device="cuda")
     torch.cuda.empty_cache()
     st = states[0]
     npart = st["xp"].shape[0]

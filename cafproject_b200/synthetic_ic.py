@@ -172,3 +172,27 @@ def make_clustered_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, nblob=6, blob
     states, sigma_vi = pack_states(xs, vels, nn, nc, nnt)
     info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, npglobal=ntot, seed=seed, rhoc_max=max(int(st["rhoc"].max()) for st in states))
     return states, sigma_vi, info
+
+
+def tile_state(st, nnt, reps):
+    """Periodic replication of one image's state ``reps`` times per dimension: the state of an image with ``reps*nnt`` tiles
+    per dimension (same ``nt``), built on the host from per-tile runs.  Lets the HBM-sized configurations (1024^3 particles per
+    GPU) be loaded without generating a 1024^3 field first (the torch generator above needs ~170 GB of temporaries for that)."""
+    rhoc, vfield = st["rhoc"], st["vfield"]
+    per_tile = rhoc.reshape(nnt ** 3, -1).sum(1, dtype=np.int64)
+    start = np.concatenate([[0], np.cumsum(per_tile)])
+    big = nnt * reps
+    order = []
+    for tz in range(big):
+        for ty in range(big):
+            for tx in range(big):
+                order.append(((tz % nnt) * nnt + ty % nnt) * nnt + tx % nnt)
+    n = int(per_tile[order].sum())
+    xp = np.empty((n, 3), np.int16); vp = np.empty((n, 3), np.int16)
+    o = 0
+    for t in order:
+        m = int(per_tile[t])
+        xp[o:o + m] = st["xp"][start[t]:start[t] + m]; vp[o:o + m] = st["vp"][start[t]:start[t] + m]
+        o += m
+    return dict(xp=xp, vp=vp, rhoc=np.ascontiguousarray(np.tile(rhoc, (reps, reps, reps, 1, 1, 1))),
+                vfield=np.ascontiguousarray(np.tile(vfield, (reps, reps, reps, 1, 1, 1, 1))))
