@@ -192,7 +192,7 @@ constexpr int FD_SMEM = 125 * FS_N * (int)sizeof(float);
 // deterministic like the walk, equal to it to round-off.  (A 64-bit shared-memory atomic add compiles to a CAS loop on
 // sm_100a -- that form was measured and dropped, profiles/r01i_notes.md.)
 constexpr int FDN = (4 * FB_X) * (4 * FB_Y) * (4 * FB_Z);  // 8192 fine cells per brick
-__device__ __forceinline__ bool fine_deposit_dense(const Geom& g, unsigned* __restrict__ sm, const short* __restrict__ xp, int n, long long s,
+__device__ __noinline__ bool fine_deposit_dense(const Geom& g, unsigned* __restrict__ sm, const short* __restrict__ xp, int n, long long s,
                                                    int si0, int sj0, int sk0, float mass_p, float* __restrict__ out, const DepWin& w,
                                                    int bx, int by, int bz) {
   // layout: lo[FDN] hi[FDN] pref[256+1] start[225] (8-byte aligned)

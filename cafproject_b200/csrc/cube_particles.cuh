@@ -372,7 +372,8 @@ __device__ __forceinline__ bool mask_hit(const unsigned* __restrict__ m, int dx,
 __device__ __forceinline__ void mask_set(unsigned* m, int ox, int oy, int oz, bool tie) {
   if (!tie) {
     const int b = max(abs(ox), max(abs(oy), abs(oz))) <= 2 ? offset_bit(ox, oy, oz) : MASK_FAR_BIT;
-    atomicOr(m + (b >> 5), 1u << (b & 31));
+    // almost every particle of a cell sets the same bit: look before the atomic (a stale read only costs a redundant atomicOr)
+    if (!((*(volatile unsigned*)(m + (b >> 5)) >> (b & 31)) & 1u)) atomicOr(m + (b >> 5), 1u << (b & 31));
     return;
   }
   for (int dz = -1; dz <= 1; dz++)
@@ -551,6 +552,7 @@ template <int MINB>
 __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountArgs A, int heavy, int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
   const double weight_v = (double)0.1f;  // update_particle.f90:10
   __shared__ unsigned s_hm[DC_T / 32];
+  __shared__ double s_v[DC_T / 32][3][32];  // a warp's accepted velocities of the current 32 candidates (crowded path)
   const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool crowded = false;
   if (L < g.ncell_p) {
@@ -623,9 +625,11 @@ __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountAr
       const int r = (dest_flags(g, A.farblk, A.r, X0 + i + NCB, Y0 + j + NCB, Z0 + k + NCB) & FLAG_FAR) ? A.r : min(A.r, 1);
       int cnt = 0;
       const long long e0 = ext_index(g, X0 + i, Y0 + j, Z0 + k);
-      float vfn0 = (float)__dmul_rn((double)A.vfield_e[3 * e0], weight_v);
-      float vfn1 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 1], weight_v);
-      float vfn2 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 2], weight_v);
+      // the three components' chains run side by side in lanes 0, 1, 2 (the other lanes repeat them): an instruction costs a
+      // warp the same for one lane as for 32, so this is a third of the chain instructions of "every lane all three"
+      const int dcomp = lane % 3;
+      float vfn = (float)__dmul_rn((double)A.vfield_e[3 * e0 + dcomp], weight_v);
+      double(*sv)[32] = s_v[wp];
       for (int sk = k - r; sk <= k + r; sk++)
         for (int sj = j - r; sj <= j + r; sj++) {
           long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
@@ -639,25 +643,24 @@ __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountAr
             for (int base = 0; base < n; base += 32) {
               double v0 = 0, v1 = 0, v2 = 0;
               const bool acc = base + lane < n && drift_accept(A, s + base + lane, want, si, sj, sk, i, j, k, vf0, vf1, vf2, v0, v1, v2);
-              unsigned b = __ballot_sync(FULL, acc);
-              if (acc) A.rank[s + base + lane] = (unsigned)(cnt + __popc(b & ((1u << lane) - 1u))) | o12;
-              cnt += __popc(b);
-              while (b) {  // the chain, every lane the same
-                const int src = __ffs(b) - 1;
-                b &= b - 1;
-                vfn0 = (float)__dadd_rn((double)vfn0, __shfl_sync(FULL, v0, src));
-                vfn1 = (float)__dadd_rn((double)vfn1, __shfl_sync(FULL, v1, src));
-                vfn2 = (float)__dadd_rn((double)vfn2, __shfl_sync(FULL, v2, src));
+              const unsigned b = __ballot_sync(FULL, acc);
+              if (!b) continue;
+              if (acc) {  // accepted velocities, compacted in storage order
+                const int pos = __popc(b & ((1u << lane) - 1u));
+                A.rank[s + base + lane] = (unsigned)(cnt + pos) | o12;
+                sv[0][pos] = v0; sv[1][pos] = v1; sv[2][pos] = v2;
               }
+              const int na = __popc(b);
+              cnt += na;
+              __syncwarp();
+              for (int q = 0; q < na; q++) vfn = (float)__dadd_rn((double)vfn, sv[dcomp][q]);  // :47, f32 store after each f64 add
+              __syncwarp();
             }
           }
         }
-    
-      if (lane == 0) {
-        const double den = __dadd_rn((double)cnt, weight_v);
-        rhoc_new[D] = cnt;
-        vfield_new[3 * D] = (float)((double)vfn0 / den); vfield_new[3 * D + 1] = (float)((double)vfn1 / den); vfield_new[3 * D + 2] = (float)((double)vfn2 / den);
-      }
+      const double den = __dadd_rn((double)cnt, weight_v);
+      if (lane == 0) rhoc_new[D] = cnt;
+      if (lane < 3) vfield_new[3 * D + lane] = (float)((double)vfn / den);
     }
   }
 }
