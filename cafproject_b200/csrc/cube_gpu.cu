@@ -473,7 +473,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->st_coarse, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;
+  h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;  // multi-image runs: decided after the communicator exists (below)
   CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
   CK(cudaEventCreate(&h->tev[0])); CK(cudaEventCreate(&h->tev[1]));
@@ -1055,7 +1055,10 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   const bool pre_in_fft = pscale > 1e-12f && pscale < 1e12f;
   // The coarse mesh only needs the positions: it runs on a second stream under the fine mesh (its small FFTs and, with several
   // images, its all-to-all exchanges then cost nothing).  Phase profiling keeps everything on one stream, in the reference's order.
-  const bool overlap = h->overlap_coarse && !h->prof;
+  // Several images: the distributed coarse FFT's NCCL exchanges, launched next to a GPU full of fine-mesh CTAs, make every
+  // rank wait for the slowest peer's exchange kernel to be scheduled (measured on 8 B200s: 65.1 ms/step overlapped against
+  // 56.8 in sequence) -- one stream there unless CUBE_GPU_OVERLAP=1.
+  const bool overlap = h->overlap_coarse && !h->prof && (h->nimg == 1 || getenv("CUBE_GPU_OVERLAP") != nullptr);
   if (overlap) {
     cudaStream_t main_st = h->st;
     CK(cudaEventRecord(h->ev_fork, main_st));
