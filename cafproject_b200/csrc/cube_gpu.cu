@@ -471,7 +471,11 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   h->np_tile_max = (long long)((float)(np_image / ((long long)g.nnt * g.nnt * g.nnt)) * r3 * p->tile_buffer);
   CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&h->st_coarse, cudaStreamNonBlocking));
+  {  // highest priority: the coarse stream's small kernels (and exchange kernels) take the next CTA slots that free up
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->st_coarse, cudaStreamNonBlocking, getenv("CUBE_GPU_COARSE_PRIO0") ? lo : hi));
+  }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;  // multi-image runs: decided after the communicator exists (below)
   CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
@@ -1011,7 +1015,7 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
   {
     PhaseTimer pt(h, PH_CDEP);
     const long long nbox = (long long)(g.nc + 2) * (g.nc + 2) * (g.nc + 2);
-    k_coarse_cell_sums<<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, h->mass_p <= 16.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */,
+    k_coarse_cell_sums<<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, h->mass_p <= 8.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */,
                                                             h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum); CKL();
     k_coarse_gather27<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, nbox, h->csum, h->r3, multi ? g.nc : g.nc + 2); CKL();
     h->launches += 2;
@@ -1055,10 +1059,11 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   const bool pre_in_fft = pscale > 1e-12f && pscale < 1e12f;
   // The coarse mesh only needs the positions: it runs on a second stream under the fine mesh (its small FFTs and, with several
   // images, its all-to-all exchanges then cost nothing).  Phase profiling keeps everything on one stream, in the reference's order.
-  // Several images: the distributed coarse FFT's NCCL exchanges, launched next to a GPU full of fine-mesh CTAs, make every
-  // rank wait for the slowest peer's exchange kernel to be scheduled (measured on 8 B200s: 65.1 ms/step overlapped against
-  // 56.8 in sequence) -- one stream there unless CUBE_GPU_OVERLAP=1.
-  const bool overlap = h->overlap_coarse && !h->prof && (h->nimg == 1 || getenv("CUBE_GPU_OVERLAP") != nullptr);
+  // The coarse stream has the highest priority: with several images the exchange kernels of the distributed coarse FFT must
+  // get the next CTA slots that free up, or every rank waits for the slowest peer's exchange kernel to be scheduled behind a
+  // GPU full of fine-mesh CTAs (measured at default priority: 65.1 ms/step overlapped against 56.8 in sequence on 8 B200s,
+  // 63.4 against 52.8 on 2; at the highest priority 51.8 against 53.5 on 2).
+  const bool overlap = h->overlap_coarse && !h->prof;
   if (overlap) {
     cudaStream_t main_st = h->st;
     CK(cudaEventRecord(h->ev_fork, main_st));
