@@ -349,12 +349,12 @@ def main():
             G.particle_initialization(inp, sig_cur, npglobal=world * npart)
             G.buffer_density(); G.buffer_x(); G.buffer_v()
             G.update_particle(dt, dt)
-            G.checkpoint_begin(host, xp=True)       # positions are final for this step: stream them out under particle_mesh
+            G.checkpoint_begin(host, xp=True, cells=True)   # positions, rhoc and vfield are final for this step: stream them out under particle_mesh
             G.buffer_density(); G.buffer_x()
             G.particle_mesh(a_mid, dt)
             G.buffer_v()
             h2d = sum(v.nbytes for v in inp.values())
-            inp, sig_cur = G.checkpoint(out=host, skip=("xp",))   # result lands in the same pinned buffers = next step's input
+            inp, sig_cur = G.checkpoint(out=host, skip=("xp", "rhoc", "vfield"))   # result lands in the same pinned buffers = next step's input
             d2h = sum(v.nbytes for v in inp.values())
         barrier()
         sec = time.perf_counter() - t0

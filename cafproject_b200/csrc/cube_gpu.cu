@@ -681,6 +681,19 @@ extern "C" int cube_gpu_download_async(cube_handle* h, int16_t* xp, int16_t* vp)
   return 0;
 }
 
+extern "C" int cube_gpu_download_cells_async(cube_handle* h, int32_t* rhoc_phys, float* vfield_phys) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->p.device));
+  const Geom& g = h->g;
+  CK(cudaEventRecord(h->ev_copy[0], h->st));
+  CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
+  if (rhoc_phys) CK(cudaMemcpyAsync(rhoc_phys, h->rhoc_p, sizeof(int) * g.ncell_p, cudaMemcpyDeviceToHost, h->st_copy));
+  if (vfield_phys) CK(cudaMemcpyAsync(vfield_phys, h->vfield_p, sizeof(float) * 3 * g.ncell_p, cudaMemcpyDeviceToHost, h->st_copy));
+  CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
+  h->copy_pending = true;
+  return 0;
+}
+
 extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32_t* rhoc_phys, float* vfield_phys,
                                  int64_t* nplocal, float* sigma_vi) {
   if (!h) return fail("null handle");

@@ -94,6 +94,10 @@ int cube_gpu_download(cube_handle *h, int16_t *xp, int16_t *vp, int32_t *rhoc_ph
  * should be page-locked.  Typical use: xp right after cube_gpu_update_x -- particle_mesh does not move particles, so the
  * position traffic of checkpoint.f90:43-50 overlaps the force computation. */
 int cube_gpu_download_async(cube_handle *h, int16_t *xp, int16_t *vp);
+/* The same for the per-cell arrays rhoc(nt,nt,nt,nnt,nnt,nnt) and vfield(3,...) of checkpoint.f90:35,40: they are final once
+ * cube_gpu_update_x has returned (particle_mesh changes neither), so they too can leave under the force computation.
+ * cube_gpu_download with NULL for them waits for the stream. */
+int cube_gpu_download_cells_async(cube_handle *h, int32_t *rhoc_phys, float *vfield_phys);
 
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);

@@ -12,7 +12,7 @@ PHASE_OF = [("k_drift_key", "drift_key"), ("k_mask_ext", "drift_key"), ("k_drift
             ("k_scan_", "drift_scan"), ("k_drift_place", "drift_place"), ("k_build_ext", "buffer"), ("k_tile_counts", "buffer"),
             ("k_fine_deposit", "fine_deposit"), ("k_fft_x_fwd", "fine_fft_x"), ("k_fft_y<16, 18, 1", "fine_ifft_y"), ("k_fft_y<", "fine_fft_y"),
             ("k_fft_z_green", "fine_fft_z_green"), ("k_fft_x_inv3", "fine_ifft_x"), ("k_fine_kick", "fine_kick"),
-            ("k_coarse_deposit", "coarse_deposit"), ("regular_fft", "coarse_fft_green"), ("vector_fft", "coarse_fft_green"),
+            ("k_coarse_deposit", "coarse_deposit"), ("k_coarse_cell_sums", "coarse_deposit"), ("k_coarse_gather27", "coarse_deposit"), ("regular_fft", "coarse_fft_green"), ("vector_fft", "coarse_fft_green"),
             ("k_green", "coarse_fft_green"), ("k_force_c_finish", "coarse_fft_green"), ("k_coarse_kick", "coarse_kick")]
 
 
