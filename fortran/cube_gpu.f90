@@ -82,6 +82,17 @@ module cube_gpu
       integer(c_int64_t), intent(out) :: nplocal
       real(c_float), intent(out) :: sigma_vi
     end function
+    ! positions / velocities (and the per-cell arrays) streamed to page-locked host buffers while later calls run:
+    ! xp, rhoc and vfield are final once cube_gpu_update_x has returned (checkpoint.f90:35-50); cube_gpu_download with
+    ! c_null_ptr for what was streamed waits for the copies
+    integer(c_int) function cube_gpu_download_async(h, xp, vp) bind(C, name="cube_gpu_download_async")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, xp, vp
+    end function
+    integer(c_int) function cube_gpu_download_cells_async(h, rhoc_phys, vfield_phys) bind(C, name="cube_gpu_download_cells_async")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, rhoc_phys, vfield_phys
+    end function
     integer(c_int) function cube_gpu_finalize(h) bind(C, name="cube_gpu_finalize")
       import :: c_int, c_ptr
       type(c_ptr), value :: h
