@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nc", type=int, default=256)
+    ap.add_argument("--no-stream-vp", action="store_true", help="e2e leg: download the velocities after particle_mesh instead of streaming them per tile batch")
     ap.add_argument("--ic-tile", type=int, default=1, help="build the image by replicating an (nc/R)^3 image R times per dimension")
     ap.add_argument("--nnt", type=int, default=4)
     ap.add_argument("--fine-batch", type=int, default=0)
@@ -349,12 +350,14 @@ def main():
             G.particle_initialization(inp, sig_cur, npglobal=world * npart)
             G.buffer_density(); G.buffer_x(); G.buffer_v()
             G.update_particle(dt, dt)
-            G.checkpoint_begin(host, xp=True, cells=True)   # positions, rhoc and vfield are final for this step: stream them out under particle_mesh
+            # positions, rhoc and vfield are final for this step: stream them out under particle_mesh; the velocities follow
+            # tile batch by tile batch as their kicks are done
+            G.checkpoint_begin(host, xp=True, cells=True, vp_during_pm=not args.no_stream_vp)
             G.buffer_density(); G.buffer_x()
             G.particle_mesh(a_mid, dt)
             G.buffer_v()
             h2d = sum(v.nbytes for v in inp.values())
-            inp, sig_cur = G.checkpoint(out=host, skip=("xp", "rhoc", "vfield"))   # result lands in the same pinned buffers = next step's input
+            inp, sig_cur = G.checkpoint(out=host, skip=("xp", "rhoc", "vfield") + (() if args.no_stream_vp else ("vp",)))   # result lands in the same pinned buffers = next step's input
             d2h = sum(v.nbytes for v in inp.values())
         barrier()
         sec = time.perf_counter() - t0

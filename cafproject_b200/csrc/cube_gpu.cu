@@ -84,6 +84,8 @@ struct cube_handle {
   Geom g;
   cudaStream_t st = nullptr;
   cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false;  // cube_gpu_download_async
+  int16_t* vp_stream_host = nullptr;  // cube_gpu_stream_vp: where the next particle_mesh streams the final velocities
+  double* dvlut2 = nullptr; int* divok2 = nullptr;  // decode table of sigma_vi_new while the main one still serves the fine kick
   cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
@@ -509,7 +511,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
   CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
-  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->divok, 1));
+  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->divok, 1)); CK(dmalloc(&h->dvlut2, 65536)); CK(dmalloc(&h->divok2, 1));
   k_build_enc<<<128, 256, 0, h->st>>>(h->enc); CKL();
   CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
   {
@@ -620,7 +622,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -691,6 +693,12 @@ extern "C" int cube_gpu_download_cells_async(cube_handle* h, int32_t* rhoc_phys,
   if (vfield_phys) CK(cudaMemcpyAsync(vfield_phys, h->vfield_p, sizeof(float) * 3 * g.ncell_p, cudaMemcpyDeviceToHost, h->st_copy));
   CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
   h->copy_pending = true;
+  return 0;
+}
+
+extern "C" int cube_gpu_stream_vp(cube_handle* h, int16_t* vp) {
+  if (!h) return fail("null handle");
+  h->vp_stream_host = vp;
   return 0;
 }
 
@@ -1077,6 +1085,21 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   // GPU full of fine-mesh CTAs (measured at default priority: 65.1 ms/step overlapped against 56.8 in sequence on 8 B200s,
   // 63.4 against 52.8 on 2; at the highest priority 51.8 against 53.5 on 2).
   const bool overlap = h->overlap_coarse && !h->prof;
+  // streamed velocities (cube_gpu_stream_vp): smaller batches, coarse kick per batch, the batch's vp out under the next batch
+  int16_t* const vp_host = h->vp_stream_host;
+  h->vp_stream_host = nullptr;
+  const int step_batch = vp_host ? std::max(1, std::min(h->batch, (ntile + 3) / 4)) : h->batch;
+  std::vector<long long> tile_start(ntile + 1, 0);
+  if (vp_host) {
+    CK(cudaMemsetAsync(h->divok2, 0xff, sizeof(int), h->st));
+    k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, S_new, 1.0 / S_new, h->dvlut2, h->divok2); CKL();
+    h->launches++;
+    CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
+    CK(cudaMemcpy2DAsync(tile_start.data(), sizeof(long long), h->cstart_p, sizeof(long long) * nt3, sizeof(long long), ntile + 1,
+                         cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (!overlap && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
+  }
   if (overlap) {
     cudaStream_t main_st = h->st;
     CK(cudaEventRecord(h->ev_fork, main_st));
@@ -1088,8 +1111,8 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
     if (set_coarse_streams(h, main_st) || rc) return 1;
     CK(cudaEventRecord(h->ev_join, h->st_coarse));
   }
-  for (int t0 = 0; t0 < ntile; t0 += h->batch) {
-    const int nb = std::min(h->batch, ntile - t0);
+  for (int t0 = 0; t0 < ntile; t0 += step_batch) {
+    const int nb = std::min(step_batch, ntile - t0);
     if (fine_mesh(h, t0, nb, pre_in_fft, a_mid, dt)) return 1;
     CK(cudaMemcpyAsync(f2.data() + t0, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st));
     if (!pre_in_fft) {
@@ -1097,20 +1120,43 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
       k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(fb, h->F, a_mid, dt); CKL();
       h->launches++;
     }
-    PhaseTimer pt(h, PH_FKICK);
-    k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
-    h->launches++;
+    {
+      PhaseTimer pt(h, PH_FKICK);
+      k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
+      h->launches++;
+    }
+    if (vp_host) {
+      if (overlap && t0 == 0) CK(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+      const long long c_begin = (long long)t0 * nt3, c_end = (long long)(t0 + nb) * nt3;
+      {
+        PhaseTimer pc(h, PH_CKICK);
+        k_coarse_kick_w<<<pw_grid(h, c_end - c_begin), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(
+            g, VTab{h->tanh, h->enc, h->dvlut2, h->divok2, h->vt_hot}, S_new, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->vmax_bits, c_begin, c_end); CKL();
+        h->launches++;
+      }
+      CK(cudaEventRecord(h->ev_copy[0], h->st));
+      CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
+      const long long p_begin = tile_start[t0], p_end = tile_start[t0 + nb];
+      if (p_end > p_begin)
+        CK(cudaMemcpyAsync(vp_host + 3 * p_begin, h->vp + 3 * p_begin, sizeof(short) * 3 * (p_end - p_begin), cudaMemcpyDeviceToHost, h->st_copy));
+      CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
+      h->copy_pending = true;
+    }
   }
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
   if (build_dvlut(h, h->sigma_vi)) return 1;
   if (overlap) { CK(cudaStreamWaitEvent(h->st, h->ev_join, 0)); }
-  else if (coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
+  else if (!vp_host && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   float f2c = 0; unsigned long long vb = 0;
-  {
+  if (vp_host) {  // every batch already had its coarse kick
+    CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  } else {
     PhaseTimer pt(h, PH_CKICK);
     CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
     k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(h->sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
-                                                                         h->vmax_bits); CKL();
+                                                                         h->vmax_bits, 0, g.ncell_p); CKL();
     h->launches++;
     CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
@@ -1260,7 +1306,7 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
   k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
   k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
-                                                                       h->vmax_bits); CKL();
+                                                                       h->vmax_bits, 0, h->g.ncell_p); CKL();
   float f2c = 0; unsigned long long vb = 0;
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));

@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, double S, const short* __restrict__ xp, short* __restrict__ vp,
                                                           const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
-                                                          const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits) {
+                                                          const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits,
+                                                          long long c_begin, long long c_end /* file-order cell range */) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -272,9 +273,9 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
   __syncthreads();
   const int m = g.nc + 2;
   double vm = 0.0;
-  for (long long c0 = ((long long)blockIdx.x * PW_W + warp) * WC; c0 < g.ncell_p; c0 += (long long)gridDim.x * PW_W * WC) {
+  for (long long c0 = c_begin + ((long long)blockIdx.x * PW_W + warp) * WC; c0 < c_end; c0 += (long long)gridDim.x * PW_W * WC) {
     long long p0;
-    const int np = warp_chunk_setup(g, cstart_p, c0, g.ncell_p, ws, lane, p0);
+    const int np = warp_chunk_setup(g, cstart_p, c0, c_end, ws, lane, p0);
     for (int q = lane; q < np; q += 32) {
       const int cl = warp_chunk_find(ws, q);
       const long long L = c0 + cl;

@@ -55,6 +55,7 @@ def load_library():
     L.cube_gpu_finalize.argtypes = [vp]
     L.cube_gpu_download_async.argtypes = [vp, vp, vp]
     L.cube_gpu_download_cells_async.argtypes = [vp, vp, vp]
+    L.cube_gpu_stream_vp.argtypes = [vp, vp]
     L.cube_gpu_last_error.restype = C.c_char_p
     L.cube_gpu_query.restype = i64
     L.cube_gpu_query.argtypes = [vp, C.c_char_p]
@@ -86,7 +87,7 @@ ABI_SYMBOLS = [
     "cube_gpu_get_kern_c", "cube_gpu_fine_density", "cube_gpu_fine_force", "cube_gpu_fine_kick_with",
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
-    "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_selftest_codes",
+    "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
 ]
 
 
@@ -225,16 +226,19 @@ class CubeGPU:
             out = dict(out, xp=out["xp"][:n], vp=out["vp"][:n])
         return out, F32(sig.value)
 
-    def checkpoint_begin(self, out, xp=True, vp=False, cells=False):
+    def checkpoint_begin(self, out, xp=True, vp=False, cells=False, vp_during_pm=False):
         """Start streaming xp and/or vp (and, with ``cells``, rhoc and vfield) of the current disjoint state into ``out``
         (page-locked arrays; xp, vp with capacity >= nplocal rows) while later calls run; finish with
-        ``checkpoint(out=out, skip=...)``."""
+        ``checkpoint(out=out, skip=...)``.  ``vp_during_pm``: the next ``particle_mesh`` streams every tile batch's final
+        velocities into ``out["vp"]`` as soon as that batch has had its kicks (cube_gpu_stream_vp)."""
         n = self.query("nplocal")
         assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n
         if xp or vp:
             self._ck(self.L.cube_gpu_download_async(self.h, _p(out["xp"]) if xp else None, _p(out["vp"]) if vp else None))
         if cells:
             self._ck(self.L.cube_gpu_download_cells_async(self.h, _p(out["rhoc"]), _p(out["vfield"])))
+        if vp_during_pm:
+            self._ck(self.L.cube_gpu_stream_vp(self.h, _p(out["vp"])))
 
     # ---- step subroutines -------------------------------------------------------------------
     def update_particle(self, dt_old, dt):

@@ -93,6 +93,11 @@ module cube_gpu
       import :: c_int, c_ptr
       type(c_ptr), value :: h, rhoc_phys, vfield_phys
     end function
+    ! registers a page-locked buffer: the next cube_gpu_particle_mesh streams every tile batch's final velocities into it
+    integer(c_int) function cube_gpu_stream_vp(h, vp) bind(C, name="cube_gpu_stream_vp")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, vp
+    end function
     integer(c_int) function cube_gpu_finalize(h) bind(C, name="cube_gpu_finalize")
       import :: c_int, c_ptr
       type(c_ptr), value :: h

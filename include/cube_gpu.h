@@ -98,6 +98,12 @@ int cube_gpu_download_async(cube_handle *h, int16_t *xp, int16_t *vp);
  * cube_gpu_update_x has returned (particle_mesh changes neither), so they too can leave under the force computation.
  * cube_gpu_download with NULL for them waits for the stream. */
 int cube_gpu_download_cells_async(cube_handle *h, int32_t *rhoc_phys, float *vfield_phys);
+/* Velocities: registers a page-locked buffer for the NEXT cube_gpu_particle_mesh call only.  That call then works through the
+ * tiles in (at least four) batches, gives every batch its coarse kick right after its fine kick (the coarse force only needs
+ * positions and is ready by then; per particle the two kicks are the same operations in the same order as pm.f90:88-228) and
+ * streams the batch's final velocities into vp while the next batch's force is computed -- the velocity half of
+ * checkpoint.f90:51-58 leaves under the computation.  cube_gpu_download with NULL for vp waits for the stream. */
+int cube_gpu_stream_vp(cube_handle *h, int16_t *vp);
 
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);

@@ -273,3 +273,41 @@ def test_streamed_checkpoint_equals_direct(tables):
         assert np.array_equal(streamed[k], direct[k]), k
     G.update_particle(dt, dt)          # the next drift must not race the finished stream
     G.close()
+
+
+def test_velocities_streamed_per_batch_equal_the_plain_step(tables):
+    """cube_gpu_stream_vp: particle_mesh in (at least four) tile batches, coarse kick right after each batch's fine kick,
+    velocities streamed out batch by batch -- the same codes, time-step limits and vmax as the plain step."""
+    import torch
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=9, disp_rms=0.6)
+    dt, a_mid = np.float32(0.8), np.float32(0.021)
+    res = []
+    for streamed in (False, True):
+        G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC)
+        G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+        G.update_particle(np.float32(0), dt)
+        n = G.query("nplocal")
+        pin = dict(xp=torch.zeros((n + 64, 3), dtype=torch.int16).pin_memory().numpy(), vp=torch.zeros((n + 64, 3), dtype=torch.int16).pin_memory().numpy(),
+                   rhoc=np.empty((NNT,) * 3 + (NC // NNT,) * 3, np.int32), vfield=np.empty((NNT,) * 3 + (NC // NNT,) * 3 + (3,), np.float32))
+        if streamed:
+            G.checkpoint_begin(pin, xp=True, cells=True, vp_during_pm=True)
+        G.buffer_density(); G.buffer_x()
+        pm = G.particle_mesh(a_mid, dt)
+        G.buffer_v()
+        st, s_out = G.checkpoint(out=pin, skip=("xp", "rhoc", "vfield", "vp") if streamed else ())
+        res.append(({k: np.array(v, copy=True) for k, v in st.items()}, pm, s_out))
+        if streamed:                       # the device state is what was streamed, and the next step runs from it
+            direct, _ = G.checkpoint()
+            for k in ("xp", "vp", "rhoc", "vfield"):
+                assert np.array_equal(direct[k], st[k]), k
+            G.update_particle(dt, dt)
+        G.close()
+    (a, pa, sa), (b, pb, sb) = res
+    for k in ("xp", "vp", "rhoc", "vfield"):
+        assert np.array_equal(a[k], b[k]), k
+    assert sa == sb
+    for k in ("dt_fine", "dt_coarse", "dt_vmax"):
+        assert pa[k] == pb[k], k
