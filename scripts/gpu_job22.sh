@@ -1,0 +1,7 @@
+# final check of the round: whole GPU suite, smoke(), the complete bench line
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 4200 gpurun_out/bench.log; tail -3 gpurun_out/bench.err
