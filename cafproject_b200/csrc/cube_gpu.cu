@@ -650,6 +650,8 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
   const Geom& g = h->g;
   if (nplocal > h->np_image_max)
     return fail("error: too many particles in this image+buffer: %lld > %lld; please set image_buffer larger", (long long)nplocal, h->np_image_max);
+  if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // a streamed download still reads the arrays overwritten here
+  h->vp_stream_host = nullptr;
   CK(cudaMemcpyAsync(h->xp, xp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->vp, vp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->rhoc_p, rhoc_phys, sizeof(int) * g.ncell_p, cudaMemcpyHostToDevice, h->st));
