@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--max-steps", type=int, default=2000)
     ap.add_argument("--window", type=int, default=25, help="steps per reported timing window")
     ap.add_argument("--max-seconds", type=float, default=600.0)
+    ap.add_argument("--pk", action="store_true", help="matter power spectrum of the final state (cicpower/powerspectrum estimator, torch on the GPU)")
     ap.add_argument("--sweep", default="", help='";"-separated environment settings ("A=1,B=2;A=3") re-timed on the final state')
     args = ap.parse_args()
     import torch
@@ -81,6 +82,16 @@ def main():
     print(json.dumps(dict(final=True, steps=nstep, z=1.0 / float(ts.a) - 1.0, wall_s=time.perf_counter() - t_start, phases_ms=ph,
                           rhoc_max=int(rc.max()), rhoc_mean=float(rc.mean()), empty_cell_fraction=float((rc == 0).mean()), nparticles=int(npart))), flush=True)
     G.close()
+    if args.pk:
+        from cafproject_b200.power import cic_delta_torch, cross_power_torch
+        torch.cuda.empty_cache()
+        d = cic_delta_torch([final_state], 1, args.nc, args.nnt, device="cuda")
+        xi = cross_power_torch(d, d, 200.0)
+        del d
+        torch.cuda.empty_cache()
+        sel = [i for i in range(xi.shape[1]) if xi[0][i] > 0][:: max(1, xi.shape[1] // 24)]
+        print(json.dumps(dict(power_spectrum=dict(k_h_per_Mpc=[float(xi[1][i]) for i in sel], Delta2=[float(xi[2][i]) for i in sel],
+                                                  ng=4 * args.nc))), flush=True)
     # the same final state under other settings of the library's environment switches (read at init)
     dts = (ts.dt, ts.a_mid)
     for setting in [x for x in args.sweep.split(";") if x]:
