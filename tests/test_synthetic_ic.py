@@ -1,7 +1,6 @@
 """Host-side input generators (cafproject_b200/synthetic_ic.py): the states they return must be valid CUBE checkpoints
 (cell-ordered, counts consistent) that the CPU oracle steps without complaint -- the GPU parity tests feed on them."""
 import numpy as np
-import pytest
 
 
 def _check_state(st, nc, nnt):
