@@ -1,0 +1,52 @@
+"""examples/cafcube_driver.c: the reference's step loop over the C ABI from compiled C (no Python in between).  Here: it builds
+against include/cube_gpu.h, links against libcubegpu.so, reads a CUBE checkpoint + the ASCII kernel tables, and -- on a machine
+without a CUDA device -- stops with the library's message (the product has no CPU path)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_ascii_table(path, tab):
+    """rows "i j k fx fy fz", i fastest (CUBE/kernels/wfxyz*.ascii, kernel_f.f90:19); ``tab`` is [k][j][i][3]."""
+    n = tab.shape[0]
+    with open(path, "w") as f:
+        for k in range(n):
+            for j in range(n):
+                for i in range(n):
+                    f.write("%d %d %d %.9e %.9e %.9e\n" % ((i + 1, j + 1, k + 1) + tuple(float(v) for v in tab[k, j, i])))
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="needs gcc")
+def test_c_driver_builds_links_and_fails_loudly_without_a_gpu(tmp_path, tables):
+    from cafproject_b200 import checkpoint as ck
+    from cafproject_b200.synthetic_ic import make_ic
+    lib = os.path.join(ROOT, "cafproject_b200", "libcubegpu.so")
+    if not os.path.exists(lib):
+        pytest.skip("libcubegpu.so not built (run __graft_entry__.build())")
+    exe = str(tmp_path / "cafcube_driver")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "examples", "cafcube_driver.c"), "-I" + os.path.join(ROOT, "include"),
+           "-L" + os.path.join(ROOT, "cafproject_b200"), "-lcubegpu", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "cafproject_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    fk, ckt = tables
+    kdir = tmp_path / "kernels"; kdir.mkdir()
+    _write_ascii_table(str(kdir / "wfxyzf.3.ascii"), fk)
+    _write_ascii_table(str(kdir / "wfxyzc.2.ascii"), ckt)
+    nc, nnt = 24, 2          # cube_gpu_init wants nc >= 24, nt >= 12 (parameters.f90:23-24)
+    states, sig, info = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=1)
+    hdr = ck.make_header(izipx=2, izipv=2, image=1, nn=1, nnt=nnt, nt=nc // nnt, ncell=4, ncb=6, sigma_vi=sig, mass_p=8.0, box=200.0)
+    ck.write_checkpoint(str(tmp_path / "out"), 49.0, 1, hdr, states[0])
+    run = subprocess.run([exe, str(kdir), str(tmp_path / "out"), "49.0", "1", "0.5", "0.0205", "48.0"], capture_output=True, text=True, timeout=300)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "done: %d particles" % info["npglobal"] in run.stdout, run.stdout + run.stderr
+        _, st = ck.read_checkpoint(str(tmp_path / "out"), 48.0, 1)
+        assert st["xp"].shape[0] == info["npglobal"] and int(st["rhoc"].sum()) == info["npglobal"]
+    else:
+        assert run.returncode != 0
+        assert "no CUDA device" in run.stderr or "CUDA" in run.stderr, run.stderr
