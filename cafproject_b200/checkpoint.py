@@ -64,10 +64,15 @@ def make_header(convention: str = "cube", **kw) -> np.ndarray:
 
 
 def write_checkpoint(opath: str, z: float, image: int, header: np.ndarray, state: dict, convention: str = "cube") -> None:
-    """``state``: xp (n,3) i16, vp (n,3) i16, rhoc [tz][ty][tx][k][j][i] i32, vfield [...][3] f32."""
+    """``state``: xp (n,3) int8|int16, vp (n,3) int8|int16 (the header's izipx/izipv bytes per code, variables.f90:41-42),
+    rhoc [tz][ty][tx][k][j][i] i32, vfield [...][3] f32."""
     os.makedirs(os.path.join(opath, "image%d" % image), exist_ok=True)
     header = header.copy()
     header["nplocal"] = state["xp"].shape[0]
+    xdt, vdt = _code_dtypes(header)
+    if state["xp"].dtype != xdt or state["vp"].dtype != vdt:
+        raise ValueError("zip format incompatable: header says izipx=%d izipv=%d, state holds %s/%s"
+                         % (int(header["izipx"]), int(header["izipv"]), state["xp"].dtype, state["vp"].dtype))
     if convention == "cubenu":
         if header.dtype != HEADER_NU_DTYPE:
             raise ValueError("convention='cubenu' needs a HEADER_NU_DTYPE header (make_header('cubenu', ...))")
@@ -79,30 +84,46 @@ def write_checkpoint(opath: str, z: float, image: int, header: np.ndarray, state
             f.write(header.tobytes())
             f.write(np.ascontiguousarray(state["rhoc"], "<i4").tobytes())
     np.ascontiguousarray(state["vfield"], "<f4").tofile(file_name(opath, z, image, "vfield", convention))
-    np.ascontiguousarray(state["xp"], "<i2").tofile(file_name(opath, z, image, "zip0", convention))
-    np.ascontiguousarray(state["vp"], "<i2").tofile(file_name(opath, z, image, "zip1", convention))
+    np.ascontiguousarray(state["xp"], xdt).tofile(file_name(opath, z, image, "zip0", convention))
+    np.ascontiguousarray(state["vp"], vdt).tofile(file_name(opath, z, image, "zip1", convention))
 
 
-def read_checkpoint(opath: str, z: float, image: int, convention: str = "cube"):
+def _code_dtypes(header):
+    """numpy dtypes of xp and vp for a header's izipx, izipv (1 or 2 bytes; CUBE/main/universe*.fh:2-3)."""
+    zx, zv = int(header["izipx"]), int(header["izipv"])
+    if zx not in (1, 2) or zv not in (1, 2):
+        raise ValueError("zip format incompatable: izipx=%d izipv=%d" % (zx, zv))
+    return np.dtype("<i%d" % zx), np.dtype("<i%d" % zv)
+
+
+def _check_zip(header, expect):
+    """particle_initialization.f90:14-18: a run built for (izipx, izipv) stops on a file written in another format."""
+    if expect is not None and (int(header["izipx"]), int(header["izipv"])) != tuple(expect):
+        raise ValueError("zip format incompatable")
+
+
+def read_checkpoint(opath: str, z: float, image: int, convention: str = "cube", expect_zip=None):
+    """Returns ``(header, state)``; ``xp``/``vp`` come back in the file's own 1- or 2-byte format.  ``expect_zip=(izipx,
+    izipv)`` makes a mismatch the reference's "zip format incompatable" stop (the GPU step is built for (2, 2))."""
     if convention == "cubenu":
         header = np.fromfile(file_name(opath, z, image, "zip2", convention), HEADER_NU_DTYPE)[0]
         nnt, nt = int(header["nnt"]), int(header["nt"])
         rhoc = np.fromfile(file_name(opath, z, image, "rhoc", convention), "<i4").reshape((nnt,) * 3 + (nt,) * 3)
-        if int(header["izipx"]) != 2 or int(header["izipv"]) != 2:
-            raise ValueError("zip format incompatable")
+        _check_zip(header, expect_zip)
+        xdt, vdt = _code_dtypes(header)
         n = int(header["nplocal"])
         vfield = np.fromfile(file_name(opath, z, image, "vfield", convention), "<f4").reshape(rhoc.shape + (3,))
-        xp = np.fromfile(file_name(opath, z, image, "zip0", convention), "<i2").reshape(n, 3)
-        vp = np.fromfile(file_name(opath, z, image, "zip1", convention), "<i2").reshape(n, 3)
+        xp = np.fromfile(file_name(opath, z, image, "zip0", convention), xdt).reshape(n, 3)
+        vp = np.fromfile(file_name(opath, z, image, "zip1", convention), vdt).reshape(n, 3)
         return header, dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield)
     with open(file_name(opath, z, image, "zip2"), "rb") as f:
         header = np.frombuffer(f.read(HEADER_DTYPE.itemsize), HEADER_DTYPE)[0]
         nnt, nt = int(header["nnt"]), int(header["nt"])
         rhoc = np.frombuffer(f.read(), "<i4").reshape((nnt,) * 3 + (nt,) * 3).copy()
-    if int(header["izipx"]) != 2 or int(header["izipv"]) != 2:
-        raise ValueError("zip format incompatable")  # particle_initialization.f90:14-18
+    _check_zip(header, expect_zip)
+    xdt, vdt = _code_dtypes(header)
     n = int(header["nplocal"])
     vfield = np.fromfile(file_name(opath, z, image, "vfield"), "<f4").reshape(rhoc.shape + (3,))
-    xp = np.fromfile(file_name(opath, z, image, "zip0"), "<i2").reshape(n, 3)
-    vp = np.fromfile(file_name(opath, z, image, "zip1"), "<i2").reshape(n, 3)
+    xp = np.fromfile(file_name(opath, z, image, "zip0"), xdt).reshape(n, 3)
+    vp = np.fromfile(file_name(opath, z, image, "zip1"), vdt).reshape(n, 3)
     return header, dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield)

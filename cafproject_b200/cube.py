@@ -201,6 +201,10 @@ class CubeGPU:
 
     # ---- particle_initialization / checkpoint ------------------------------------------------
     def particle_initialization(self, state, sigma_vi, npglobal=None):
+        if np.asarray(state["xp"]).dtype != np.int16 or np.asarray(state["vp"]).dtype != np.int16:
+            # particle_initialization.f90:14-18; the library is built for izipx=izipv=2 (cube_gpu_init rejects the rest)
+            raise RuntimeError("zip format incompatable: libcubegpu.so takes 2-byte xp/vp (izipx=izipv=2), got %s/%s"
+                               % (np.asarray(state["xp"]).dtype, np.asarray(state["vp"]).dtype))
         xp = np.ascontiguousarray(state["xp"], np.int16); vp = np.ascontiguousarray(state["vp"], np.int16)
         rc = np.ascontiguousarray(state["rhoc"], np.int32); vf = np.ascontiguousarray(state["vfield"], np.float32)
         n = xp.shape[0]

@@ -37,9 +37,14 @@ def vfactor(a, omega_m=0.32, omega_l=0.68):
     return a ** 2 * H
 
 
-def pack_states(xs, vels, nn, nc, nnt):
+def pack_states(xs, vels, nn, nc, nnt, izipx=2, izipv=2):
     """Particles at global positions ``xs[d]`` (coarse cells, any real; wrapped periodically) with velocities ``vels[d]``
-    (f64 torch vectors) -> ``(states, sigma_vi)`` in CUBE's cell-ordered integer format, one state per image."""
+    (f64 torch vectors) -> ``(states, sigma_vi)`` in CUBE's cell-ordered integer format, one state per image.
+    ``izipx``/``izipv`` = bytes per position / velocity code (1 or 2; CUBE/main/universe*.fh:2-3): ``xp`` comes back
+    int8 or int16, likewise ``vp``."""
+    assert izipx in (1, 2) and izipv in (1, 2)
+    nxbin, nvbin = 1 << (8 * izipx), 1 << (8 * izipv)
+    xdt, vdt = (torch.int8, torch.int16)[izipx - 1], (torch.int8, torch.int16)[izipv - 1]
     nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
     nt = nc // nnt
     dev = xs[0].device
@@ -48,7 +53,7 @@ def pack_states(xs, vels, nn, nc, nnt):
     for d in range(3):
         x = torch.remainder(xs[d].double(), float(ncg[d]))
         c = torch.floor(x).clamp_(0, ncg[d] - 1)
-        u = torch.floor((x - c) * 65536.0).clamp_(0, 65535).to(torch.int64)
+        u = torch.floor((x - c) * float(nxbin)).clamp_(0, nxbin - 1).to(torch.int64)
         cells.append(c.to(torch.int64))
         codes.append(u)
     vels = [v.double() for v in vels]
@@ -76,9 +81,9 @@ def pack_states(xs, vels, nn, nc, nnt):
     res = v_s - vfield[key_s].double()
     sigma_vi = np.float32(math.sqrt(float((res ** 2).sum(1).mean())) / math.sqrt(3.0))
     S = float(np.float64(np.sqrt(np.float32(PI_F / 2), dtype=np.float32)) / (np.float64(sigma_vi) * 2.5))
-    vp = torch.round(65535.0 * torch.atan(S * res) / PI_F).clamp_(-32767, 32767).to(torch.int16)
+    vp = torch.round(float(nvbin - 1) * torch.atan(S * res) / PI_F).clamp_(-(nvbin // 2 - 1), nvbin // 2 - 1).to(vdt)
     xp = u_s.to(torch.int32)
-    xp = torch.where(xp >= 32768, xp - 65536, xp).to(torch.int16)
+    xp = torch.where(xp >= nxbin // 2, xp - nxbin, xp).to(xdt)
     bounds = torch.cumsum(counts.view(nimg, -1).sum(1), 0).cpu().numpy()
     starts = np.concatenate([[0], bounds[:-1]])
     states = []
@@ -93,7 +98,7 @@ def pack_states(xs, vels, nn, nc, nnt):
 
 
 def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_image=200.0, z_i=49.0,
-            n_s=0.9619, h=0.67, omega_m=0.32, device="cpu", velocity_boost=1.0):
+            n_s=0.9619, h=0.67, omega_m=0.32, device="cpu", velocity_boost=1.0, izipx=2, izipv=2):
     """Return ``(states, sigma_vi, info)``; ``states[m]`` = dict(xp, vp, rhoc, vfield) numpy arrays in
     file order for image ``m`` (image order x fastest, parameters.f90:200-203).
 
@@ -137,7 +142,7 @@ def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_i
     xs = [(qb[d] + psi[d].double() * (scale / ncell)).reshape(-1) for d in range(3)]
     vels = [(psi[d].double() * (scale * vf)).reshape(-1) for d in range(3)]
     del psi
-    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt)
+    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt, izipx, izipv)
     npglobal = sum(int(st["xp"].shape[0]) for st in states)
     info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, a=a, vf=vf, npglobal=npglobal, seed=seed,
                 disp_rms=disp_rms)
@@ -145,7 +150,7 @@ def make_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, disp_rms=0.6, box_per_i
 
 
 def make_clustered_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, nblob=6, blob_fraction=0.5, blob_sigma=0.35, v_rms=0.3,
-                      device="cpu"):
+                      device="cpu", izipx=2, izipv=2):
     """A late-time-like state for the tests of the crowded-cell paths: ``blob_fraction`` of the ``(np_nc nc)^3`` particles per
     image sit in ``nblob`` Gaussian clumps per image (``blob_sigma`` coarse cells wide, so single coarse cells hold hundreds
     of particles, next to empty ones), the rest are uniform; velocities = a per-clump bulk flow + Gaussian dispersion
@@ -169,7 +174,7 @@ def make_clustered_ic(nn=(1, 1, 1), nc=32, nnt=2, np_nc=2, seed=1, nblob=6, blob
         v = torch.randn(ntot, generator=gen, device=dev, dtype=torch.float64) * v_rms
         v[:nb] += bulk[which]
         vels.append(v)
-    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt)
+    states, sigma_vi = pack_states(xs, vels, nn, nc, nnt, izipx, izipv)
     info = dict(nn=nn, nc=nc, nnt=nnt, np_nc=np_nc, npglobal=ntot, seed=seed, rhoc_max=max(int(st["rhoc"].max()) for st in states))
     return states, sigma_vi, info
 
@@ -188,7 +193,7 @@ def tile_state(st, nnt, reps):
             for tx in range(big):
                 order.append(((tz % nnt) * nnt + ty % nnt) * nnt + tx % nnt)
     n = int(per_tile[order].sum())
-    xp = np.empty((n, 3), np.int16); vp = np.empty((n, 3), np.int16)
+    xp = np.empty((n, 3), st["xp"].dtype); vp = np.empty((n, 3), st["vp"].dtype)
     o = 0
     for t in order:
         m = int(per_tile[t])

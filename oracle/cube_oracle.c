@@ -17,6 +17,9 @@
  * (paper decode example ms_caf.tex:78, kernel tables, conservation invariants) are
  * exercised in tests/test_oracle_pins.py.
  *
+ * Zip formats: izipx, izipv in {1,2} bytes per code (CUBE/main/universe*.fh:2-3), chosen per run with oracle_set_zip;
+ * the default is x2v2, the format the GPU library is built for.
+ *
  * Generalisation beyond the reference: the image grid is (nnx,nny,nnz) instead of
  * nn^3 so that 2- and 4-GPU weak-scaling points exist; with nnx=nny=nnz=nn it is the
  * reference's geometry (parameters.f90:178-203).  All images of a run live in one
@@ -49,7 +52,10 @@ typedef struct {
   i64 nte, nft, nfb, nfe;
   i64 np_image_max, np_tile_max;
   i64 nimg;
-  i64 nvbin; /* 2^(8*izipv), izipx=izipv=2 only */
+  i64 izipx, izipv; /* bytes per position / velocity code: 1 or 2 (universe*.fh) */
+  i64 nvbin;        /* 2^(8*izipv)        parameters.f90:13 */
+  i64 ishift;       /* -2^(8*izipx-1)     parameters.f90:14 */
+  double x_resolution; /* 1/2^(8*izipx) */
 } geom_t;
 
 typedef struct {
@@ -99,20 +105,24 @@ static inline i64 image1d(const geom_t *g, i64 cx, i64 cy, i64 cz) {
 static inline i64 modulo_i(i64 a, i64 n) { i64 r = a % n; return r < 0 ? r + n : r; }
 
 /* ---- codes -------------------------------------------------------- */
-/* int(xp+ishift,izipx)+rshift   with ishift=-2^15, rshift=0.5-ishift  (parameters.f90:14-15) */
-static inline double xp_decode(i16 xp) {
-  const i64 ishift = -32768;
-  const double rshift = 0.5 - (double)ishift; /* 32768.5 */
-  i16 t = (i16)(uint16_t)((i64)xp + ishift);  /* int(...,izipx): wraps */
+/* Zip formats (parameters.f90:10-15, universe*.fh): izipx, izipv in {1,2} bytes.  The oracle keeps every code in an int16
+ * slot; a 1-byte code sits there sign-extended and each site that Fortran evaluates in kind=izipx / kind=izipv wraps to
+ * that kind explicitly (to_kind), so the x2v2 arithmetic is unchanged and x1/v1 follow the same source lines. */
+static inline i16 to_kind(i64 v, i64 izip) { return izip == 1 ? (i16)(int8_t)(uint8_t)v : (i16)(uint16_t)v; }
+/* int(xp+ishift,izipx)+rshift   with ishift=-2^(8*izipx-1), rshift=0.5-ishift  (parameters.f90:14-15) */
+static inline double xp_decode(const geom_t *g, i16 xp) {
+  const i64 ishift = g->ishift;
+  const double rshift = 0.5 - (double)ishift; /* 32768.5 (x2), 128.5 (x1) */
+  i16 t = to_kind((i64)xp + ishift, g->izipx); /* int(...,izipx): wraps */
   return (double)t + rshift;
 }
 /* tan((pi*real(vp))/real(nvbin-1))  -- all f32, libm tanf */
-static inline float vp_tan(i16 vp) { return tanf((PI_F * (float)vp) / 65535.0f); }
+static inline float vp_tan(const geom_t *g, i16 vp) { return tanf((PI_F * (float)vp) / (float)(g->nvbin - 1)); }
 /* sqrt(pi/2)/(sigma_vi*vrel_boost)  -> f64   (vrel_boost is real(8)=2.5, parameters.f90:103) */
 static inline double vscale(float sigma) { return (double)sqrtf(PI_F / 2) / ((double)sigma * 2.5); }
 /* nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv) */
-static inline i16 vp_encode(double v, double S) {
-  return (i16)llround((double)65535.0f * atan(S * v) / (double)PI_F);
+static inline i16 vp_encode(const geom_t *g, double v, double S) {
+  return to_kind(llround((double)(float)(g->nvbin - 1) * atan(S * v) / (double)PI_F), g->izipv);
 }
 
 /* ---- lifecycle --------------------------------------------------------------------- */
@@ -127,7 +137,7 @@ ctx_t *oracle_create(i64 nnx, i64 nny, i64 nnz, i64 nnt, i64 nc, i64 np_nc,
   g->nft = g->nt * g->ncell;
   g->nfb = g->ncb * g->ncell;
   g->nfe = g->nft + 2 * g->nfb;
-  g->nvbin = 65536;
+  g->izipx = g->izipv = 2; g->nvbin = 65536; g->ishift = -32768; g->x_resolution = 1.0 / 65536.0; /* oracle_set_zip changes them */
   g->nimg = nnx * nny * nnz;
   /* variables.f90:7-9 (real(4) arithmetic, truncated to integer(8)) */
   i64 np_image = (nc * np_nc) * (nc * np_nc) * (nc * np_nc);
@@ -203,8 +213,36 @@ float oracle_vmax(ctx_t *c, i64 m) { return c->im[m].vmax; }
 
 /* host-libm tanf table, indexed by the raw 16-bit code (SURVEY sec. 7 hard part 1) */
 void oracle_tanf_lut(float *lut) {
-  for (int u = 0; u < 65536; u++) lut[u] = vp_tan((i16)(uint16_t)u);
+  geom_t g2; g2.nvbin = 65536;
+  for (int u = 0; u < 65536; u++) lut[u] = vp_tan(&g2, (i16)(uint16_t)u);
 }
+/* the same for either velocity format: 2^(8*izipv) entries indexed by the raw unsigned code */
+void oracle_tanf_lut_zip(float *lut, i64 izipv) {
+  geom_t g2; g2.nvbin = (i64)1 << (8 * izipv);
+  for (i64 u = 0; u < g2.nvbin; u++) lut[u] = vp_tan(&g2, to_kind(u, izipv));
+}
+/* choose the zip formats of a run (universe*.fh:2-3); call before oracle_load_image */
+int oracle_set_zip(ctx_t *c, i64 izipx, i64 izipv) {
+  if ((izipx != 1 && izipx != 2) || (izipv != 1 && izipv != 2)) return 1;
+  geom_t *g = &c->g;
+  g->izipx = izipx; g->izipv = izipv;
+  g->nvbin = (i64)1 << (8 * izipv);
+  g->ishift = -((i64)1 << (8 * izipx - 1));
+  g->x_resolution = (double)(1.0f / (float)((i64)1 << (8 * izipx)));
+  return 0;
+}
+
+/* probes of the code arithmetic for the pin tests: xq of update_particle.f90:41 for coarse cell index `cell` (1-based),
+ * the decoded velocity of :42 (without vfield) and the encoder of :86 */
+double oracle_probe_xq(ctx_t *c, i64 cell, i64 code) {
+  const geom_t *g = &c->g;
+  return ((double)cell - 1.0) + xp_decode(g, to_kind(code, g->izipx)) * g->x_resolution;
+}
+double oracle_probe_vdecode(ctx_t *c, i64 code, float sigma) {
+  const geom_t *g = &c->g;
+  return (double)vp_tan(g, to_kind(code, g->izipv)) / vscale(sigma);
+}
+i64 oracle_probe_vencode(ctx_t *c, double v, float sigma) { return (i64)vp_encode(&c->g, v, vscale(sigma)); }
 
 /* ---- cumsum (variables.f90:74-110) ------------------------------------------------- */
 static void cumsum6(const geom_t *g, const i32 *rho, i64 *cum) {
@@ -432,7 +470,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
   const i64 nt = g->nt, ncb = g->ncb, nnt = g->nnt, lo = 1 - ncb, hi = nt + ncb;
   const i64 lo2 = 1 - 2 * ncb, hi2 = nt + 2 * ncb, ne2 = nt + 4 * ncb, n2 = ne2 * ne2 * ne2;
   const double weight_v = (double)0.1f; /* real(8),parameter :: weight_v=0.1  (f32 literal) :10 */
-  const double x_resolution = 1.0 / 65536.0;
+  const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   const float dt_mid = (dt_old + dt) / 2; /* :16 */
   const double S = vscale(c->sigma_vi);
   float ovh_all = 0;
@@ -456,8 +494,8 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
           i64 ip = nlast - np + l - 1; /* 0-based */
           i64 gg[3]; double vreal[3];
           for (int d = 0; d < 3; d++) {
-            double xq = ((double)cell[d] - 1.0) + xp_decode(im->xp[3 * ip + d]) * x_resolution;
-            vreal[d] = (double)vp_tan(im->vp[3 * ip + d]) / S;
+            double xq = ((double)cell[d] - 1.0) + xp_decode(g, im->xp[3 * ip + d]) * x_resolution;
+            vreal[d] = (double)vp_tan(g, im->vp[3 * ip + d]) / S;
             vreal[d] = vreal[d] + (double)im->vfield[3 * r + d];
             double deltax = ((double)dt_mid * vreal[d]) / (double)g->ncell;
             gg[d] = (i64)ceil(xq + deltax);
@@ -492,8 +530,8 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
           i64 ip = nlast - np + l - 1;
           i64 gg[3]; double vreal[3];
           for (int d = 0; d < 3; d++) {
-            double xq = ((double)cell[d] - 1.0) + xp_decode(im->xp[3 * ip + d]) * x_resolution;
-            vreal[d] = (double)vp_tan(im->vp[3 * ip + d]) / S;
+            double xq = ((double)cell[d] - 1.0) + xp_decode(g, im->xp[3 * ip + d]) * x_resolution;
+            vreal[d] = (double)vp_tan(g, im->vp[3 * ip + d]) / S;
             vreal[d] = vreal[d] + (double)im->vfield[3 * r + d];
             double deltax = ((double)dt_mid * vreal[d]) / (double)g->ncell;
             gg[d] = (i64)ceil(xq + deltax);
@@ -502,11 +540,11 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
           c->rholocal[e] += 1;
           i64 idx = c->cume[e] - c->rhoce[e] + c->rholocal[e] - 1; /* 0-based */
           for (int d = 0; d < 3; d++) {
-            /* xp+nint(dt_mid*vreal/(x_resolution*ncell)) : i16 + i32 -> i32 -> i16 (wraps) :84 */
+            /* xp+nint(dt_mid*vreal/(x_resolution*ncell)) : int(izipx) + i32 -> i32 -> int(izipx) (wraps) :84 */
             i32 dxi = (i32)lround((double)dt_mid * vreal[d] / (x_resolution * (double)g->ncell));
-            c->xp_new[3 * idx + d] = (i16)(uint16_t)((i32)im->xp[3 * ip + d] + dxi);
+            c->xp_new[3 * idx + d] = to_kind((i64)((i32)im->xp[3 * ip + d] + dxi), g->izipx);
             double vr = vreal[d] - (double)c->vfield_new[3 * e + d];
-            c->vp_new[3 * idx + d] = vp_encode(vr, S);
+            c->vp_new[3 * idx + d] = vp_encode(g, vr, S);
           }
         }
       }
@@ -543,7 +581,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
         b = b + (double)((vf[0] * vf[0] + vf[1] * vf[1]) + vf[2] * vf[2]);
         for (i64 l = 1; l <= im->rhoc[r]; l++, ip++) {
           double v[3];
-          for (int d = 0; d < 3; d++) v[d] = (double)vp_tan(im->vp[3 * ip + d]) / S;
+          for (int d = 0; d < 3; d++) v[d] = (double)vp_tan(g, im->vp[3 * ip + d]) / S;
           r_ = r_ + ((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
           for (int d = 0; d < 3; d++) v[d] = v[d] + (double)vf[d];
           a = a + ((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
@@ -591,7 +629,7 @@ void oracle_fine_deposit(ctx_t *c, i64 m, i64 tx, i64 ty, i64 tz, float *rho_f) 
   const geom_t *g = &c->g; image_t *im = &c->im[m];
   const i64 nt = g->nt, ncb = g->ncb, nfe = g->nfe, nfb = g->nfb, ld = nfe + 2;
   const float mass_p = c->mass_p;
-  const double x_resolution = 1.0 / 65536.0;
+  const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   memset(rho_f, 0, ld * nfe * nfe * sizeof(float));
 #define RF(a, b, cc) rho_f[((a)-1) + ld * (((b)-1) + nfe * ((cc)-1))]
   for (i64 k = 2 - ncb; k <= nt + ncb - 1; k++) for (i64 j = 2 - ncb; j <= nt + ncb - 1; j++) for (i64 i = 2 - ncb; i <= nt + ncb - 1; i++) {
@@ -602,7 +640,7 @@ void oracle_fine_deposit(ctx_t *c, i64 m, i64 tx, i64 ty, i64 tz, float *rho_f) 
       i64 i1[3], i2[3]; float d1[3], d2[3];
       for (int d = 0; d < 3; d++) {
         /* tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution  (f32 + f64 -> f32) */
-        float tempx = (float)((double)(4.f * (float)(cell[d] - 1)) + 4 * xp_decode(im->xp[3 * ip + d]) * x_resolution);
+        float tempx = (float)((double)(4.f * (float)(cell[d] - 1)) + 4 * xp_decode(g, im->xp[3 * ip + d]) * x_resolution);
         cic(tempx, &i1[d], &d1[d], &d2[d]);
         i1[d] += nfb; i2[d] = i1[d] + 1;
       }
@@ -636,7 +674,7 @@ void oracle_fine_deposit(ctx_t *c, i64 m, i64 tx, i64 ty, i64 tz, float *rho_f) 
 void oracle_fine_kick(ctx_t *c, i64 m, i64 tx, i64 ty, i64 tz, const float *force_f, float a_mid, float dt) {
   const geom_t *g = &c->g; image_t *im = &c->im[m];
   const i64 nt = g->nt, nfb = g->nfb, nff = g->nft + 2;
-  const double x_resolution = 1.0 / 65536.0;
+  const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   const double S = vscale(c->sigma_vi), Snew = vscale(c->sigma_vi_new);
 #define FF(a, b, cc) (&force_f[3 * (((a)-nfb) + nff * (((b)-nfb) + nff * ((cc)-nfb)))])
   /* f2_max_fine(itx,ity,itz)=maxval(sum(force_f**2,1)) :85 */
@@ -655,13 +693,13 @@ void oracle_fine_kick(ctx_t *c, i64 m, i64 tx, i64 ty, i64 tz, const float *forc
       i64 ip = nlast + l - 1;
       i64 i1[3], i2[3]; float d1[3], d2[3]; double vreal[3];
       for (int d = 0; d < 3; d++) {
-        float tempx = (float)((double)(4.f * (float)(cell[d] - 1)) + 4 * xp_decode(im->xp[3 * ip + d]) * x_resolution);
+        float tempx = (float)((double)(4.f * (float)(cell[d] - 1)) + 4 * xp_decode(g, im->xp[3 * ip + d]) * x_resolution);
         cic(tempx, &i1[d], &d1[d], &d2[d]);
         i1[d] += nfb; i2[d] = i1[d] + 1;
-        vreal[d] = (double)vp_tan(im->vp[3 * ip + d]) / S;
+        vreal[d] = (double)vp_tan(g, im->vp[3 * ip + d]) / S;
       }
       KICK8(FF);
-      for (int d = 0; d < 3; d++) im->vp[3 * ip + d] = vp_encode(vreal[d], Snew);
+      for (int d = 0; d < 3; d++) im->vp[3 * ip + d] = vp_encode(g, vreal[d], Snew);
     }
   }
 #undef FF
@@ -673,7 +711,7 @@ void oracle_coarse_deposit(ctx_t *c, i64 m, float *r3) {
   const geom_t *g = &c->g; image_t *im = &c->im[m];
   const i64 nt = g->nt, nnt = g->nnt, nc = g->nc, e = nt + 4;
   const float mass_p = c->mass_p;
-  const double x_resolution = 1.0 / 65536.0;
+  const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   float *r3t = (float *)malloc(e * e * e * sizeof(float));
 #define RT(a, b, cc) r3t[((a) + 1) + e * (((b) + 1) + e * ((cc) + 1))]
   for (i64 tz = 1; tz <= nnt; tz++) for (i64 ty = 1; ty <= nnt; ty++) for (i64 tx = 1; tx <= nnt; tx++) {
@@ -686,7 +724,7 @@ void oracle_coarse_deposit(ctx_t *c, i64 m, float *r3) {
         i64 i1[3], i2[3]; float d1[3], d2[3];
         for (int d = 0; d < 3; d++) {
           /* tempx=((/i,j,k/)-1)+(int(xp+ishift,izipx)+rshift)*x_resolution-0.5  (i64 + f64 - f32 -> f64 -> f32) */
-          float tempx = (float)((double)(cell[d] - 1) + xp_decode(im->xp[3 * ip + d]) * x_resolution - (double)0.5f);
+          float tempx = (float)((double)(cell[d] - 1) + xp_decode(g, im->xp[3 * ip + d]) * x_resolution - (double)0.5f);
           cic(tempx, &i1[d], &d1[d], &d2[d]);
           i2[d] = i1[d] + 1;
         }
@@ -711,7 +749,7 @@ void oracle_coarse_deposit(ctx_t *c, i64 m, float *r3) {
 void oracle_coarse_kick(ctx_t *c, i64 m, const float *force_c, float a_mid, float dt) {
   const geom_t *g = &c->g; image_t *im = &c->im[m];
   const i64 nt = g->nt, nnt = g->nnt, nc = g->nc, e = nc + 2;
-  const double x_resolution = 1.0 / 65536.0;
+  const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   const double S = vscale(c->sigma_vi);
 #define FC(a, b, cc) (&force_c[3 * ((a) + e * ((b) + e * (cc)))])
   float f2 = -INFINITY; /* f2_max_coarse=maxval(sum(force_c**2,1)) :192 */
@@ -733,17 +771,17 @@ void oracle_coarse_kick(ctx_t *c, i64 m, const float *force_c, float a_mid, floa
         i64 i1[3], i2[3]; float d1[3], d2[3]; double vreal[3];
         for (int d = 0; d < 3; d++) {
           /* tempx=((/itx,ity,itz/)-1)*nt+((/i,j,k/)-1)+(...)*x_resolution-0.5 */
-          float tempx = (float)((double)((tile[d] - 1) * nt + (cell[d] - 1)) + xp_decode(im->xp[3 * ip + d]) * x_resolution - (double)0.5f);
+          float tempx = (float)((double)((tile[d] - 1) * nt + (cell[d] - 1)) + xp_decode(g, im->xp[3 * ip + d]) * x_resolution - (double)0.5f);
           cic(tempx, &i1[d], &d1[d], &d2[d]);
           i2[d] = i1[d] + 1;
-          vreal[d] = (double)vp_tan(im->vp[3 * ip + d]) / S;
+          vreal[d] = (double)vp_tan(g, im->vp[3 * ip + d]) / S;
         }
         KICK8(FC);
         /* vmax=max(vmax,maxval(vreal+vfield(:,i,j,k,...)))  f64 max assigned to f32 :220 */
         double mx = vreal[0] + (double)im->vfield[3 * r + 0];
         for (int d = 1; d < 3; d++) { double t = vreal[d] + (double)im->vfield[3 * r + d]; if (t > mx) mx = t; }
         if (mx > (double)vmax) vmax = (float)mx;
-        for (int d = 0; d < 3; d++) im->vp[3 * ip + d] = vp_encode(vreal[d], S);
+        for (int d = 0; d < 3; d++) im->vp[3 * ip + d] = vp_encode(g, vreal[d], S);
       }
     }
   }

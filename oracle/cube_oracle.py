@@ -86,6 +86,15 @@ def lib():
         L.oracle_std_vsim.restype = C.c_double
         L.oracle_std_vsim.argtypes = [vp, C.c_int]
         L.oracle_tanf_lut.argtypes = [vp]
+        L.oracle_tanf_lut_zip.argtypes = [vp, i64]
+        L.oracle_set_zip.restype = C.c_int
+        L.oracle_set_zip.argtypes = [vp, i64, i64]
+        L.oracle_probe_xq.restype = C.c_double
+        L.oracle_probe_xq.argtypes = [vp, i64, i64]
+        L.oracle_probe_vdecode.restype = C.c_double
+        L.oracle_probe_vdecode.argtypes = [vp, i64, f32]
+        L.oracle_probe_vencode.restype = i64
+        L.oracle_probe_vencode.argtypes = [vp, C.c_double, f32]
         L.oracle_load_image.argtypes = [vp, i64, vp, vp, vp, vp, i64]
         L.oracle_finish_load.argtypes = [vp, f32]
         L.oracle_store_image.argtypes = [vp, i64, vp, vp]
@@ -100,10 +109,14 @@ def lib():
     return _lib
 
 
-def tanf_lut() -> np.ndarray:
-    """65536 host-libm values ``tanf((pi_f*float(code))/65535f)`` indexed by the raw uint16 code."""
-    out = np.empty(65536, F32)
-    lib().oracle_tanf_lut(out.ctypes.data)
+def tanf_lut(izipv: int = 2) -> np.ndarray:
+    """``2^(8*izipv)`` host-libm values ``tanf((pi_f*float(code))/float(nvbin-1))`` indexed by the raw unsigned code
+    (65536 entries for the 2-byte format the product is built for)."""
+    out = np.empty(1 << (8 * izipv), F32)
+    if izipv == 2:
+        lib().oracle_tanf_lut(out.ctypes.data)
+    else:
+        lib().oracle_tanf_lut_zip(out.ctypes.data, izipv)
     return out
 
 
@@ -320,7 +333,8 @@ class Oracle:
     """All images of one CUBE run in one process.  Geometry mirrors parameters.f90:20-60."""
 
     def __init__(self, nn=1, nnt=2, nc=32, np_nc=2, image_buffer=1.5, tile_buffer=2.5,
-                 fk_table=None, ck_table=None):
+                 fk_table=None, ck_table=None, izipx=2, izipv=2):
+        self.izipx, self.izipv = int(izipx), int(izipv)   # universe*.fh:2-3: bytes per position / velocity code
         self.nn = (int(nn),) * 3 if np.isscalar(nn) else tuple(int(v) for v in nn)
         self.nnt, self.nc, self.np_nc = int(nnt), int(nc), int(np_nc)
         assert nc % nnt == 0
@@ -334,6 +348,8 @@ class Oracle:
         L = lib()
         self.h = L.oracle_create(self.nn[0], self.nn[1], self.nn[2], self.nnt, self.nc, self.np_nc,
                                  F32(image_buffer), F32(tile_buffer))
+        if L.oracle_set_zip(self.h, self.izipx, self.izipv):
+            raise ValueError("izipx, izipv must be 1 or 2")
         self.np_image_max = L.oracle_np_image_max(self.h)
         self.np_tile_max = L.oracle_np_tile_max(self.h)
         self.kern_f = None if fk_table is None else kernel_f(fk_table, self.nfe)
@@ -406,6 +422,9 @@ class Oracle:
     def load(self, states, sigma_vi):
         """``states[m] = dict(xp, vp, rhoc, vfield)`` in file order (particle_initialization.f90)."""
         for m, s in enumerate(states):
+            for name, z in (("xp", self.izipx), ("vp", self.izipv)):   # particle_initialization.f90:14 "zip format incompatable"
+                assert np.asarray(s[name]).dtype == (np.int8, np.int16)[z - 1], f"{name} must be int{8 * z} for izip={z}"
+            # 1-byte codes are held sign-extended in the oracle's int16 slots (cube_oracle.c, to_kind)
             xp = np.ascontiguousarray(s["xp"], np.int16); vp = np.ascontiguousarray(s["vp"], np.int16)
             rc = np.ascontiguousarray(s["rhoc"], np.int32); vf = np.ascontiguousarray(s["vfield"], np.float32)
             n = xp.shape[0]
@@ -418,7 +437,13 @@ class Oracle:
         shp = (self.nnt,) * 3 + (self.nt,) * 3
         rc = np.empty(shp, np.int32); vf = np.empty(shp + (3,), np.float32)
         lib().oracle_store_image(self.h, m, _ptr(rc), _ptr(vf))
-        return dict(xp=self.xp(m)[:n].copy(), vp=self.vp(m)[:n].copy(), rhoc=rc, vfield=vf)
+        xp, vp = self.xp(m)[:n], self.vp(m)[:n]
+        if self.izipx == 1:
+            assert xp.min(initial=0) >= -128 and xp.max(initial=0) <= 127
+        if self.izipv == 1:
+            assert vp.min(initial=0) >= -128 and vp.max(initial=0) <= 127
+        return dict(xp=xp.astype((np.int8, np.int16)[self.izipx - 1]), vp=vp.astype((np.int8, np.int16)[self.izipv - 1]),
+                    rhoc=rc, vfield=vf)
 
     # ---- step subroutines ---------------------------------------------------------------------
     def buffer_density(self):
