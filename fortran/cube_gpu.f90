@@ -22,7 +22,8 @@ module cube_gpu
     real(c_float)      :: tile_buffer  ! parameters.f90:60
     integer(c_int32_t) :: device       ! CUDA device ordinal
     integer(c_int32_t) :: fine_batch   ! 0 = automatic
-    integer(c_int32_t) :: reserved(4)
+    integer(c_int32_t) :: local_group  ! 0: one process per image; k>0: images are threads of this process (in-process group k)
+    integer(c_int32_t) :: reserved(3)
   end type
 
   interface

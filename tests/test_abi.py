@@ -71,3 +71,47 @@ def test_init_rejects_bad_configuration(tables):
     h = C.c_void_p()
     rc = L.cube_gpu_init(C.byref(p), fk.ctypes.data, ck.ctypes.data, lut.ctypes.data, None, C.byref(h))
     assert rc != 0 and b"zip format incompatable" in L.cube_gpu_last_error()
+
+
+def _strip_c_comments(src):
+    return re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+
+def test_fortran_module_mirrors_the_header():
+    """fortran/cube_gpu.f90 cannot be compiled here (no Fortran compiler), so keep it in step with include/cube_gpu.h
+    textually: the bind(C) cube_params has the header's fields in the header's order (same counts), and every
+    interface names an exported symbol with the header's number of arguments."""
+    hdr = _strip_c_comments(open(os.path.join(ROOT, "include", "cube_gpu.h")).read())
+    f90 = open(os.path.join(ROOT, "fortran", "cube_gpu.f90")).read()
+    f90 = "\n".join(line.split("!")[0] for line in f90.splitlines())
+    # struct fields
+    body = re.search(r"typedef struct cube_params \{(.*?)\} cube_params;", hdr, re.S).group(1)
+    c_fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        for nm in names.split(","):
+            m = re.match(r"\s*(\w+)(?:\[(\d+)\])?", nm)
+            c_fields.append((m.group(1), int(m.group(2) or 1), "float" if ctype == "float" else "int"))
+    tbody = re.search(r"type, bind\(C\) :: cube_params(.*?)end type", f90, re.S).group(1)
+    f_fields = []
+    for line in tbody.strip().splitlines():
+        m = re.match(r"\s*(integer\(c_int32_t\)|real\(c_float\))\s*::\s*(.*)", line)
+        assert m, line
+        for nm in m.group(2).split(","):
+            mm = re.match(r"\s*(\w+)(?:\((\d+)\))?", nm)
+            f_fields.append((mm.group(1), int(mm.group(2) or 1), "float" if m.group(1).startswith("real") else "int"))
+    assert f_fields == c_fields
+    # interfaces: name and arity
+    c_protos = {m.group(1): m.group(2) for m in re.finditer(r"\b(cube_gpu_\w+)\s*\(([^)]*)\)\s*;", hdr)}
+    arity = lambda a: 0 if a.strip() in ("", "void") else len(a.split(","))
+    found = re.findall(r"function\s+(cube_gpu_\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)", f90)
+    assert len(found) >= 12
+    for fname, fargs, cname in found:
+        assert fname == cname and cname in c_protos, cname
+        assert arity(fargs) == arity(c_protos[cname]), cname
+    step_calls = {"cube_gpu_init", "cube_gpu_upload", "cube_gpu_update_x", "cube_gpu_buffer", "cube_gpu_particle_mesh",
+                  "cube_gpu_download", "cube_gpu_finalize", "cube_gpu_last_error"}
+    assert step_calls <= {c for _, _, c in found}
