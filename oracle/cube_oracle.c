@@ -68,6 +68,7 @@ typedef struct {
   double std_vsim, std_vsim_c, std_vsim_res;
   float overhead_tile, overhead_image;
   float vmax;
+  float vmax3[3]; /* CUBEnu pm.f90:398: vmax(3)=max(vmax,abs(v)) per component */
   float f2_max_coarse;
   float *f2_max_fine; /* (nnt,nnt,nnt) */
 } image_t;
@@ -79,6 +80,7 @@ typedef struct {
   float mass_p;
   i64 npglobal;
   int error; /* set instead of Fortran `stop` */
+  i64 nlayer; /* 1 = CUBE/main source order; >1 = CUBEnu's colour passes over k (CUBEnu update_particle.f90:37,55-58) */
   char errmsg[256];
   /* scratch of update_particle (update_particle.f90:8-12) */
   i32 *rhoce, *rholocal;
@@ -210,6 +212,13 @@ double oracle_std_vsim(ctx_t *c, int which) {
 float oracle_overhead_tile(ctx_t *c) { return c->im[0].overhead_tile; }
 float oracle_overhead_image(ctx_t *c) { return c->im[0].overhead_image; }
 float oracle_vmax(ctx_t *c, i64 m) { return c->im[m].vmax; }
+float oracle_vmax3(ctx_t *c, i64 m, int d) { return c->im[m].vmax3[d]; }
+/* CUBEnu update_particle.f90:37: nlayer=2*ceiling(dt_mid*sim%vz_max/ncell)+1 (f32 product and quotient); 0 or 1 = CUBE/main */
+void oracle_set_nlayer(ctx_t *c, i64 nlayer) { c->nlayer = nlayer; }
+i64 oracle_nlayer_for(ctx_t *c, float dt_old, float dt, float vz_max) {
+  const float dt_mid = (dt_old + dt) / 2;
+  return 2 * (i64)ceilf(dt_mid * vz_max / (float)c->g.ncell) + 1;
+}
 
 /* host-libm tanf table, indexed by the raw 16-bit code (SURVEY sec. 7 hard part 1) */
 void oracle_tanf_lut(float *lut) {
@@ -473,6 +482,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
   const double x_resolution = g->x_resolution; /* 2^-(8*izipx), parameters.f90:101 */
   const float dt_mid = (dt_old + dt) / 2; /* :16 */
   const double S = vscale(c->sigma_vi);
+  const i64 nlayer = c->nlayer > 1 ? c->nlayer : 1;
   float ovh_all = 0;
   for (i64 m = 0; m < g->nimg; m++) {
     image_t *im = &c->im[m];
@@ -485,8 +495,10 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
       for (i64 k = lo; k <= hi; k++) for (i64 j = lo; j <= hi; j++) for (i64 i = lo; i <= hi; i++) /* :27 */
         for (int d = 0; d < 3; d++)
           c->vfield_new[3 * RE(g, i, j, k) + d] = (float)((double)im->vfield[3 * RH(g, i, j, k, tx, ty, tz) + d] * weight_v);
-      /* pass 1 :34-51 */
-      for (i64 k = lo; k <= hi; k++) for (i64 j = lo; j <= hi; j++) for (i64 i = lo; i <= hi; i++) {
+      /* pass 1 :34-51; CUBEnu visits the k planes in nlayer colour passes (k = 1-ncb+ilayer step nlayer), which fixes the
+       * order of the f32 additions into vfield_new and of the particles inside a destination cell; nlayer = 1 is CUBE/main */
+      for (i64 ilayer = 0; ilayer < nlayer; ilayer++)
+      for (i64 k = lo + ilayer; k <= hi; k += nlayer) for (i64 j = lo; j <= hi; j++) for (i64 i = lo; i <= hi; i++) {
         i64 r = RH(g, i, j, k, tx, ty, tz);
         i64 nlast = im->cum[r], np = im->rhoc[r];
         const i64 cell[3] = {i, j, k};
@@ -521,8 +533,9 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
                  (long long)ntot, (long long)g->np_tile_max, (long long)(m + 1), (long long)tx, (long long)ty, (long long)tz);
         return;
       }
-      /* pass 2 :70-93 */
-      for (i64 k = lo; k <= hi; k++) for (i64 j = lo; j <= hi; j++) for (i64 i = lo; i <= hi; i++) {
+      /* pass 2 :70-93 (CUBEnu update_particle.f90:97-103: the same colour passes) */
+      for (i64 ilayer = 0; ilayer < nlayer; ilayer++)
+      for (i64 k = lo + ilayer; k <= hi; k += nlayer) for (i64 j = lo; j <= hi; j++) for (i64 i = lo; i <= hi; i++) {
         i64 r = RH(g, i, j, k, tx, ty, tz);
         i64 nlast = im->cum[r], np = im->rhoc[r];
         const i64 cell[3] = {i, j, k};
@@ -612,7 +625,7 @@ void oracle_pm_begin(ctx_t *c) { /* pm.f90:27-35 */
   for (i64 m = 0; m < c->g.nimg; m++) {
     image_t *im = &c->im[m];
     cumsum6(&c->g, im->rhoc, im->cum);
-    im->vmax = 0; im->f2_max_coarse = 0;
+    im->vmax = 0; im->f2_max_coarse = 0; im->vmax3[0] = im->vmax3[1] = im->vmax3[2] = 0;
     for (i64 q = 0; q < c->g.nnt * c->g.nnt * c->g.nnt; q++) im->f2_max_fine[q] = 0;
   }
 }
@@ -781,6 +794,10 @@ void oracle_coarse_kick(ctx_t *c, i64 m, const float *force_c, float a_mid, floa
         double mx = vreal[0] + (double)im->vfield[3 * r + 0];
         for (int d = 1; d < 3; d++) { double t = vreal[d] + (double)im->vfield[3 * r + d]; if (t > mx) mx = t; }
         if (mx > (double)vmax) vmax = (float)mx;
+        for (int d = 0; d < 3; d++) { /* CUBEnu pm.f90:349: vmax=max(vmax,abs(vreal+vfield)) per component, f64 max -> f32 */
+          double t = fabs(vreal[d] + (double)im->vfield[3 * r + d]);
+          if (t > (double)im->vmax3[d]) im->vmax3[d] = (float)t;
+        }
         for (int d = 0; d < 3; d++) im->vp[3 * ip + d] = vp_encode(g, vreal[d], S);
       }
     }

@@ -77,6 +77,11 @@ def lib():
         L.oracle_set_sigma_vi_new.argtypes = [vp, f32]
         L.oracle_vmax.restype = f32
         L.oracle_vmax.argtypes = [vp, i64]
+        L.oracle_vmax3.restype = f32
+        L.oracle_vmax3.argtypes = [vp, i64, C.c_int]
+        L.oracle_set_nlayer.argtypes = [vp, i64]
+        L.oracle_nlayer_for.restype = i64
+        L.oracle_nlayer_for.argtypes = [vp, f32, f32, f32]
         L.oracle_f2_max_coarse.restype = f32
         L.oracle_f2_max_coarse.argtypes = [vp, i64]
         L.oracle_error.restype = C.c_int
@@ -456,8 +461,15 @@ class Oracle:
     def buffer_v(self):
         lib().oracle_buffer_v(self.h)
 
-    def update_particle(self, dt_old, dt):
-        lib().oracle_update_particle(self.h, F32(dt_old), F32(dt)); self._check()
+    def update_particle(self, dt_old, dt, vz_max=None):
+        """``vz_max=None``: CUBE/main (source cells in storage order).  With ``vz_max`` (CUBEnu's ``sim%vz_max`` of the
+        previous ``particle_mesh``, pm.f90:398) the k planes are visited in ``nlayer = 2*ceiling(dt_mid*vz_max/ncell)+1``
+        colour passes as CUBEnu's ``update_xp`` does (update_particle.f90:37,55-58,97-103): same arithmetic, another
+        order of the particles inside a destination cell and of the f32 sums into ``vfield_new``."""
+        L = lib()
+        self.nlayer = 1 if vz_max is None else int(L.oracle_nlayer_for(self.h, F32(dt_old), F32(dt), F32(vz_max)))
+        L.oracle_set_nlayer(self.h, self.nlayer)
+        L.oracle_update_particle(self.h, F32(dt_old), F32(dt)); self._check()
         return dict(sigma_vi_new=self.sigma_vi_new,
                     std_vsim=lib().oracle_std_vsim(self.h, 0), std_vsim_c=lib().oracle_std_vsim(self.h, 1),
                     std_vsim_res=lib().oracle_std_vsim(self.h, 2),
@@ -562,7 +574,9 @@ class Oracle:
                 dtv.append(F32(0.9) * F32(20) / F32(L.oracle_vmax(self.h, m)))
         self.dt_fine, self.dt_coarse, self.dt_vmax = F32(min(dtf)), F32(min(dtc)), F32(min(dtv))
         out = dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000),
-                   vmax=[F32(L.oracle_vmax(self.h, m)) for m in range(self.nimg)], f2_max_fine=F32(f2f),
+                   vmax=[F32(L.oracle_vmax(self.h, m)) for m in range(self.nimg)],
+                   vmax3=[[F32(L.oracle_vmax3(self.h, m, d)) for d in range(3)] for m in range(self.nimg)],  # CUBEnu pm.f90:349,398
+                   f2_max_fine=F32(f2f),
                    f2_max_coarse=[F32(L.oracle_f2_max_coarse(self.h, m)) for m in range(self.nimg)])
         if keep:
             kept["r3"] = r3g; kept["force_c"] = fcg

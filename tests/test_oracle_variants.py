@@ -1,4 +1,7 @@
-"""CPU tests of the oracle in the reference's other zip formats: izipx, izipv in {1, 2} bytes per code
+"""CPU tests of the oracle's variants beyond CUBE/main x2v2: (1) the reference's other zip formats and (2) CUBEnu's order of
+the particles inside a destination cell (bottom of the file).
+
+(1) izipx, izipv in {1, 2} bytes per code
 (CUBE/main/universe6.fh: x1v2, universe7.fh: x2v1, universe8.fh: x1v1; parameters.f90:13-15,101; variables.f90:41-42).
 
 The GPU library is built for x2v2 only and rejects the rest at init ("zip format incompatable",
@@ -209,3 +212,88 @@ def test_checkpoint_files_in_one_byte_formats(tmp_path, izipx, izipv):
     bad = ck.make_header(izipx=2, izipv=2, image=1, nn=1, nnt=2, nt=12, ncell=4, ncb=6)
     with pytest.raises(ValueError, match="zip format incompatable"):
         ck.write_checkpoint(str(tmp_path), 48.0, 1, bad, s)
+
+
+# ---- CUBEnu's order of the particles inside a destination cell ---------------------------------------
+def _predicted_order(co, O, s0, sig, nlayer):
+    """xp after the drift predicted without the oracle's loops: integer increments give every particle its destination cell;
+    inside a destination cell the particles arrive in the order the tile's double loop visits their source cells --
+    colour pass ilayer = (k_rel-(1-ncb)) mod nlayer first (CUBEnu update_particle.f90:55-58; nlayer = 1: CUBE/main
+    update_particle.f90:70-75), then k, j, i of the source cell relative to the destination's tile, then storage order."""
+    rho = s0["rhoc"]
+    nt, nc, nnt, ncb = O.nt, O.nc, O.nnt, O.ncb
+    lut = co.tanf_lut(2)
+    S = float(np.float64(np.sqrt(F32(co.PI_F / F32(2)))) / (np.float64(sig) * 2.5))
+    tz, ty, tx, k, j, i = np.meshgrid(*[np.arange(n) for n in rho.shape], indexing="ij")
+    src = np.stack([np.repeat((t * nt + c).ravel(), rho.ravel()) for t, c in ((tx, i), (ty, j), (tz, k))], 1).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(rho.ravel())[:-1]])
+    l = np.arange(src.shape[0]) - np.repeat(start, rho.ravel())
+    vf = np.repeat(s0["vfield"].reshape(-1, 3), rho.ravel(), axis=0).astype(np.float64)
+    v = lut[s0["vp"].view(np.uint16)].astype(np.float64) / S + vf
+    dt_mid = np.float64(F32((F32(0) + F32(1.0)) / F32(2)))
+    inc = (np.rint(np.abs(dt_mid * v * 16384.0)) * np.sign(v)).astype(np.int64)
+    pos1 = ((src << 16) + s0["xp"].view(np.uint16).astype(np.int64) + inc) % (nc << 16)
+    dst = pos1 >> 16
+    dt_, dc = dst // nt, dst % nt                      # destination tile and cell in it
+    rel = (src - dt_ * nt + ncb - 1) % nc - (ncb - 1)   # source cell relative to the destination's tile, in 1-ncb..nt+ncb (0-based: -ncb..)
+    ilayer = (rel[:, 2] + ncb) % nlayer                 # 0-based rel = Fortran k-1, so k-(1-ncb) = rel+ncb
+    dkey = ((((dt_[:, 2] * nnt + dt_[:, 1]) * nnt + dt_[:, 0]) * nt + dc[:, 2]) * nt + dc[:, 1]) * nt + dc[:, 0]
+    order = np.lexsort((l, rel[:, 0], rel[:, 1], rel[:, 2], ilayer, dkey))
+    xp1 = (pos1 & 0xFFFF).astype(np.uint16).view(np.int16)
+    return xp1[order], np.bincount(dkey, minlength=rho.size).reshape(rho.shape)
+
+
+@pytest.mark.parametrize("vz_max", [None, 0.0, 1.0, 7.0])
+def test_in_cell_order_main_and_cubenu(co, tables, vz_max):
+    """The oracle's re-sorted positions equal an independent prediction of (destination cell, arrival order) for CUBE/main
+    (vz_max None: storage order) and for CUBEnu's colour passes (nlayer = 1, 3, 9 here)."""
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=24, nnt=2, np_nc=2, seed=11, disp_rms=0.8)
+    O = co.Oracle(nn=1, nnt=2, nc=24, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    O.update_particle(F32(0), F32(1.0), vz_max=vz_max)
+    want_nlayer = 1 if vz_max is None else 2 * int(np.ceil(F32(0.5) * F32(vz_max) / F32(4))) + 1
+    assert O.nlayer == want_nlayer
+    s1 = O.store(0)
+    xp_pred, rho_pred = _predicted_order(co, O, states[0], sig, O.nlayer)
+    assert np.array_equal(s1["rhoc"], rho_pred)
+    assert np.array_equal(s1["xp"], xp_pred)
+    O.close()
+
+
+def test_cubenu_order_changes_only_the_order(co, tables):
+    """Colour passes permute particles inside cells and reorder the f32 sums of vfield_new: counts are identical, vfield agrees to
+    f32 round-off, per-cell multisets of positions are identical."""
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=24, nnt=2, np_nc=2, seed=12, disp_rms=0.8)
+    out = []
+    for vz in (None, 9.0):
+        O = co.Oracle(nn=1, nnt=2, nc=24, np_nc=2, fk_table=fk, ck_table=ck)
+        O.load(states, sig)
+        O.buffer_density(); O.buffer_x(); O.buffer_v()
+        up = O.update_particle(F32(0), F32(1.0), vz_max=vz)
+        out.append((O.store(0), up, O.nlayer))
+        O.close()
+    (a, ua, la), (b, ub, lb) = out
+    assert la == 1 and lb == 5
+    assert np.array_equal(a["rhoc"], b["rhoc"])
+    assert not np.array_equal(a["xp"], b["xp"])
+    cell = np.repeat(np.arange(a["rhoc"].size), a["rhoc"].ravel())
+    canon = lambda s: s["xp"][np.lexsort((s["xp"][:, 2], s["xp"][:, 1], s["xp"][:, 0], cell))]
+    assert np.array_equal(canon(a), canon(b))
+    scale = float(np.abs(a["vfield"]).max())
+    assert float(np.abs(a["vfield"] - b["vfield"]).max()) < 1e-5 * scale
+    assert abs(float(ua["sigma_vi_new"]) - float(ub["sigma_vi_new"])) < 1e-5 * float(ua["sigma_vi_new"])
+
+
+def test_cubenu_vmax3(co, tables):
+    """CUBEnu pm.f90:349,398: vmax(3) = max |v| per component (CUBE/main: one scalar, no abs, pm.f90:220)."""
+    O, states, sig = make(co, tables, 2, 2)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    up, pm = O.step(F32(0), F32(0.5), F32(0.021))
+    v3 = np.array(pm["vmax3"][0], np.float64)
+    assert (v3 > 0).all() and float(pm["vmax"][0]) <= v3.max() * (1 + 1e-6)
+    O.close()
