@@ -52,7 +52,33 @@ def run():
     return out
 
 
+VARIANTS = {"x1v1": dict(izipx=1, izipv=1), "x1v2": dict(izipx=1, izipv=2), "x2v1": dict(izipx=2, izipv=1),
+            "cubenu_order_nlayer5": dict(vz_max=9.0)}
+
+
+def run_variants():
+    """The drift (update_particle) of the same seeded field in the reference's other zip formats (CUBE/main/universe6-8.fh)
+    and in CUBEnu's colour-pass order (CUBEnu update_particle.f90:37,55-58): md5 of the integer outputs."""
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = np.load(os.path.join(HERE, "fk_table.npy")), np.load(os.path.join(HERE, "ck_table.npy"))
+    out = {}
+    for name, v in VARIANTS.items():
+        zx, zv = v.get("izipx", 2), v.get("izipv", 2)
+        states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=2, seed=SEED, disp_rms=0.8, izipx=zx, izipv=zv)
+        O = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=2, fk_table=fk, ck_table=ck, izipx=zx, izipv=zv)
+        O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+        u = O.update_particle(np.float32(DT_OLD), np.float32(DT), vz_max=v.get("vz_max"))
+        st = O.store(0)
+        out[name] = dict(input=dict(xp=md5(states[0]["xp"]), vp=md5(states[0]["vp"]), sigma_vi=float(sig)), nlayer=int(O.nlayer),
+                         xp=md5(st["xp"]), vp=md5(st["vp"]), rhoc=md5(st["rhoc"]), vfield=md5(st["vfield"].view(np.uint32)),
+                         nplocal=int(O.nplocal(0)), sigma_vi_new=float(u["sigma_vi_new"]))
+        O.close()
+    return out
+
+
 if __name__ == "__main__":
     res = run()
+    res["variants_after_update_particle"] = run_variants()
     json.dump(res, open(os.path.join(HERE, "oracle_step_nc32.json"), "w"), indent=1)
     print(json.dumps(res, indent=1))

@@ -358,3 +358,9 @@ def test_oracle_reproduces_its_golden_step():
     assert abs(a["vp_abs_sum"] - b["vp_abs_sum"]) <= 1e-6 * b["vp_abs_sum"]
     for k in ("dt_fine", "dt_coarse", "dt_vmax"):
         assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]), k
+    gv, wv = mod.run_variants(), want["variants_after_update_particle"]
+    assert sorted(gv) == sorted(wv)
+    for name in wv:      # 1-byte zip formats and CUBEnu's in-cell order: integer outputs of the drift bit for bit
+        if gv[name]["input"] != wv[name]["input"]:
+            continue     # same host-FFT caveat as above, per variant
+        assert gv[name] == wv[name], name
