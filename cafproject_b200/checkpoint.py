@@ -44,6 +44,9 @@ assert HEADER_NU_DTYPE.itemsize == 224
 NU_NAMES = {"zip2": "info", "zip0": "xp", "zip1": "vp", "rhoc": "np", "vfield": "vc", "zipid": "id"}
 
 
+PID_DTYPE = {"cube": np.dtype("<i8"), "cubenu": np.dtype("<i4")}
+
+
 def z2str(z: float) -> str:
     """parameters.f90:213-219: write(str,'(f7.3)') z ; trim(adjustl(str))."""
     return ("%7.3f" % z).strip()
@@ -86,6 +89,8 @@ def write_checkpoint(opath: str, z: float, image: int, header: np.ndarray, state
     np.ascontiguousarray(state["vfield"], "<f4").tofile(file_name(opath, z, image, "vfield", convention))
     np.ascontiguousarray(state["xp"], xdt).tofile(file_name(opath, z, image, "zip0", convention))
     np.ascontiguousarray(state["vp"], vdt).tofile(file_name(opath, z, image, "zip1", convention))
+    if "pid" in state:   # -DPID: CUBE/main `zipid`, integer(8) (variables.f90:44); CUBEnu `id`, integer(4) (variables.f90:47, checkpoint.f90:47)
+        np.ascontiguousarray(state["pid"], PID_DTYPE[convention]).tofile(file_name(opath, z, image, "zipid", convention))
 
 
 def _code_dtypes(header):
@@ -94,6 +99,16 @@ def _code_dtypes(header):
     if zx not in (1, 2) or zv not in (1, 2):
         raise ValueError("zip format incompatable: izipx=%d izipv=%d" % (zx, zv))
     return np.dtype("<i%d" % zx), np.dtype("<i%d" % zv)
+
+
+def _with_pid(state, opath, z, image, convention):
+    """Adds ``pid`` when the checkpoint has an ID file (runs built with -DPID; particle_initialization.f90:56)."""
+    fn = file_name(opath, z, image, "zipid", convention)
+    if os.path.exists(fn):
+        state["pid"] = np.fromfile(fn, PID_DTYPE[convention])
+        if state["pid"].shape[0] != state["xp"].shape[0]:
+            raise ValueError("ID file holds %d IDs for %d particles" % (state["pid"].shape[0], state["xp"].shape[0]))
+    return state
 
 
 def _check_zip(header, expect):
@@ -115,7 +130,7 @@ def read_checkpoint(opath: str, z: float, image: int, convention: str = "cube", 
         vfield = np.fromfile(file_name(opath, z, image, "vfield", convention), "<f4").reshape(rhoc.shape + (3,))
         xp = np.fromfile(file_name(opath, z, image, "zip0", convention), xdt).reshape(n, 3)
         vp = np.fromfile(file_name(opath, z, image, "zip1", convention), vdt).reshape(n, 3)
-        return header, dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield)
+        return header, _with_pid(dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield), opath, z, image, convention)
     with open(file_name(opath, z, image, "zip2"), "rb") as f:
         header = np.frombuffer(f.read(HEADER_DTYPE.itemsize), HEADER_DTYPE)[0]
         nnt, nt = int(header["nnt"]), int(header["nt"])
@@ -126,4 +141,4 @@ def read_checkpoint(opath: str, z: float, image: int, convention: str = "cube", 
     vfield = np.fromfile(file_name(opath, z, image, "vfield"), "<f4").reshape(rhoc.shape + (3,))
     xp = np.fromfile(file_name(opath, z, image, "zip0"), xdt).reshape(n, 3)
     vp = np.fromfile(file_name(opath, z, image, "zip1"), vdt).reshape(n, 3)
-    return header, dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield)
+    return header, _with_pid(dict(xp=xp, vp=vp, rhoc=rhoc, vfield=vfield), opath, z, image, convention)

@@ -60,6 +60,7 @@ typedef struct {
 
 typedef struct {
   i16 *xp, *vp;   /* (3, np_image_max) */
+  i64 *pid;       /* (np_image_max) particle IDs, -DPID (CUBE/main variables.f90:44 integer(8); CUBEnu variables.f90:47 integer(4)) */
   i32 *rhoc;      /* (nte,nte,nte,nnt,nnt,nnt), lower bound 1-ncb */
   float *vfield;  /* (3,nte,nte,nte,nnt,nnt,nnt) */
   i64 *cum;       /* same shape as rhoc */
@@ -87,6 +88,8 @@ typedef struct {
   float *vfield_new;
   i64 *cume;
   i16 *xp_new, *vp_new;
+  i64 *pid_new;
+  int has_pid; /* -DPID: IDs ride with vp through buffer_density, buffer_v and update_particle */
 } ctx_t;
 
 /* ---- Fortran-style index helpers ------------------------------------------------ */
@@ -153,6 +156,7 @@ ctx_t *oracle_create(i64 nnx, i64 nny, i64 nnz, i64 nnt, i64 nc, i64 np_nc,
     image_t *im = &c->im[m];
     im->xp = (i16 *)calloc(3 * g->np_image_max, sizeof(i16));
     im->vp = (i16 *)calloc(3 * g->np_image_max, sizeof(i16));
+    im->pid = NULL; /* allocated by oracle_load_pid */
     im->rhoc = (i32 *)calloc(ncell_e, sizeof(i32));
     im->vfield = (float *)calloc(3 * ncell_e, sizeof(float));
     im->cum = (i64 *)calloc(ncell_e, sizeof(i64));
@@ -176,16 +180,17 @@ ctx_t *oracle_create(i64 nnx, i64 nny, i64 nnz, i64 nnt, i64 nc, i64 np_nc,
   c->cume = (i64 *)calloc(n2, sizeof(i64));
   c->xp_new = (i16 *)calloc(3 * g->np_tile_max, sizeof(i16));
   c->vp_new = (i16 *)calloc(3 * g->np_tile_max, sizeof(i16));
+  c->pid_new = NULL;
   return c;
 }
 
 void oracle_destroy(ctx_t *c) {
   for (i64 m = 0; m < c->g.nimg; m++) {
     image_t *im = &c->im[m];
-    free(im->xp); free(im->vp); free(im->rhoc); free(im->vfield); free(im->cum); free(im->f2_max_fine);
+    free(im->xp); free(im->vp); free(im->pid); free(im->rhoc); free(im->vfield); free(im->cum); free(im->f2_max_fine);
   }
   free(c->im); free(c->rhoce); free(c->rholocal); free(c->vfield_new); free(c->cume);
-  free(c->xp_new); free(c->vp_new); free(c);
+  free(c->xp_new); free(c->vp_new); free(c->pid_new); free(c);
 }
 
 /* accessors for the Python side */
@@ -193,6 +198,7 @@ i64 oracle_np_image_max(ctx_t *c) { return c->g.np_image_max; }
 i64 oracle_np_tile_max(ctx_t *c) { return c->g.np_tile_max; }
 i16 *oracle_xp(ctx_t *c, i64 m) { return c->im[m].xp; }
 i16 *oracle_vp(ctx_t *c, i64 m) { return c->im[m].vp; }
+i64 *oracle_pid(ctx_t *c, i64 m) { return c->im[m].pid; }
 i32 *oracle_rhoc(ctx_t *c, i64 m) { return c->im[m].rhoc; }
 float *oracle_vfield(ctx_t *c, i64 m) { return c->im[m].vfield; }
 i64 *oracle_cum(ctx_t *c, i64 m) { return c->im[m].cum; }
@@ -283,6 +289,17 @@ void oracle_load_image(ctx_t *c, i64 m, const i16 *xp, const i16 *vp, const i32 
   memcpy(im->xp, xp, 3 * nplocal * sizeof(i16));
   memcpy(im->vp, vp, 3 * nplocal * sizeof(i16));
   im->nplocal = nplocal;
+}
+/* -DPID (particle_initialization.f90, `read(14) pid(:nplocal)`): IDs of the nplocal particles just loaded, file order.
+ * Every image of the run must be given IDs before oracle_finish_load. */
+void oracle_load_pid(ctx_t *c, i64 m, const i64 *pid) {
+  const geom_t *g = &c->g;
+  image_t *im = &c->im[m];
+  if (!im->pid) im->pid = (i64 *)calloc(g->np_image_max, sizeof(i64));
+  if (!c->pid_new) c->pid_new = (i64 *)calloc(g->np_tile_max, sizeof(i64));
+  memset(im->pid, 0, g->np_image_max * sizeof(i64));
+  memcpy(im->pid, pid, im->nplocal * sizeof(i64));
+  c->has_pid = 1;
 }
 /* particle_initialization.f90:65-72: npglobal, mass_p = real((nf*nn)**3)/npglobal */
 void oracle_finish_load(ctx_t *c, float sigma_vi) {
@@ -379,6 +396,10 @@ void oracle_buffer_density(ctx_t *c) {
     memmove(im->vp + 3 * nshift, im->vp, 3 * im->nplocal * sizeof(i16));
     memset(im->xp, 0, 3 * nshift * sizeof(i16));
     memset(im->vp, 0, 3 * nshift * sizeof(i16));
+    if (c->has_pid) { /* buffer_density.f90:111-114 */
+      memmove(im->pid + nshift, im->pid, im->nplocal * sizeof(i64));
+      memset(im->pid, 0, nshift * sizeof(i64));
+    }
     cumsum6(g, im->rhoc, im->cum);
     i64 ifrom = nshift;
     for (i64 tz = 1; tz <= nnt; tz++) for (i64 ty = 1; ty <= nnt; ty++) for (i64 tx = 1; tx <= nnt; tx++)
@@ -393,6 +414,10 @@ void oracle_buffer_density(ctx_t *c) {
            nearly full) the reference would destroy data here and report it through its checksum. */
         memset(im->xp + 3 * ifrom, 0, 3 * nlen * sizeof(i16));
         memset(im->vp + 3 * ifrom, 0, 3 * nlen * sizeof(i16));
+        if (c->has_pid) { /* buffer_density.f90:132-135 */
+          memmove(im->pid + (nlast - nlen), im->pid + ifrom, nlen * sizeof(i64));
+          memset(im->pid + ifrom, 0, nlen * sizeof(i64));
+        }
         ifrom += nlen;
       }
   }
@@ -425,6 +450,7 @@ static void buffer_particles(ctx_t *c, int which /*0=xp,1=vp*/) {
             else mlast = im->cum[RH(g, ncb, iy, iz, tx + 1, ty, tz)];
           }
           memcpy(ARR(im) + 3 * (nlast - nlen), ARR(src) + 3 * (mlast - nlen), 3 * nlen * sizeof(i16));
+          if (which == 1 && c->has_pid) memcpy(im->pid + (nlast - nlen), src->pid + (mlast - nlen), nlen * sizeof(i64)); /* buffer_v.f90:22-23,41-42 */
         }
     }
   /* y- then y+ (buffer_x.f90:82-137) */
@@ -446,6 +472,7 @@ static void buffer_particles(ctx_t *c, int which /*0=xp,1=vp*/) {
             else mlast = im->cum[RH(g, hi, ncb, iz, tx, ty + 1, tz)];
           }
           memcpy(ARR(im) + 3 * (nlast - nlen), ARR(src) + 3 * (mlast - nlen), 3 * nlen * sizeof(i16));
+          if (which == 1 && c->has_pid) memcpy(im->pid + (nlast - nlen), src->pid + (mlast - nlen), nlen * sizeof(i64)); /* buffer_v.f90:22-23,41-42 */
         }
     }
   /* z- then z+ (buffer_x.f90:144-191) */
@@ -466,6 +493,7 @@ static void buffer_particles(ctx_t *c, int which /*0=xp,1=vp*/) {
           else mlast = im->cum[RH(g, hi, hi, ncb, tx, ty, tz + 1)];
         }
         memcpy(ARR(im) + 3 * (nlast - nlen), ARR(src) + 3 * (mlast - nlen), 3 * nlen * sizeof(i16));
+          if (which == 1 && c->has_pid) memcpy(im->pid + (nlast - nlen), src->pid + (mlast - nlen), nlen * sizeof(i64)); /* buffer_v.f90:22-23,41-42 */
       }
     }
 #undef ARR
@@ -559,6 +587,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
             double vr = vreal[d] - (double)c->vfield_new[3 * e + d];
             c->vp_new[3 * idx + d] = vp_encode(g, vr, S);
           }
+          if (c->has_pid) c->pid_new[idx] = im->pid[ip]; /* :88 */
         }
       }
       /* delete buffer particles :97-109 */
@@ -567,6 +596,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
         i64 nlen = nlast - c->cume[RE(g, 0, j, k)];
         memcpy(im->xp + 3 * iright, c->xp_new + 3 * (nlast - nlen), 3 * nlen * sizeof(i16));
         memcpy(im->vp + 3 * iright, c->vp_new + 3 * (nlast - nlen), 3 * nlen * sizeof(i16));
+        if (c->has_pid) memcpy(im->pid + iright, c->pid_new + (nlast - nlen), nlen * sizeof(i64)); /* :106 */
         iright += nlen;
       }
       /* :111-112 */
@@ -579,6 +609,7 @@ void oracle_update_particle(ctx_t *c, float dt_old, float dt) {
     im->nplocal = iright; /* :117-119 */
     memset(im->xp + 3 * iright, 0, 3 * (g->np_image_max - iright) * sizeof(i16));
     memset(im->vp + 3 * iright, 0, 3 * (g->np_image_max - iright) * sizeof(i16));
+    if (c->has_pid) memset(im->pid + iright, 0, (g->np_image_max - iright) * sizeof(i64)); /* :121 */
     if (im->overhead_tile > ovh_all) ovh_all = im->overhead_tile;
   }
   /* velocity statistics :129-175 */

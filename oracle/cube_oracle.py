@@ -102,6 +102,9 @@ def lib():
         L.oracle_probe_vencode.argtypes = [vp, C.c_double, f32]
         L.oracle_load_image.argtypes = [vp, i64, vp, vp, vp, vp, i64]
         L.oracle_finish_load.argtypes = [vp, f32]
+        L.oracle_load_pid.argtypes = [vp, i64, vp]
+        L.oracle_pid.restype = vp
+        L.oracle_pid.argtypes = [vp, i64]
         L.oracle_store_image.argtypes = [vp, i64, vp, vp]
         for name in ("buffer_density", "buffer_x", "buffer_v", "pm_begin", "pm_fine_end"):
             getattr(L, "oracle_" + name).argtypes = [vp]
@@ -364,6 +367,7 @@ class Oracle:
         self.dt_fine = self.dt_coarse = self.dt_vmax = F32(1000)
         self.dt_pp = F32(1000)
         self.last = {}
+        self.has_pid = False
 
     def close(self):
         if self.h:
@@ -387,6 +391,11 @@ class Oracle:
 
     def vp(self, m=0):
         return self._view("vp", m, (self.np_image_max, 3), np.int16)
+
+    def pid(self, m=0):
+        """Particle IDs (-DPID), same slots as ``vp``; only after a ``load`` whose states carried ``pid``."""
+        assert self.has_pid
+        return self._view("pid", m, (self.np_image_max,), np.int64)
 
     def rhoc(self, m=0):
         t, e = self.nnt, self.nte
@@ -435,6 +444,12 @@ class Oracle:
             n = xp.shape[0]
             assert n == int(rc.sum()) and n <= self.np_image_max
             lib().oracle_load_image(self.h, m, _ptr(xp), _ptr(vp), _ptr(rc), _ptr(vf), n)
+            if "pid" in s:   # -DPID: integer IDs that ride with vp (buffer_density/buffer_v/update_particle `#ifdef PID` lines)
+                pid = np.ascontiguousarray(s["pid"], np.int64)
+                assert pid.shape == (n,)
+                lib().oracle_load_pid(self.h, m, _ptr(pid))
+        self.has_pid = all("pid" in s for s in states)
+        assert self.has_pid or not any("pid" in s for s in states), "give every image IDs or none"
         lib().oracle_finish_load(self.h, F32(sigma_vi))
 
     def store(self, m=0):
@@ -447,8 +462,11 @@ class Oracle:
             assert xp.min(initial=0) >= -128 and xp.max(initial=0) <= 127
         if self.izipv == 1:
             assert vp.min(initial=0) >= -128 and vp.max(initial=0) <= 127
-        return dict(xp=xp.astype((np.int8, np.int16)[self.izipx - 1]), vp=vp.astype((np.int8, np.int16)[self.izipv - 1]),
-                    rhoc=rc, vfield=vf)
+        out = dict(xp=xp.astype((np.int8, np.int16)[self.izipx - 1]), vp=vp.astype((np.int8, np.int16)[self.izipv - 1]),
+                   rhoc=rc, vfield=vf)
+        if self.has_pid:
+            out["pid"] = self.pid(m)[:n].copy()
+        return out
 
     # ---- step subroutines ---------------------------------------------------------------------
     def buffer_density(self):

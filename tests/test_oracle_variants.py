@@ -297,3 +297,94 @@ def test_cubenu_vmax3(co, tables):
     v3 = np.array(pm["vmax3"][0], np.float64)
     assert (v3 > 0).all() and float(pm["vmax"][0]) <= v3.max() * (1 + 1e-6)
     O.close()
+
+
+# ---- -DPID: particle IDs ride with vp (CUBE/main buffer_density.f90:111-135, buffer_v.f90:22-42, update_particle.f90:88,106) ------
+def _with_pid(states):
+    out, base = [], 0
+    for s in states:
+        n = s["xp"].shape[0]
+        out.append(dict(s, pid=np.arange(base + 1, base + n + 1, dtype=np.int64)))   # all positive (checkpoint.f90 checks that)
+        base += n
+    return out
+
+
+@pytest.mark.parametrize("vz_max", [None, 9.0])
+def test_pid_tracks_every_particle_through_the_drift(co, tables, vz_max):
+    """With IDs the drift can be checked particle by particle instead of as a multiset: the particle with ID p ends in the
+    cell and with the position code that the integer increment predicts for it, buffers keep the IDs of the physical
+    particles, ghosts carry their source's ID, and particle_mesh does not touch them."""
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=24, nnt=2, np_nc=2, seed=21, disp_rms=0.8)
+    states = _with_pid(states)
+    s0 = states[0]
+    n = s0["xp"].shape[0]
+    O = co.Oracle(nn=1, nnt=2, nc=24, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    assert np.array_equal(physical(O, "pid"), s0["pid"])
+    # every slot of the buffered layout that holds a particle holds an ID in 1..n, and a ghost's codes are its source's
+    pid_all, vp_all, xp_all = O.pid(0), O.vp(0), O.xp(0)
+    used = pid_all > 0
+    assert int(used.sum()) == int(O.rhoc(0).sum()) and int(pid_all.max()) == n
+    assert np.array_equal(vp_all[used], s0["vp"][pid_all[used] - 1])
+    assert np.array_equal(xp_all[used], s0["xp"][pid_all[used] - 1])
+    # prediction per ID
+    rho, nt, nc = s0["rhoc"], O.nt, O.nc
+    tz, ty, tx, k, j, i = np.meshgrid(*[np.arange(m) for m in rho.shape], indexing="ij")
+    cells = lambda r: np.stack([np.repeat((t * nt + c).ravel(), r.ravel()) for t, c in ((tx, i), (ty, j), (tz, k))], 1).astype(np.int64)
+    lut = co.tanf_lut(2)
+    S = float(np.float64(np.sqrt(F32(co.PI_F / F32(2)))) / (np.float64(sig) * 2.5))
+    vf = np.repeat(s0["vfield"].reshape(-1, 3), rho.ravel(), axis=0).astype(np.float64)
+    v = lut[s0["vp"].view(np.uint16)].astype(np.float64) / S + vf
+    inc = (np.rint(np.abs(0.5 * v * 16384.0)) * np.sign(v)).astype(np.int64)
+    pos1 = ((cells(rho) << 16) + s0["xp"].view(np.uint16).astype(np.int64) + inc) % (nc << 16)
+    O.update_particle(F32(0), F32(1.0), vz_max=vz_max)
+    s1 = O.store(0)
+    assert np.array_equal(np.sort(s1["pid"]), s0["pid"])                      # a permutation
+    got = (cells(s1["rhoc"]) << 16) + s1["xp"].view(np.uint16).astype(np.int64)
+    assert np.array_equal(got, pos1[s1["pid"] - 1])                           # particle by particle
+    O.buffer_density(); O.buffer_x()
+    O.particle_mesh(F32(0.021), F32(1.0))
+    O.buffer_v()
+    assert np.array_equal(physical(O, "pid"), s1["pid"])
+    O.close()
+
+
+def test_pid_across_images(co, tables):
+    """Two images in x: IDs are global, the drift hands particles (and their IDs) across the image boundary through the
+    ghost zones, nothing is lost or duplicated (update_particle.f90:205-211 with IDs)."""
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    nn = (2, 1, 1)
+    states, sig, _ = make_ic(nn=nn, nc=24, nnt=2, np_nc=1, seed=22, disp_rms=1.5)
+    states = _with_pid(states)
+    ntot = sum(s["xp"].shape[0] for s in states)
+    O = co.Oracle(nn=nn, nnt=2, nc=24, np_nc=1, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    O.update_particle(F32(0), F32(1.0))
+    after = [O.store(m) for m in range(2)]
+    allp = np.concatenate([s["pid"] for s in after])
+    assert np.array_equal(np.sort(allp), np.arange(1, ntot + 1))
+    n0 = states[0]["xp"].shape[0]
+    moved = int((after[0]["pid"] > n0).sum()) + int((after[1]["pid"] <= n0).sum())
+    assert moved > 0                                                           # some particles did change image
+    O.close()
+
+
+@pytest.mark.parametrize("convention,idbytes,idname", [("cube", 8, "49.000zipid_1.bin"), ("cubenu", 4, "49.000_id_1.bin")])
+def test_checkpoint_id_files(tmp_path, convention, idbytes, idname):
+    """-DPID checkpoints: CUBE/main `zipid` integer(8) (particle_initialization.f90:56), CUBEnu `id` integer(4)
+    (checkpoint.f90:17,47)."""
+    from cafproject_b200 import checkpoint as ck
+    from cafproject_b200.synthetic_ic import make_ic
+    states, sig, _ = make_ic(nn=1, nc=24, nnt=2, np_nc=1, seed=4)
+    s = _with_pid(states)[0]
+    n = s["xp"].shape[0]
+    h = ck.make_header(convention, izipx=2, izipv=2, image=1, nn=1, nnt=2, nt=12, ncell=4, ncb=6, sigma_vi=sig)
+    ck.write_checkpoint(str(tmp_path), 49.0, 1, h, s, convention=convention)
+    assert os.path.getsize(tmp_path / "image1" / idname) == idbytes * n
+    _, s2 = ck.read_checkpoint(str(tmp_path), 49.0, 1, convention=convention)
+    assert np.array_equal(s2["pid"], s["pid"])
