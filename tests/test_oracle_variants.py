@@ -388,3 +388,58 @@ def test_checkpoint_id_files(tmp_path, convention, idbytes, idname):
     assert os.path.getsize(tmp_path / "image1" / idname) == idbytes * n
     _, s2 = ck.read_checkpoint(str(tmp_path), 49.0, 1, convention=convention)
     assert np.array_equal(s2["pid"], s["pid"])
+
+
+# ---- edge cases of the domain -----------------------------------------------------------------------------------------
+def test_zero_time_step_keeps_positions_and_counts(co, tables):
+    """dt_mid = 0: nobody moves -- counts, order and position codes are unchanged (the velocities are only re-expressed against
+    the rebuilt vfield); a second zero step changes nothing in them either (idempotence)."""
+    O, states, sig = make(co, tables, 2, 2)
+    s0 = states[0]
+    for _ in range(2):
+        O.buffer_density(); O.buffer_x(); O.buffer_v()
+        O.update_particle(F32(0), F32(0))
+        s1 = O.store(0)
+        assert np.array_equal(s1["rhoc"], s0["rhoc"]) and np.array_equal(s1["xp"], s0["xp"])
+    O.close()
+
+
+def test_empty_tiles_and_one_crowded_cell(co, tables):
+    """Ragged input: every particle of the image in one coarse cell of one tile (7 tiles empty, 13 823 empty cells), at rest
+    relative to the cell flow.  Buffers, drift and both meshes go through; the count stays in the cell (or moves as a block
+    with the common velocity), the coarse mesh carries the whole mass on the 8 nodes around it."""
+    fk, ck = tables
+    nc, nnt, n = 24, 2, 500
+    nt = nc // nnt
+    rng = np.random.default_rng(5)
+    rhoc = np.zeros((nnt,) * 3 + (nt,) * 3, np.int32)
+    rhoc[1, 0, 1, 3, 4, 5] = n
+    vfield = np.zeros(rhoc.shape + (3,), np.float32)
+    state = dict(xp=rng.integers(-32768, 32768, (n, 3)).astype(np.int16), vp=np.zeros((n, 3), np.int16), rhoc=rhoc, vfield=vfield)
+    O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load([state], F32(0.1))
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    r3 = O.coarse_density()
+    mp = float(O.mass_p)
+    assert abs(float(r3.sum(dtype=np.float64)) - n * mp) < 1e-5 * n * mp
+    assert int((r3 != 0).sum()) <= 27 and int((r3 != 0).sum()) >= 8
+    up, pm = O.step(F32(0), F32(0.01), F32(0.02))
+    s1 = O.store(0)
+    assert int(s1["rhoc"].sum()) == n and O.nplocal(0) == n
+    assert int((s1["rhoc"] != 0).sum()) <= 8                                   # a tiny step: at most the neighbouring cells
+    assert all(np.isfinite(float(pm[k])) and float(pm[k]) > 0 for k in ("dt_fine", "dt_coarse"))
+    O.close()
+
+
+def test_extreme_velocity_codes_round_trip(co):
+    """The largest codes (+-32767 at v2, +-127 at v1) decode to finite velocities and encode back to themselves; the code
+    -32768 / -128 is never produced by the encoder (|nint(N*atan(x)/pi)| <= (N-1)/2)."""
+    for izipv in (1, 2):
+        O = co.Oracle(nc=24, nnt=2, izipx=2, izipv=izipv)
+        L = co.lib()
+        top = (1 << (8 * izipv - 1)) - 1
+        for c in (top, -top):
+            v = L.oracle_probe_vdecode(O.h, c, F32(0.2))
+            assert np.isfinite(v) and L.oracle_probe_vencode(O.h, v, F32(0.2)) == c
+        assert L.oracle_probe_vencode(O.h, 1e300, F32(0.2)) == top and L.oracle_probe_vencode(O.h, -1e300, F32(0.2)) == -top
+        O.close()
