@@ -2,8 +2,9 @@
 nc = 256, 64 tiles of nt = 64) -- a size the CPU oracle does not finish in seconds, so parity proper is left to the small cases
 of test_gpu_parity.py and this file checks what must hold at any size: the upload/download round trip, conservation of the
 particle number through drift and re-sort (update_particle.f90:205-211), the mass on the coarse mesh (CUBEnu pm.f90:267), the
-time-step limits, and run-to-run determinism bit for bit (no floating-point atomics anywhere on the path).  Named to sort
-after the other GPU tests.
+time-step limits, and run-to-run determinism bit for bit (no floating-point atomics anywhere on the path).  Below them two small edge
+cases against the oracle, bit for bit: a zero time step (idempotence of counts and positions) and a ragged state (one crowded
+cell, seven empty tiles).  Named to sort after the other GPU tests.
 
 Status: written at the end of round 1 after the round's GPU minutes were spent -- every call in it is one bench.py or the
 small parity tests already make on a B200, but this file itself has not run on hardware yet.
@@ -70,3 +71,51 @@ def test_full_size_step_properties(tables):
             assert pm1[k] == pm2[k], k
     finally:
         G.close()
+
+
+# ---- edge cases against the oracle (small sizes; same status note as above) ---------------------------------------------
+def _drift_parity(tables, state, sig, dt_old, dt, nc=24, nnt=2):
+    from cafproject_b200.cube import CubeGPU
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load([state], sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(nc, nnt, fk, ck, np_nc=2, tanf_lut=co.tanf_lut())
+    try:
+        G.particle_initialization(state, sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+        uo = O.update_particle(dt_old, dt)
+        ug = G.update_particle(dt_old, dt)
+        so = O.store(0)
+        sg, _ = G.checkpoint()
+        assert ug["nplocal"] == O.nplocal(0)
+        assert np.array_equal(so["rhoc"], sg["rhoc"])
+        assert np.array_equal(so["xp"], sg["xp"])
+        assert np.array_equal(so["vfield"].view(np.uint32), sg["vfield"].view(np.uint32))
+        assert np.array_equal(so["vp"], sg["vp"])
+        assert ug["sigma_vi_new"] == uo["sigma_vi_new"]
+        return sg
+    finally:
+        G.close(); O.close()
+
+
+def test_zero_time_step_is_idempotent_and_matches_the_oracle(tables):
+    """dt_mid = 0: counts and position codes come back unchanged, everything bit-identical to the oracle."""
+    from cafproject_b200.synthetic_ic import make_ic
+    states, sig, _ = make_ic(nn=1, nc=24, nnt=2, np_nc=2, seed=31, disp_rms=0.7)
+    sg = _drift_parity(tables, states[0], sig, np.float32(0), np.float32(0))
+    assert np.array_equal(sg["rhoc"], states[0]["rhoc"]) and np.array_equal(sg["xp"], states[0]["xp"])
+
+
+def test_one_crowded_cell_and_empty_tiles_match_the_oracle(tables):
+    """Ragged input: all 500 particles of the image in one coarse cell of one tile, the other seven tiles empty."""
+    nc, nnt, n = 24, 2, 500
+    nt = nc // nnt
+    rng = np.random.default_rng(6)
+    rhoc = np.zeros((nnt,) * 3 + (nt,) * 3, np.int32)
+    rhoc[1, 0, 1, 3, 4, 5] = n
+    vfield = np.zeros(rhoc.shape + (3,), np.float32)
+    vfield[1, 0, 1, 3, 4, 5] = (0.3, -0.2, 0.1)
+    state = dict(xp=rng.integers(-32768, 32768, (n, 3)).astype(np.int16), vp=rng.integers(-2000, 2001, (n, 3)).astype(np.int16),
+                 rhoc=rhoc, vfield=vfield)
+    sg = _drift_parity(tables, state, np.float32(0.1), np.float32(0), np.float32(1.0))
+    assert int(sg["rhoc"].sum()) == n
