@@ -93,6 +93,7 @@ struct cube_handle {
   bool buffered = false;
   // particles (double buffered)
   short *xp = nullptr, *vp = nullptr, *xp2 = nullptr, *vp2 = nullptr;
+  long long *pid = nullptr, *pid2 = nullptr; bool pid_valid = false;  // -DPID: optional particle IDs (cube_gpu_upload_pid), single image
   unsigned short* key = nullptr;
   // coarse-cell arrays, file order
   int *rhoc_p = nullptr, *rhoc_p2 = nullptr;
@@ -622,7 +623,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -652,6 +653,7 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
     return fail("error: too many particles in this image+buffer: %lld > %lld; please set image_buffer larger", (long long)nplocal, h->np_image_max);
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // a streamed download still reads the arrays overwritten here
   h->vp_stream_host = nullptr;
+  h->pid_valid = false;  // a new state: its IDs, if any, come with cube_gpu_upload_pid
   CK(cudaMemcpyAsync(h->xp, xp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->vp, vp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->rhoc_p, rhoc_phys, sizeof(int) * g.ncell_p, cudaMemcpyHostToDevice, h->st));
@@ -667,6 +669,28 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
   long long nf = (long long)g.nc * NCELL;
   h->mass_p = (float)((nf * g.nn[0]) * (nf * g.nn[1]) * (nf * g.nn[2])) / (float)npglobal;
   h->buffered = false;
+  return 0;
+}
+
+// -DPID: the IDs of the nplocal particles of the last cube_gpu_upload, file order (particle_initialization.f90:56-59).  They ride
+// through update_x (the buffers of a single image hold no ghost copies, and particle_mesh does not move particles).
+extern "C" int cube_gpu_upload_pid(cube_handle* h, const int64_t* pid) {
+  if (!h) return fail("null handle");
+  if (!pid) return fail("cube_gpu_upload_pid: null array");
+  if (h->nimg > 1) return fail("particle IDs with several images are not built (the ghost exchange carries xp and vp only)");
+  CK(cudaSetDevice(h->p.device));
+  if (!h->pid) { CK(dmalloc(&h->pid, h->np_image_max)); CK(dmalloc(&h->pid2, h->np_image_max)); }
+  CK(cudaMemcpyAsync(h->pid, pid, sizeof(long long) * h->nplocal, cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  h->pid_valid = true;
+  return 0;
+}
+extern "C" int cube_gpu_download_pid(cube_handle* h, int64_t* pid) {
+  if (!h) return fail("null handle");
+  if (!h->pid_valid) return fail("no particle IDs were uploaded for this state");
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaMemcpyAsync(pid, h->pid, sizeof(long long) * h->nplocal, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
   return 0;
 }
 
@@ -900,6 +924,10 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 0, h->stat3); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 1, h->stat3 + 2); CKL();
     h->launches += 3;
+    if (h->pid_valid) {  // update_particle.f90:88,106: the IDs take the same permutation
+      k_pid_place<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, h->pid, h->rank, h->cstart_p, h->cstart_p2, h->pid2); CKL();
+      h->launches += 1;
+    }
     double stg[2] = {0, 0};
     if (multi && ng) {
       k_drift_place_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->rank, h->vfield_e, h->cstart_p2,
@@ -931,6 +959,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   if (multi && npsum != h->npglobal)  // update_particle.f90:205-211
     return fail("np check failed: sum(nplocal)=%lld differs from npglobal=%lld", npsum, h->npglobal);
   std::swap(h->xp, h->xp2); std::swap(h->vp, h->vp2);
+  if (h->pid_valid) std::swap(h->pid, h->pid2);
   std::swap(h->rhoc_p, h->rhoc_p2); std::swap(h->vfield_p, h->vfield_p2); std::swap(h->cstart_p, h->cstart_p2);
   h->nplocal = tot;
   h->buffered = false;

@@ -827,4 +827,32 @@ __global__ void __launch_bounds__(1024) k_reduce_strided(const double* __restric
   if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 32; w++) t += sm[w]; *out = t; }
 }
 
+// -DPID (update_particle.f90:88 `pid_new(idx)=pid(ip)`): the particle IDs follow the permutation of pass C.  IDs are optional and off
+// the hot path: one thread per source cell, the destination arithmetic of k_drift_place_w (single image: periodic wrap).
+__global__ void __launch_bounds__(256) k_pid_place(Geom g, const long long* __restrict__ pid, const unsigned* __restrict__ rank,
+                                                   const long long* __restrict__ cstart_p, const long long* __restrict__ cstart_new,
+                                                   long long* __restrict__ pid_new) {
+  const long long L = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (L >= g.ncell_p) return;
+  int tx0, ty0, tz0, i0, j0, k0;
+  phys_decompose(g, L, tx0, ty0, tz0, i0, j0, k0);
+  const int nt = g.nt, nnt = g.nnt;
+  const long long pend = cstart_p[L + 1];
+  for (long long p = cstart_p[L]; p < pend; p++) {
+    const unsigned rk = rank[p];
+    if (rk == RANK_LOST) continue;
+    const unsigned o = rk >> RANK_BITS;
+    int i = i0 + (int)(o & 15u) - 8, j = j0 + (int)((o >> 4) & 15u) - 8, k = k0 + (int)((o >> 8) & 15u) - 8;
+    int tx = tx0, ty = ty0, tz = tz0;
+    if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
+    if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
+    if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
+    tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
+    ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
+    tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
+    const long long D = phys_index(g, tx, ty, tz, i, j, k);
+    pid_new[cstart_new[D] + (rk & ((1u << RANK_BITS) - 1))] = pid[p];
+  }
+}
+
 }  // namespace cube

@@ -56,6 +56,8 @@ def load_library():
     L.cube_gpu_download_async.argtypes = [vp, vp, vp]
     L.cube_gpu_download_cells_async.argtypes = [vp, vp, vp]
     L.cube_gpu_stream_vp.argtypes = [vp, vp]
+    L.cube_gpu_upload_pid.argtypes = [vp, vp]
+    L.cube_gpu_download_pid.argtypes = [vp, vp]
     L.cube_gpu_last_error.restype = C.c_char_p
     L.cube_gpu_query.restype = i64
     L.cube_gpu_query.argtypes = [vp, C.c_char_p]
@@ -88,6 +90,7 @@ ABI_SYMBOLS = [
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
     "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
+    "cube_gpu_upload_pid", "cube_gpu_download_pid",
 ]
 
 
@@ -211,6 +214,11 @@ class CubeGPU:
         self._ck(self.L.cube_gpu_upload(self.h, _p(xp), _p(vp), _p(rc), _p(vf), n, npglobal or n, F32(sigma_vi)))
         self.nplocal = n
         self.sigma_vi = F32(sigma_vi)
+        self.has_pid = "pid" in state
+        if self.has_pid:   # -DPID: IDs ride with the particles through update_particle (single image; include/cube_gpu.h)
+            pid = np.ascontiguousarray(state["pid"], np.int64)
+            assert pid.shape == (n,)
+            self._ck(self.L.cube_gpu_upload_pid(self.h, _p(pid)))
 
     def checkpoint(self, out=None, skip=()):
         """Disjoint state back on the host (what checkpoint.f90 writes).  ``out`` may hold preallocated
@@ -228,6 +236,10 @@ class CubeGPU:
                                           C.byref(npl), C.byref(sig)))
         if out["xp"].shape[0] != n:
             out = dict(out, xp=out["xp"][:n], vp=out["vp"][:n])
+        if getattr(self, "has_pid", False):
+            pid = np.empty(n, np.int64)
+            self._ck(self.L.cube_gpu_download_pid(self.h, _p(pid)))
+            out = dict(out, pid=pid)
         return out, F32(sig.value)
 
     def checkpoint_begin(self, out, xp=True, vp=False, cells=False, vp_during_pm=False):

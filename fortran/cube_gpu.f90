@@ -99,6 +99,17 @@ module cube_gpu
       import :: c_int, c_ptr
       type(c_ptr), value :: h, vp
     end function
+    ! -DPID: IDs of the particles of the last cube_gpu_upload (file order); they follow every cube_gpu_update_x (single image)
+    integer(c_int) function cube_gpu_upload_pid(h, pid) bind(C, name="cube_gpu_upload_pid")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(in) :: pid(*)
+    end function
+    integer(c_int) function cube_gpu_download_pid(h, pid) bind(C, name="cube_gpu_download_pid")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(out) :: pid(*)
+    end function
     integer(c_int) function cube_gpu_finalize(h) bind(C, name="cube_gpu_finalize")
       import :: c_int, c_ptr
       type(c_ptr), value :: h

@@ -89,6 +89,14 @@ int cube_gpu_particle_mesh(cube_handle *h, float a_mid, float dt, float *dt_fine
 int cube_gpu_download(cube_handle *h, int16_t *xp, int16_t *vp, int32_t *rhoc_phys, float *vfield_phys,
                       int64_t *nplocal, float *sigma_vi);
 
+/* -DPID (CUBE/main variables.f90:44, particle_initialization.f90:56-59; on by default in CUBEnu's Makefile): optional particle
+ * IDs.  upload_pid gives the IDs of the nplocal particles of the LAST cube_gpu_upload, in the same file order; they then take the
+ * permutation of every cube_gpu_update_x (update_particle.f90:88,106) and download_pid returns them in the order of the current
+ * disjoint state (what checkpoint.f90 writes to `zipid`).  Single image only: the ghost exchange between images carries xp and
+ * vp, not IDs -- upload_pid fails on a multi-image handle.  A new cube_gpu_upload drops the IDs. */
+int cube_gpu_upload_pid(cube_handle *h, const int64_t *pid);
+int cube_gpu_download_pid(cube_handle *h, int64_t *pid);
+
 /* Streamed checkpoint: start the device->host copy of xp and/or vp (NULL = skip) of the current disjoint state behind the
  * work already queued and return at once; cube_gpu_download (with NULL for what was streamed) waits for it.  Host buffers
  * should be page-locked.  Typical use: xp right after cube_gpu_update_x -- particle_mesh does not move particles, so the

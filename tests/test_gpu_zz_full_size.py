@@ -119,3 +119,37 @@ def test_one_crowded_cell_and_empty_tiles_match_the_oracle(tables):
                  rhoc=rhoc, vfield=vfield)
     sg = _drift_parity(tables, state, np.float32(0.1), np.float32(0), np.float32(1.0))
     assert int(sg["rhoc"].sum()) == n
+
+
+def test_particle_ids_follow_the_drift_like_the_oracle(tables):
+    """-DPID through cube_gpu_upload_pid / cube_gpu_download_pid (single image): after two steps the IDs sit where the
+    oracle's `pid_new(idx)=pid(ip)` (update_particle.f90:88) puts them, and they are a permutation of 1..N."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    nc, nnt = 24, 2
+    states, sig, _ = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=41, disp_rms=0.8)
+    n = states[0]["xp"].shape[0]
+    st = dict(states[0], pid=np.arange(1, n + 1, dtype=np.int64))
+    O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load([st], sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(nc, nnt, fk, ck, np_nc=2, tanf_lut=co.tanf_lut())
+    try:
+        G.particle_initialization(st, sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+        back, _ = G.checkpoint()
+        assert np.array_equal(back["pid"], st["pid"])
+        dt_old = np.float32(0)
+        for dt in (np.float32(1.0), np.float32(0.7)):
+            O.update_particle(dt_old, dt); G.update_particle(dt_old, dt)
+            so = O.store(0)
+            sg, _ = G.checkpoint()
+            assert np.array_equal(so["xp"], sg["xp"]) and np.array_equal(so["rhoc"], sg["rhoc"])
+            assert np.array_equal(so["pid"], sg["pid"])
+            assert np.array_equal(np.sort(sg["pid"]), st["pid"])
+            # drift only (no kicks): both sides re-buffer and go on from their own, identical, states
+            O.buffer_density(); O.buffer_x(); O.buffer_v()
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+            dt_old = dt
+    finally:
+        G.close(); O.close()
