@@ -103,6 +103,10 @@ int main(int argc, char **argv) {
   ckpt_name(path, sizeof path, cdir, z_in, "vfield"); read_exact(path, 0, vfield, 12 * ncell);
   ckpt_name(path, sizeof path, cdir, z_in, "zip0");   read_exact(path, 0, xp, 6 * np);
   ckpt_name(path, sizeof path, cdir, z_in, "zip1");   read_exact(path, 0, vp, 6 * np);
+  /* -DPID runs also have <z>zipid_1.bin, integer(8) IDs (particle_initialization.f90:56-59); optional here */
+  int64_t *pid = NULL;
+  ckpt_name(path, sizeof path, cdir, z_in, "zipid");
+  { FILE *f = fopen(path, "rb"); if (f) { fclose(f); pid = xmalloc(8 * np); read_exact(path, 0, pid, 8 * np); } }
 
   /* ---- initialize.f90: kernel tables; the host's own tanf table (pm.f90:102) ---------------- */
   float *fk_kji = xmalloc(sizeof(float) * 16 * 16 * 16 * 3), *fk = xmalloc(sizeof(float) * 3 * 16 * 16 * 16);
@@ -126,6 +130,7 @@ int main(int argc, char **argv) {
   cube_handle *h = NULL;
   check(cube_gpu_init(&p, fk, ck, lut, NULL, &h));
   check(cube_gpu_upload(h, xp, vp, rhoc, vfield, (int64_t)np, (int64_t)np, hd.sigma_vi));
+  if (pid) check(cube_gpu_upload_pid(h, pid));
 
   /* ---- cafcube.f90:16-20 then the loop :25-46 ---------------------------------------------- */
   float ovh_image = 0.f;
@@ -151,6 +156,10 @@ int main(int argc, char **argv) {
   check(cube_gpu_download(h, NULL, NULL, NULL, NULL, &nplocal, &sigma));
   if ((size_t)nplocal > np) { free(xp); free(vp); xp = xmalloc(6 * (size_t)nplocal); vp = xmalloc(6 * (size_t)nplocal); }
   check(cube_gpu_download(h, xp, vp, rhoc, vfield, &nplocal, &sigma));
+  if (pid) {
+    if ((size_t)nplocal > np) { free(pid); pid = xmalloc(8 * (size_t)nplocal); }
+    check(cube_gpu_download_pid(h, pid));
+  }
   if (argc > 7) {
     const double z_out = atof(argv[7]);
     hd.nplocal = nplocal; hd.sigma_vi = sigma; hd.istep += nsteps;
@@ -158,9 +167,10 @@ int main(int argc, char **argv) {
     ckpt_name(path, sizeof path, cdir, z_out, "vfield"); write_two(path, vfield, 12 * ncell, NULL, 0);
     ckpt_name(path, sizeof path, cdir, z_out, "zip0");   write_two(path, xp, 6 * (size_t)nplocal, NULL, 0);
     ckpt_name(path, sizeof path, cdir, z_out, "zip1");   write_two(path, vp, 6 * (size_t)nplocal, NULL, 0);
+    if (pid) { ckpt_name(path, sizeof path, cdir, z_out, "zipid"); write_two(path, pid, 8 * (size_t)nplocal, NULL, 0); }
   }
   printf("done: %lld particles, sigma_vi %g\n", (long long)nplocal, sigma);
   check(cube_gpu_finalize(h));
-  free(xp); free(vp); free(rhoc); free(vfield); free(fk); free(fk_kji); free(ck); free(ck_kji); free(lut);
+  free(xp); free(vp); free(pid); free(rhoc); free(vfield); free(fk); free(fk_kji); free(ck); free(ck_kji); free(lut);
   return 0;
 }
