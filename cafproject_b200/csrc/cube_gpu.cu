@@ -83,7 +83,7 @@ struct cube_handle {
   cube_params p;
   Geom g;
   cudaStream_t st = nullptr;
-  cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false;  // cube_gpu_download_async
+  cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false, copy_reads_vp = false;  // cube_gpu_download_async
   int16_t* vp_stream_host = nullptr;  // cube_gpu_stream_vp: where the next particle_mesh streams the final velocities
   double* dvlut2 = nullptr; int* divok2 = nullptr;  // decode table of sigma_vi_new while the main one still serves the fine kick
   cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
@@ -120,6 +120,7 @@ struct cube_handle {
   const FftPlan* plan = nullptr; FftGeom fg = {};
   size_t rho_n = 0, A_n = 0, B_n = 0, F_n = 0;  // elements per tile
   float* rho = nullptr;      // [batch][N][N][N]            (aliases the head of Bk: dead before Bk is written)
+  float* rho_own = nullptr;  // its own allocation when the alias does not fit (CUBE_GPU_NFFT on small tiles)
   float2* Ak = nullptr;      // [batch][N][N][P]
   float2* Bk = nullptr;      // [3][batch][M][N][P]
   float* F = nullptr;        // [batch][M][M][3][FP]
@@ -542,14 +543,17 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   const int ntile = g.nnt * g.nnt * g.nnt;
   {
     const int need = g.nft + 32;  // M + 2*(nf_cutoff-1), M = nft+2
+    // test hook: CUBE_GPU_NFFT=N forces the window length (any built N >= need gives the same forces; lets the parity tests
+    // run every instantiation of the line-FFT kernels at a size the oracle finishes in seconds)
+    const int forced = getenv("CUBE_GPU_NFFT") ? atoi(getenv("CUBE_GPU_NFFT")) : 0;
     for (const FftPlan& pl : kPlans)
-      if (pl.N() >= need && (!h->plan || pl.N() < h->plan->N())) h->plan = &pl;
+      if (forced ? pl.N() == forced && forced >= need : (pl.N() >= need && (!h->plan || pl.N() < h->plan->N()))) h->plan = &pl;
+    if (forced && !h->plan) return fail("cube_gpu_init: CUBE_GPU_NFFT=%d is not a built transform length >= %d", forced, need);
     if (!h->plan) return fail("cube_gpu_init: no fine-mesh FFT plan for nt=%d (needs N>=%d; largest built N is 576, i.e. nt<=136)", g.nt, need);
     FftGeom& f = h->fg;
     f.N = h->plan->N(); f.NH = f.N / 2 + 1; f.P = (f.NH + FL - 1) / FL * FL; f.M = g.nft + 2; f.off = 15; f.FP = (f.M + 7) / 8 * 8;
     h->rho_n = (size_t)f.N * f.N * f.N; h->A_n = (size_t)f.N * f.N * f.P; h->B_n = 3 * (size_t)f.M * f.N * f.P;
     h->F_n = (size_t)f.M * f.M * 3 * f.FP;
-    if (h->rho_n * sizeof(float) > h->B_n * sizeof(float2)) return fail("cube_gpu_init: internal: rho does not fit its alias");
   }
   CK(dmalloc(&h->csum, 27LL * (g.nc + 2) * (g.nc + 2) * (g.nc + 2)));  // partial sums of the coarse deposit (cube_kernels.cuh)
   int batch = p->fine_batch;
@@ -565,7 +569,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   h->fg.nbatch = batch;
   CK(dmalloc(&h->f2max, batch + 1));
   CK(dmalloc(&h->Ak, (long long)(h->A_n * batch))); CK(dmalloc(&h->Bk, (long long)(h->B_n * batch))); CK(dmalloc(&h->F, (long long)(h->F_n * batch)));
-  h->rho = reinterpret_cast<float*>(h->Bk);
+  if (h->rho_n * sizeof(float) <= h->B_n * sizeof(float2)) h->rho = reinterpret_cast<float*>(h->Bk);  // dead before Bk is written
+  else { CK(dmalloc(&h->rho_own, (long long)(h->rho_n * batch))); h->rho = h->rho_own; }  // forced long windows on small tiles (test hook)
   CK(dmalloc(&h->kern_f, 3LL * h->fg.N * h->fg.N * h->fg.P));
   CK(dmalloc(&h->tw, h->fg.N));
   {
@@ -623,7 +628,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2, h->rho_own};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -703,7 +708,7 @@ extern "C" int cube_gpu_download_async(cube_handle* h, int16_t* xp, int16_t* vp)
   CK(cudaEventRecord(h->ev_copy[0], h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
   if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
-  if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
+  if (vp) { CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy)); h->copy_reads_vp = true; }
   CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
   h->copy_pending = true;
   return 0;
@@ -733,7 +738,7 @@ extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   const Geom& g = h->g;
-  if (h->copy_pending) { CK(cudaEventSynchronize(h->ev_copy[1])); h->copy_pending = false; }
+  if (h->copy_pending) { CK(cudaEventSynchronize(h->ev_copy[1])); h->copy_pending = false; h->copy_reads_vp = false; }
   if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   if (rhoc_phys) CK(cudaMemcpyAsync(rhoc_phys, h->rhoc_p, sizeof(int) * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
@@ -1097,6 +1102,8 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("cube_gpu_particle_mesh: state is not buffered (call cube_gpu_buffer first)");
+  // a cube_gpu_download_async of vp still reads the velocities the kicks rewrite in place (positions may keep streaming)
+  if (h->copy_pending && h->copy_reads_vp) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); h->copy_reads_vp = false; }
   const Geom& g = h->g;
   const int ntile = g.nnt * g.nnt * g.nnt;
   const long long nt3 = (long long)g.nt * g.nt * g.nt;

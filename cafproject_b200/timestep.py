@@ -92,6 +92,8 @@ class TimeStepper:
                 dt = f32(f32(dt * f32(a_chk - self.a)) / da)
                 da1, da2 = expansion(c, self.a, dt)
                 da = f32(da1 + da2)
+            else:   # the reference's `do while` has no cap (timestep.f90:53-58): it would spin; say so instead of stepping past a_checkpoint
+                raise RuntimeError("timestep: a+da does not converge onto the checkpoint scale factor %r (a=%r, da=%r)" % (a_chk, self.a, da))
         self.a_mid = f32(self.a + f32(da / f32(2)))
         self.dt, self.da = f32(dt), da
         self.tau, self.t = f32(self.tau + dt), f32(self.t + dt)

@@ -13,6 +13,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _gpu_ready():
+    """Is there a CUDA device?  (A device WITHOUT the built library is not a reason to skip: the tests then fail loudly.)"""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return False, "no CUDA device"
+    except Exception as e:  # pragma: no cover
+        return False, "torch is not importable: %s" % e
+    return True, ""
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a CPU box skips the gpu-marked tests (they would all stop with the library's
+    "no CUDA device" error); on a GPU box nothing is skipped -- a missing library fails there -- and `-m gpu`
+    without a device reports every test as skipped, never as passed."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    ok, why = _gpu_ready()
+    if ok:
+        return
+    skip = pytest.mark.skip(reason="gpu test: " + why)
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def tables():
     g = os.path.join(ROOT, "tests", "golden")

@@ -1,0 +1,116 @@
+"""GPU parity at the BENCHMARKED tile size: nt = 64, i.e. the <16,18> (N = 288) instantiation of the line-FFT kernels, the
+64^3-cell tile of the deposit / kick / drift kernels -- the code BENCH/SCALE time (BASELINE.json configs[1..2]).
+
+* nc = 64, nnt = 1: one tile of 2 M particles (its ghost layers alias the periodic image): every intermediate mesh, the drift
+  and both kicks against the oracle, then one full step each side with its own FFT.
+* nc = 128, nnt = 2 (BASELINE.json configs[0], the reference's own CPU-runnable case): a full step and one tile's force.
+
+Gates as in test_gpu_parity.py: counts, positions, velocity codes bit-exact where both sides see the same
+forces; densities 1e-6, forces 1e-5 norm-relative.  Parity is unpinned by the reference (no golden vectors upstream).
+"""
+import numpy as np
+import pytest
+
+from conftest import norm_rel, physical
+from test_gpu_parity import _check_drift_then_kicks
+
+pytestmark = pytest.mark.gpu
+NP_NC = 2
+
+
+def _pair(tables, nc, nnt, seed, disp_rms=0.8):
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=NP_NC, seed=seed, disp_rms=disp_rms)
+    O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    O.load(states, sig)
+    O.buffer_density(); O.buffer_x(); O.buffer_v()
+    G = CubeGPU(nc, nnt, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+    G.particle_initialization(states[0], sig)
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    return O, G
+
+
+@pytest.fixture(scope="module")
+def tile64(tables):
+    O, G = _pair(tables, 64, 1, seed=64)
+    yield O, G
+    G.close(); O.close()
+
+
+def test_bench_plan_is_the_one_under_test(tile64):
+    _, G = tile64
+    assert G.query("nt") == 64 and G.query("nfft") == 288      # k_fft_*<16,18>: what bench.py runs
+
+
+def test_kernels_nt64(tile64, tables):
+    from oracle import cube_oracle as co
+    O, G = tile64
+    assert norm_rel(G.kern_f(), co.kernel_f(tables[0], 288)) < 1e-5
+    assert norm_rel(G.kern_c(), O.kern_c) < 1e-5
+
+
+def test_fine_density_and_force_nt64(tile64):
+    O, G = tile64
+    ro, rg = O.fine_density(0, 1, 1, 1), G.fine_density(1, 1, 1)
+    assert norm_rel(rg[:, :, :O.nfe], ro[:, :, :O.nfe]) < 1e-6
+    assert np.array_equal(rg[:, :, :O.nfe] == 0, ro[:, :, :O.nfe] == 0)
+    assert abs(float(rg[:, :, :O.nfe].sum(dtype=np.float64)) - float(ro[:, :, :O.nfe].sum(dtype=np.float64))) < 1e-6 * float(ro.sum(dtype=np.float64))
+    fo, fg = O.fine_force(ro), G.fine_force(1, 1, 1)
+    assert norm_rel(fg, fo) < 1e-5                                # the 1e-5 force gate on the <16,18> kernels
+    for d in range(3):                                          # ... and per component (a wrong twiddle hides in none)
+        assert norm_rel(fg[..., d], fo[..., d]) < 1e-5, d
+    assert np.array_equal(fg, G.fine_force(1, 1, 1))            # deterministic
+
+
+def test_coarse_density_and_force_nt64(tile64):
+    O, G = tile64
+    ro, rg = O.coarse_density(), G.coarse_density()
+    assert norm_rel(rg, ro) < 1e-6
+    fo = O.force_c_image(O.coarse_force(ro), 0)
+    assert norm_rel(G.coarse_force(), fo) < 1e-5
+
+
+def test_drift_then_kicks_bit_exact_nt64(tile64):
+    O, G = tile64
+    _check_drift_then_kicks(O, G, nnt=1)
+
+
+def _one_full_step(O, G, dt_old, dt, a_mid):
+    uo, po = O.step(dt_old, dt, a_mid)
+    ug, pg = G.step(dt_old, dt, a_mid)
+    sg, _ = G.checkpoint()
+    so = O.store(0)
+    xp_o, vp_o = physical(O, "xp"), physical(O, "vp")
+    assert ug["nplocal"] == O.nplocal(0) == xp_o.shape[0]
+    assert np.array_equal(so["rhoc"], sg["rhoc"])               # the drift only sees input velocities: bit-exact
+    assert np.array_equal(xp_o, sg["xp"])
+    assert np.array_equal(so["vfield"].view(np.uint32), sg["vfield"].view(np.uint32))
+    assert ug["sigma_vi_new"] == uo["sigma_vi_new"]
+    # each side convolves with its own FFT: a code may flip by one unit per kick where round-off crosses a quantiser boundary
+    dv = np.abs(vp_o.astype(np.int32) - sg["vp"].astype(np.int32))
+    assert dv.max() <= 2 and (dv != 0).mean() < 2e-3
+    for k in ("dt_fine", "dt_coarse", "dt_vmax"):
+        assert abs(float(pg[k]) - float(po[k])) <= 1e-4 * abs(float(po[k])), k
+
+
+def test_full_step_nt64(tables):
+    O, G = _pair(tables, 64, 1, seed=65, disp_rms=0.6)
+    try:
+        _one_full_step(O, G, np.float32(0), np.float32(0.7), np.float32(0.021))
+    finally:
+        G.close(); O.close()
+
+
+def test_full_step_cfg1(tables):
+    """BASELINE.json configs[0]: 128^3 coarse cells, 256^3 particles, 8 tiles of nt = 64."""
+    O, G = _pair(tables, 128, 2, seed=1000, disp_rms=0.6)
+    try:
+        assert G.query("nfft") == 288
+        fo = O.fine_force(O.fine_density(0, 2, 1, 2))
+        assert norm_rel(G.fine_force(2, 1, 2), fo) < 1e-5
+        _one_full_step(O, G, np.float32(0), np.float32(0.7), np.float32(0.021))
+    finally:
+        G.close(); O.close()

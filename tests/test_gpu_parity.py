@@ -100,7 +100,7 @@ def test_drift_then_kicks_bit_exact(setup):
     _check_drift_then_kicks(O, G)
 
 
-def _check_drift_then_kicks(O, G):
+def _check_drift_then_kicks(O, G, nnt=NNT):
     dt_old, dt, a_mid = np.float32(0.0), np.float32(1.0), np.float32(0.021)
     uo = O.update_particle(dt_old, dt)
     ug = G.update_particle(dt_old, dt)
@@ -121,9 +121,9 @@ def _check_drift_then_kicks(O, G):
     sig_old, sig_new = O.sigma_vi, O.sigma_vi_new
     pm = O.particle_mesh(a_mid, dt, keep=True)
     f2 = []
-    for tz in range(1, NNT + 1):
-        for ty in range(1, NNT + 1):
-            for tx in range(1, NNT + 1):
+    for tz in range(1, nnt + 1):
+        for ty in range(1, nnt + 1):
+            for tx in range(1, nnt + 1):
                 f2.append(G.fine_kick_with(tx, ty, tz, pm["meshes"]["force_f"][(0, tx, ty, tz)], a_mid, dt, sig_old, sig_new))
     assert np.float32(max(f2)) == pm["f2_max_fine"]
     vmax, f2c = G.coarse_kick_with(O.force_c_image(pm["meshes"]["force_c"], 0), a_mid, dt, sig_new)

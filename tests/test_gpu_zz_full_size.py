@@ -6,17 +6,12 @@ time-step limits, and run-to-run determinism bit for bit (no floating-point atom
 cases against the oracle, bit for bit: a zero time step (idempotence of counts and positions) and a ragged state (one crowded
 cell, seven empty tiles).  Named to sort after the other GPU tests.
 
-Status: written at the end of round 1 after the round's GPU minutes were spent -- every call in it is one bench.py or the
-small parity tests already make on a B200, but this file itself has not run on hardware yet.
+First run on a B200 by the round-1 driver (all four passed); a failure here is a regression.
 """
 import numpy as np
 import pytest
 
-# Not strict: these tests were written after the round's GPU minutes were spent.  Until they have run once on a B200 a failure is
-# reported as "xfailed" and a pass as "xpassed" instead of turning the suite red on a mistake in the test itself; the marker goes
-# away with the first hardware run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written without GPU access at the end of round 1; not yet run on hardware")]
+pytestmark = pytest.mark.gpu
 
 NC, NNT, NP_NC = 256, 4, 2
 
