@@ -208,12 +208,26 @@ __device__ __forceinline__ void load_tw(float2* tw_s, const float2* __restrict__
   for (int t = threadIdx.x; t < N; t += blockDim.x) tw_s[t] = tw_g[t];
 }
 
+// Where tile b of a batch finds its N^3 window of fine density: inside one region grid shared by the batch (tvol == 0; the
+// tiles' windows overlap there, cube_kernels.cuh) or as the b-th of nb separate windows.
+struct RhoView {
+  const float* p; long long ldy, ldz, tvol;
+  int t0[3];  // first tile of the batch's box
+  int nnt, tile0, tstep /* 4 nt */;
+};
+__device__ __forceinline__ const float* rho_window(const RhoView& v, int b) {
+  if (v.tvol) return v.p + (size_t)b * v.tvol;
+  const int t = v.tile0 + b;
+  const int tx = t % v.nnt - v.t0[0], ty = (t / v.nnt) % v.nnt - v.t0[1], tz = t / (v.nnt * v.nnt) - v.t0[2];
+  return v.p + ((size_t)tz * v.ldz + (size_t)ty * v.ldy + tx) * v.tstep;
+}
+
 // ---------------------------------------------------------------------------------------------
-// x forward (r2c): rho[b][z][y][x] -> A[b][z][y][kx].  One CTA = 32 real rows = 16 complex lines.
+// x forward (r2c): window of rho [z][y][x] -> A[b][z][y][kx].  One CTA = 32 real rows = 16 complex lines.
 // grid = (ceil(N/32), N, nbatch)
 // ---------------------------------------------------------------------------------------------
 template <int R1, int R2>
-__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom g, const float* __restrict__ rho, float2* __restrict__ A,
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom g, RhoView rho, float2* __restrict__ A,
                                                                        const float2* __restrict__ tw_g) {
   constexpr int N = R1 * R2, LW = FL + 1, NT = FL * (R1 > R2 ? R1 : R2);
   extern __shared__ float2 smem[];
@@ -222,14 +236,14 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int y0 = blockIdx.x * 32, z = blockIdx.y, b = blockIdx.z;
   load_tw(tw, tw_g, N);
-  const float* src = rho + ((size_t)b * N + z) * (size_t)N * N;
+  const float* src = rho_window(rho, b) + (size_t)z * rho.ldz;
   // rows y0+2l (re), y0+2l+1 (im); lanes along x
   for (int r = warp; r < 32; r += NT / 32) {
     const int y = y0 + r;
     const int l = r >> 1, im = r & 1;
     float* dst = reinterpret_cast<float*>(s) + im;
     if (y < N) {  // asynchronous copies: every load of the CTA is in flight at once (the pass was bound by global-load latency)
-      const float* row = src + (size_t)y * N;
+      const float* row = src + (size_t)y * rho.ldy;
       for (int x = lane; x < N; x += 32) cp_async4(&dst[(x * LW + l) * 2], row + x);
     } else {
       for (int x = lane; x < N; x += 32) dst[(x * LW + l) * 2] = 0.f;

@@ -19,7 +19,6 @@
 #include "../../include/cube_gpu.h"
 #include "cube_kernels.cuh"
 #include "cube_fft.cuh"
-#include "cube_fft2d.cuh"
 #include "cube_particles.cuh"
 #include "cube_comm.cuh"
 #include "cube_exchange.cuh"
@@ -49,31 +48,27 @@ static int fail(const char* fmt, ...) {
 #define CKL() CK(cudaGetLastError())
 
 enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFTX, PH_FFTY, PH_FFTZ, PH_IFFTY, PH_IFFTX, PH_FMAX, PH_FKICK,
-             PH_CDEP, PH_CFFT, PH_CKICK, PH_FFTXY, PH_IFFTYX, PH_N };
+             PH_CDEP, PH_CFFT, PH_CKICK, PH_N };
 static const char* kPhaseNames[PH_N] = {"drift_key", "drift_count", "drift_scan", "drift_place", "buffer", "fine_deposit",
                                         "fine_fft_x", "fine_fft_y", "fine_fft_z_green", "fine_ifft_y", "fine_ifft_x", "fine_f2max",
-                                        "fine_kick", "coarse_deposit", "coarse_fft_green", "coarse_kick", "fine_fft_xy", "fine_ifft_yx_f2max"};
+                                        "fine_kick", "coarse_deposit", "coarse_fft_green", "coarse_kick"};
 
 // one instantiation of the hand-written fine-mesh FFT kernels per supported transform length N = R1*R2
 struct FftPlan {
   int R1, R2;
-  void (*x_fwd)(FftGeom, const float*, float2*, const float2*);
+  void (*x_fwd)(FftGeom, RhoView, float2*, const float2*);
   void (*y_fwd)(FftGeom, float2*, const float2*);
   void (*y_inv)(FftGeom, float2*, const float2*);
   void (*z_green)(FftGeom, const float2*, float2*, const float*, float, const float2*);
   void (*x_inv)(FftGeom, const float2*, float*, const float2*, unsigned*);
   int x_inv_threads; size_t x_inv_smem;
-  // plane-fused cluster kernels (cube_fft2d.cuh); used when their shared memory fits one SM
-  void (*xy_fwd)(FftGeom, const float*, float2*, const float2*);
-  void (*yx_inv)(FftGeom, const float2*, float*, unsigned*, const float2*);
-  size_t smem2d;
   int N() const { return R1 * R2; }
   int threads() const { return FL * (R1 > R2 ? R1 : R2); }
 };
 template <int R1, int R2> static FftPlan make_plan() {
   return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1, (R1 * R2 <= 320 ? 4 : 0)>,
           k_fft_z_green<R1, R2>, k_fft_x_inv3<R1, R2>,
-          X3Cfg<R1, R2>::NT, X3Cfg<R1, R2>::SMEM, k_fft_xy_fwd<R1, R2>, k_fft_yx_inv<R1, R2>, Fft2dCfg<R1, R2>::SMEM};
+          X3Cfg<R1, R2>::NT, X3Cfg<R1, R2>::SMEM};
 }
 // N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
 static const FftPlan kPlans[] = {make_plan<8, 10>(), make_plan<8, 12>(), make_plan<8, 16>(), make_plan<10, 16>(), make_plan<12, 16>(),
@@ -111,14 +106,16 @@ struct cube_handle {
   // LUTs
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
   // cells above these particle counts are processed by a whole warp instead of one thread (cube_kernels.cuh, cube_particles.cuh)
-  int heavy_deposit = 32, dense_deposit = 32, heavy_count = 64, count_minb = 8;
+  int heavy_deposit = 32, heavy_count = 64, count_minb = 8;
+  int fd_brick = 884;       // brick of the fine deposit: 888 | 884 | 844 coarse cells (cube_kernels.cuh)
+  bool shared_region = true;  // one fine-density grid per batch of tiles (nt <= 123); else one window per tile in the tile's own frame
   float* tanh = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
   int nsm = 1;
   // fine mesh (cube_fft.cuh)
   int batch = 1;
-  bool fused2d = false;
   const FftPlan* plan = nullptr; FftGeom fg = {};
-  size_t rho_n = 0, A_n = 0, B_n = 0, F_n = 0;  // elements per tile
+  size_t rho_n = 0;                    // elements of the fine-density buffer (the largest batch's region)
+  size_t A_n = 0, B_n = 0, F_n = 0;  // elements per tile
   float* rho = nullptr;      // [batch][N][N][N]            (aliases the head of Bk: dead before Bk is written)
   float* rho_own = nullptr;  // its own allocation when the alias does not fit (CUBE_GPU_NFFT on small tiles)
   float2* Ak = nullptr;      // [batch][N][N][P]
@@ -196,6 +193,49 @@ static VTab vtab(const cube_handle* h) { return VTab{h->tanh, h->enc, h->dvlut, 
 static unsigned pw_grid(const cube_handle* h, long long ncells) {
   const long long nwc = (ncells + WC - 1) / WC;
   return (unsigned)std::max<long long>(1, std::min<long long>(h->nsm, (nwc + PW_W - 1) / PW_W));
+}
+
+
+using Fd888 = FdCfg<8, 8, 8, 1024>;
+using Fd884 = FdCfg<8, 8, 4, 512>;
+using Fd844 = FdCfg<8, 4, 4, 256>;
+
+// A batch of tiles [tile0, tile0+nb) must be a box of the tile grid (x fastest): part of a row, whole rows of one layer, or whole
+// layers.  Largest batch <= want with that property for every tile0 that is a multiple of it.
+static int align_batch(int nnt, int want) {
+  const int layer = nnt * nnt;
+  if (want >= layer) return want / layer * layer;
+  int best = 1;
+  if (want >= nnt) { for (int k = 1; k <= want / nnt; k++) if (nnt % k == 0) best = k * nnt; return best; }
+  for (int k = 1; k <= want; k++) if (nnt % k == 0) best = k;
+  return best;
+}
+// tile box of an aligned batch: first tile and extent per dimension
+static void batch_box(const Geom& g, int tile0, int nb, int t0[3], int k[3]) {
+  const int nnt = g.nnt, layer = nnt * nnt;
+  t0[0] = tile0 % nnt; t0[1] = (tile0 / nnt) % nnt; t0[2] = tile0 / layer;
+  if (nb >= layer) { k[0] = nnt; k[1] = nnt; k[2] = (nb + layer - 1) / layer; }
+  else if (nb >= nnt) { k[0] = nnt; k[1] = nb / nnt; k[2] = 1; }
+  else { k[0] = nb; k[1] = 1; k[2] = 1; }
+}
+// fine-density region of a batch: the tiles' FFT windows (N nodes from 16 nodes below each tile) on one grid
+static FineRegion batch_region(const cube_handle* h, int tile0, int nb) {
+  const Geom& g = h->g;
+  int t0[3], k[3];
+  batch_box(g, tile0, nb, t0, k);
+  FineRegion R;
+  for (int d = 0; d < 3; d++) {
+    R.c0[d] = t0[d] * g.nt - (NCB - 1); R.c1[d] = (t0[d] + k[d]) * g.nt + (NCB - 1);  // cells 2-ncb .. nt+ncb-1 of pm.f90:50-52
+    R.f0[d] = 4 * (t0[d] * g.nt) - 16;
+    R.n[d] = 4 * g.nt * (k[d] - 1) + h->fg.N;
+  }
+  R.ldy = R.n[0]; R.ldz = R.ldy * R.n[1];
+  return R;
+}
+static size_t region_elems(const cube_handle* h, int batch) {
+  if (!h->shared_region) return (size_t)h->fg.N * h->fg.N * h->fg.N * batch;
+  const FineRegion R = batch_region(h, 0, batch);
+  return (size_t)R.ldz * R.n[2];
 }
 
 extern "C" const char* cube_gpu_last_error(void) { return g_err.c_str(); }
@@ -529,7 +569,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     if (const char* e = getenv("CUBE_GPU_VT_HOT")) { if (h->vt_hot) h->vt_hot = std::min(VT_ALL, std::max(4, atoi(e) & ~3)); }
     if (const char* e = getenv("CUBE_GPU_HEAVY_DEPOSIT")) h->heavy_deposit = atoi(e);
     if (const char* e = getenv("CUBE_GPU_HEAVY_COUNT")) h->heavy_count = atoi(e);
-    if (const char* e = getenv("CUBE_GPU_DENSE_DEPOSIT")) h->dense_deposit = atoi(e);
+    if (const char* e = getenv("CUBE_GPU_FD_BRICK")) h->fd_brick = atoi(e);
     if (const char* e = getenv("CUBE_GPU_COUNT_MINB")) h->count_minb = atoi(e);
     CK(cudaMemcpyAsync(h->tanh, half.data(), 32772 * sizeof(float), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -552,7 +592,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     if (!h->plan) return fail("cube_gpu_init: no fine-mesh FFT plan for nt=%d (needs N>=%d; largest built N is 576, i.e. nt<=136)", g.nt, need);
     FftGeom& f = h->fg;
     f.N = h->plan->N(); f.NH = f.N / 2 + 1; f.P = (f.NH + FL - 1) / FL * FL; f.M = g.nft + 2; f.off = 15; f.FP = (f.M + 7) / 8 * 8;
-    h->rho_n = (size_t)f.N * f.N * f.N; h->A_n = (size_t)f.N * f.N * f.P; h->B_n = 3 * (size_t)f.M * f.N * f.P;
+    h->rho_n = 0; h->A_n = (size_t)f.N * f.N * f.P; h->B_n = 3 * (size_t)f.M * f.N * f.P;
     h->F_n = (size_t)f.M * f.M * 3 * f.FP;
   }
   CK(dmalloc(&h->csum, 27LL * (g.nc + 2) * (g.nc + 2) * (g.nc + 2)));  // partial sums of the coarse deposit (cube_kernels.cuh)
@@ -564,13 +604,17 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
       batch = (int)std::max<long long>(1, std::min<long long>(64, (long long)(fr * 0.6) / (long long)per));
     }
   }
-  batch = std::min(batch, ntile);
+  batch = align_batch(g.nnt, std::min(batch, ntile));
   h->batch = batch;
+  // pm.f90:54-58 in f32 is exact below 512 fine cells of tile-local coordinate (cells up to nt+5): then the weights do not depend
+  // on the tile frame and one density grid serves a whole batch of tiles
+  h->shared_region = g.nt + 5 <= 128 && getenv("CUBE_GPU_TILE_REGIONS") == nullptr;
+  h->rho_n = std::max(h->rho_n, region_elems(h, batch));
   h->fg.nbatch = batch;
   CK(dmalloc(&h->f2max, batch + 1));
   CK(dmalloc(&h->Ak, (long long)(h->A_n * batch))); CK(dmalloc(&h->Bk, (long long)(h->B_n * batch))); CK(dmalloc(&h->F, (long long)(h->F_n * batch)));
-  if (h->rho_n * sizeof(float) <= h->B_n * sizeof(float2)) h->rho = reinterpret_cast<float*>(h->Bk);  // dead before Bk is written
-  else { CK(dmalloc(&h->rho_own, (long long)(h->rho_n * batch))); h->rho = h->rho_own; }  // forced long windows on small tiles (test hook)
+  if (h->rho_n * sizeof(float) <= h->B_n * batch * sizeof(float2)) h->rho = reinterpret_cast<float*>(h->Bk);  // dead before Bk is written
+  else { CK(dmalloc(&h->rho_own, (long long)h->rho_n)); h->rho = h->rho_own; }  // forced long windows on small tiles (test hook)
   CK(dmalloc(&h->kern_f, 3LL * h->fg.N * h->fg.N * h->fg.P));
   CK(dmalloc(&h->tw, h->fg.N));
   {
@@ -590,16 +634,6 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
     CK(cudaFuncSetAttribute((const void*)h->plan->z_green, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
-    int smem_max = 0;
-    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    // measured on B200 (profiles/r01e_fused_fft.md): with one 288-thread CTA per SM the plane-fused kernels cannot hide
-    // their own phase latencies (xy 13.0 ms vs 6.7 ms, yx 28.1 ms vs 17.4 ms for the line kernels at cfg 2), so they are
-    // opt-in until they are warp-specialised
-    h->fused2d = h->plan->smem2d <= (size_t)smem_max && getenv("CUBE_GPU_FUSED_FFT") != nullptr;
-    if (h->fused2d) {
-      CK(cudaFuncSetAttribute((const void*)h->plan->xy_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->smem2d));
-      CK(cudaFuncSetAttribute((const void*)h->plan->yx_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->plan->smem2d));
-    }
   }
   // coarse mesh
   h->cvol = (long long)g.nc * g.nc * (g.nc + 2);
@@ -616,7 +650,12 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CF(cufftPlanMany(&h->cplan_c2r, 3, n, cembed, 1, (int)h->cnk, rembed, 1, (int)h->cvol, CUFFT_C2R, 3));
     CF(cufftSetStream(h->cplan_r2c, h->st)); CF(cufftSetStream(h->cplan_c2r, h->st));
   }
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd888, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd888::SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd884, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd884::SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd844, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd844::SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd888, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd888::SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd884, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd884::SMEM));
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd844, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd844::SMEM));
   if (build_kernels(h, fk_table, ck_table)) { return 1; }
   *out = h;
   return 0;
@@ -984,14 +1023,40 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
 // ---------------------------------------------------------------------------------------------
 // fine mesh of tiles [tile0, tile0+nb): deposit -> x,y forward -> z forward * i kern_f, z inverse (x3) -> y,x inverse
 // (pm.f90:44-84).  Leaves force_f of the nb tiles in h->F.
-static int fine_deposit(cube_handle* h, int tile0, int nb, const DepWin& w, float* out) {
-  const Geom& g = h->g;
+// deposit the particles of source cells R.c0..R.c1 onto the fine-grid region R (frame: FRAME_NONE, or the tile's first cell)
+static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* out) {
   PhaseTimer pt(h, PH_FDEP);
-  const int nc4 = w.n / 4;
-  const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y, nbz = (nc4 + FB_Z - 1) / FB_Z;
-  dim3 grid(nbx * nby * nbz, nb);
-  k_fine_deposit<<<grid, FD_T, FD_SMEM, h->st>>>(g, w, tile0, h->dense_deposit, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out); CKL();
+  auto launch = [&](auto cfg) {
+    using C = decltype(cfg);
+    const unsigned nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY, nbz = (R.n[2] + C::NZ - 1) / C::NZ;
+    if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+    else k_fine_deposit_r<C, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+  };
+  if (h->fd_brick == 888) launch(Fd888{}); else if (h->fd_brick == 844) launch(Fd844{}); else launch(Fd884{});
+  CKL();
   h->launches++;
+  return 0;
+}
+// fine density of the tiles [tile0, tile0+nb) in h->rho; returns how the x pass finds each tile's window
+static int fine_density_batch(cube_handle* h, int tile0, int nb, RhoView& v) {
+  const Geom& g = h->g;
+  const int N = h->fg.N;
+  v.p = h->rho; v.nnt = g.nnt; v.tile0 = tile0; v.tstep = 4 * g.nt;
+  if (h->shared_region) {
+    const FineRegion R = batch_region(h, tile0, nb);
+    int k[3];
+    batch_box(g, tile0, nb, v.t0, k);
+    v.ldy = R.ldy; v.ldz = R.ldz; v.tvol = 0;
+    return fine_deposit(h, R, make_int3(FRAME_NONE, 0, 0), h->rho);
+  }
+  v.ldy = N; v.ldz = (long long)N * N; v.tvol = (long long)N * N * N; v.t0[0] = v.t0[1] = v.t0[2] = 0;
+  for (int b = 0; b < nb; b++) {  // large tiles: each in its own frame (f32 rounding of tempx, cube_kernels.cuh)
+    const int t = tile0 + b, tc[3] = {t % g.nnt, (t / g.nnt) % g.nnt, t / (g.nnt * g.nnt)};
+    FineRegion R;
+    for (int d = 0; d < 3; d++) { R.c0[d] = tc[d] * g.nt - (NCB - 1); R.c1[d] = (tc[d] + 1) * g.nt + (NCB - 1); R.f0[d] = 4 * tc[d] * g.nt - 16; R.n[d] = N; }
+    R.ldy = N; R.ldz = (long long)N * N;
+    if (fine_deposit(h, R, make_int3(tc[0] * g.nt, tc[1] * g.nt, tc[2] * g.nt), h->rho + (size_t)b * v.tvol)) return 1;
+  }
   return 0;
 }
 
@@ -1004,34 +1069,11 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
   const int N = f.N, T = pl.threads();
   const size_t smem_x = (size_t)(N * (FL + 1) + N) * sizeof(float2), smem_y = (size_t)(N * FL + N) * sizeof(float2);
   const size_t smem_z = (size_t)(2 * N * FL + N) * sizeof(float2) + (size_t)3 * (N / 2 + 1) * FL * sizeof(float);
-  DepWin w{8, N, N, (long long)h->rho_n};
-  if (fine_deposit(h, tile0, nb, w, h->rho)) return 1;
-  if (h->fused2d) {  // plane-fused passes (cube_fft2d.cuh): k-space makes one HBM trip per plane on each side of the z pass
-    {
-      PhaseTimer pt(h, PH_FFTXY);
-      pl.xy_fwd<<<dim3(2, N, nb), T, pl.smem2d, h->st>>>(f, h->rho, h->Ak, h->tw); CKL();
-    }
-    {
-      PhaseTimer pt(h, PH_FFTZ);
-      const float scale = 1.0f / ((float)N * (float)N * (float)N);
-      pl.z_green<<<dim3(f.P / FL, N), T, smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
-    }
-    {
-      PhaseTimer pt(h, PH_IFFTYX);
-      CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
-      pl.yx_inv<<<dim3(2, f.M, nb), T, pl.smem2d, h->st>>>(f, h->Bk, h->F, h->f2max, h->tw); CKL();
-      if (prefix) {  // same contract as the line kernels: prefixed mesh, f2_max over the prefixed values
-        k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, a_mid, dt); CKL();
-        CK(cudaMemsetAsync(h->f2max, 0, sizeof(unsigned) * nb, h->st));
-        k_f2max_rows<<<dim3(592, nb), 256, 0, h->st>>>(f, h->F, h->f2max); CKL();
-      }
-    }
-    h->launches += 4;
-    return 0;
-  }
+  RhoView rv;
+  if (fine_density_batch(h, tile0, nb, rv)) return 1;
   {
     PhaseTimer pt(h, PH_FFTX);
-    pl.x_fwd<<<dim3((N + 31) / 32, N, nb), T, smem_x, h->st>>>(f, h->rho, h->Ak, h->tw); CKL();
+    pl.x_fwd<<<dim3((N + 31) / 32, N, nb), T, smem_x, h->st>>>(f, rv, h->Ak, h->tw); CKL();
   }
   {
     PhaseTimer pt(h, PH_FFTY);
@@ -1126,7 +1168,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   // streamed velocities (cube_gpu_stream_vp): smaller batches, coarse kick per batch, the batch's vp out under the next batch
   int16_t* const vp_host = h->vp_stream_host;
   h->vp_stream_host = nullptr;
-  const int step_batch = vp_host ? std::max(1, std::min(h->batch, (ntile + 3) / 4)) : h->batch;
+  const int step_batch = vp_host ? align_batch(g.nnt, std::max(1, std::min(h->batch, (ntile + 3) / 4))) : h->batch;
   std::vector<long long> tile_start(ntile + 1, 0);
   if (vp_host) {
     CK(cudaMemsetAsync(h->divok2, 0xff, sizeof(int), h->st));
@@ -1236,7 +1278,6 @@ extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   if (w == "nfft") return h->fg.N;
   if (w == "nfft_pitch") return h->fg.P;
   if (w == "kernel_launches") return h->launches;
-  if (w == "fused_fft") return h->fused2d ? 1 : 0;
   if (w == "nplocal") return h->nplocal;
   return -1;
 }
@@ -1268,8 +1309,12 @@ extern "C" int cube_gpu_fine_density(cube_handle* h, int itx, int ity, int itz, 
   const long long vol = (long long)g.nfe * g.nfe * (g.nfe + 2);
   float* tmp = nullptr; CK(dmalloc(&tmp, vol));
   CK(cudaMemsetAsync(tmp, 0, sizeof(float) * vol, h->st));
-  DepWin w{0, g.nfe, g.nfe + 2, vol};
-  if (fine_deposit(h, t, 1, w, tmp)) { cudaFree(tmp); return 1; }
+  const int tc[3] = {t % g.nnt, (t / g.nnt) % g.nnt, t / (g.nnt * g.nnt)};
+  FineRegion R;
+  for (int d = 0; d < 3; d++) { R.c0[d] = tc[d] * g.nt - (NCB - 1); R.c1[d] = (tc[d] + 1) * g.nt + (NCB - 1); R.f0[d] = 4 * tc[d] * g.nt - NFB; R.n[d] = g.nfe; }
+  R.ldy = g.nfe + 2; R.ldz = R.ldy * g.nfe;
+  const int3 frame = h->shared_region ? make_int3(FRAME_NONE, 0, 0) : make_int3(tc[0] * g.nt, tc[1] * g.nt, tc[2] * g.nt);
+  if (fine_deposit(h, R, frame, tmp)) { cudaFree(tmp); return 1; }
   CK(cudaMemcpyAsync(rho_f, tmp, sizeof(float) * vol, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   cudaFree(tmp);

@@ -7,6 +7,7 @@
 // results do not depend on scheduling; for the densities they are bit-identical to the reference's
 // sequential scatter loop.
 #pragma once
+#include <climits>
 #include "cube_common.cuh"
 
 namespace cube {
@@ -167,204 +168,163 @@ __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
   return __int2float_rn(2 * (65536 * (cell1 - 1) + (int)(unsigned short)xp) + 1) * 0x1p-15f;
 }
 
-// Output window of the fine deposit on the reference's padded tile grid rho_f(1:nfe): the window starts at
-// 0-based fine index f0 (a multiple of 4) and spans n cells per dim; rows have pitch ld, tiles stride vol.
-struct DepWin { int f0, n; long long ld, vol; };
+// ---------------------------------------------------------------------------------------------
+// Fine CIC deposit (pm.f90:44-72) on a REGION of the image's fine grid.
+//
+// The reference deposits every tile's particles (cells 2-ncb..nt+ncb-1) into that tile's padded grid rho_f.  A fine node's
+// value is the sum of the terms of ALL particles within one fine cell of it, whichever tile's grid it is read from, and for
+// tile-local coordinates below 512 fine cells (nte = nt + 12 <= 128) every f32 step of pm.f90:54-58 is exact: the weights are
+//     upper node: h = (2 (u mod 2^14) + 1) 2^-15,  lower node: 1 - h,   lower node index = 4 cell + (u >> 14)
+// (u = raw 16-bit position code), independent of the tile frame.  So one deposit of the image's cells onto one grid that spans
+// a whole batch of tiles serves every tile of the batch: the FFT's x pass reads each tile's window out of it, and the 1.42x
+// of work that overlapping windows cost disappears.  (Larger tiles are deposited one by one in their own frame, with the
+// reference's f32 rounding of tempx reproduced: `frame0` = image-local cell index of the tile's cell 1.)
+//
+// One CTA = one brick of BX x BY x BZ coarse cells of output = 4BX x 4BY x 4BZ nodes held in shared memory as 32-bit
+// FIXED-POINT accumulators; one thread per particle of the brick's (BX+1)(BY+1)(BZ+1) source cells (its own cells plus the
+// low-side neighbour layer whose upper nodes land in the brick), native 32-bit integer shared-memory atomics.  Integer sums do
+// not depend on the order in which the hardware serialises them: deterministic, bit-identical run to run, and equal to the
+// reference's sequential f32 scatter to round-off.  The scale 2^S is chosen per brick from its fullest source cell so that no
+// node can overflow (a node receives terms from at most 8 coarse cells, each term <= mass_p): S = 21 for the uniform z = 49
+// state (resolution 5e-7 of a mass unit, per-term rounding 3e-8 of the mean node), smaller inside haloes where the f32 sum it
+// replaces has long lost those bits.  Accumulator layout x + 36 y + (36*4BY+16) z: the 4x4x4 nodes of a coarse cell fall on 32
+// different banks (a dense x + 32 y + .. layout puts them on 4).
+// ---------------------------------------------------------------------------------------------
+struct FineRegion {
+  int c0[3], c1[3];    // source coarse cells [c0, c1) per dimension, image-local 0-based (ghost layers: < 0 or >= nc)
+  int f0[3];           // image-local fine node index of output element (0,0,0), a multiple of 4
+  int n[3];            // output extent in nodes
+  long long ldy, ldz;  // output pitches
+};
+constexpr int FRAME_NONE = INT_MIN;
 
-// One thread per SOURCE coarse cell: it walks its particles once, in storage order, and adds their eight CIC
-// weights into a private 5x5x5 block of shared-memory accumulators (its own 4^3 fine cells plus the +1 spill planes,
-// pm.f90:54-68).  A CTA covers a brick of FB_X x FB_Y x FB_Z output coarse cells plus the low-side neighbour layer
-// whose spill lands in the brick.  The spill planes are then handed to the +x, +y, +z neighbour blocks in three
-// barrier-separated sweeps (every accumulator has exactly one writer per sweep; edges and corners travel transitively,
-// like the reference's x,y,z buffer syncs), after which every fine cell of the brick is one accumulator.  No atomics,
-// every fine cell of the window written exactly once (no zero-fill), run-to-run deterministic.  The summation is
-// grouped per source cell, so rho equals the reference's sequential scatter to round-off (~1e-7 relative), not bit for bit.
-constexpr int FB_X = 8, FB_Y = 4, FB_Z = 4;
-constexpr int FS_X = FB_X + 1, FS_Y = FB_Y + 1, FS_Z = FB_Z + 1, FS_N = FS_X * FS_Y * FS_Z;  // 225 source cells
-constexpr int FD_T = 256;
-constexpr int FD_SMEM = 125 * FS_N * (int)sizeof(float);
+template <int BX, int BY, int BZ, int NT_>
+struct FdCfg {
+  static constexpr int NT = NT_;
+  static constexpr int SX = BX + 1, SY = BY + 1, SZ = BZ + 1, NS = SX * SY * SZ;
+  static constexpr int NX = 4 * BX, NY = 4 * BY, NZ = 4 * BZ;
+  static constexpr int PY = NX + 4, PZ = PY * NY + 16;
+  static constexpr int P2 = NS < 256 ? 256 : NS < 512 ? 512 : 1024;
+  static constexpr int ACC = PZ * NZ;  // words
+  static constexpr int CAP = NS <= 256 ? 4096 : NS <= 512 ? 8192 : 16384;  // particle slots of the cell-id list (~2.5x the mean brick)
+  static constexpr int EXPAND_MAX = 64;  // bricks whose fullest cell holds more find each particle's cell by binary search instead
+  static constexpr size_t SMEM = (size_t)ACC * 4 + (size_t)P2 * 4 + (size_t)NS * 8 + (size_t)CAP * 2 + 64;
+  static_assert(NX == 32, "a brick row is one warp-wide 128-byte store");
+  static_assert(PZ % 32 == 16 && PY % 32 == 4, "bank layout");
+  static_assert(NS < P2 && NS <= NT_, "one thread per source cell in the set-up");
+};
 
-// Bricks that hold a crowded cell (more than `dense` particles; haloes at late times put 10^3-10^4 particles into one coarse
-// cell, where a per-cell walk leaves a warp waiting for its fullest lane) are deposited particle-parallel instead: one thread
-// per particle of the brick's 225 source cells, the brick's 32x16x16 fine cells as fixed-point accumulators in shared
-// memory (two 32-bit words per cell, split at bit 13, resolution 2^-24: finer than the f32 sum it replaces), native 32-bit integer atomics.
-// Integer addition is associative, so the result does not depend on the order in which the hardware serialises the atomics:
-// deterministic like the walk, equal to it to round-off.  (A 64-bit shared-memory atomic add compiles to a CAS loop on
-// sm_100a -- that form was measured and dropped, profiles/r01i_notes.md.)
-constexpr int FDN = (4 * FB_X) * (4 * FB_Y) * (4 * FB_Z);  // 8192 fine cells per brick
-__device__ __noinline__ bool fine_deposit_dense(const Geom& g, unsigned* __restrict__ sm, const short* __restrict__ xp, int n, long long s,
-                                                   int si0, int sj0, int sk0, float mass_p, float* __restrict__ out, const DepWin& w,
-                                                   int bx, int by, int bz) {
-  // layout: lo[FDN] hi[FDN] pref[256+1] start[225] (8-byte aligned)
-  unsigned* lo = sm;
-  unsigned* hi = sm + FDN;
-  int* pref = reinterpret_cast<int*>(sm + 2 * FDN);
-  long long* start = reinterpret_cast<long long*>(sm + 2 * FDN + 260);
+// lower node (image-local fine index) and the two weights of one coordinate
+__device__ __forceinline__ void fine_cic(int cell, unsigned u, int frame0, int& L, float& w0, float& w1) {
+  if (frame0 == FRAME_NONE) {
+    L = 4 * cell + (int)(u >> 14);
+    w1 = __int2float_rn(2 * (int)(u & 0x3fffu) + 1) * 0x1p-15f;
+    w0 = 1.0f - w1;  // exact
+  } else {  // the tile's own frame: tempx may round (pm.f90:54 in f32 beyond 512 fine cells)
+    int idx1;
+    cic_split(fine_tempx(cell - frame0 + 1, (short)u), idx1, w0, w1);
+    L = 4 * frame0 + idx1 - 1;
+  }
+}
+
+template <class C, bool FRAME>
+__global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const short* __restrict__ xp,
+                                                          const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
+                                                          float mass_p, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned fd_smem[];
+  unsigned* acc = fd_smem;                                             // [NZ][PZ]
+  int* pref = reinterpret_cast<int*>(fd_smem + C::ACC);                // [P2]
+  long long* start = reinterpret_cast<long long*>(pref + C::P2);       // [NS]
+  unsigned short* cid = reinterpret_cast<unsigned short*>(start + C::NS);  // [CAP] source cell of every particle slot (sparse bricks)
+  __shared__ int s_w[32], s_m[32];
   const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
-  // exclusive prefix of the 225 counts (256 threads: warp scans + one pass over the 8 warp totals)
-  int incl = n;
+  const int nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY;
+  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
+  // image-local node index of the brick's first node; its first own coarse cell
+  const int N0x = R.f0[0] + bx * C::NX, N0y = R.f0[1] + by * C::NY, N0z = R.f0[2] + bz * C::NZ;
+  const int cbx = N0x >> 2, cby = N0y >> 2, cbz = N0z >> 2;
+  // --- the brick's source cells: counts, starts, prefix, fullest cell
+  int n = 0; long long s = 0;
+  if (t < C::NS) {
+    const int sx = t % C::SX, sy = (t / C::SX) % C::SY, sz = t / (C::SX * C::SY);
+    const int cx = cbx - 1 + sx, cy = cby - 1 + sy, cz = cbz - 1 + sz;
+    if (cx >= R.c0[0] && cx < R.c1[0] && cy >= R.c0[1] && cy < R.c1[1] && cz >= R.c0[2] && cz < R.c1[2]) {
+      const long long e = ext_index(g, cx, cy, cz);
+      n = rhoc_e[e]; s = cstart_e[e];
+    }
+    start[t] = s;
+  }
+  int incl = n, mx = n;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  __shared__ int s_wsum[FD_T / 32];
-  if (lane == 31) s_wsum[wp] = incl;
-  if (t < FS_N) start[t] = s;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 31) { s_w[wp] = incl; s_m[wp] = mx; }
   __syncthreads();
-  int woff = 0, total = 0;
+  int woff = 0, total = 0, cmax = 0;
 #pragma unroll
-  for (int q = 0; q < FD_T / 32; q++) { const int v = s_wsum[q]; if (q < wp) woff += v; total += v; }
-  // a fine cell receives at most one term per particle of the brick: the low word (13 bits per term) holds 2^19 terms, the high
-  // word (mass_p 2^11 per term) 2^21/mass_p; a brick beyond that (never seen: 30x the fullest cell of a z=0 run) is left to the walk
-  if ((float)total > fminf(524288.f, 2097152.f / mass_p)) return false;
-  for (int e = t; e < 2 * FDN / 4; e += FD_T) reinterpret_cast<uint4*>(sm)[e] = make_uint4(0u, 0u, 0u, 0u);
-  pref[t] = woff + incl - n;
-  if (t == 0) pref[FD_T] = total;
+  for (int q = 0; q < C::NT / 32; q++) { const int v = s_w[q]; if (q < wp) woff += v; total += v; cmax = max(cmax, s_m[q]); }
+  const int ox = bx * C::NX, oy = by * C::NY, oz = bz * C::NZ;  // brick offset inside the region
+  if (total == 0) {  // empty brick: zeros, no accumulators
+    for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {
+      const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+      if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = 0.f;
+    }
+    return;
+  }
+  if (t < C::NS) pref[t] = woff + incl - n;
+  for (int e = C::NS + t; e < C::P2; e += C::NT) pref[e] = total;  // sentinels: the search never steps onto them (q < total)
+  for (int e = t; e < C::ACC / 4; e += C::NT) reinterpret_cast<uint4*>(acc)[e] = make_uint4(0u, 0u, 0u, 0u);
+  // a node gets terms from the particles of at most 8 coarse cells, each term <= mass_p: 2^S mass_p 8 cmax <= 2^31, which leaves
+  // 2^31 units for the half unit of rounding per term
+  int S = 31 - (int)ceilf(log2f(__fmul_rn(__fmul_rn(mass_p, 8.0f), (float)cmax)));
+  S = min(max(S, -32), 40);
+  const float scale = __fmul_rn(mass_p, exp2f((float)S)), inv = exp2f(-(float)S);
+  // Sparse bricks (the uniform state): every source cell's thread writes its index into the slots of its particles, one shared
+  // store per particle instead of a ten-step search; bricks with a crowded cell keep the search (a thread would loop for long).
+  const bool expand = cmax <= C::EXPAND_MAX && total <= C::CAP;
+  if (expand && t < C::NS) {
+    const int b0 = woff + incl - n;
+    for (int k = 0; k < n; k++) cid[b0 + k] = (unsigned short)t;
+  }
   __syncthreads();
-  const float scale = __fmul_rn(mass_p, 16777216.0f);  // weights in units of 2^-24 (mass_p < 2^8: a term fits 32 bits)
-  for (int q = t; q < total; q += FD_T) {
+  // --- one thread per particle
+  for (int q = t; q < total; q += C::NT) {
     int c = 0;
+    if (expand) c = cid[q];
+    else {
 #pragma unroll
-    for (int step = 128; step > 0; step >>= 1)
-      if (pref[c + step] <= q) c += step;  // largest c with pref[c] <= q (empty cells share their successor's offset)
+      for (int step = C::P2 / 2; step > 0; step >>= 1)
+        if (pref[c + step] <= q) c += step;  // largest c with pref[c] <= q (empty cells share their successor's offset)
+    }
     const long long p = start[c] + (q - pref[c]);
-    const int sx = c % FS_X, sy = (c / FS_X) % FS_Y, sz = c / (FS_X * FS_Y);
     const Code3 cur = load_code3(xp, p);
-    int i1, j1, k1; float ax[2], ay[2], az[2];
-    cic_split(fine_tempx(si0 + sx, cur.x), i1, ax[0], ax[1]);
-    cic_split(fine_tempx(sj0 + sy, cur.y), j1, ay[0], ay[1]);
-    cic_split(fine_tempx(sk0 + sz, cur.z), k1, az[0], az[1]);
-    // brick-local fine index of the lower corner: source layer 0 is the low-side neighbour (only its +1 spill lands in the brick)
-    const int gx = i1 - (4 * (si0 + sx - 1) + 1) + 4 * (sx - 1), gy = j1 - (4 * (sj0 + sy - 1) + 1) + 4 * (sy - 1),
-              gz = k1 - (4 * (sk0 + sz - 1) + 1) + 4 * (sz - 1);
+    const int sx = c % C::SX, sy = (c / C::SX) % C::SY, sz = c / (C::SX * C::SY);
+    int lx, ly, lz; float ax[2], ay[2], az[2];
+    fine_cic(cbx - 1 + sx, (unsigned short)cur.x, FRAME ? frame0.x : FRAME_NONE, lx, ax[0], ax[1]);
+    fine_cic(cby - 1 + sy, (unsigned short)cur.y, FRAME ? frame0.y : FRAME_NONE, ly, ay[0], ay[1]);
+    fine_cic(cbz - 1 + sz, (unsigned short)cur.z, FRAME ? frame0.z : FRAME_NONE, lz, az[0], az[1]);
+    lx -= N0x; ly -= N0y; lz -= N0z;  // brick-local lower node, -4 .. 4B-1 (the upper node is the next one)
+    if (lx < -1 || ly < -1 || lz < -1) continue;  // low-side layer: only particles next to the brick reach into it
+    const bool vx[2] = {lx >= 0, lx + 1 < C::NX}, vy[2] = {ly >= 0, ly + 1 < C::NY}, vz[2] = {lz >= 0, lz + 1 < C::NZ};
+    unsigned* a0 = acc + lz * C::PZ + ly * C::PY + lx;
 #pragma unroll
     for (int qq = 0; qq < 8; qq++) {
       const int qa = qq & 1, qb = (qq >> 1) & 1, qc = qq >> 2;
-      const int X = gx + qa, Y = gy + qb, Z = gz + qc;
-      if ((unsigned)X < 4u * FB_X && (unsigned)Y < 4u * FB_Y && (unsigned)Z < 4u * FB_Z) {
+      if (vx[qa] && vy[qb] && vz[qc]) {
+        // dx(1)*dx(2)*dx(3)*mass_p (pm.f90:61-68) with the power-of-two scale riding on mass_p
         const unsigned wf = __float2uint_rn(__fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), scale));
-        const int o = (Z * (4 * FB_Y) + Y) * (4 * FB_X) + X;
-        atomicAdd(lo + o, wf & 0x1fffu);
-        atomicAdd(hi + o, wf >> 13);
+        atomicAdd(a0 + qc * C::PZ + qb * C::PY + qa, wf);
       }
     }
   }
   __syncthreads();
-  for (int o = t; o < FDN; o += FD_T) {  // one 32-float row per warp and iteration
-    const int X = o % (4 * FB_X), Y = (o / (4 * FB_X)) % (4 * FB_Y), Z = o / (16 * FB_X * FB_Y);
-    const int gx = bx * 4 * FB_X + X, gy = by * 4 * FB_Y + Y, gz = bz * 4 * FB_Z + Z;
-    if (gx < w.n && gy < w.n && gz < w.n) {
-      const unsigned long long v = ((unsigned long long)hi[o] << 13) + lo[o];
-      out[((long long)gz * w.n + gy) * w.ld + gx] = __fmul_rn(__ull2float_rn(v), 0x1p-24f);
-    }
-  }
-  return true;
-}
-
-__global__ void __launch_bounds__(FD_T, 2) k_fine_deposit(Geom g, DepWin w, int tile0, int dense, const short* __restrict__ xp,
-                                                         const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                         float mass_p, float* __restrict__ rho /*[batch][n][n][ld]*/) {
-  extern __shared__ float acc[];  // [125 = (a*5+b)*5+c][FS_N]
-  const int t = threadIdx.x;
-  const int tile = tile0 + blockIdx.y;
-  const int tx = tile % g.nnt, ty = (tile / g.nnt) % g.nnt, tz = tile / (g.nnt * g.nnt);
-  const int nc4 = w.n / 4, c0 = w.f0 / 4;
-  const int nbx = (nc4 + FB_X - 1) / FB_X, nby = (nc4 + FB_Y - 1) / FB_Y;
-  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
-  // my source cell: its particle run is fetched before the accumulators are cleared (the loads overlap the clearing)
-  const int sx = t % FS_X, sy = (t / FS_X) % FS_Y, sz = t / (FS_X * FS_Y);
-  // tile-local Fortran index of my source cell (sx = 0 is the low-side neighbour layer)
-  const int si = c0 + bx * FB_X + sx - NCB, sj = c0 + by * FB_Y + sy - NCB, sk = c0 + bz * FB_Z + sz - NCB;
-  const int lo = 2 - NCB, hi = g.nt + NCB - 1;  // source cells of the reference loop (pm.f90:50-52)
-  int n = 0; long long s = 0;
-  if (t < FS_N && si >= lo && si <= hi && sj >= lo && sj <= hi && sk >= lo && sk <= hi) {
-    const long long e = ext_index(g, tx * g.nt - 1 + si, ty * g.nt - 1 + sj, tz * g.nt - 1 + sk);
-    n = rhoc_e[e];
-    s = cstart_e[e];
-  }
-  if (__syncthreads_or(n > dense) &&
-      fine_deposit_dense(g, reinterpret_cast<unsigned*>(acc), xp, n, s, c0 + bx * FB_X - NCB, c0 + by * FB_Y - NCB, c0 + bz * FB_Z - NCB, mass_p,
-                         rho + (long long)blockIdx.y * w.vol, w, bx, by, bz))
-    return;
-  {
-    float4* a4 = reinterpret_cast<float4*>(acc);
-    for (int e = t; e < 125 * FS_N / 4 + 1; e += FD_T)
-      if (e < 125 * FS_N / 4) a4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t == 0) acc[125 * FS_N - 1] = 0.f;  // 28125 = 4*7031 + 1
-  }
-  __syncthreads();
-  if (n) {
-    float* my = acc + t;
-    Code3 c = load_code3(xp, s);
-    for (int l = 0; l < n; l++) {
-      const Code3 cur = c;
-      if (l + 1 < n) c = load_code3(xp, s + l + 1);  // next particle in flight while this one is spread
-      int i1, j1, k1; float ax[2], ay[2], az[2];
-      cic_split(fine_tempx(si, cur.x), i1, ax[0], ax[1]);
-      cic_split(fine_tempx(sj, cur.y), j1, ay[0], ay[1]);
-      cic_split(fine_tempx(sk, cur.z), k1, az[0], az[1]);
-      const int fa = i1 - (4 * (si - 1) + 1), fb = j1 - (4 * (sj - 1) + 1), fc = k1 - (4 * (sk - 1) + 1);  // 0..3 (4 on an f32 tie)
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int qa = q & 1, qb = (q >> 1) & 1, qc = q >> 2;
-        const int a = fa + qa, b = fb + qb, cc = fc + qc;
-        if (a <= 4 && b <= 4 && cc <= 4) {  // index 5 only occurs with weight exactly 0
-          const float wgt = __fmul_rn(__fmul_rn(__fmul_rn(ax[qa], ay[qb]), az[qc]), mass_p);  // pm.f90:61-68
-          float* p = my + ((a * 5 + b) * 5 + cc) * FS_N;
-          *p = __fadd_rn(*p, wgt);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // spill planes -> neighbour blocks: thread t = source cell S hands its planes on, every offset a compile-time constant
-  // (4 instructions per accumulator); consecutive threads touch consecutive banks
-  if (t < FS_N) {
-    float* my = acc + t;
-    if (sx != FS_X - 1) {  // +x: (4,b,c) of S -> (0,b,c) of S+1
-#pragma unroll
-      for (int bc = 0; bc < 25; bc++) my[bc * FS_N + 1] = __fadd_rn(my[bc * FS_N + 1], my[(100 + bc) * FS_N]);
-    }
-  }
-  __syncthreads();
-  if (t < FS_N && sy != FS_Y - 1) {  // +y: (a,4,c) of S -> (a,0,c) of S+FS_X, a = 0..3
-    float* my = acc + t;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int c = 0; c < 5; c++)
-        my[(a * 25 + c) * FS_N + FS_X] = __fadd_rn(my[(a * 25 + c) * FS_N + FS_X], my[(a * 25 + 20 + c) * FS_N]);
-  }
-  __syncthreads();
-  if (t < FS_N && sz != FS_Z - 1) {  // +z: (a,b,4) of S -> (a,b,0) of S+FS_X*FS_Y, a,b = 0..3
-    float* my = acc + t;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++)
-        my[(a * 25 + b * 5) * FS_N + FS_X * FS_Y] = __fadd_rn(my[(a * 25 + b * 5) * FS_N + FS_X * FS_Y], my[(a * 25 + b * 5 + 4) * FS_N]);
-  }
-  __syncthreads();
-  // write-out: one 32-float row (8 coarse cells x 4 fine cells) per warp and iteration; with 8 warps and 16 fine rows per
-  // z plane the row pattern of a warp is fixed, so all shared-memory offsets are compile-time constants
-  static_assert(FD_T == 256 && FB_X == 8 && FB_Y == 4 && FB_Z == 4, "write-out loop is unrolled for this brick");
-  const int lane = t & 31, wp = t >> 5;
-  float* out = rho + (long long)blockIdx.y * w.vol;
-  const int ocx = lane >> 2, a = lane & 3, b = wp & 3;
-  const int gx = (bx * FB_X + ocx) * 4 + a;
-  const float* src = acc + ((a * 5 + b) * 5) * FS_N + (FS_Y + (wp >> 2) + 1) * FS_X + (ocx + 1);  // ocz = 0, ocy = wp>>2, cc = 0
-  const bool okx = gx < w.n;
-#pragma unroll
-  for (int it = 0; it < 32; it++) {  // row = wp + 8*it: fy = wp + 8*(it&1), fz = it>>1
-    const int ocy = (wp >> 2) + 2 * (it & 1), cc = (it >> 1) & 3, ocz = it >> 3;
-    const int gy = (by * FB_Y + ocy) * 4 + b, gz = (bz * FB_Z + ocz) * 4 + cc;
-    const float v = src[cc * FS_N + (ocz * FS_Y + 2 * (it & 1)) * FS_X];
-    if (okx && gy < w.n && gz < w.n) out[((long long)gz * w.n + gy) * w.ld + gx] = v;
+  for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {  // one 32-float row per warp and iteration
+    const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+    if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2])
+      out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
   }
 }
 
-// (Measured and dropped, profiles/r01i_notes.md: a particle-parallel form -- one thread per particle, 64-bit fixed-point
-//  accumulators for one 32x16x16 block per CTA, shared-memory integer atomics, order-independent and therefore just as
-//  deterministic -- runs at full lane efficiency but needs ~270 instructions per particle for search, bounds and two
-//  atomics per target: 6.5 ms against 6.2 ms for the per-cell walk at cfg 2.)
 // k-space: F_d = i * kern_d * rho_k (pm.f90:79-80), with the 1/nfe^3 of pm.f90:82 folded in.
 // One thread per k-space element, looping over the tiles of the batch so that kern is read once.
 __global__ void __launch_bounds__(256) k_green(long long nk, int nbatch, const float2* __restrict__ crho,
