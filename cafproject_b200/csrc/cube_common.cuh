@@ -7,6 +7,7 @@
 // device; f32 division uses __fdiv_rn.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace cube {
@@ -54,13 +55,28 @@ __host__ __device__ inline bool ext_is_remote(const Geom& g, int x, int y, int z
 }
 
 // ---- codes -----------------------------------------------------------------------------------
-// int(xp+ishift,izipx)+rshift == u + 0.5 with u the raw 16-bit pattern (parameters.f90:14-15)
-__device__ __forceinline__ double xp_frac(short xp) {  // (u+0.5)*x_resolution, exact
-  return ((double)(unsigned short)xp + 0.5) * 0x1p-16;
+// The zip format of a run (CUBE/main/universe*.fh, parameters.f90:13-15): izipx, izipv = bytes per position / velocity code.
+//   x_resolution = 2^-(8 izipx), ishift = -2^(8 izipx - 1), rshift = 0.5 - ishift;  nvbin = 2^(8 izipv)
+// Kernels are instantiated per format; a code travels as a sign-extended `short` in registers whatever its storage type.
+template <int ZX, int ZV>
+struct Fmt {
+  static_assert((ZX == 1 || ZX == 2) && (ZV == 1 || ZV == 2), "izipx, izipv are 1 or 2 (universe*.fh)");
+  static constexpr int ZXB = ZX, ZVB = ZV;
+  static constexpr int XB = 8 * ZX, VB = 8 * ZV;      // bits per code
+  using XT = typename std::conditional<ZX == 1, signed char, short>::type;
+  using VT = typename std::conditional<ZV == 1, signed char, short>::type;
+  static constexpr int NV = (1 << VB) - 1;           // nvbin-1
+  static constexpr int VHALF = 1 << (VB - 1);        // velocity codes are -VHALF .. VHALF-1; size of the half tables
+};
+// raw B-bit pattern of a sign-extended code
+template <int B> __host__ __device__ __forceinline__ unsigned upat(short c) { return (unsigned)(int)c & ((1u << B) - 1u); }
+// int(xp+ishift,izipx)+rshift == u + 0.5 with u the raw pattern (parameters.f90:14-15)
+template <int XB> __device__ __forceinline__ double xp_frac(short xp) {  // (u+0.5)*x_resolution, exact
+  return ((double)upat<XB>(xp) + 0.5) * (1.0 / (double)(1 << XB));
 }
 // nint(real(nvbin-1)*atan(S*v)/pi,kind=izipv)  (pm.f90:113, update_particle.f90:86)
-__device__ __forceinline__ short vp_encode(double v, double S) {
-  double t = __dmul_rn(65535.0, atan(__dmul_rn(S, v)));
+template <int VB> __device__ __forceinline__ short vp_encode(double v, double S) {
+  double t = __dmul_rn((double)((1 << VB) - 1), atan(__dmul_rn(S, v)));
   return (short)llround(t / (double)PI_F);
 }
 // sqrt(pi/2)/(sigma_vi*vrel_boost): f32 sqrt promoted, f64 product (update_particle.f90:42)
@@ -111,15 +127,15 @@ __device__ __forceinline__ float kick_weight(float G, float wx, float wy, float 
   return __fmul_rn(__fmul_rn(__fmul_rn(G, wx), wy), wz);
 }
 
-// three 16-bit codes of one particle (AoS, 6-byte stride: only 2-byte alignment is guaranteed)
+// the three codes of one particle (AoS: only the code's own alignment is guaranteed), sign-extended
 struct Code3 { short x, y, z; };
-__device__ __forceinline__ Code3 load_code3(const short* __restrict__ a, long long p) {
-  const short* q = a + 3 * p;
-  Code3 c; c.x = __ldg(q); c.y = __ldg(q + 1); c.z = __ldg(q + 2);
+template <class T> __device__ __forceinline__ Code3 load_code3(const T* __restrict__ a, long long p) {
+  const T* q = a + 3 * p;
+  Code3 c; c.x = (short)__ldg(q); c.y = (short)__ldg(q + 1); c.z = (short)__ldg(q + 2);
   return c;
 }
-__device__ __forceinline__ void store_code3(short* a, long long p, short x, short y, short z) {
-  short* q = a + 3 * p; q[0] = x; q[1] = y; q[2] = z;
+template <class T> __device__ __forceinline__ void store_code3(T* a, long long p, short x, short y, short z) {
+  T* q = a + 3 * p; q[0] = (T)x; q[1] = (T)y; q[2] = (T)z;
 }
 
 // drift key: destination-minus-source cell offset per dim (5 bits each, biased by 16) + near-tie flag

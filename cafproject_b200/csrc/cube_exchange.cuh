@@ -106,9 +106,10 @@ __global__ void k_dir_bounds(int ndir, const long long* __restrict__ cell0 /*[nd
 
 // pack the particles of the cells I send: a CTA owns PC_CELLS consecutive send cells = one contiguous run of the
 // message buffer (coalesced stores); loads are contiguous per cell
+template <class T>
 __global__ void __launch_bounds__(PC_T) k_particle_pack(long long ng, const int* __restrict__ scell_L, const long long* __restrict__ sstart,
-                                                        const long long* __restrict__ cstart_p, const short* __restrict__ arr,
-                                                        short* __restrict__ out) {
+                                                        const long long* __restrict__ cstart_p, const T* __restrict__ arr,
+                                                        T* __restrict__ out) {
   __shared__ int soff[PC_CELLS + 1];
   __shared__ long long ssrc[PC_CELLS];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;

@@ -20,6 +20,7 @@
 #include "cube_kernels.cuh"
 #include "cube_fft.cuh"
 #include "cube_particles.cuh"
+#include "cube_kick.cuh"
 #include "cube_comm.cuh"
 #include "cube_exchange.cuh"
 #include "cube_coarse.cuh"
@@ -46,6 +47,18 @@ static int fail(const char* fmt, ...) {
     if (r_ != CUFFT_SUCCESS) return fail("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)r_, #call); \
   } while (0)
 #define CKL() CK(cudaGetLastError())
+// one instantiation of the particle kernels per zip format (izipx, izipv in {1,2}; CUBE/main/universe*.fh)
+#define FMT_SWITCH(h, ...)                                                       \
+  do {                                                                           \
+    if ((h)->zx == 2 && (h)->zv == 2) { using F = Fmt<2, 2>; __VA_ARGS__; }      \
+    else if ((h)->zx == 1 && (h)->zv == 2) { using F = Fmt<1, 2>; __VA_ARGS__; } \
+    else if ((h)->zx == 2 && (h)->zv == 1) { using F = Fmt<2, 1>; __VA_ARGS__; } \
+    else { using F = Fmt<1, 1>; __VA_ARGS__; }                                   \
+  } while (0)
+#define XPC(p) ((const typename F::XT*)(p))
+#define VPC(p) ((const typename F::VT*)(p))
+#define XPM(p) ((typename F::XT*)(p))
+#define VPM(p) ((typename F::VT*)(p))
 
 enum Phase { PH_KEY, PH_COUNT, PH_SCAN, PH_PLACE, PH_BUFFER, PH_FDEP, PH_FFTX, PH_FFTY, PH_FFTZ, PH_IFFTY, PH_IFFTX, PH_FMAX, PH_FKICK,
              PH_CDEP, PH_CFFT, PH_CKICK, PH_N };
@@ -79,15 +92,19 @@ struct cube_handle {
   Geom g;
   cudaStream_t st = nullptr;
   cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy[2] = {}; bool copy_pending = false, copy_reads_vp = false;  // cube_gpu_download_async
-  int16_t* vp_stream_host = nullptr;  // cube_gpu_stream_vp: where the next particle_mesh streams the final velocities
+  int zx = 2, zv = 2;                 // bytes per position / velocity code (izipx, izipv)
+  int nvbin = 65536;                  // 2^(8 izipv): size of the velocity tables
+  void* vp_stream_host = nullptr;     // cube_gpu_stream_vp: where the next particle_mesh streams the final velocities
   double* dvlut2 = nullptr; int* divok2 = nullptr;  // decode table of sigma_vi_new while the main one still serves the fine kick
+  unsigned long long* kick_next = nullptr; int kb_hot = 0; bool old_kick = false;  // merged brick kick (cube_kick.cuh)
+  CUtensorMap fmap = {}; int kick_stage = 2;  // TMA view of F[batch][M][M][3][FP]
   cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
   bool buffered = false;
   // particles (double buffered)
-  short *xp = nullptr, *vp = nullptr, *xp2 = nullptr, *vp2 = nullptr;
+  void *xp = nullptr, *vp = nullptr, *xp2 = nullptr, *vp2 = nullptr;  // integer(izipx) xp(3,np), integer(izipv) vp(3,np)
   long long *pid = nullptr, *pid2 = nullptr; bool pid_valid = false;  // -DPID: optional particle IDs (cube_gpu_upload_pid), single image
   unsigned short* key = nullptr;
   // coarse-cell arrays, file order
@@ -97,6 +114,7 @@ struct cube_handle {
   // extended image grid
   int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
   int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr; int* farblk = nullptr; float* csum = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
+  unsigned char* inflag = nullptr; int *flist = nullptr, *nflag = nullptr; bool count_all = false;  // destination cells with arrivals (pass B's work list)
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
@@ -107,7 +125,7 @@ struct cube_handle {
   float* tanlut = nullptr; double* dvlut = nullptr; float lut_sigma = -1.f; double* enc = nullptr;
   // cells above these particle counts are processed by a whole warp instead of one thread (cube_kernels.cuh, cube_particles.cuh)
   int heavy_deposit = 32, heavy_count = 64, count_minb = 8;
-  int fd_brick = 884;       // brick of the fine deposit: 888 | 884 | 844 coarse cells (cube_kernels.cuh)
+  int fd_brick = 844;       // brick of the fine deposit: 888 | 884 | 844 coarse cells (cube_kernels.cuh)
   bool shared_region = true;  // one fine-density grid per batch of tiles (nt <= 123); else one window per tile in the tile's own frame
   float* tanh = nullptr; int* divok = nullptr; int vt_hot = 0;  // shared-memory copies of the tables (cube_particles.cuh)
   int nsm = 1;
@@ -134,7 +152,7 @@ struct cube_handle {
   int *gcell_ext = nullptr, *scell_L = nullptr, *gcnt = nullptr, *scnt = nullptr;
   long long *gstart = nullptr, *sstart = nullptr, *dir_cell0 = nullptr, *dir_bounds = nullptr;
   HaloRec *hsend = nullptr, *hrecv = nullptr;
-  short* psend = nullptr; long long sendcap = 0;
+  void* psend = nullptr; long long sendcap = 0;
   std::vector<long long> gbound, sbound;  // host copies of the message offsets [ndir+1]
   long long nghost = 0;
   double* stat_partial_g = nullptr;
@@ -183,12 +201,12 @@ static int scan_counts(cube_handle* h, const int* in, long long n, long long* ou
 static int build_dvlut(cube_handle* h, float sigma) {
   if (h->lut_sigma == sigma) return 0;
   CK(cudaMemsetAsync(h->divok, 0xff, sizeof(int), h->st));  // cleared by the kernel if the FMA division misses t/S anywhere
-  k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, vscale(sigma), 1.0 / vscale(sigma), h->dvlut, h->divok); CKL();
+  k_build_dvlut<<<nblk(h->nvbin, 256), 256, 0, h->st>>>(h->nvbin, h->tanlut, vscale(sigma), 1.0 / vscale(sigma), h->dvlut, h->divok); CKL();
   h->launches++;
   h->lut_sigma = sigma;
   return 0;
 }
-static VTab vtab(const cube_handle* h) { return VTab{h->tanh, h->enc, h->dvlut, h->divok, h->vt_hot}; }
+static VTab vtab(const cube_handle* h) { return VTab{h->tanlut, h->tanh, h->enc, h->dvlut, h->divok, h->vt_hot}; }
 // one 1024-thread CTA per SM, fewer when there are not enough warp chunks
 static unsigned pw_grid(const cube_handle* h, long long ncells) {
   const long long nwc = (ncells + WC - 1) / WC;
@@ -236,6 +254,81 @@ static size_t region_elems(const cube_handle* h, int batch) {
   if (!h->shared_region) return (size_t)h->fg.N * h->fg.N * h->fg.N * batch;
   const FineRegion R = batch_region(h, 0, batch);
   return (size_t)R.ldz * R.n[2];
+}
+
+
+// TMA descriptor of the fine force F[batch][M][M][3][FP] (f32): the kick fetches a brick's 36 x 3 x 9 x 9 nodes with one box copy
+static int make_force_map(cube_handle* h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    if (h->kick_stage == 2) h->kick_stage = 1;  // no TMA descriptors on this driver: cp.async staging
+    return 0;
+  }
+  const FftGeom& f = h->fg;
+  const cuuint64_t dims[5] = {(cuuint64_t)f.FP, 3, (cuuint64_t)f.M, (cuuint64_t)f.M, (cuuint64_t)h->batch};
+  const cuuint64_t strides[4] = {(cuuint64_t)f.FP * 4, (cuuint64_t)f.FP * 12, (cuuint64_t)f.M * f.FP * 12, (cuuint64_t)f.M * f.M * f.FP * 12};
+  const cuuint32_t box[5] = {(cuuint32_t)KB_NX, 3, (cuuint32_t)KB_NY, (cuuint32_t)KB_NZ, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = ((EncodeFn)fn)(&h->fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, h->F, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cube_gpu_init: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// fine kick of the tiles [tile0, tile0+nb) with the force in h->F (pm.f90:88-118); codes come in with h->dvlut's sigma
+static int run_fine_kick(cube_handle* h, int tile0, int nb, double S_new) {
+  const Geom& g = h->g;
+  const long long nt3 = (long long)g.nt * g.nt * g.nt;
+  if (h->kick_stage == 2 && h->zx == 2 && h->zv == 2 && getenv("CUBE_GPU_FKICK_BRICK")) {
+    const int bpt = ((g.nt + KB_X - 1) / KB_X) * ((g.nt + KB_Y - 1) / KB_Y) * ((g.nt + KB_Z - 1) / KB_Z);
+    k_fine_kick_brick<<<dim3(bpt, nb), FKB_T, 0, h->st>>>(g, tile0, h->fg.M, (const short*)h->xp, (short*)h->vp, h->cstart_p, h->dvlut, h->enc, S_new, h->fmap);
+  } else {
+    FMT_SWITCH(h, k_fine_kick_p<F><<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, tile0, h->fg.M, h->fg.FP, XPC(h->xp), VPM(h->vp), h->cstart_p, h->F, h->dvlut, h->enc, S_new));
+  }
+  CKL();
+  h->launches++;
+  return 0;
+}
+// coarse kick of the file-order cells [c_begin, c_end) with the force in h->fc (pm.f90:196-228)
+static int run_coarse_kick(cube_handle* h, const VTab& vt, double S, long long c_begin, long long c_end) {
+  FMT_SWITCH(h, k_coarse_kick_w<F><<<pw_grid(h, c_end - c_begin), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(h->g, vt, S, XPC(h->xp), VPM(h->vp), h->cstart_p, h->vfield_p, h->fc,
+                                                                                                       h->vmax_bits, c_begin, c_end));
+  CKL();
+  h->launches++;
+  return 0;
+}
+
+// fine and/or coarse kick of the tiles [tile0, tile0+nb) in one pass (cube_kick.cuh); F = force_f of those tiles (nullptr: none),
+// Gc = force_c (nullptr: none), both already multiplied by a_mid*dt/6/pi
+static int launch_kick(cube_handle* h, int tile0, int nb, const float* F, const float* Gc, double S_in, double S_out) {
+  const Geom& g = h->g;
+  KickArgs A;
+  A.g = g; A.tile0 = tile0; A.nb = nb; A.M = h->fg.M; A.FP = h->fg.FP; A.F = F; A.Gc = Gc;
+  A.xp = (const short*)h->xp; A.vp = (short*)h->vp; A.cstart_p = h->cstart_p; A.vfield_p = h->vfield_p;
+  A.vt_in = VTab{h->tanlut, h->tanh, h->enc, h->dvlut, h->divok, h->kb_hot}; A.S_in = S_in;
+  A.vt_out = VTab{h->tanlut, h->tanh, h->enc, h->dvlut2, h->divok2, h->kb_hot}; A.S_out = S_out;
+  A.vmax_bits = h->vmax_bits; A.next_brick = h->kick_next;
+  const long long nbrick = (long long)nb * ((g.nt + KB_X - 1) / KB_X) * ((g.nt + KB_Y - 1) / KB_Y) * ((g.nt + KB_Z - 1) / KB_Z);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(h->nsm, (nbrick + KB_G - 1) / KB_G));
+  CK(cudaMemsetAsync(h->kick_next, 0, sizeof(unsigned long long), h->st));
+  if (h->kick_stage == 2) k_kick_brick<2><<<grid, KB_T, kb_smem_bytes(h->kb_hot), h->st>>>(A, h->fmap);
+  else if (h->kick_stage == 1) k_kick_brick<1><<<grid, KB_T, kb_smem_bytes(h->kb_hot), h->st>>>(A, h->fmap);
+  else k_kick_brick<0><<<grid, KB_T, kb_smem_bytes(h->kb_hot), h->st>>>(A, h->fmap);
+  CKL();
+  h->launches++;
+  return 0;
+}
+// decode table of `sigma` in dvlut2/divok2 (the codes the fine kick writes)
+static int build_dvlut2(cube_handle* h, float sigma) {
+  const double S = vscale(sigma);
+  CK(cudaMemsetAsync(h->divok2, 0xff, sizeof(int), h->st));
+  k_build_dvlut<<<nblk(h->nvbin, 256), 256, 0, h->st>>>(h->nvbin, h->tanlut, S, 1.0 / S, h->dvlut2, h->divok2); CKL();
+  h->launches++;
+  return 0;
 }
 
 extern "C" const char* cube_gpu_last_error(void) { return g_err.c_str(); }
@@ -322,7 +415,7 @@ static int init_exchange(cube_handle* h) {
   // message buffer for the particles I send: mean occupancy of the send cells with the image_buffer margin, x2
   const double mean = (double)h->p.np_nc * h->p.np_nc * h->p.np_nc;
   h->sendcap = (long long)((double)ng * mean * (double)h->p.image_buffer * 2.0) + 4096;
-  CK(dmalloc(&h->psend, 3 * h->sendcap));
+  CK(cudaMalloc(&h->psend, (size_t)3 * std::max(h->zx, h->zv) * h->sendcap + 16));
   CK(dmalloc(&h->stat_partial_g, 2 * (long long)nblk(ng, PC_CELLS) + 2));
   return 0;
 }
@@ -492,7 +585,8 @@ static int build_kernels(cube_handle* h, const float* fk_table, const float* ck_
 extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const float* ck_table, const float* tanf_lut,
                              const void* nccl_unique_id, cube_handle** out) {
   if (!p || !fk_table || !ck_table || !tanf_lut || !out) return fail("cube_gpu_init: null argument");
-  if (p->izipx != 2 || p->izipv != 2) return fail("zip format incompatable: only izipx=izipv=2 is built (got %d,%d)", p->izipx, p->izipv);
+  if ((p->izipx != 1 && p->izipx != 2) || (p->izipv != 1 && p->izipv != 2))
+    return fail("zip format incompatable: izipx and izipv are 1 or 2 bytes (got %d,%d)", p->izipx, p->izipv);
   if (p->ncell != NCELL || p->ncb != NCB) return fail("cube_gpu_init: ncell must be 4 and ncb 6");
   const int nimg = p->nn[0] * p->nn[1] * p->nn[2];
   if (p->nn[0] < 1 || p->nn[1] < 1 || p->nn[2] < 1 || p->rank < 0 || p->rank >= nimg) return fail("cube_gpu_init: bad image grid / rank");
@@ -505,6 +599,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(cudaSetDevice(p->device));
   cube_handle* h = new cube_handle();
   h->p = *p;
+  h->zx = p->izipx; h->zv = p->izipv; h->nvbin = 1 << (8 * p->izipv);
   h->nimg = nimg;
   Geom& g = h->g;
   fill_geom(p, g);
@@ -526,7 +621,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
   CK(cudaEventCreate(&h->tev[0])); CK(cudaEventCreate(&h->tev[1]));
   const long long cap = h->np_image_max;
-  CK(dmalloc(&h->xp, 3 * cap)); CK(dmalloc(&h->vp, 3 * cap)); CK(dmalloc(&h->xp2, 3 * cap)); CK(dmalloc(&h->vp2, 3 * cap));
+  CK(cudaMalloc(&h->xp, (size_t)3 * h->zx * cap + 16)); CK(cudaMalloc(&h->vp, (size_t)3 * h->zv * cap + 16));
+  CK(cudaMalloc(&h->xp2, (size_t)3 * h->zx * cap + 16)); CK(cudaMalloc(&h->vp2, (size_t)3 * h->zv * cap + 16));
   CK(dmalloc(&h->key, cap));
   CK(dmalloc(&h->rhoc_p, g.ncell_p)); CK(dmalloc(&h->rhoc_p2, g.ncell_p));
   CK(dmalloc(&h->vfield_p, 3 * g.ncell_p)); CK(dmalloc(&h->vfield_p2, 3 * g.ncell_p));
@@ -546,38 +642,53 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   }
   CK(dmalloc(&h->sid_e, g.ncell_e)); CK(dmalloc(&h->mask_e, MASK_W * g.ncell_e)); CK(dmalloc(&h->mask_s, MASK_W * (g.ncell_p + h->ex.ng)));
   CK(dmalloc(&h->farblk, (long long)farblk_dim(g) * farblk_dim(g) * farblk_dim(g)));
+  CK(dmalloc(&h->inflag, g.ncell_p)); CK(dmalloc(&h->flist, g.ncell_p)); CK(dmalloc(&h->nflag, 1));
+  h->count_all = getenv("CUBE_GPU_COUNT_ALL") != nullptr;
+
   h->nscan_blocks = (int)((std::max(g.ncell_p, h->ex.ng) + SCAN_B - 1) / SCAN_B);
   CK(dmalloc(&h->bsum, h->nscan_blocks + 1));
   CK(dmalloc(&h->stat_partial, std::max<long long>(2 * 4096 * PW_W, (long long)nblk(g.ncell_p, 128)))); CK(dmalloc(&h->stat3, 8));
   CK(dmalloc(&h->rank, cap));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
   CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
-  CK(dmalloc(&h->tanlut, 65536)); CK(dmalloc(&h->dvlut, 65536)); CK(dmalloc(&h->enc, 32768));
-  CK(dmalloc(&h->tanh, 32772)); CK(dmalloc(&h->divok, 1)); CK(dmalloc(&h->dvlut2, 65536)); CK(dmalloc(&h->divok2, 1));
-  k_build_enc<<<128, 256, 0, h->st>>>(h->enc); CKL();
-  CK(cudaMemcpyAsync(h->tanlut, tanf_lut, 65536 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+  const int nvb = h->nvbin, vh = nvb / 2;  // table sizes of this velocity format
+  CK(dmalloc(&h->tanlut, nvb)); CK(dmalloc(&h->dvlut, nvb)); CK(dmalloc(&h->enc, vh));
+  CK(dmalloc(&h->tanh, vh + 4)); CK(dmalloc(&h->divok, 1)); CK(dmalloc(&h->dvlut2, nvb)); CK(dmalloc(&h->divok2, 1));
+  if (h->zv == 2) k_build_enc<16><<<nblk(vh, 256), 256, 0, h->st>>>(h->enc); else k_build_enc<8><<<nblk(vh, 256), 256, 0, h->st>>>(h->enc);
+  CKL();
+  CK(cudaMemcpyAsync(h->tanlut, tanf_lut, nvb * sizeof(float), cudaMemcpyHostToDevice, h->st));
   {
-    // half table for shared memory: index = |code|.  tanf_lut is indexed by the code's 16-bit pattern, so -c sits at 65536-c.
+    // half table for shared memory: index = |code|.  tanf_lut is indexed by the code's raw pattern, so -c sits at nvbin-c.
     // The host tanf must be odd for this (glibc's is); if it is not, hot = 0 sends every lookup to the full global tables.
-    std::vector<float> half(32772, 0.f);
+    std::vector<float> half(vh + 4, 0.f);
     bool odd = true;
-    for (int c = 0; c <= 32767; c++) half[c] = tanf_lut[c];
-    half[32768] = -tanf_lut[32768];
-    for (int c = 1; c <= 32767; c++) { const float neg = -tanf_lut[65536 - c]; if (memcmp(&neg, &tanf_lut[c], 4) != 0) { odd = false; break; } }
+    for (int c = 0; c <= vh - 1; c++) half[c] = tanf_lut[c];
+    half[vh] = -tanf_lut[vh];
+    for (int c = 1; c <= vh - 1; c++) { const float neg = -tanf_lut[nvb - c]; if (memcmp(&neg, &tanf_lut[c], 4) != 0) { odd = false; break; } }
     if (tanf_lut[0] != 0.f || std::signbit(tanf_lut[0])) odd = false;
-    h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? VT_ALL : 0;
-    if (const char* e = getenv("CUBE_GPU_VT_HOT")) { if (h->vt_hot) h->vt_hot = std::min(VT_ALL, std::max(4, atoi(e) & ~3)); }
+    h->vt_hot = (odd && !getenv("CUBE_GPU_GLOBAL_TABLES")) ? vh : 0;
+    if (const char* e = getenv("CUBE_GPU_VT_HOT")) { if (h->vt_hot) h->vt_hot = std::min(vh, std::max(4, atoi(e) & ~3)); }
     if (const char* e = getenv("CUBE_GPU_HEAVY_DEPOSIT")) h->heavy_deposit = atoi(e);
     if (const char* e = getenv("CUBE_GPU_HEAVY_COUNT")) h->heavy_count = atoi(e);
     if (const char* e = getenv("CUBE_GPU_FD_BRICK")) h->fd_brick = atoi(e);
     if (const char* e = getenv("CUBE_GPU_COUNT_MINB")) h->count_minb = atoi(e);
-    CK(cudaMemcpyAsync(h->tanh, half.data(), 32772 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->tanh, half.data(), (vh + 4) * sizeof(float), cudaMemcpyHostToDevice, h->st));
     CK(cudaStreamSynchronize(h->st));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
     h->nsm = prop.multiProcessorCount;
-    CK(cudaFuncSetAttribute((const void*)k_drift_place_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
-    CK(cudaFuncSetAttribute((const void*)k_selftest_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
-    CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+    FMT_SWITCH(h, CK(cudaFuncSetAttribute((const void*)k_drift_place_w<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+               CK(cudaFuncSetAttribute((const void*)k_coarse_kick_w<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+               CK(cudaFuncSetAttribute((const void*)k_drift_key_chain<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC_SMEM)));
+    CK(cudaFuncSetAttribute((const void*)k_selftest_decode<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+    CK(cudaFuncSetAttribute((const void*)k_selftest_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_MAX));
+    h->kb_hot = h->vt_hot ? std::min(KB_HOT_DEFAULT, vh) : 0;
+    if (const char* e = getenv("CUBE_GPU_KICK_HOT")) { if (h->kb_hot) h->kb_hot = std::min(VT_ALL, std::max(4, atoi(e) & ~3)); }
+    h->old_kick = getenv("CUBE_GPU_MERGED_KICK") == nullptr || h->zx != 2 || h->zv != 2;  // measured (profiles/r02_notes.md): the two separate kicks are faster
+    if (const char* e = getenv("CUBE_GPU_KICK_STAGE")) h->kick_stage = atoi(e);
+    CK(cudaFuncSetAttribute((const void*)k_kick_brick<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_smem_bytes(h->kb_hot)));
+    CK(cudaFuncSetAttribute((const void*)k_kick_brick<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_smem_bytes(h->kb_hot)));
+    CK(cudaFuncSetAttribute((const void*)k_kick_brick<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_smem_bytes(h->kb_hot)));
+    CK(dmalloc(&h->kick_next, 1));
   }
   // fine mesh: pick the transform length, size the batch, allocate the pipeline arrays
   const int ntile = g.nnt * g.nnt * g.nnt;
@@ -610,11 +721,13 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   // on the tile frame and one density grid serves a whole batch of tiles
   h->shared_region = g.nt + 5 <= 128 && getenv("CUBE_GPU_TILE_REGIONS") == nullptr;
   h->rho_n = std::max(h->rho_n, region_elems(h, batch));
+  // (the tensor map of F is encoded below, once F exists)
   h->fg.nbatch = batch;
   CK(dmalloc(&h->f2max, batch + 1));
-  CK(dmalloc(&h->Ak, (long long)(h->A_n * batch))); CK(dmalloc(&h->Bk, (long long)(h->B_n * batch))); CK(dmalloc(&h->F, (long long)(h->F_n * batch)));
+  CK(dmalloc(&h->Ak, (long long)(h->A_n * batch))); CK(dmalloc(&h->Bk, (long long)(h->B_n * batch))); CK(dmalloc(&h->F, (long long)(h->F_n * batch) + 1024));  // + slack: the kick's 144-byte row copies may run past the last kept point
   if (h->rho_n * sizeof(float) <= h->B_n * batch * sizeof(float2)) h->rho = reinterpret_cast<float*>(h->Bk);  // dead before Bk is written
   else { CK(dmalloc(&h->rho_own, (long long)h->rho_n)); h->rho = h->rho_own; }  // forced long windows on small tiles (test hook)
+  if (make_force_map(h)) return 1;
   CK(dmalloc(&h->kern_f, 3LL * h->fg.N * h->fg.N * h->fg.P));
   CK(dmalloc(&h->tw, h->fg.N));
   {
@@ -650,12 +763,12 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CF(cufftPlanMany(&h->cplan_c2r, 3, n, cembed, 1, (int)h->cnk, rembed, 1, (int)h->cvol, CUFFT_C2R, 3));
     CF(cufftSetStream(h->cplan_r2c, h->st)); CF(cufftSetStream(h->cplan_c2r, h->st));
   }
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd888, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd888::SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd884, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd884::SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd844, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd844::SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd888, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd888::SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd884, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd884::SMEM));
-  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<Fd844, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fd844::SMEM));
+#define FD_ATTR(C, XT)                                                                                                                          \
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM)); \
+  CK(cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, true, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM))
+  if (h->zx == 2) { FD_ATTR(Fd888, short); FD_ATTR(Fd884, short); FD_ATTR(Fd844, short); }
+  else { FD_ATTR(Fd888, signed char); FD_ATTR(Fd884, signed char); FD_ATTR(Fd844, signed char); }
+#undef FD_ATTR
   if (build_kernels(h, fk_table, ck_table)) { return 1; }
   *out = h;
   return 0;
@@ -666,8 +779,8 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
-                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2, h->rho_own};
+                  h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->inflag, h->flist, h->nflag, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->kick_next, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2, h->rho_own};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -688,7 +801,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------
-extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t* vp, const int32_t* rhoc_phys,
+extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys,
                                const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
@@ -698,8 +811,8 @@ extern "C" int cube_gpu_upload(cube_handle* h, const int16_t* xp, const int16_t*
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // a streamed download still reads the arrays overwritten here
   h->vp_stream_host = nullptr;
   h->pid_valid = false;  // a new state: its IDs, if any, come with cube_gpu_upload_pid
-  CK(cudaMemcpyAsync(h->xp, xp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
-  CK(cudaMemcpyAsync(h->vp, vp, sizeof(short) * 3 * nplocal, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->xp, xp, (size_t)3 * h->zx * nplocal, cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->vp, vp, (size_t)3 * h->zv * nplocal, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->rhoc_p, rhoc_phys, sizeof(int) * g.ncell_p, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->vfield_p, vfield_phys, sizeof(float) * 3 * g.ncell_p, cudaMemcpyHostToDevice, h->st));
   if (scan_counts(h, h->rhoc_p, g.ncell_p, h->cstart_p)) return 1;
@@ -741,13 +854,13 @@ extern "C" int cube_gpu_download_pid(cube_handle* h, int64_t* pid) {
 // Start copying xp and/or vp (whichever is not NULL) of the current disjoint state to the host on a second stream, behind
 // everything already queued; returns at once.  Lets the checkpoint's device->host traffic overlap the rest of the step
 // (e.g. xp right after update_x: particle_mesh does not change positions).  cube_gpu_download waits for it.
-extern "C" int cube_gpu_download_async(cube_handle* h, int16_t* xp, int16_t* vp) {
+extern "C" int cube_gpu_download_async(cube_handle* h, void* xp, void* vp) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   CK(cudaEventRecord(h->ev_copy[0], h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
-  if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
-  if (vp) { CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy)); h->copy_reads_vp = true; }
+  if (xp) CK(cudaMemcpyAsync(xp, h->xp, (size_t)3 * h->zx * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
+  if (vp) { CK(cudaMemcpyAsync(vp, h->vp, (size_t)3 * h->zv * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy)); h->copy_reads_vp = true; }
   CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
   h->copy_pending = true;
   return 0;
@@ -766,20 +879,20 @@ extern "C" int cube_gpu_download_cells_async(cube_handle* h, int32_t* rhoc_phys,
   return 0;
 }
 
-extern "C" int cube_gpu_stream_vp(cube_handle* h, int16_t* vp) {
+extern "C" int cube_gpu_stream_vp(cube_handle* h, void* vp) {
   if (!h) return fail("null handle");
   h->vp_stream_host = vp;
   return 0;
 }
 
-extern "C" int cube_gpu_download(cube_handle* h, int16_t* xp, int16_t* vp, int32_t* rhoc_phys, float* vfield_phys,
+extern "C" int cube_gpu_download(cube_handle* h, void* xp, void* vp, int32_t* rhoc_phys, float* vfield_phys,
                                  int64_t* nplocal, float* sigma_vi) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   const Geom& g = h->g;
   if (h->copy_pending) { CK(cudaEventSynchronize(h->ev_copy[1])); h->copy_pending = false; h->copy_reads_vp = false; }
-  if (xp) CK(cudaMemcpyAsync(xp, h->xp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
-  if (vp) CK(cudaMemcpyAsync(vp, h->vp, sizeof(short) * 3 * h->nplocal, cudaMemcpyDeviceToHost, h->st));
+  if (xp) CK(cudaMemcpyAsync(xp, h->xp, (size_t)3 * h->zx * h->nplocal, cudaMemcpyDeviceToHost, h->st));
+  if (vp) CK(cudaMemcpyAsync(vp, h->vp, (size_t)3 * h->zv * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   if (rhoc_phys) CK(cudaMemcpyAsync(rhoc_phys, h->rhoc_p, sizeof(int) * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
   if (vfield_phys) CK(cudaMemcpyAsync(vfield_phys, h->vfield_p, sizeof(float) * 3 * g.ncell_p, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
@@ -814,20 +927,23 @@ static int exchange_density(cube_handle* h, int* status) {
 }
 
 // ghost particles (buffer_x.f90 for xp, buffer_v.f90 for vp): received behind the physical particles
-static int exchange_particles(cube_handle* h, short* arr) {
+static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per code */) {
+  char* arr = (char*)arr_v; char* psend = (char*)h->psend;
   const long long ng = h->ex.ng;
   const int nd = (int)h->ex.dirs.size();
   Comm* cm = h->comm.get();
-  k_particle_pack<<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, arr, h->psend); CKL();
+  if (z == 2) k_particle_pack<short><<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, (const short*)arr, (short*)psend);
+  else k_particle_pack<signed char><<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, (const signed char*)arr, (signed char*)psend);
+  CKL();
   h->launches++;
   CC(cm->begin(h->st));
   for (int i = 0; i < nd; i++) {
     const size_t n = (size_t)(h->sbound[i + 1] - h->sbound[i]);
-    if (n) CC(cm->send(h->psend + 3 * h->sbound[i], n * 3 * sizeof(short), h->ex.dirs[i].dst_rank));
+    if (n) CC(cm->send(psend + (size_t)3 * z * h->sbound[i], n * 3 * z, h->ex.dirs[i].dst_rank));
   }
   for (int i = 0; i < nd; i++) {
     const size_t n = (size_t)(h->gbound[i + 1] - h->gbound[i]);
-    if (n) CC(cm->recv(arr + 3 * (h->nplocal + h->gbound[i]), n * 3 * sizeof(short), h->ex.dirs[i].src_rank));
+    if (n) CC(cm->recv(arr + (size_t)3 * z * (h->nplocal + h->gbound[i]), n * 3 * z, h->ex.dirs[i].src_rank));
   }
   CC(cm->end());
   return 0;
@@ -873,8 +989,8 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
     h->buffered = true;
   }
   // one image: ghost particles alias the periodic image, nothing to copy
-  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp)) return 1; }
-  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp)) return 1; }
+  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp, h->zx)) return 1; }
+  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp, h->zv)) return 1; }
   return 0;
 }
 
@@ -900,11 +1016,16 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   const unsigned npw = pw_grid(h, g.ncell_p), nchunk_g = nblk(ng, PC_CELLS);
   {
     PhaseTimer pt(h, PH_KEY);
-    k_drift_key_p<<<nblk(g.ncell_p, PC_CELLS), PC_T, 0, h->st>>>(g, h->xp, h->vp, h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key, h->rank, h->maxoff, h->mask_s); CKL();
+    CK(cudaMemsetAsync(h->inflag, 0, (size_t)g.ncell_p, h->st));
+    CK(cudaMemsetAsync(h->nflag, 0, sizeof(int), h->st));
+    FMT_SWITCH(h, k_drift_key_chain<F><<<nblk(g.ncell_p, PC_CELLS), PC_T, KC_SMEM, h->st>>>(g, XPC(h->xp), VPC(h->vp), h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key,
+                                                                                            h->rank, h->maxoff, h->mask_s, h->inflag, h->rhoc_p2, h->vfield_p2));
+    CKL();
     h->launches++;
     if (multi && ng) {
-      k_drift_key_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->vfield_e, h->dvlut, dt_mid, h->key,
-                                                 h->rank, h->maxoff, h->mask_s + MASK_W * g.ncell_p); CKL();
+      FMT_SWITCH(h, k_drift_key_g<F><<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, XPC(h->xp), VPC(h->vp), h->vfield_e, h->dvlut, dt_mid,
+                                                                   h->key, h->rank, h->maxoff, h->mask_s + MASK_W * g.ncell_p, h->inflag));
+      CKL();
       h->launches++;
     }
     CK(cudaMemsetAsync(h->farblk, 0, sizeof(int) * (size_t)farblk_dim(g) * farblk_dim(g) * farblk_dim(g), h->st));
@@ -940,9 +1061,12 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     const unsigned nb = nblk(g.ncell_p, 128);
     {
       PhaseTimer pt(h, PH_COUNT);
-      const DriftCountArgs A{h->xp, h->vp, h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, h->mask_e, h->farblk, h->rank, dt_mid, r};
-      if (h->count_minb == 8) k_drift_count<8><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, h->rhoc_p2, h->vfield_p2);
-      else k_drift_count<5><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, h->rhoc_p2, h->vfield_p2);
+      // pass B only redoes the cells that receive somebody; the others were finished by k_drift_key_chain
+      const int* flist = h->count_all ? nullptr : h->flist;
+      if (flist) { k_flag_compact<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g.ncell_p, h->inflag, h->flist, h->nflag); CKL(); h->launches++; }
+      FMT_SWITCH(h, const DriftCountArgs<F> A{XPC(h->xp), VPC(h->vp), h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, h->mask_e, h->farblk, h->rank, dt_mid, r};
+                 if (h->count_minb == 8) k_drift_count<8, F><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, flist, h->nflag, h->rhoc_p2, h->vfield_p2);
+                 else k_drift_count<5, F><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, flist, h->nflag, h->rhoc_p2, h->vfield_p2));
       CKL();
       k_vfield_sq<<<nb, 128, 0, h->st>>>(g.ncell_p, h->vfield_p2, h->stat_partial); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, nb, 1, 0, h->stat3 + 1); CKL();
@@ -963,8 +1087,9 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
   }
   if (!status) {
     PhaseTimer pt(h, PH_PLACE);
-    k_drift_place_w<<<npw, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), S, h->xp, h->vp, h->rank, h->cstart_p, h->vfield_p, h->cstart_p2, h->vfield_p2,
-                                                       dt_mid, h->xp2, h->vp2, h->stat_partial); CKL();
+    FMT_SWITCH(h, k_drift_place_w<F><<<npw, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), S, XPC(h->xp), VPC(h->vp), h->rank, h->cstart_p, h->vfield_p, h->cstart_p2,
+                                                                                     h->vfield_p2, dt_mid, XPM(h->xp2), VPM(h->vp2), h->stat_partial));
+    CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 0, h->stat3); CKL();
     k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial, (long long)npw * PW_W, 2, 1, h->stat3 + 2); CKL();
     h->launches += 3;
@@ -974,8 +1099,9 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     }
     double stg[2] = {0, 0};
     if (multi && ng) {
-      k_drift_place_g<<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->xp, h->vp, h->rank, h->vfield_e, h->cstart_p2,
-                                                   h->vfield_p2, h->dvlut, h->enc, dt_mid, S, h->xp2, h->vp2, h->stat_partial_g); CKL();
+      FMT_SWITCH(h, k_drift_place_g<F><<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, XPC(h->xp), VPC(h->vp), h->rank, h->vfield_e, h->cstart_p2,
+                                                                     h->vfield_p2, h->dvlut, h->enc, dt_mid, S, XPM(h->xp2), VPM(h->vp2), h->stat_partial_g));
+      CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial_g, (long long)nchunk_g, 2, 0, h->stat3 + 3); CKL();
       k_reduce_strided<<<1, 1024, 0, h->st>>>(h->stat_partial_g, (long long)nchunk_g, 2, 1, h->stat3 + 4); CKL();
       h->launches += 3;
@@ -1029,8 +1155,12 @@ static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* 
   auto launch = [&](auto cfg) {
     using C = decltype(cfg);
     const unsigned nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY, nbz = (R.n[2] + C::NZ - 1) / C::NZ;
-    if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
-    else k_fine_deposit_r<C, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+    auto go = [&](auto xt) {
+      using XT = decltype(xt);
+      if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+      else k_fine_deposit_r<C, true, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+    };
+    if (h->zx == 2) go((short)0); else go((signed char)0);
   };
   if (h->fd_brick == 888) launch(Fd888{}); else if (h->fd_brick == 844) launch(Fd844{}); else launch(Fd884{});
   CKL();
@@ -1114,8 +1244,10 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
   {
     PhaseTimer pt(h, PH_CDEP);
     const long long nbox = (long long)(g.nc + 2) * (g.nc + 2) * (g.nc + 2);
-    k_coarse_cell_sums<<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, h->mass_p <= 8.f ? h->heavy_deposit : INT_MAX /* REDUX sums of 32 terms stay below 2^32 */,
-                                                            h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum); CKL();
+    const int heavy = h->mass_p <= 8.f ? h->heavy_deposit : INT_MAX;  // REDUX sums of 32 terms stay below 2^32
+    if (h->zx == 2) k_coarse_cell_sums<short><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum);
+    else k_coarse_cell_sums<signed char><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum);
+    CKL();
     k_coarse_gather27<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, nbox, h->csum, h->r3, multi ? g.nc : g.nc + 2); CKL();
     h->launches += 2;
   }
@@ -1166,20 +1298,20 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   // 63.4 against 52.8 on 2; at the highest priority 51.8 against 53.5 on 2).
   const bool overlap = h->overlap_coarse && !h->prof;
   // streamed velocities (cube_gpu_stream_vp): smaller batches, coarse kick per batch, the batch's vp out under the next batch
-  int16_t* const vp_host = h->vp_stream_host;
+  void* const vp_host = h->vp_stream_host;
   h->vp_stream_host = nullptr;
   const int step_batch = vp_host ? align_batch(g.nnt, std::max(1, std::min(h->batch, (ntile + 3) / 4))) : h->batch;
   std::vector<long long> tile_start(ntile + 1, 0);
+  const bool merged = !h->old_kick;  // one pass per batch does both kicks (cube_kick.cuh); else fine kick per batch, coarse kick at the end
+  const bool kick_c_per_batch = merged || vp_host;
+  if (build_dvlut2(h, h->sigma_vi_new)) return 1;
+  CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
   if (vp_host) {
-    CK(cudaMemsetAsync(h->divok2, 0xff, sizeof(int), h->st));
-    k_build_dvlut<<<256, 256, 0, h->st>>>(h->tanlut, S_new, 1.0 / S_new, h->dvlut2, h->divok2); CKL();
-    h->launches++;
-    CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
     CK(cudaMemcpy2DAsync(tile_start.data(), sizeof(long long), h->cstart_p, sizeof(long long) * nt3, sizeof(long long), ntile + 1,
                          cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    if (!overlap && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   }
+  if (!overlap && kick_c_per_batch && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   if (overlap) {
     cudaStream_t main_st = h->st;
     CK(cudaEventRecord(h->ev_fork, main_st));
@@ -1200,25 +1332,27 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
       k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(fb, h->F, a_mid, dt); CKL();
       h->launches++;
     }
-    {
-      PhaseTimer pt(h, PH_FKICK);
-      k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, t0, h->fg.M, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, S_new); CKL();
-      h->launches++;
+    if (kick_c_per_batch && overlap && t0 == 0) CK(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+    if (merged) {
+      PhaseTimer pt(h, PH_FKICK);  // both kicks
+      if (launch_kick(h, t0, nb, h->F, h->fc, vscale(h->sigma_vi), S_new)) return 1;
+    } else {
+      {
+        PhaseTimer pt(h, PH_FKICK);
+        if (run_fine_kick(h, t0, nb, S_new)) return 1;
+      }
+      if (vp_host) {
+        const long long c_begin = (long long)t0 * nt3, c_end = (long long)(t0 + nb) * nt3;
+        PhaseTimer pc(h, PH_CKICK);
+        if (run_coarse_kick(h, VTab{h->tanlut, h->tanh, h->enc, h->dvlut2, h->divok2, h->vt_hot}, S_new, c_begin, c_end)) return 1;
+      }
     }
     if (vp_host) {
-      if (overlap && t0 == 0) CK(cudaStreamWaitEvent(h->st, h->ev_join, 0));
-      const long long c_begin = (long long)t0 * nt3, c_end = (long long)(t0 + nb) * nt3;
-      {
-        PhaseTimer pc(h, PH_CKICK);
-        k_coarse_kick_w<<<pw_grid(h, c_end - c_begin), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(
-            g, VTab{h->tanh, h->enc, h->dvlut2, h->divok2, h->vt_hot}, S_new, h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc, h->vmax_bits, c_begin, c_end); CKL();
-        h->launches++;
-      }
       CK(cudaEventRecord(h->ev_copy[0], h->st));
       CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
       const long long p_begin = tile_start[t0], p_end = tile_start[t0 + nb];
       if (p_end > p_begin)
-        CK(cudaMemcpyAsync(vp_host + 3 * p_begin, h->vp + 3 * p_begin, sizeof(short) * 3 * (p_end - p_begin), cudaMemcpyDeviceToHost, h->st_copy));
+        CK(cudaMemcpyAsync((char*)vp_host + (size_t)3 * h->zv * p_begin, (char*)h->vp + (size_t)3 * h->zv * p_begin, (size_t)3 * h->zv * (p_end - p_begin), cudaMemcpyDeviceToHost, h->st_copy));
       CK(cudaEventRecord(h->ev_copy[1], h->st_copy));
       h->copy_pending = true;
     }
@@ -1226,22 +1360,15 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   h->sigma_vi = h->sigma_vi_new;  // pm.f90:122
   if (build_dvlut(h, h->sigma_vi)) return 1;
   if (overlap) { CK(cudaStreamWaitEvent(h->st, h->ev_join, 0)); }
-  else if (!vp_host && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
+  else if (!kick_c_per_batch && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
   float f2c = 0; unsigned long long vb = 0;
-  if (vp_host) {  // every batch already had its coarse kick
-    CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-  } else {
+  if (!kick_c_per_batch) {
     PhaseTimer pt(h, PH_CKICK);
-    CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
-    k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(h->sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
-                                                                         h->vmax_bits, 0, g.ncell_p); CKL();
-    h->launches++;
-    CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    if (run_coarse_kick(h, vtab(h), vscale(h->sigma_vi), 0, g.ncell_p)) return 1;
   }
+  CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
   double vmd; memcpy(&vmd, &vb, sizeof vmd);
   const float vmax = (float)vmd;  // f32 <- max(f32, f64) is monotone, so one final rounding is the same
   float f2f = 0; for (float v : f2) f2f = std::max(f2f, v);
@@ -1350,7 +1477,8 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   k_f2max_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, h->f2max); CKL();
   CK(cudaMemcpyAsync(&f2, h->f2max, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   k_prefix_rows<<<dim3(592, 1), 256, 0, h->st>>>(f1, h->F, a_mid, dt); CKL();
-  k_fine_kick_p<<<dim3(nblk(nt3, PC_CELLS), 1), PC_T, 0, h->st>>>(g, t, (int)m, h->fg.FP, h->xp, h->vp, h->cstart_p, h->F, h->dvlut, h->enc, vscale(sigma_vi_new)); CKL();
+  if (h->old_kick) { if (run_fine_kick(h, t, 1, vscale(sigma_vi_new))) return 1; }
+  else { if (build_dvlut2(h, sigma_vi_new) || launch_kick(h, t, 1, h->F, nullptr, vscale(sigma_vi), vscale(sigma_vi_new))) return 1; }
   CK(cudaStreamSynchronize(h->st));
   cudaFree(tmp);
   if (f2_max) *f2_max = f2;
@@ -1388,8 +1516,9 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
   k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
-  k_coarse_kick_w<<<pw_grid(h, g.ncell_p), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(g, vtab(h), vscale(sigma_vi), h->xp, h->vp, h->cstart_p, h->vfield_p, h->fc,
-                                                                       h->vmax_bits, 0, h->g.ncell_p); CKL();
+  if (h->old_kick) {
+    if (run_coarse_kick(h, vtab(h), vscale(sigma_vi), 0, g.ncell_p)) return 1;
+  } else if (build_dvlut2(h, sigma_vi) || launch_kick(h, 0, g.nnt * g.nnt * g.nnt, nullptr, h->fc, vscale(sigma_vi), vscale(sigma_vi))) return 1;
   float f2c = 0; unsigned long long vb = 0;
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
@@ -1432,9 +1561,14 @@ extern "C" int cube_gpu_selftest_codes(cube_handle* h, float sigma_vi, int64_t n
   if (build_dvlut(h, sigma_vi)) return 1;
   unsigned long long* cnt = nullptr; CK(dmalloc(&cnt, 2));
   CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->st));
-  const long long n = 3LL * 32767 + std::max<long long>(0, nsweep);
-  k_selftest_encode<<<nblk(n, 256), 256, 0, h->st>>>(h->enc, std::max<long long>(0, nsweep), cnt); CKL();
-  k_selftest_decode<<<1, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
+  const long long n = 3LL * (h->nvbin / 2 - 1) + std::max<long long>(0, nsweep);
+  if (h->zv == 2) {
+    k_selftest_encode<16><<<nblk(n, 256), 256, 0, h->st>>>(h->enc, std::max<long long>(0, nsweep), cnt); CKL();
+    k_selftest_decode<16><<<1, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
+  } else {
+    k_selftest_encode<8><<<nblk(n, 256), 256, 0, h->st>>>(h->enc, std::max<long long>(0, nsweep), cnt); CKL();
+    k_selftest_decode<8><<<1, PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(vtab(h), vscale(sigma_vi), cnt + 1); CKL();
+  }
   unsigned long long out[2] = {0, 0}; int ok = 0;
   CK(cudaMemcpyAsync(out, cnt, sizeof out, cudaMemcpyDeviceToHost, h->st));
   CK(cudaMemcpyAsync(&ok, h->divok, sizeof ok, cudaMemcpyDeviceToHost, h->st));

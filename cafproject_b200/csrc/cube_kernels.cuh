@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(256) k_tile_counts(Geom g, const int* __restri
 // dv table: dble(tan((pi*real(vp))/real(nvbin-1))) / (sqrt(pi/2)/(sigma_vi*vrel_boost))
 // Also checks, entry by entry, that t/S equals its FMA form q0 = t*rS, q = fma(fma(-S,q0,t), rS, q0) (rS = 1/S): the
 // particle kernels then divide that way (cube_particles.cuh, v_decode); *divok is cleared on any mismatch.
-__global__ void k_build_dvlut(const float* __restrict__ tanlut, double S, double rS, double* __restrict__ dvlut, int* __restrict__ divok) {
+__global__ void k_build_dvlut(int ncode /* nvbin */, const float* __restrict__ tanlut, double S, double rS, double* __restrict__ dvlut,
+                              int* __restrict__ divok) {
   int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= 65536) return;
+  if (u >= ncode) return;
   const double t = (double)tanlut[u], q = t / S;
   dvlut[u] = q;
   const double q0 = __dmul_rn(t, rS);
@@ -162,10 +163,10 @@ __global__ void __launch_bounds__(1024) k_reduce3(const double* __restrict__ par
 // =============================================================================================
 
 // tempx=4.*((/i,j,k/)-1)+4*(int(xp+ishift,izipx)+rshift)*x_resolution, rounded to f32 (pm.f90:54).
-// = (2K+1)/2^15 with K = 65536*(cell-1) + u an integer: the f64 expression is exact, so its f32 rounding equals the
-// round-to-nearest int->float conversion of 2K+1 scaled by a power of two (no f64 instructions)
-__device__ __forceinline__ float fine_tempx(int cell1, short xp) {
-  return __int2float_rn(2 * (65536 * (cell1 - 1) + (int)(unsigned short)xp) + 1) * 0x1p-15f;
+// = (2K+1)/2^(XB-1) with K = 2^XB*(cell-1) + u an integer (XB = 8 izipx bits): the f64 expression is exact, so its f32 rounding
+// equals the round-to-nearest int->float conversion of 2K+1 scaled by a power of two (no f64 instructions)
+template <int XB> __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
+  return __int2float_rn(2 * ((1 << XB) * (cell1 - 1) + (int)upat<XB>(xp)) + 1) * (1.0f / (float)(1 << (XB - 1)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,9 +174,9 @@ __device__ __forceinline__ float fine_tempx(int cell1, short xp) {
 //
 // The reference deposits every tile's particles (cells 2-ncb..nt+ncb-1) into that tile's padded grid rho_f.  A fine node's
 // value is the sum of the terms of ALL particles within one fine cell of it, whichever tile's grid it is read from, and for
-// tile-local coordinates below 512 fine cells (nte = nt + 12 <= 128) every f32 step of pm.f90:54-58 is exact: the weights are
-//     upper node: h = (2 (u mod 2^14) + 1) 2^-15,  lower node: 1 - h,   lower node index = 4 cell + (u >> 14)
-// (u = raw 16-bit position code), independent of the tile frame.  So one deposit of the image's cells onto one grid that spans
+// tile-local coordinates below 512 fine cells (cells up to nt + 5 <= 128) every f32 step of pm.f90:54-58 is exact: the weights are
+//     upper node: h = (2 (u mod 2^(XB-2)) + 1) 2^-(XB-1),  lower node: 1 - h,   lower node index = 4 cell + (u >> (XB-2))
+// (u = raw XB-bit position code), independent of the tile frame.  So one deposit of the image's cells onto one grid that spans
 // a whole batch of tiles serves every tile of the batch: the FFT's x pass reads each tile's window out of it, and the 1.42x
 // of work that overlapping windows cost disappears.  (Larger tiles are deposited one by one in their own frame, with the
 // reference's f32 rounding of tempx reproduced: `frame0` = image-local cell index of the tile's cell 1.)
@@ -215,20 +216,21 @@ struct FdCfg {
 };
 
 // lower node (image-local fine index) and the two weights of one coordinate
-__device__ __forceinline__ void fine_cic(int cell, unsigned u, int frame0, int& L, float& w0, float& w1) {
+template <int XB> __device__ __forceinline__ void fine_cic(int cell, short xp, int frame0, int& L, float& w0, float& w1) {
   if (frame0 == FRAME_NONE) {
-    L = 4 * cell + (int)(u >> 14);
-    w1 = __int2float_rn(2 * (int)(u & 0x3fffu) + 1) * 0x1p-15f;
+    const unsigned u = upat<XB>(xp);
+    L = 4 * cell + (int)(u >> (XB - 2));
+    w1 = __int2float_rn(2 * (int)(u & ((1u << (XB - 2)) - 1u)) + 1) * (1.0f / (float)(1 << (XB - 1)));
     w0 = 1.0f - w1;  // exact
   } else {  // the tile's own frame: tempx may round (pm.f90:54 in f32 beyond 512 fine cells)
     int idx1;
-    cic_split(fine_tempx(cell - frame0 + 1, (short)u), idx1, w0, w1);
+    cic_split(fine_tempx<XB>(cell - frame0 + 1, xp), idx1, w0, w1);
     L = 4 * frame0 + idx1 - 1;
   }
 }
 
-template <class C, bool FRAME>
-__global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const short* __restrict__ xp,
+template <class C, bool FRAME, class XT>
+__global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const XT* __restrict__ xp,
                                                           const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
                                                           float mass_p, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned fd_smem[];
@@ -300,9 +302,10 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
     const Code3 cur = load_code3(xp, p);
     const int sx = c % C::SX, sy = (c / C::SX) % C::SY, sz = c / (C::SX * C::SY);
     int lx, ly, lz; float ax[2], ay[2], az[2];
-    fine_cic(cbx - 1 + sx, (unsigned short)cur.x, FRAME ? frame0.x : FRAME_NONE, lx, ax[0], ax[1]);
-    fine_cic(cby - 1 + sy, (unsigned short)cur.y, FRAME ? frame0.y : FRAME_NONE, ly, ay[0], ay[1]);
-    fine_cic(cbz - 1 + sz, (unsigned short)cur.z, FRAME ? frame0.z : FRAME_NONE, lz, az[0], az[1]);
+    constexpr int XB = 8 * (int)sizeof(XT);
+    fine_cic<XB>(cbx - 1 + sx, cur.x, FRAME ? frame0.x : FRAME_NONE, lx, ax[0], ax[1]);
+    fine_cic<XB>(cby - 1 + sy, cur.y, FRAME ? frame0.y : FRAME_NONE, ly, ay[0], ay[1]);
+    fine_cic<XB>(cbz - 1 + sz, cur.z, FRAME ? frame0.z : FRAME_NONE, lz, az[0], az[1]);
     lx -= N0x; ly -= N0y; lz -= N0z;  // brick-local lower node, -4 .. 4B-1 (the upper node is the next one)
     if (lx < -1 || ly < -1 || lz < -1) continue;  // low-side layer: only particles next to the brick reach into it
     const bool vx[2] = {lx >= 0, lx + 1 < C::NX}, vy[2] = {ly >= 0, ly + 1 < C::NY}, vz[2] = {lz >= 0, lz + 1 < C::NZ};
@@ -359,9 +362,9 @@ __global__ void k_force_from_ref(int M, int FP, const float* __restrict__ in, fl
 // coarse mesh (pm.f90:127-228)
 // =============================================================================================
 // tempx=((/i,j,k/)-1)+(...)*x_resolution-0.5 -> f32 (pm.f90:142); cell0 = Fortran index - 1.
-// = (2K+1)/2^17 with K = 65536*cell0 + u - 32768 (every f64 step of the reference expression is exact)
-__device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
-  return __int2float_rn(2 * (65536 * cell0 + (int)(unsigned short)xp - 32768) + 1) * 0x1p-17f;
+// = (2K+1)/2^(XB+1) with K = 2^XB*cell0 + u - 2^(XB-1) (every f64 step of the reference expression is exact)
+template <int XB> __device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
+  return __int2float_rn(2 * ((1 << XB) * cell0 + (int)upat<XB>(xp) - (1 << (XB - 1))) + 1) * (1.0f / (float)(1 << (XB + 1)));
 }
 
 // Coarse CIC deposit (pm.f90:130-163) in two passes over the image, no atomics, deterministic:
@@ -378,8 +381,10 @@ __device__ __forceinline__ float coarse_tempx(int cell0, short xp) {
 // fixed point (2^-23) and added over the warp with the integer warp reduction (REDUX); lane T keeps the 64-bit total of
 // accumulator T.  Integer sums: independent of any order, deterministic.
 constexpr int CD_T = 256;
-__device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my /*[27] stride CD_T*/, const short* __restrict__ xp, long long s, int n,
+template <class XT>
+__device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my /*[27] stride CD_T*/, const XT* __restrict__ xp, long long s, int n,
                                                 float mass_p, int lane) {
+  constexpr int XB = 8 * (int)sizeof(XT);
   unsigned long long tot = 0;
   const float scale = __fmul_rn(mass_p, 8388608.0f);
   for (int base = 0; base < n; base += 32) {
@@ -387,11 +392,11 @@ __device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my /*[27] st
     if (base + lane < n) {
       const Code3 c = load_code3(xp, s + base + lane);
       int i1, j1, k1; float d1, d2;
-      cic_split(coarse_tempx(1, c.x), i1, d1, d2);  // i1 = 1 or 2: lower target = cell-1 or cell
+      cic_split(coarse_tempx<XB>(1, c.x), i1, d1, d2);  // i1 = 1 or 2: lower target = cell-1 or cell
       if (i1 == 1) { wx[0] = d1; wx[1] = d2; } else { wx[1] = d1; wx[2] = d2; }
-      cic_split(coarse_tempx(1, c.y), j1, d1, d2);
+      cic_split(coarse_tempx<XB>(1, c.y), j1, d1, d2);
       if (j1 == 1) { wy[0] = d1; wy[1] = d2; } else { wy[1] = d1; wy[2] = d2; }
-      cic_split(coarse_tempx(1, c.z), k1, d1, d2);
+      cic_split(coarse_tempx<XB>(1, c.z), k1, d1, d2);
       if (k1 == 1) { wz[0] = d1; wz[1] = d2; } else { wz[1] = d1; wz[2] = d2; }
     }
 #pragma unroll
@@ -405,9 +410,11 @@ __device__ __forceinline__ void coarse_sum_warp(float* __restrict__ my /*[27] st
 }
 
 // S[T][nbox], box cell b = ((z+1)*(nc+2) + (y+1))*(nc+2) + (x+1), x,y,z = -1..nc
-__global__ void __launch_bounds__(CD_T) k_coarse_cell_sums(Geom g, int heavy, const short* __restrict__ xp, const int* __restrict__ rhoc_e,
+template <class XT>
+__global__ void __launch_bounds__(CD_T) k_coarse_cell_sums(Geom g, int heavy, const XT* __restrict__ xp, const int* __restrict__ rhoc_e,
                                                            const long long* __restrict__ cstart_e, float mass_p, long long nbox,
                                                            float* __restrict__ S) {
+  constexpr int XB = 8 * (int)sizeof(XT);
   __shared__ float acc[27 * CD_T];  // [T][thread]: a thread's 27 sums sit in one bank
   __shared__ unsigned s_hm[CD_T / 32];
   const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
@@ -432,9 +439,9 @@ __global__ void __launch_bounds__(CD_T) k_coarse_cell_sums(Geom g, int heavy, co
     for (int l = 0; l < n; l++) {
       const Code3 c = load_code3(xp, s + l);
       int i1, j1, k1; float ax[2], ay[2], az[2];
-      cic_split(coarse_tempx(1, c.x), i1, ax[0], ax[1]);  // lower target: i1 - 1 = 0 (cell-1) or 1 (cell)
-      cic_split(coarse_tempx(1, c.y), j1, ay[0], ay[1]);
-      cic_split(coarse_tempx(1, c.z), k1, az[0], az[1]);
+      cic_split(coarse_tempx<XB>(1, c.x), i1, ax[0], ax[1]);  // lower target: i1 - 1 = 0 (cell-1) or 1 (cell)
+      cic_split(coarse_tempx<XB>(1, c.y), j1, ay[0], ay[1]);
+      cic_split(coarse_tempx<XB>(1, c.z), k1, az[0], az[1]);
       const int ra = i1 - 1, rb = j1 - 1, rc = k1 - 1;
 #pragma unroll
       for (int q = 0; q < 8; q++) {

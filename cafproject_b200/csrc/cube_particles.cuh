@@ -36,17 +36,18 @@ __device__ __forceinline__ int chunk_find(const int* soff, int q) {
 // table holds, for c = 0..32767, the smallest double X with code(X) >= c+1, found at start-up by bisection on
 // the double bit pattern with the exact formula (same device atan), so the lookup reproduces it for every X.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long enc_exact(double X) {
-  return llround(__dmul_rn(65535.0, atan(X)) / (double)PI_F);
+template <int VB> __device__ __forceinline__ long long enc_exact(double X) {
+  return llround(__dmul_rn((double)((1 << VB) - 1), atan(X)) / (double)PI_F);
 }
-__global__ void k_build_enc(double* __restrict__ B) {
+template <int VB> __global__ void k_build_enc(double* __restrict__ B) {
+  constexpr int VH = 1 << (VB - 1);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > 32767) return;
-  if (c == 32767) { B[c] = __longlong_as_double(0x7ff0000000000000LL); return; }
+  if (c > VH - 1) return;
+  if (c == VH - 1) { B[c] = __longlong_as_double(0x7ff0000000000000LL); return; }
   unsigned long long lo = 0, hi = (unsigned long long)__double_as_longlong(1e300);
   while (lo < hi) {
     const unsigned long long mid = lo + ((hi - lo) >> 1);
-    if (enc_exact(__longlong_as_double((long long)mid)) >= c + 1) hi = mid; else lo = mid + 1;
+    if (enc_exact<VB>(__longlong_as_double((long long)mid)) >= c + 1) hi = mid; else lo = mid + 1;
   }
   B[c] = __longlong_as_double((long long)hi);
 }
@@ -55,15 +56,16 @@ __global__ void k_build_enc(double* __restrict__ B) {
 // roundings of a and of the product add < 0.005), and the code is its rounding to nearest: unless cr lies within 1/16 of a
 // half-integer that rounding is already decided; otherwise (1 encode in 8) the exact threshold T[c] between codes c and
 // c+1, c = floor(cr), decides it.  Same result as the formula for every input, 1/8 table load per encode instead of 2.
-__device__ __forceinline__ short vp_encode_lut(double v, double S, const double* __restrict__ B) {
+template <int VB> __device__ __forceinline__ short vp_encode_lut(double v, double S, const double* __restrict__ B) {
+  constexpr int CMAX = (1 << (VB - 1)) - 1;
   const double X = __dmul_rn(S, v);
   const double a = fabs(X);
-  const float cr = atanf((float)a) * (65535.0f / PI_F);
+  const float cr = atanf((float)a) * ((float)((1 << VB) - 1) / PI_F);
   const float fl = floorf(cr), fr = cr - fl;
   int c = (int)fl;
-  if (fabsf(fr - 0.5f) <= 0.0625f) { c = min(c, 32767); c += (int)(a >= __ldg(B + c)); }
+  if (fabsf(fr - 0.5f) <= 0.0625f) { c = min(c, CMAX); c += (int)(a >= __ldg(B + c)); }
   else c += (int)(fr > 0.5f);
-  c = min(c, 32767);
+  c = min(c, CMAX);
   return (short)(X < 0.0 ? -c : c);
 }
 
@@ -84,17 +86,18 @@ __device__ __forceinline__ short vp_encode_lut(double v, double S, const double*
 // prefix offsets, no block barriers after the table fill.
 // =============================================================================================
 constexpr int VT_HOT = 24576;   // |code| < VT_HOT = 4.8 sigma: the part of the half table the kernels were first given
-constexpr int VT_ALL = 32768;   // the whole half table, the default: the velocity distribution of a clustered state has long tails
-                                // (z = 0 state of cfg 2: place 7.28 -> 6.78 ms, coarse kick 5.11 -> 4.99; z = 49: no change)
+constexpr int VT_ALL = 32768;   // the whole half table (2-byte codes; 128 entries for 1-byte codes), the default: the velocity distribution of
+                                // a clustered state has long tails (z = 0 state of cfg 2: place 7.28 -> 6.78 ms, coarse kick 5.11 -> 4.99)
 constexpr int WC = 32;         // cells per warp chunk
 constexpr int PW_T = 1024;     // threads per CTA
 constexpr int PW_W = PW_T / 32;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct VTab {
-  const float* tanh;    // [32769] host tanf of codes 0..32768 (tanh[32768] = -tanf(code -32768))
-  const double* thr;    // [32768] exact encoder thresholds
-  const double* dvlut;  // [65536] f64 decode table of the current S
+  const float* tanlut;  // [nvbin] host tanf, indexed by the code's raw pattern
+  const float* tanh;    // [nvbin/2+1] host tanf of codes 0..nvbin/2 (the last one = -tanf(most negative code))
+  const double* thr;    // [nvbin/2] exact encoder thresholds
+  const double* dvlut;  // [nvbin] f64 decode table of the current S
   const int* divok;     // != 0: the FMA division reproduces t/S for every table entry (current S)
   int hot;              // VT_HOT, or 0 when the host tanf table is not odd (everything takes the global tables)
 };
@@ -117,7 +120,7 @@ __device__ __forceinline__ VDec make_dec(const VTab& vt, const float* s_tan, dou
   VDec d; d.s_tan = s_tan; d.dvlut = vt.dvlut; d.S = S; d.rS = 1.0 / S; d.hot = vt.hot; d.fast = *vt.divok;
   return d;
 }
-__device__ __forceinline__ double v_decode(const VDec& d, short c) {
+template <int VB> __device__ __forceinline__ double v_decode(const VDec& d, short c) {
   const int a = abs((int)c);
   if (a < d.hot) {
     const float t = d.s_tan[a];
@@ -125,7 +128,13 @@ __device__ __forceinline__ double v_decode(const VDec& d, short c) {
     if (d.fast) { const double q0 = __dmul_rn(td, d.rS); return __fma_rn(__fma_rn(-d.S, q0, td), d.rS, q0); }
     return __ddiv_rn(td, d.S);
   }
-  return __ldg(d.dvlut + (unsigned short)c);
+  return __ldg(d.dvlut + upat<VB>(c));
+}
+// host tanf value of a code: shared-memory half table below `hot`, the full global table beyond
+template <int VB> __device__ __forceinline__ float tan_value(const VDec& d, const float* __restrict__ tanlut, short c) {
+  const int a = abs((int)c);
+  if (a < d.hot) { const float t = d.s_tan[a]; return c < 0 ? -t : t; }
+  return __ldg(tanlut + upat<VB>(c));
 }
 // prefix offsets and coordinates of the warp's cells [c0, c0+WC) (clipped at cend); returns the number of particles,
 // p0 = index of the first one.  cstart[cend] must be readable (next cell's start or the sentinel).
@@ -179,22 +188,25 @@ __device__ __forceinline__ void chunk_cells(const Geom& g, long long c0, long lo
 //           above every threshold, both signs, plus a geometric sweep of `nsweep` values over [1e-12, 1e8];
 //   decode: v_decode (shared-memory f32 table + FMA division) vs dvlut[] for all 65536 codes.
 // ---------------------------------------------------------------------------------------------
+template <int VB>
 __global__ void __launch_bounds__(256) k_selftest_encode(const double* __restrict__ T, long long nsweep, unsigned long long* __restrict__ bad) {
+  constexpr long long NT3 = 3LL * ((1 << (VB - 1)) - 1);
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double X;
-  if (q < 3LL * 32767) {
+  if (q < NT3) {
     const int c = (int)(q / 3), w = (int)(q % 3);
     const long long bits = __double_as_longlong(T[c]);
     X = __longlong_as_double(bits + (w - 1));
-  } else if (q < 3LL * 32767 + nsweep) {
-    const double f = (double)(q - 3LL * 32767) / (double)nsweep;
+  } else if (q < NT3 + nsweep) {
+    const double f = (double)(q - NT3) / (double)nsweep;
     X = exp(-27.631021115928547 + f * 46.051701859880914);  // 1e-12 .. 1e8
   } else return;
   int n = 0;
-  if (vp_encode_lut(X, 1.0, T) != vp_encode(X, 1.0)) n++;
-  if (vp_encode_lut(-X, 1.0, T) != vp_encode(-X, 1.0)) n++;
+  if (vp_encode_lut<VB>(X, 1.0, T) != vp_encode<VB>(X, 1.0)) n++;
+  if (vp_encode_lut<VB>(-X, 1.0, T) != vp_encode<VB>(-X, 1.0)) n++;
   if (n) atomicAdd(bad, (unsigned long long)n);
 }
+template <int VB>
 __global__ void __launch_bounds__(PW_T, 1) k_selftest_decode(VTab vt, double S, unsigned long long* __restrict__ bad) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
@@ -202,9 +214,9 @@ __global__ void __launch_bounds__(PW_T, 1) k_selftest_decode(VTab vt, double S, 
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
   int n = 0;
-  for (int u = threadIdx.x; u < 65536; u += PW_T) {
-    const short c = (short)(unsigned short)u;
-    if (__double_as_longlong(v_decode(dec, c)) != __double_as_longlong(vt.dvlut[u])) n++;
+  for (int u = threadIdx.x; u < (1 << VB); u += PW_T) {
+    const short c = (short)(u >= (1 << (VB - 1)) ? u - (1 << VB) : u);
+    if (__double_as_longlong(v_decode<VB>(dec, c)) != __double_as_longlong(vt.dvlut[u])) n++;
   }
   if (n) atomicAdd(bad, (unsigned long long)n);
 }
@@ -216,7 +228,8 @@ __global__ void __launch_bounds__(PW_T, 1) k_selftest_decode(VTab vt, double S, 
 // G[b][z'][y'][d][x'] = force_f*a_mid*dt/6/pi (the per-node prefix of every kick term, applied once per mesh node in
 // the epilogue of the x inverse, cube_fft.cuh) on the M kept points
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, int FP, const short* __restrict__ xp, short* __restrict__ vp,
+template <class F>
+__global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, int FP, const typename F::XT* __restrict__ xp, typename F::VT* __restrict__ vp,
                                                      const long long* __restrict__ cstart_p, const float* __restrict__ G,
                                                      const double* __restrict__ dvlut, const double* __restrict__ enc, double S_new) {
   __shared__ int soff[PC_CELLS + 1];
@@ -235,10 +248,10 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
     int i1, j1, k1; float ax[2], ay[2], az[2];
-    cic_split(fine_tempx(i, xc.x), i1, ax[0], ax[1]);  // idx1 of pm.f90:96 = 0-based kept index
-    cic_split(fine_tempx(j, xc.y), j1, ay[0], ay[1]);
-    cic_split(fine_tempx(k, xc.z), k1, az[0], az[1]);
-    double v0 = dvlut[(unsigned short)vc.x], v1 = dvlut[(unsigned short)vc.y], v2 = dvlut[(unsigned short)vc.z];
+    cic_split(fine_tempx<F::XB>(i, xc.x), i1, ax[0], ax[1]);  // idx1 of pm.f90:96 = 0-based kept index
+    cic_split(fine_tempx<F::XB>(j, xc.y), j1, ay[0], ay[1]);
+    cic_split(fine_tempx<F::XB>(k, xc.z), k1, az[0], az[1]);
+    double v0 = dvlut[upat<F::VB>(vc.x)], v1 = dvlut[upat<F::VB>(vc.y)], v2 = dvlut[upat<F::VB>(vc.z)];
     const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};  // pm.f90:104-111
     float f0[8], f1[8], f2[8];
 #pragma unroll
@@ -253,14 +266,15 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
       v1 = __dadd_rn(v1, (double)kick_weight(f1[t], wx, wy, wz));
       v2 = __dadd_rn(v2, (double)kick_weight(f2[t], wx, wy, wz));
     }
-    store_code3(vp, p, vp_encode_lut(v0, S_new, enc), vp_encode_lut(v1, S_new, enc), vp_encode_lut(v2, S_new, enc));
+    store_code3(vp, p, vp_encode_lut<F::VB>(v0, S_new, enc), vp_encode_lut<F::VB>(v1, S_new, enc), vp_encode_lut<F::VB>(v2, S_new, enc));
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // coarse kick (pm.f90:196-228); Gc(3,0:nc+1,0:nc+1,0:nc+1) = kick_prefix(force_c), vmax over v+vfield (no abs)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, double S, const short* __restrict__ xp, short* __restrict__ vp,
+template <class F>
+__global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, double S, const typename F::XT* __restrict__ xp, typename F::VT* __restrict__ vp,
                                                           const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
                                                           const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits,
                                                           long long c_begin, long long c_end /* file-order cell range */) {
@@ -284,10 +298,10 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
       const long long p = p0 + q;
       const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
       int i1, j1, k1; float ax[2], ay[2], az[2];
-      cic_split(coarse_tempx(X, xc.x), i1, ax[0], ax[1]);
-      cic_split(coarse_tempx(Y, xc.y), j1, ay[0], ay[1]);
-      cic_split(coarse_tempx(Z, xc.z), k1, az[0], az[1]);
-      double v0 = v_decode(dec, vc.x), v1 = v_decode(dec, vc.y), v2 = v_decode(dec, vc.z);
+      cic_split(coarse_tempx<F::XB>(X, xc.x), i1, ax[0], ax[1]);
+      cic_split(coarse_tempx<F::XB>(Y, xc.y), j1, ay[0], ay[1]);
+      cic_split(coarse_tempx<F::XB>(Z, xc.z), k1, az[0], az[1]);
+      double v0 = v_decode<F::VB>(dec, vc.x), v1 = v_decode<F::VB>(dec, vc.y), v2 = v_decode<F::VB>(dec, vc.z);
       const int qx[8] = {0, 1, 0, 0, 0, 1, 1, 1}, qy[8] = {0, 0, 1, 0, 1, 0, 1, 1}, qz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
 #pragma unroll
       for (int t = 0; t < 8; t++) {
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
       }
       const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
       vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));  // pm.f90:220
-      store_code3(vp, p, vp_encode_lut(v0, S, vt.thr), vp_encode_lut(v1, S, vt.thr), vp_encode_lut(v2, S, vt.thr));
+      store_code3(vp, p, vp_encode_lut<F::VB>(v0, S, vt.thr), vp_encode_lut<F::VB>(v1, S, vt.thr), vp_encode_lut<F::VB>(v2, S, vt.thr));
     }
   }
   for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(FULL, vm, o));
@@ -405,8 +419,8 @@ constexpr int FLAG_FAR = 1, FLAG_CROWD = 2;
 __host__ __device__ inline int farblk_dim(const Geom& g) { return (g.ne + FARB - 1) / FARB; }
 
 // destination cell of one coordinate, tile-local Fortran index `cell1` (update_particle.f90:41-45)
-__device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
-  double xq = __dadd_rn((double)(cell1 - 1), xp_frac(xp));
+template <int XB> __device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double dt_mid, bool& tie) {
+  double xq = __dadd_rn((double)(cell1 - 1), xp_frac<XB>(xp));
   double dx = __dmul_rn(__dmul_rn(dt_mid, v), 0.25);  // (dt_mid*vreal)/ncell, ncell=4: exact scaling
   double s = __dadd_rn(xq, dx);
   double c = ceil(s);
@@ -414,50 +428,157 @@ __device__ __forceinline__ int drift_dest(int cell1, short xp, double v, double 
   return (int)c;
 }
 
-__global__ void __launch_bounds__(PC_T) k_drift_key_p(Geom g, const short* __restrict__ xp, const short* __restrict__ vp,
-                                                     const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
-                                                     const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
-                                                     unsigned* __restrict__ rank, int* __restrict__ maxoff, unsigned* __restrict__ mask_s) {
+// file-order index of the physical cell at offset (ox,oy,oz) from the cell `cp`; false when that cell belongs to another image
+// (|offset| <= ncb < nt: at most one tile step per dimension, no divisions)
+__device__ __forceinline__ bool dest_cell(const Geom& g, const CellPos& cp, int ox, int oy, int oz, long long& D) {
+  const int nt = g.nt, nnt = g.nnt;
+  int i = cp.i + ox, j = cp.j + oy, k = cp.k + oz, tx = cp.tx, ty = cp.ty, tz = cp.tz;
+  if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
+  if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
+  if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
+  // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: the cell is another image's
+  if (g.nn[0] == 1) tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
+  if (g.nn[1] == 1) ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
+  if (g.nn[2] == 1) tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
+  if ((unsigned)tx >= (unsigned)nnt || (unsigned)ty >= (unsigned)nnt || (unsigned)tz >= (unsigned)nnt) return false;
+  D = phys_index(g, tx, ty, tz, i, j, k);
+  return true;
+}
+// a particle of cell `cp` heads for offset (ox,oy,oz): mark the destination "has arrivals" (pass B then walks it); a near-tie may
+// come out one cell off in the destination tile's frame: mark the 27 cells around (its own cell is among them or marked too)
+__device__ __noinline__ void flag_arrival_tie(const Geom& g, const CellPos& cp, int ox, int oy, int oz, unsigned char* __restrict__ inflag) {
+  long long D;
+  for (int dz = -1; dz <= 1; dz++)
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++)
+        if (dest_cell(g, cp, ox + dx, oy + dy, oz + dz, D)) inflag[D] = 1;
+  if (dest_cell(g, cp, 0, 0, 0, D)) inflag[D] = 1;
+}
+__device__ __forceinline__ void flag_arrival(const Geom& g, const CellPos& cp, int ox, int oy, int oz, bool tie, unsigned char* __restrict__ inflag) {
+  long long D;
+  if (tie) flag_arrival_tie(g, cp, ox, oy, oz, inflag);
+  else if (dest_cell(g, cp, ox, oy, oz, D)) inflag[D] = 1;
+}
+
+// Pass A (+ the bulk of pass B).  Per particle: destination offset key (+ near-tie flag), max |offset|, per-source-cell mover
+// summary -- and every mover marks its destination cell in `inflag`.  At the time steps of a run almost every particle stays in
+// its cell and most cells receive nobody: for such a cell the reference's arrival order IS its own storage order, so this kernel
+// also walks every cell's stayers (their velocities are still in shared memory), ranks them, chains vfield_new
+// (update_particle.f90:47) and writes the cell's count and mean velocity.  Cells that do receive somebody (inflag) are redone by
+// pass B from scratch -- only those.  A chunk with more particles than the velocity stash holds marks all its cells for pass B.
+constexpr int KC_CAPV = 1280;  // particles whose velocities a CTA stashes (a uniform chunk of 128 cells holds ~1024)
+constexpr int KC_SMEM = KC_CAPV * (3 * 8 + 1);
+template <class F>
+__global__ void __launch_bounds__(PC_T, 4) k_drift_key_chain(Geom g, const typename F::XT* __restrict__ xp, const typename F::VT* __restrict__ vp,
+                                                            const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
+                                                            const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
+                                                            unsigned* __restrict__ rank, int* __restrict__ maxoff, unsigned* __restrict__ mask_s,
+                                                            unsigned char* __restrict__ inflag, int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
+  extern __shared__ __align__(16) unsigned char kc_smem[];
+  double* sv = reinterpret_cast<double*>(kc_smem);                               // [3][KC_CAPV] velocities of the chunk's particles
+  unsigned char* scl = reinterpret_cast<unsigned char*>(sv + 3 * KC_CAPV);       // [KC_CAPV] cell of the particle | 0x80 = leaves its cell
   __shared__ int soff[PC_CELLS + 1];
   __shared__ unsigned smask[PC_CELLS * MASK_W];
   __shared__ CellPos spos[PC_CELLS];
+  __shared__ float svf[PC_CELLS * 3];
+  __shared__ int s_cnt[PC_CELLS];  // movers of the cell
+  static_assert(PC_CELLS <= 128, "cell index and mover flag share a byte");
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
   for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T) smask[t] = 0u;
+  for (int t = threadIdx.x; t < PC_CELLS * 3; t += PC_T) svf[t] = c0 * 3 + t < g.ncell_p * 3 ? vfield_p[c0 * 3 + t] : 0.f;
+  for (int t = threadIdx.x; t < PC_CELLS; t += PC_T) s_cnt[t] = 0;
   chunk_cells(g, c0, g.ncell_p, spos);
   const int np = chunk_setup(cstart_p, c0, g.ncell_p, soff);
   const long long p0 = cstart_p[c0];
+  const bool stash = np <= KC_CAPV;
   int m = 0;
   for (int q = threadIdx.x; q < np; q += PC_T) {
     const int cl = chunk_find(soff, q);
-    const long long L = c0 + cl;
-    const int i = spos[cl].i, j = spos[cl].j, k = spos[cl].k;
+    const CellPos cp = spos[cl];
+    const int i = cp.i, j = cp.j, k = cp.k;
     const long long p = p0 + q;
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
-    const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
+    const double v0 = __dadd_rn(dvlut[upat<F::VB>(vc.x)], (double)svf[3 * cl]);
+    const double v1 = __dadd_rn(dvlut[upat<F::VB>(vc.y)], (double)svf[3 * cl + 1]);
+    const double v2 = __dadd_rn(dvlut[upat<F::VB>(vc.z)], (double)svf[3 * cl + 2]);
     bool tie = false;
-    int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
-    int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
-    int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
-    m = max(m, max(abs(ox), max(abs(oy), abs(oz))));
-    mask_set(smask + cl * MASK_W, ox, oy, oz, tie);
+    int ox = drift_dest<F::XB>(i + 1, xc.x, v0, dt_mid, tie) - (i + 1);
+    int oy = drift_dest<F::XB>(j + 1, xc.y, v1, dt_mid, tie) - (j + 1);
+    int oz = drift_dest<F::XB>(k + 1, xc.z, v2, dt_mid, tie) - (k + 1);
+    const int far = max(abs(ox), max(abs(oy), abs(oz)));
+    m = max(m, far);
+    const bool mover = tie || far != 0;
+    if (mover) {
+      mask_set(smask + cl * MASK_W, ox, oy, oz, tie);
+      // movers beyond the tile buffer stop the step (maxoff); their clamped offsets are never used
+      if (far <= NCB) flag_arrival(g, cp, ox, oy, oz, tie, inflag);
+      if (stash) atomicAdd(&s_cnt[cl], 1);
+    }
+    if (stash) {
+      scl[q] = (unsigned char)(cl | (mover ? 0x80 : 0));
+      // a mover's slot holds -0.0: x + (-0.0) == x for every x, zeros of either sign included, so the chains below need no test
+      sv[q] = mover ? -0.0 : v0; sv[KC_CAPV + q] = mover ? -0.0 : v1; sv[2 * KC_CAPV + q] = mover ? -0.0 : v2;
+    } else rank[p] = RANK_LOST;  // pass B overwrites it for the one destination cell of this image that accepts the particle
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
-    rank[p] = RANK_LOST;  // pass B overwrites it for the one destination cell of this image that accepts the particle
   }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxoff, m);
   __syncthreads();
-  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T)
-    if (c0 + t / MASK_W < g.ncell_p) mask_s[c0 * MASK_W + t] = smask[t];
+  for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T) {
+    const int cl = t / MASK_W;
+    if (c0 + cl < g.ncell_p) {
+      unsigned w = smask[t];
+      // stayers are not in the shared summary (they never needed an atomic): the "offset 0" bit is set for every occupied cell,
+      // which is all pass B's mask test needs (it re-checks every candidate's key)
+      if ((t % MASK_W) == (offset_bit(0, 0, 0) >> 5) && soff[cl + 1] > soff[cl]) w |= 1u << (offset_bit(0, 0, 0) & 31);
+      mask_s[c0 * MASK_W + t] = w;
+    }
+  }
+  if (!stash) {  // crowded chunk: all of it goes to pass B (its warp path)
+    for (int t = threadIdx.x; t < PC_CELLS; t += PC_T) if (c0 + t < g.ncell_p) inflag[c0 + t] = 1;
+    return;
+  }
+  // ranks of the stayers among the stayers of their cell (= their arrival order when nobody else arrives), coalesced
+  const unsigned o12 = off_pack12(0, 0, 0) << RANK_BITS;
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const unsigned c = scl[q];
+    unsigned r = RANK_LOST;
+    if (!(c & 0x80u)) {
+      int before = q - soff[c];
+      if (s_cnt[c]) for (int q2 = soff[c]; q2 < q; q2++) before -= scl[q2] >> 7;
+      r = (unsigned)before | o12;
+    }
+    rank[p0 + q] = r;
+  }
+  // vfield_new chains (update_particle.f90:47): one thread per cell, its three components side by side
+  const double weight_v = (double)0.1f;  // update_particle.f90:10
+  const int cl = threadIdx.x;
+  if (cl < PC_CELLS && c0 + cl < g.ncell_p) {
+    const long long L = c0 + cl;
+    float vfn0 = (float)__dmul_rn((double)svf[3 * cl], weight_v), vfn1 = (float)__dmul_rn((double)svf[3 * cl + 1], weight_v),
+          vfn2 = (float)__dmul_rn((double)svf[3 * cl + 2], weight_v);  // :27
+    const int qe = soff[cl + 1];
+    for (int q = soff[cl]; q < qe; q++) {  // :47, f32 store after each f64 add
+      vfn0 = (float)__dadd_rn((double)vfn0, sv[q]);
+      vfn1 = (float)__dadd_rn((double)vfn1, sv[KC_CAPV + q]);
+      vfn2 = (float)__dadd_rn((double)vfn2, sv[2 * KC_CAPV + q]);
+    }
+    const int cnt = qe - soff[cl] - s_cnt[cl];
+    const double den = __dadd_rn((double)cnt, weight_v);  // :55-57
+    rhoc_new[L] = cnt;
+    vfield_new[3 * L] = (float)((double)vfn0 / den); vfield_new[3 * L + 1] = (float)((double)vfn1 / den); vfield_new[3 * L + 2] = (float)((double)vfn2 / den);
+  }
 }
 
 // pass A for the ghost particles received from other images (cube_exchange.cuh): cells in message order,
 // gstart = exclusive prefix of their counts (+ sentinel), particles at base + gstart[.]
+template <class F>
 __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
-                                                     long long base, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                     long long base, const typename F::XT* __restrict__ xp, const typename F::VT* __restrict__ vp,
                                                      const float* __restrict__ vfield_e, const double* __restrict__ dvlut, double dt_mid,
                                                      unsigned short* __restrict__ key, unsigned* __restrict__ rank, int* __restrict__ maxoff,
-                                                     unsigned* __restrict__ mask_g) {
+                                                     unsigned* __restrict__ mask_g, unsigned char* __restrict__ inflag) {
   __shared__ int soff[PC_CELLS + 1];
   __shared__ unsigned smask[PC_CELLS * MASK_W];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
@@ -473,12 +594,22 @@ __global__ void __launch_bounds__(PC_T) k_drift_key_g(Geom g, long long ng, cons
     const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
     const double vf0 = vfield_e[3 * e], vf1 = vfield_e[3 * e + 1], vf2 = vfield_e[3 * e + 2];
     bool tie = false;
-    int ox = drift_dest(i + 1, xc.x, __dadd_rn(dvlut[(unsigned short)vc.x], vf0), dt_mid, tie) - (i + 1);
-    int oy = drift_dest(j + 1, xc.y, __dadd_rn(dvlut[(unsigned short)vc.y], vf1), dt_mid, tie) - (j + 1);
-    int oz = drift_dest(k + 1, xc.z, __dadd_rn(dvlut[(unsigned short)vc.z], vf2), dt_mid, tie) - (k + 1);
+    int ox = drift_dest<F::XB>(i + 1, xc.x, __dadd_rn(dvlut[upat<F::VB>(vc.x)], vf0), dt_mid, tie) - (i + 1);
+    int oy = drift_dest<F::XB>(j + 1, xc.y, __dadd_rn(dvlut[upat<F::VB>(vc.y)], vf1), dt_mid, tie) - (j + 1);
+    int oz = drift_dest<F::XB>(k + 1, xc.z, __dadd_rn(dvlut[upat<F::VB>(vc.z)], vf2), dt_mid, tie) - (k + 1);
     // a ghost can only enter from at most ncb cells away; its owner image checks the full offset of the same particle
     m = max(m, min(NCB, max(abs(ox), max(abs(oy), abs(oz)))));
     mask_set(smask + cl * MASK_W, ox, oy, oz, tie);
+    {  // physical cells this ghost may arrive in (a near-tie: the 27 around its computed destination)
+      const int tr = tie ? 1 : 0;
+      for (int dz = -tr; dz <= tr; dz++)
+        for (int dy = -tr; dy <= tr; dy++)
+          for (int dx = -tr; dx <= tr; dx++) {
+            const int X = i + ox + dx, Y = j + oy + dy, Z = k + oz + dz;
+            if ((unsigned)X < (unsigned)g.nc && (unsigned)Y < (unsigned)g.nc && (unsigned)Z < (unsigned)g.nc)
+              inflag[phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt)] = 1;
+          }
+    }
     ox = min(max(ox, -15), 15); oy = min(max(oy, -15), 15); oz = min(max(oz, -15), 15);
     key[p] = (unsigned short)(key_pack(ox, oy, oz) | (tie ? KEY_FLAG : 0u));
     rank[p] = RANK_LOST;
@@ -520,25 +651,26 @@ __device__ __forceinline__ int dest_flags(const Geom& g, const int* __restrict__
 // (Measured and dropped, profiles/r01i_notes.md: staging the warp's own keys/codes or host-tanf values in shared memory and
 //  batching the 27 summary loads at radius 1 did not help -- 3.0 -> 3.0 / 3.4 ms.  ncu: 18 of 32 lanes active on average,
 //  25 inner iterations per warp: the cost is the divergence of per-cell particle counts and of the neighbour visits.)
-struct DriftCountArgs {
-  const short* xp; const short* vp; const unsigned short* key; const int* rhoc_e; const long long* cstart_e; const float* vfield_e;
+template <class F> struct DriftCountArgs {
+  const typename F::XT* xp; const typename F::VT* vp; const unsigned short* key; const int* rhoc_e; const long long* cstart_e; const float* vfield_e;
   const double* dvlut; const unsigned* mask_e; const int* farblk; unsigned* rank; double dt_mid; int r;
 };
 // one candidate particle of source cell (si,sj,sk) for destination (i,j,k): accepted? and its velocity
-__device__ __forceinline__ bool drift_accept(const DriftCountArgs& A, long long p, unsigned want, int si, int sj, int sk, int i, int j, int k,
+template <class F>
+__device__ __forceinline__ bool drift_accept(const DriftCountArgs<F>& A, long long p, unsigned want, int si, int sj, int sk, int i, int j, int k,
                                              double vf0, double vf1, double vf2, double& v0, double& v1, double& v2) {
   const unsigned kk = A.key[p];
   if (kk == want) {  // common case: one predictable branch, the body is straight-line code
     const Code3 vc = load_code3(A.vp, p);
-    v0 = __dadd_rn(A.dvlut[(unsigned short)vc.x], vf0); v1 = __dadd_rn(A.dvlut[(unsigned short)vc.y], vf1); v2 = __dadd_rn(A.dvlut[(unsigned short)vc.z], vf2);
+    v0 = __dadd_rn(A.dvlut[upat<F::VB>(vc.x)], vf0); v1 = __dadd_rn(A.dvlut[upat<F::VB>(vc.y)], vf1); v2 = __dadd_rn(A.dvlut[upat<F::VB>(vc.z)], vf2);
     return true;
   }
   if (kk & KEY_FLAG) {  // near a cell boundary: redo the ceiling in THIS tile's frame
     const Code3 vc = load_code3(A.vp, p), xc = load_code3(A.xp, p);
-    v0 = __dadd_rn(A.dvlut[(unsigned short)vc.x], vf0); v1 = __dadd_rn(A.dvlut[(unsigned short)vc.y], vf1); v2 = __dadd_rn(A.dvlut[(unsigned short)vc.z], vf2);
+    v0 = __dadd_rn(A.dvlut[upat<F::VB>(vc.x)], vf0); v1 = __dadd_rn(A.dvlut[upat<F::VB>(vc.y)], vf1); v2 = __dadd_rn(A.dvlut[upat<F::VB>(vc.z)], vf2);
     bool t = false;
-    return (drift_dest(si + 1, xc.x, v0, A.dt_mid, t) == i + 1) & (drift_dest(sj + 1, xc.y, v1, A.dt_mid, t) == j + 1) &
-           (drift_dest(sk + 1, xc.z, v2, A.dt_mid, t) == k + 1);
+    return (drift_dest<F::XB>(si + 1, xc.x, v0, A.dt_mid, t) == i + 1) & (drift_dest<F::XB>(sj + 1, xc.y, v1, A.dt_mid, t) == j + 1) &
+           (drift_dest<F::XB>(sk + 1, xc.z, v2, A.dt_mid, t) == k + 1);
   }
   return false;
 }
@@ -549,12 +681,32 @@ __device__ __forceinline__ bool drift_accept(const DriftCountArgs& A, long long 
 // 32 candidates are tested at once, ranks come from a ballot prefix, and only the vfield_new chain (f32 rounding after every
 // add, update_particle.f90:47) stays serial, fed by shuffles in storage order.  Same traversal order, same results.
 constexpr int DC_T = 128;
-template <int MINB>
-__global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountArgs A, int heavy, int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
+// the cells marked in `inflag`, in any order (each is processed independently; which thread gets which cell changes nothing)
+__global__ void __launch_bounds__(256) k_flag_compact(long long ncell, const unsigned char* __restrict__ inflag, int* __restrict__ flist, int* __restrict__ nflag) {
+  const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool f = L < ncell && inflag[L];
+  const unsigned b = __ballot_sync(FULL, f);
+  if (!b) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(nflag, __popc(b));
+  base = __shfl_sync(FULL, base, 0);
+  if (f) flist[base + __popc(b & ((1u << lane) - 1u))] = (int)L;
+}
+
+// flist == nullptr: every physical cell; else the cells flist[0 .. *nflag)
+template <int MINB, class F>
+__global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountArgs<F> A, int heavy, const int* __restrict__ flist, const int* __restrict__ nflag,
+                                                            int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
   const double weight_v = (double)0.1f;  // update_particle.f90:10
   __shared__ unsigned s_hm[DC_T / 32];
   __shared__ double s_v[DC_T / 32][3][32];  // a warp's accepted velocities of the current 32 candidates (crowded path)
-  const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_dest[DC_T];
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nslot = flist ? (long long)*nflag : g.ncell_p;
+  if ((long long)blockIdx.x * blockDim.x >= nslot) return;
+  const long long L = slot < nslot ? (flist ? (long long)flist[slot] : slot) : g.ncell_p;
+  s_dest[threadIdx.x] = (int)L;
   bool crowded = false;
   if (L < g.ncell_p) {
     int tx, ty, tz, i, j, k;
@@ -617,7 +769,7 @@ __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountAr
   for (int wd = 0; wd < DC_T / 32; wd++) {
     unsigned bits = s_hm[wd];
     while (bits) {
-      const long long D = (long long)blockIdx.x * blockDim.x + wd * 32 + __ffs(bits) - 1;
+      const long long D = s_dest[wd * 32 + __ffs(bits) - 1];
       bits &= bits - 1;
       if ((ord++ & (DC_T / 32 - 1)) != wp) continue;
       int tx, ty, tz, i, j, k;
@@ -681,26 +833,28 @@ __global__ void __launch_bounds__(128) k_vfield_sq(long long ncell, const float*
 }
 
 // one particle: new codes at slot `pos` of the re-sorted arrays + its terms of the velocity statistics
-__device__ __forceinline__ void drift_move(long long p, long long pos, const short* __restrict__ xp, const short* __restrict__ vp,
+template <class F>
+__device__ __forceinline__ void drift_move(long long p, long long pos, const typename F::XT* __restrict__ xp, const typename F::VT* __restrict__ vp,
                                            const float* __restrict__ vf_src, const float* __restrict__ vf_new,
                                            const double* __restrict__ dvlut, const double* __restrict__ enc, double dt_mid, double S,
-                                           short* __restrict__ xp_new, short* __restrict__ vp_new, double& st_tot, double& st_res) {
+                                           typename F::XT* __restrict__ xp_new, typename F::VT* __restrict__ vp_new, double& st_tot, double& st_res) {
+  constexpr double XSCALE = (double)(1 << (F::XB - 2));  // 1/(x_resolution*ncell): an exact scaling
   const Code3 xc = load_code3(xp, p), vc = load_code3(vp, p);
-  const double v0 = __dadd_rn(dvlut[(unsigned short)vc.x], (double)vf_src[0]);
-  const double v1 = __dadd_rn(dvlut[(unsigned short)vc.y], (double)vf_src[1]);
-  const double v2 = __dadd_rn(dvlut[(unsigned short)vc.z], (double)vf_src[2]);
-  // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
-  const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
-  const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
-  const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
+  const double v0 = __dadd_rn(dvlut[upat<F::VB>(vc.x)], (double)vf_src[0]);
+  const double v1 = __dadd_rn(dvlut[upat<F::VB>(vc.y)], (double)vf_src[1]);
+  const double v2 = __dadd_rn(dvlut[upat<F::VB>(vc.z)], (double)vf_src[2]);
+  // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell))  :84 (the store wraps to the code's width)
+  const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), XSCALE)));
+  const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), XSCALE)));
+  const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), XSCALE)));
   const float n0 = vf_new[0], n1 = vf_new[1], n2 = vf_new[2];
-  const short w0 = vp_encode_lut(__dsub_rn(v0, (double)n0), S, enc);  // :85-86
-  const short w1 = vp_encode_lut(__dsub_rn(v1, (double)n1), S, enc);
-  const short w2 = vp_encode_lut(__dsub_rn(v2, (double)n2), S, enc);
+  const short w0 = vp_encode_lut<F::VB>(__dsub_rn(v0, (double)n0), S, enc);  // :85-86
+  const short w1 = vp_encode_lut<F::VB>(__dsub_rn(v1, (double)n1), S, enc);
+  const short w2 = vp_encode_lut<F::VB>(__dsub_rn(v2, (double)n2), S, enc);
   store_code3(xp_new, pos, x0, x1, x2);
   store_code3(vp_new, pos, w0, w1, w2);
   // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
-  double a0 = dvlut[(unsigned short)w0], a1 = dvlut[(unsigned short)w1], a2 = dvlut[(unsigned short)w2];
+  double a0 = dvlut[upat<F::VB>(w0)], a1 = dvlut[upat<F::VB>(w1)], a2 = dvlut[upat<F::VB>(w2)];
   st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
   a0 = __dadd_rn(a0, (double)n0); a1 = __dadd_rn(a1, (double)n1); a2 = __dadd_rn(a2, (double)n2);
   st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
@@ -720,11 +874,13 @@ __device__ __forceinline__ void block_sum2(double a, double b, double* __restric
 
 // pass C: one thread per particle; single image: destinations wrap periodically.  stat_partial gets one (total, residual)
 // pair per warp of the launch (fixed order for a fixed grid).
-__global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, double S, const short* __restrict__ xp, const short* __restrict__ vp,
+template <class F>
+__global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, double S, const typename F::XT* __restrict__ xp, const typename F::VT* __restrict__ vp,
                                                           const unsigned* __restrict__ rank, const long long* __restrict__ cstart_p,
                                                           const float* __restrict__ vfield_p, const long long* __restrict__ cstart_new,
-                                                          const float* __restrict__ vfield_new, double dt_mid, short* __restrict__ xp_new,
-                                                          short* __restrict__ vp_new, double* __restrict__ stat_partial) {
+                                                          const float* __restrict__ vfield_new, double dt_mid, typename F::XT* __restrict__ xp_new,
+                                                          typename F::VT* __restrict__ vp_new, double* __restrict__ stat_partial) {
+  constexpr double XSCALE = (double)(1 << (F::XB - 2));  // 1/(x_resolution*ncell): an exact scaling
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -732,8 +888,7 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
   if (vt.hot) fill_tab(s_tan, vt.tanh, vt.hot);
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
-  const int nt = g.nt, nnt = g.nnt;
-  double st_tot = 0, st_res = 0;
+  double s_t2 = 0, s_tn = 0, s_n2 = 0;
   for (long long c0 = ((long long)blockIdx.x * PW_W + warp) * WC; c0 < g.ncell_p; c0 += (long long)gridDim.x * PW_W * WC) {
     long long p0;
     const int np = warp_chunk_setup(g, cstart_p, c0, g.ncell_p, ws, lane, p0);
@@ -746,42 +901,41 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
       const long long L = c0 + cl;
       const CellPos cp = ws->pos[cl];
       const unsigned o = rk >> RANK_BITS;
-      // destination = source + offset (|offset| <= ncb < nt): at most one tile step per dimension, no divisions
-      int i = cp.i + (int)(o & 15u) - 8, j = cp.j + (int)((o >> 4) & 15u) - 8, k = cp.k + (int)((o >> 8) & 15u) - 8;
-      int tx = cp.tx, ty = cp.ty, tz = cp.tz;
-      if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
-      if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
-      if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
-      // nn_d == 1: the neighbour image is this image (periodic wrap); nn_d > 1: an accepted particle stays inside
-      if (g.nn[0] == 1) tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
-      if (g.nn[1] == 1) ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
-      if (g.nn[2] == 1) tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
-      if ((unsigned)tx >= (unsigned)nnt || (unsigned)ty >= (unsigned)nnt || (unsigned)tz >= (unsigned)nnt) continue;
-      const long long D = phys_index(g, tx, ty, tz, i, j, k);
+      long long D = L;
+      if (o != off_pack12(0, 0, 0)) {  // a mover (a few per cent): destination = source + offset
+        if (!dest_cell(g, cp, (int)(o & 15u) - 8, (int)((o >> 4) & 15u) - 8, (int)((o >> 8) & 15u) - 8, D)) continue;  // cannot happen for an accepted particle
+      }
       const long long pos = cstart_new[D] + (rk & ((1u << RANK_BITS) - 1));
       const float* vf_src = vfield_p + 3 * L;
       const float* vf_new = vfield_new + 3 * D;
-      const double v0 = __dadd_rn(v_decode(dec, vc.x), (double)vf_src[0]);
-      const double v1 = __dadd_rn(v_decode(dec, vc.y), (double)vf_src[1]);
-      const double v2 = __dadd_rn(v_decode(dec, vc.z), (double)vf_src[2]);
-      // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell)) : /2^-14 is an exact scaling  :84
-      const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), 16384.0)));
-      const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), 16384.0)));
-      const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), 16384.0)));
+      const double v0 = __dadd_rn(v_decode<F::VB>(dec, vc.x), (double)vf_src[0]);
+      const double v1 = __dadd_rn(v_decode<F::VB>(dec, vc.y), (double)vf_src[1]);
+      const double v2 = __dadd_rn(v_decode<F::VB>(dec, vc.z), (double)vf_src[2]);
+      // xp_new=xp+nint(dt_mid*vreal/(x_resolution*ncell))  :84 (the store wraps to the code's width)
+      const short x0 = (short)((int)xc.x + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v0), XSCALE)));
+      const short x1 = (short)((int)xc.y + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v1), XSCALE)));
+      const short x2 = (short)((int)xc.z + (int)llround(__dmul_rn(__dmul_rn(dt_mid, v2), XSCALE)));
       const float n0 = vf_new[0], n1 = vf_new[1], n2 = vf_new[2];
-      const short w0 = vp_encode_lut(__dsub_rn(v0, (double)n0), S, vt.thr);  // :85-86
-      const short w1 = vp_encode_lut(__dsub_rn(v1, (double)n1), S, vt.thr);
-      const short w2 = vp_encode_lut(__dsub_rn(v2, (double)n2), S, vt.thr);
+      const short w0 = vp_encode_lut<F::VB>(__dsub_rn(v0, (double)n0), S, vt.thr);  // :85-86
+      const short w1 = vp_encode_lut<F::VB>(__dsub_rn(v1, (double)n1), S, vt.thr);
+      const short w2 = vp_encode_lut<F::VB>(__dsub_rn(v2, (double)n2), S, vt.thr);
       store_code3(xp_new, pos, x0, x1, x2);
       store_code3(vp_new, pos, w0, w1, w2);
-      // velocity statistics, update_particle.f90:140-143 (decoded with the old sigma_vi)
-      double a0 = v_decode(dec, w0), a1 = v_decode(dec, w1), a2 = v_decode(dec, w2);
-      st_res += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-      a0 = __dadd_rn(a0, (double)n0); a1 = __dadd_rn(a1, (double)n1); a2 = __dadd_rn(a2, (double)n2);
-      st_tot += __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+      // velocity statistics, update_particle.f90:140-143 (the new codes decoded with the old sigma_vi: dv = t/S, t the host tanf
+      // value).  sum dv^2 = (sum t^2)/S^2 and sum (dv+n)^2 = sum dv^2 + 2 (sum t n)/S + sum n^2: the sums of t^2 (exact products in
+      // f64), t*n and n^2 are taken here and scaled once per warp -- equal to the term-by-term form to a few 1e-16, which is the
+      // size of its own rounding; the statistics are only ever used rounded to f32.
+      const double t0 = (double)tan_value<F::VB>(dec, vt.tanlut, w0), t1 = (double)tan_value<F::VB>(dec, vt.tanlut, w1),
+                   t2 = (double)tan_value<F::VB>(dec, vt.tanlut, w2);
+      s_t2 = __fma_rn(t0, t0, __fma_rn(t1, t1, __fma_rn(t2, t2, s_t2)));
+      s_tn = __fma_rn(t0, (double)n0, __fma_rn(t1, (double)n1, __fma_rn(t2, (double)n2, s_tn)));
+      s_n2 = __fma_rn((double)n0, (double)n0, __fma_rn((double)n1, (double)n1, __fma_rn((double)n2, (double)n2, s_n2)));
     }
   }
-  for (int o = 16; o; o >>= 1) { st_tot += __shfl_down_sync(FULL, st_tot, o); st_res += __shfl_down_sync(FULL, st_res, o); }
+  for (int o = 16; o; o >>= 1) {
+    s_t2 += __shfl_down_sync(FULL, s_t2, o); s_tn += __shfl_down_sync(FULL, s_tn, o); s_n2 += __shfl_down_sync(FULL, s_n2, o);
+  }
+  const double st_res = s_t2 / (S * S), st_tot = st_res + 2.0 * s_tn / S + s_n2;
   if (lane == 0) {
     stat_partial[2 * ((long long)blockIdx.x * PW_W + warp)] = st_tot;
     stat_partial[2 * ((long long)blockIdx.x * PW_W + warp) + 1] = st_res;
@@ -789,12 +943,13 @@ __global__ void __launch_bounds__(PW_T, 1) k_drift_place_w(Geom g, VTab vt, doub
 }
 
 // pass C for the ghost particles that enter this image
+template <class F>
 __global__ void __launch_bounds__(PC_T) k_drift_place_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
-                                                       long long base, const short* __restrict__ xp, const short* __restrict__ vp,
+                                                       long long base, const typename F::XT* __restrict__ xp, const typename F::VT* __restrict__ vp,
                                                        const unsigned* __restrict__ rank, const float* __restrict__ vfield_e,
                                                        const long long* __restrict__ cstart_new, const float* __restrict__ vfield_new,
                                                        const double* __restrict__ dvlut, const double* __restrict__ enc, double dt_mid, double S,
-                                                       short* __restrict__ xp_new, short* __restrict__ vp_new, double* __restrict__ stat_partial) {
+                                                       typename F::XT* __restrict__ xp_new, typename F::VT* __restrict__ vp_new, double* __restrict__ stat_partial) {
   __shared__ int soff[PC_CELLS + 1];
   const long long c0 = (long long)blockIdx.x * PC_CELLS;
   const int np = chunk_setup(gstart, c0, ng, soff);
@@ -810,7 +965,7 @@ __global__ void __launch_bounds__(PC_T) k_drift_place_g(Geom g, long long ng, co
               Z = (int)(e / ((long long)g.ne * g.ne)) - NCB + (int)((o >> 8) & 15u) - 8;
     if ((unsigned)X >= (unsigned)g.nc || (unsigned)Y >= (unsigned)g.nc || (unsigned)Z >= (unsigned)g.nc) continue;  // cannot happen for an accepted particle
     const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
-    drift_move(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_e + 3 * e, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
+    drift_move<F>(p, cstart_new[D] + (rk & ((1u << RANK_BITS) - 1)), xp, vp, vfield_e + 3 * e, vfield_new + 3 * D, dvlut, enc, dt_mid, S, xp_new,
                vp_new, st_tot, st_res);
   }
   block_sum2(st_tot, st_res, stat_partial + 2 * (long long)blockIdx.x);

@@ -128,15 +128,24 @@ def image_grid(n: int):
     return grids[n]
 
 
-def host_tanf_lut() -> np.ndarray:
-    """``tan((pi*real(v))/real(nvbin-1))`` for all 65536 codes with the *host's* libm ``tanf``
-    (what the Fortran host passes to ``cube_gpu_init``).  Uses libm through ctypes, not the oracle."""
+def host_tanf_lut(izipv: int = 2) -> np.ndarray:
+    """``tan((pi*real(v))/real(nvbin-1))`` for all ``nvbin = 2**(8*izipv)`` codes (indexed by the raw pattern) with the
+    *host's* libm ``tanf`` (what the Fortran host passes to ``cube_gpu_init``).  Uses libm through ctypes, not the oracle."""
     libm = C.CDLL("libm.so.6")
     libm.tanf.restype = C.c_float
     libm.tanf.argtypes = [C.c_float]
-    codes = np.arange(65536, dtype=np.uint16).view(np.int16).astype(F32)
-    arg = (PI_F * codes) / F32(65535.0)
+    nvbin = 1 << (8 * izipv)
+    if izipv == 2:
+        codes = np.arange(nvbin, dtype=np.uint16).view(np.int16).astype(F32)
+    else:
+        codes = np.arange(nvbin, dtype=np.uint8).view(np.int8).astype(F32)
+    arg = (PI_F * codes) / F32(nvbin - 1)
     return np.array([libm.tanf(float(a)) for a in arg], dtype=F32)
+
+
+def code_dtypes(izipx: int, izipv: int):
+    """numpy dtypes of xp and vp (integer(izipx), integer(izipv): CUBE/main/variables.f90:41-42)."""
+    return (np.int8, np.int16)[izipx - 1], (np.int8, np.int16)[izipv - 1]
 
 
 def _p(a):
@@ -147,7 +156,7 @@ class CubeGPU:
     """One image of a CUBE run on one B200.  Mirrors the step subroutines of CUBE/main."""
 
     def __init__(self, nc, nnt, fk_table, ck_table, nn=(1, 1, 1), rank=0, np_nc=2, image_buffer=1.5, tile_buffer=2.5,
-                 device=0, fine_batch=0, tanf_lut=None, nccl_id=None, local_group=0):
+                 device=0, fine_batch=0, tanf_lut=None, nccl_id=None, local_group=0, izipx=2, izipv=2):
         """``nn``: image grid; ``rank``: this image (0-based, x fastest).  More than one image needs either ``nccl_id``
         (one process per GPU; the 128 bytes of :func:`nccl_unique_id` broadcast from image 1) or ``local_group`` > 0
         (every image is a host thread of this process, e.g. several images per GPU)."""
@@ -157,7 +166,9 @@ class CubeGPU:
         p = CubeParams()
         p.nn[:] = nn
         p.rank, p.nnt, p.nc, p.ncell, p.ncb = rank, nnt, nc, 4, 6
-        p.izipx = p.izipv = 2
+        p.izipx, p.izipv = int(izipx), int(izipv)    # the run's zip format (CUBE/main/universe*.fh:2-3)
+        self.izipx, self.izipv = int(izipx), int(izipv)
+        self.xdt, self.vdt = code_dtypes(self.izipx, self.izipv) if izipx in (1, 2) and izipv in (1, 2) else (np.int16, np.int16)
         p.np_nc, p.image_buffer, p.tile_buffer, p.device, p.fine_batch = np_nc, image_buffer, tile_buffer, device, fine_batch
         p.local_group = int(local_group)
         self.params = p
@@ -167,8 +178,8 @@ class CubeGPU:
         # reference layouts: fk_table(16,16,16,3) [dim slowest], ck_table(3,4,4,4) [dim fastest]
         fk = np.ascontiguousarray(np.moveaxis(np.asarray(fk_table, F32), 3, 0))  # fixture is [k][j][i][dim]
         ck = np.ascontiguousarray(np.asarray(ck_table, F32))
-        lut = np.ascontiguousarray(host_tanf_lut() if tanf_lut is None else tanf_lut, F32)
-        assert lut.shape == (65536,)
+        lut = np.ascontiguousarray(host_tanf_lut(p.izipv if p.izipv in (1, 2) else 2) if tanf_lut is None else tanf_lut, F32)
+        assert p.izipv not in (1, 2) or lut.shape == (1 << (8 * p.izipv),)
         h = C.c_void_p()
         self.h = None
         idbuf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
@@ -204,11 +215,11 @@ class CubeGPU:
 
     # ---- particle_initialization / checkpoint ------------------------------------------------
     def particle_initialization(self, state, sigma_vi, npglobal=None):
-        if np.asarray(state["xp"]).dtype != np.int16 or np.asarray(state["vp"]).dtype != np.int16:
-            # particle_initialization.f90:14-18; the library is built for izipx=izipv=2 (cube_gpu_init rejects the rest)
-            raise RuntimeError("zip format incompatable: libcubegpu.so takes 2-byte xp/vp (izipx=izipv=2), got %s/%s"
-                               % (np.asarray(state["xp"]).dtype, np.asarray(state["vp"]).dtype))
-        xp = np.ascontiguousarray(state["xp"], np.int16); vp = np.ascontiguousarray(state["vp"], np.int16)
+        if np.asarray(state["xp"]).dtype != self.xdt or np.asarray(state["vp"]).dtype != self.vdt:
+            # particle_initialization.f90:14-18: a run built for (izipx, izipv) stops on a state in another format
+            raise RuntimeError("zip format incompatable: this run has izipx=%d izipv=%d, the state holds %s/%s"
+                               % (self.izipx, self.izipv, np.asarray(state["xp"]).dtype, np.asarray(state["vp"]).dtype))
+        xp = np.ascontiguousarray(state["xp"], self.xdt); vp = np.ascontiguousarray(state["vp"], self.vdt)
         rc = np.ascontiguousarray(state["rhoc"], np.int32); vf = np.ascontiguousarray(state["vfield"], np.float32)
         n = xp.shape[0]
         self._ck(self.L.cube_gpu_upload(self.h, _p(xp), _p(vp), _p(rc), _p(vf), n, npglobal or n, F32(sigma_vi)))
@@ -227,9 +238,9 @@ class CubeGPU:
         n = self.query("nplocal")
         shp = (self.nnt,) * 3 + (self.nt,) * 3
         if out is None:
-            out = dict(xp=np.empty((n, 3), np.int16), vp=np.empty((n, 3), np.int16), rhoc=np.empty(shp, np.int32),
+            out = dict(xp=np.empty((n, 3), self.xdt), vp=np.empty((n, 3), self.vdt), rhoc=np.empty(shp, np.int32),
                        vfield=np.empty(shp + (3,), np.float32))
-        assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n
+        assert out["xp"].shape[0] >= n and out["vp"].shape[0] >= n and out["xp"].dtype == self.xdt and out["vp"].dtype == self.vdt
         npl = C.c_int64(); sig = C.c_float()
         self._ck(self.L.cube_gpu_download(self.h, None if "xp" in skip else _p(out["xp"]), None if "vp" in skip else _p(out["vp"]),
                                           None if "rhoc" in skip else _p(out["rhoc"]), None if "vfield" in skip else _p(out["vfield"]),

@@ -11,7 +11,8 @@
  *  - plain pointers and sizes only; all arrays are host memory owned by the caller and touched
  *    only inside the call; the authoritative state lives in HBM between upload and download.
  *  - arrays use the reference's own memory layout (Fortran column-major, first index fastest):
- *      xp, vp            integer(2)  (3, nplocal)                          variables.f90:41-42
+ *      xp                integer(izipx) (3, nplocal)   izipx, izipv = 1 or 2 bytes per code, the run's zip format
+ *      vp                integer(izipv) (3, nplocal)   (CUBE/main/universe*.fh:2-3, variables.f90:41-42, parameters.f90:13-15)
  *      rhoc_phys         integer(4)  (nt,nt,nt,nnt,nnt,nnt)   = rhoc(1:nt,1:nt,1:nt,:,:,:)   checkpoint.f90:35
  *      vfield_phys       real(4)     (3,nt,nt,nt,nnt,nnt,nnt) = vfield(:,1:nt,1:nt,1:nt,:,:,:) checkpoint.f90:40
  *    i.e. exactly what the reference writes to zip0/zip1/zip2/vfield ("disjoint state").
@@ -38,7 +39,7 @@ typedef struct cube_params {
   int32_t nc;           /* coarse cells / image / dim                  parameters.f90:23           */
   int32_t ncell;        /* fine cells per coarse cell / dim (must be 4) parameters.f90:21           */
   int32_t ncb;          /* buffer depth in coarse cells (must be 6)    parameters.f90:46           */
-  int32_t izipx, izipv; /* bytes per position / velocity code (must be 2,2)  universe*.fh          */
+  int32_t izipx, izipv; /* bytes per position / velocity code, each 1 or 2   universe*.fh:2-3      */
   int32_t np_nc;        /* particles / coarse cell / dim (capacity sizing) parameters.f90:55       */
   float image_buffer;   /* parameters.f90:59 */
   float tile_buffer;    /* parameters.f90:60 */
@@ -54,9 +55,10 @@ typedef struct cube_handle cube_handle;
 /* initialize.f90:1-56: geometry, FFT plans, kernel_f (kernel_f.f90), kernel_c (kernel_c.f90).
  *   fk_table  real(4) (16,16,16,3)  = fk_table(i,j,k,dim) as read from ../kernels/wfxyzf.3.ascii
  *   ck_table  real(4) (3,4,4,4)     = ck_table(dim,i,j,k) as read from ../kernels/wfxyzc.2.ascii
- *   tanf_lut  real(4) (0:65535)     tan((pi*real(v))/real(nvbin-1)) evaluated BY THE HOST's libm for
- *                                   v = int(u,2) (u = raw 16-bit pattern) -- makes velocity decoding
- *                                   bit-identical to the host build (pm.f90:102, update_particle.f90:42)
+ *   tanf_lut  real(4) (0:nvbin-1)   tan((pi*real(v))/real(nvbin-1)) evaluated BY THE HOST's libm for
+ *                                   v = int(u,izipv) (u = raw pattern of the code, nvbin = 2**(8*izipv):
+ *                                   65536 or 256 entries) -- makes velocity decoding bit-identical to
+ *                                   the host build (pm.f90:102, update_particle.f90:42)
  *   nccl_unique_id  NULL for a single image; otherwise the 128-byte ncclUniqueId shared by all images. */
 int cube_gpu_init(const cube_params *p, const float *fk_table, const float *ck_table, const float *tanf_lut,
                   const void *nccl_unique_id, cube_handle **h);
@@ -68,7 +70,7 @@ int cube_gpu_init(const cube_params *p, const float *fk_table, const float *ck_t
 int cube_gpu_nccl_unique_id(void *id128);
 
 /* particle_initialization.f90:11-72: take the disjoint state (file order). mass_p = nf_global^3/npglobal. */
-int cube_gpu_upload(cube_handle *h, const int16_t *xp, const int16_t *vp, const int32_t *rhoc_phys,
+int cube_gpu_upload(cube_handle *h, const void *xp, const void *vp, const int32_t *rhoc_phys,
                     const float *vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi);
 
 /* update_particle (update_particle.f90:1-213): drift + cell re-sort + vfield rebuild + sigma statistics.
@@ -86,7 +88,7 @@ int cube_gpu_particle_mesh(cube_handle *h, float a_mid, float dt, float *dt_fine
 
 /* checkpoint.f90:33-70: bring the disjoint state back.  Pass NULL for anything not wanted.
  * Capacity of xp/vp must be >= nplocal as returned by the last update_x/upload. */
-int cube_gpu_download(cube_handle *h, int16_t *xp, int16_t *vp, int32_t *rhoc_phys, float *vfield_phys,
+int cube_gpu_download(cube_handle *h, void *xp, void *vp, int32_t *rhoc_phys, float *vfield_phys,
                       int64_t *nplocal, float *sigma_vi);
 
 /* -DPID (CUBE/main variables.f90:44, particle_initialization.f90:56-59; on by default in CUBEnu's Makefile): optional particle
@@ -101,7 +103,7 @@ int cube_gpu_download_pid(cube_handle *h, int64_t *pid);
  * work already queued and return at once; cube_gpu_download (with NULL for what was streamed) waits for it.  Host buffers
  * should be page-locked.  Typical use: xp right after cube_gpu_update_x -- particle_mesh does not move particles, so the
  * position traffic of checkpoint.f90:43-50 overlaps the force computation. */
-int cube_gpu_download_async(cube_handle *h, int16_t *xp, int16_t *vp);
+int cube_gpu_download_async(cube_handle *h, void *xp, void *vp);
 /* The same for the per-cell arrays rhoc(nt,nt,nt,nnt,nnt,nnt) and vfield(3,...) of checkpoint.f90:35,40: they are final once
  * cube_gpu_update_x has returned (particle_mesh changes neither), so they too can leave under the force computation.
  * cube_gpu_download with NULL for them waits for the stream. */
@@ -111,7 +113,7 @@ int cube_gpu_download_cells_async(cube_handle *h, int32_t *rhoc_phys, float *vfi
  * positions and is ready by then; per particle the two kicks are the same operations in the same order as pm.f90:88-228) and
  * streams the batch's final velocities into vp while the next batch's force is computed -- the velocity half of
  * checkpoint.f90:51-58 leaves under the computation.  cube_gpu_download with NULL for vp waits for the stream. */
-int cube_gpu_stream_vp(cube_handle *h, int16_t *vp);
+int cube_gpu_stream_vp(cube_handle *h, void *vp);
 
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);

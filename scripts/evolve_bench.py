@@ -109,7 +109,7 @@ def main():
                 G.phase_times()    # discard the first (warm-up) step
         ph = {k: v / 2 for k, v in G.phase_times().items() if v > 0}
         print(json.dumps(dict(sweep=setting, ms_per_step=sum(ph.values()),
-                              phases_ms={k: round(ph[k], 3) for k in ("drift_count", "fine_deposit", "coarse_deposit", "drift_place", "coarse_kick") if k in ph})), flush=True)
+                              phases_ms={k: round(v, 3) for k, v in ph.items()})), flush=True)
         G.close()
 
 

@@ -65,7 +65,7 @@ def test_init_rejects_bad_configuration(tables):
     L = cube.load_library()
     p = cube.CubeParams()
     p.nn[:] = (1, 1, 1)
-    p.nnt, p.nc, p.ncell, p.ncb, p.izipx, p.izipv, p.np_nc = 2, 24, 4, 6, 1, 2, 2
+    p.nnt, p.nc, p.ncell, p.ncb, p.izipx, p.izipv, p.np_nc = 2, 24, 4, 6, 4, 2, 2   # izipx = 4 does not exist (universe*.fh: 1 or 2)
     fk, ck = tables
     lut = np.zeros(65536, np.float32)
     h = C.c_void_p()
