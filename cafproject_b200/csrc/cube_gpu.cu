@@ -1391,6 +1391,73 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// cicpower + powerspectrum (CUBE/utilities/cicpower.f90:70-167, powerspectrum.f90:21-108, linear_kbin) of the resident state, with
+// the library's own deposit kernel (cell-centred variant) and cuFFT.  xi(10,nbin) row-major like the reference's xi(10,nbin):
+// rows 0 count, 1 k [h/Mpc], 2 = 3 = 4 Delta^2 (auto power), 5-6 kernels, 7 r = 1, 8 b = 1, 9 = row 2.  Single image.
+extern "C" int cube_gpu_power_spectrum(cube_handle* h, float box, double* xi, int nbin_cap, int* nbin_out) {
+  if (!h || !xi) return fail("null argument");
+  CK(cudaSetDevice(h->p.device));
+  if (!h->buffered) return fail("cube_gpu_power_spectrum: state is not buffered (call cube_gpu_buffer first)");
+  if (h->nimg > 1) return fail("cube_gpu_power_spectrum: single image (a distributed transform of the global fine grid is not built)");
+  const Geom& g = h->g;
+  const int n = NCELL * g.nc, m = n + 4;  // ng = nf (cicpower.f90: ng=nf); deposit grid with the one-node frame shift
+  const int nbin = (int)lround((double)(n / 2) * sqrt(3.0));
+  if (nbin_out) *nbin_out = nbin;
+  if (nbin_cap < nbin) return fail("cube_gpu_power_spectrum: xi holds %d bins, %d needed", nbin_cap, nbin);
+  const long long tot = (long long)n * n * n, vol = (long long)n * n * (n + 2);
+  float *dep = nullptr, *rho = nullptr; double *part = nullptr, *bins = nullptr;
+  const unsigned nb = nblk(tot, 256);
+  CK(dmalloc(&dep, (long long)m * m * m)); CK(dmalloc(&rho, vol)); CK(dmalloc(&part, (long long)nb + 1)); CK(dmalloc(&bins, PS_Q * nbin));
+  int rc = 0;
+  cufftHandle pl = 0;
+  do {
+    FineRegion R;
+    for (int d = 0; d < 3; d++) { R.c0[d] = -1; R.c1[d] = g.nc + 1; R.f0[d] = 0; R.n[d] = m; }
+    R.ldy = m; R.ldz = (long long)m * m;
+    {  // cell-centred CIC of all particles (ghost cells alias the periodic image: the wrap of cicpower.f90:118-126 comes for free)
+      using C = Fd844;
+      const unsigned nbx = (m + C::NX - 1) / C::NX, nby = (m + C::NY - 1) / C::NY, nbz = (m + C::NZ - 1) / C::NZ;
+      if (h->zx == 2) {
+        if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
+        k_fine_deposit_r<C, false, short, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
+      } else {
+        if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, signed char, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
+        k_fine_deposit_r<C, false, signed char, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
+      }
+    }
+    k_ps_extract<<<nb, 256, 0, h->st>>>(n, dep, rho, part);
+    k_reduce_strided<<<1, 1024, 0, h->st>>>(part, nb, 1, 0, part + nb);
+    k_ps_contrast<<<nb, 256, 0, h->st>>>(n, rho, part + nb);
+    if (cudaGetLastError() != cudaSuccess) { rc = fail("power spectrum: kernel launch failed"); break; }
+    int dims[3] = {n, n, n}, rembed[3] = {n, n, n + 2}, cembed[3] = {n, n, n / 2 + 1};
+    if (cufftPlanMany(&pl, 3, dims, rembed, 1, 0, cembed, 1, 0, CUFFT_R2C, 1) != CUFFT_SUCCESS || cufftSetStream(pl, h->st) != CUFFT_SUCCESS ||
+        cufftExecR2C(pl, rho, (cufftComplex*)rho) != CUFFT_SUCCESS) { rc = fail("power spectrum: cuFFT failed (n=%d)", n); break; }
+    if (cudaMemsetAsync(bins, 0, sizeof(double) * PS_Q * nbin, h->st) != cudaSuccess) { rc = fail("power spectrum: memset"); break; }
+    const size_t smem = sizeof(double) * PS_Q * nbin;
+    if (cudaFuncSetAttribute((const void*)k_ps_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { rc = fail("power spectrum: %d bins do not fit shared memory", nbin); break; }
+    k_ps_bin<<<2 * h->nsm, 256, smem, h->st>>>(n, nbin, (const float2*)rho, bins);
+    std::vector<double> b(PS_Q * (size_t)nbin);
+    if (cudaMemcpyAsync(b.data(), bins, sizeof(double) * b.size(), cudaMemcpyDeviceToHost, h->st) != cudaSuccess || cudaStreamSynchronize(h->st) != cudaSuccess) {
+      rc = fail("power spectrum: %s", cudaGetErrorString(cudaGetLastError())); break;
+    }
+    h->launches += 5;
+    for (int i = 0; i < nbin; i++) {  // powerspectrum.f90:98-106
+      const double cnt = b[i];
+      double* col = xi + i;
+      col[0] = cnt;
+      col[1 * nbin] = b[nbin + i] / cnt * (2.0 * (double)PI_F) / (double)box;
+      const double p11 = b[2 * nbin + i] / cnt;
+      col[2 * nbin] = col[3 * nbin] = col[4 * nbin] = p11;
+      col[5 * nbin] = b[3 * nbin + i] / cnt; col[6 * nbin] = b[4 * nbin + i] / cnt;
+      col[7 * nbin] = p11 / sqrt(p11 * p11); col[8 * nbin] = sqrt(p11 / p11); col[9 * nbin] = p11;
+    }
+  } while (0);
+  if (pl) cufftDestroy(pl);
+  cudaFree(dep); cudaFree(rho); cudaFree(part); cudaFree(bins);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // diagnostics
 extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   if (!h || !what) return -1;

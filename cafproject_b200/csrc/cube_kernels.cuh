@@ -216,9 +216,11 @@ struct FdCfg {
 };
 
 // lower node (image-local fine index) and the two weights of one coordinate
-template <int XB> __device__ __forceinline__ void fine_cic(int cell, short xp, int frame0, int& L, float& w0, float& w1) {
+// HALF: the cell-centred assignment of the power-spectrum estimator (cicpower.f90:84-90: pos*ng/nc - 0.5), in a node frame shifted by
+// one so that a cell still only reaches its own nodes and the next cell's: returned L = (true lower node) + 1 = 4 cell + ((u + 2^(XB-3)) >> (XB-2))
+template <int XB, bool HALF = false> __device__ __forceinline__ void fine_cic(int cell, short xp, int frame0, int& L, float& w0, float& w1) {
   if (frame0 == FRAME_NONE) {
-    const unsigned u = upat<XB>(xp);
+    const unsigned u = upat<XB>(xp) + (HALF ? (1u << (XB - 3)) : 0u);
     L = 4 * cell + (int)(u >> (XB - 2));
     w1 = __int2float_rn(2 * (int)(u & ((1u << (XB - 2)) - 1u)) + 1) * (1.0f / (float)(1 << (XB - 1)));
     w0 = 1.0f - w1;  // exact
@@ -229,7 +231,7 @@ template <int XB> __device__ __forceinline__ void fine_cic(int cell, short xp, i
   }
 }
 
-template <class C, bool FRAME, class XT>
+template <class C, bool FRAME, class XT, bool HALF = false>
 __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const XT* __restrict__ xp,
                                                           const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
                                                           float mass_p, float* __restrict__ out) {
@@ -303,12 +305,14 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
     const int sx = c % C::SX, sy = (c / C::SX) % C::SY, sz = c / (C::SX * C::SY);
     int lx, ly, lz; float ax[2], ay[2], az[2];
     constexpr int XB = 8 * (int)sizeof(XT);
-    fine_cic<XB>(cbx - 1 + sx, cur.x, FRAME ? frame0.x : FRAME_NONE, lx, ax[0], ax[1]);
-    fine_cic<XB>(cby - 1 + sy, cur.y, FRAME ? frame0.y : FRAME_NONE, ly, ay[0], ay[1]);
-    fine_cic<XB>(cbz - 1 + sz, cur.z, FRAME ? frame0.z : FRAME_NONE, lz, az[0], az[1]);
+    fine_cic<XB, HALF>(cbx - 1 + sx, cur.x, FRAME ? frame0.x : FRAME_NONE, lx, ax[0], ax[1]);
+    fine_cic<XB, HALF>(cby - 1 + sy, cur.y, FRAME ? frame0.y : FRAME_NONE, ly, ay[0], ay[1]);
+    fine_cic<XB, HALF>(cbz - 1 + sz, cur.z, FRAME ? frame0.z : FRAME_NONE, lz, az[0], az[1]);
     lx -= N0x; ly -= N0y; lz -= N0z;  // brick-local lower node, -4 .. 4B-1 (the upper node is the next one)
     if (lx < -1 || ly < -1 || lz < -1) continue;  // low-side layer: only particles next to the brick reach into it
-    const bool vx[2] = {lx >= 0, lx + 1 < C::NX}, vy[2] = {ly >= 0, ly + 1 < C::NY}, vz[2] = {lz >= 0, lz + 1 < C::NZ};
+    const bool vx[2] = {(unsigned)lx < (unsigned)C::NX, (unsigned)(lx + 1) < (unsigned)C::NX};
+    const bool vy[2] = {(unsigned)ly < (unsigned)C::NY, (unsigned)(ly + 1) < (unsigned)C::NY};
+    const bool vz[2] = {(unsigned)lz < (unsigned)C::NZ, (unsigned)(lz + 1) < (unsigned)C::NZ};
     unsigned* a0 = acc + lz * C::PZ + ly * C::PY + lx;
 #pragma unroll
     for (int qq = 0; qq < 8; qq++) {
@@ -513,6 +517,69 @@ __global__ void __launch_bounds__(256) k_f2max_aos(long long n, const float* __r
   }
   best = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best)));
   if ((threadIdx.x & 31) == 0) atomicMax(f2max, __float_as_uint(best));
+}
+
+// =============================================================================================
+// matter power spectrum of the resident state (CUBE/utilities/cicpower.f90:70-140, powerspectrum.f90:47-108, linear_kbin)
+// =============================================================================================
+// density on the (n+4)^3 deposit grid (element e = true node e-1; k_fine_deposit_r<.., HALF>) -> rho(n,n,n) in the in-place r2c
+// layout [n][n][n+2]; one partial sum per block, fixed order
+__global__ void __launch_bounds__(256) k_ps_extract(int n, const float* __restrict__ dep, float* __restrict__ rho, double* __restrict__ part) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tot = (long long)n * n * n;
+  const int m = n + 4;
+  double v = 0;
+  if (q < tot) {
+    const int x = (int)(q % n), y = (int)((q / n) % n), z = (int)(q / ((long long)n * n));
+    const float f = dep[((long long)(z + 1) * m + (y + 1)) * m + (x + 1)];
+    rho[((long long)z * n + y) * (n + 2) + x] = f;
+    v = (double)f;
+  }
+  __shared__ double sm[8];
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; w++) t += sm[w]; part[blockIdx.x] = t; }
+}
+// rho1=rho1/(rho8/ng_global^3)-1 (cicpower.f90:134)
+__global__ void __launch_bounds__(256) k_ps_contrast(int n, float* __restrict__ rho, const double* __restrict__ sum) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)n * n * n) return;
+  const int x = (int)(q % n);
+  const long long r = q / n;
+  const float mean = (float)(*sum / (double)n / (double)n / (double)n);
+  float* p = rho + r * (n + 2) + x;
+  *p = *p / mean - 1.0f;
+}
+// shell sums of powerspectrum.f90:47-86 (linear_kbin: ibin = nint(kr)) for the auto power of c = FFT(delta): per bin count, sum kr,
+// sum |c|^2 4 pi kr^3 / n^6 / sinc^4, sum 1/sinc^2, sum 1/sinc^4.  Accumulated in f64 (shared-memory bins per CTA, then global).
+constexpr int PS_Q = 5;
+__global__ void __launch_bounds__(256) k_ps_bin(int n, int nbin, const float2* __restrict__ c, double* __restrict__ bins /*[PS_Q][nbin]*/) {
+  extern __shared__ double sb[];  // [PS_Q][nbin]
+  for (int t = threadIdx.x; t < PS_Q * nbin; t += blockDim.x) sb[t] = 0.0;
+  __syncthreads();
+  const int nyq = n / 2, nh = nyq + 1;
+  const long long tot = (long long)n * n * nh;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    const int ig = (int)(q % nh), jg = (int)((q / nh) % n), kg = (int)(q / ((long long)nh * n));  // 0-based
+    if (ig == 0 && jg == 0 && kg == 0) continue;                                   // zero frequency
+    const bool edge = ig == 0 || ig == nyq;
+    if (edge && jg > nyq) continue;                                                // :57
+    if (edge && (jg == 0 || jg == nyq) && kg > nyq) continue;                      // :58
+    const float kx = (float)ig, ky = (float)((jg + nyq) % n - nyq), kz = (float)((kg + nyq) % n - nyq);
+    const float kr = sqrtf(kx * kx + ky * ky + kz * kz);
+    const float ax = PI_F * kx / (float)n, ay = PI_F * ky / (float)n, az = PI_F * kz / (float)n;
+    const float sinc = (kx == 0.f ? 1.f : sinf(ax) / ax) * (ky == 0.f ? 1.f : sinf(ay) / ay) * (kz == 0.f ? 1.f : sinf(az) / az);
+    const int ibin = (int)lrintf(kr);  // kr^2 is an integer: never a tie
+    if (ibin < 1 || ibin > nbin) continue;
+    const float2 v = c[q];
+    const double n3 = (double)n * n * n, s2 = (double)sinc * sinc, s4 = s2 * s2;
+    const double amp = ((double)v.x * v.x + (double)v.y * v.y) / n3 / n3 / s4 * 4.0 * (double)PI_F * (double)kr * kr * kr;
+    double* b = sb + (ibin - 1);
+    atomicAdd(b, 1.0); atomicAdd(b + nbin, (double)kr); atomicAdd(b + 2 * nbin, amp); atomicAdd(b + 3 * nbin, 1.0 / s2); atomicAdd(b + 4 * nbin, 1.0 / s4);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < PS_Q * nbin; t += blockDim.x) if (sb[t] != 0.0) atomicAdd(bins + t, sb[t]);
 }
 
 // =============================================================================================

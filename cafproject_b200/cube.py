@@ -78,6 +78,7 @@ def load_library():
     L.cube_gpu_nccl_unique_id.argtypes = [vp]
     L.cube_gpu_exchange_plan.argtypes = [C.POINTER(CubeParams), vp, i32]
     L.cube_gpu_selftest_codes.argtypes = [vp, f32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.cube_gpu_power_spectrum.argtypes = [vp, f32, vp, i32, C.POINTER(i32)]
     _lib = L
     return L
 
@@ -90,7 +91,7 @@ ABI_SYMBOLS = [
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
     "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
-    "cube_gpu_upload_pid", "cube_gpu_download_pid",
+    "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum",
 ]
 
 
@@ -344,6 +345,16 @@ class CubeGPU:
         f = np.ascontiguousarray(force_c, F32); vm = C.c_float(); f2 = C.c_float()
         self._ck(self.L.cube_gpu_coarse_kick_with(self.h, _p(f), F32(a_mid), F32(dt), F32(sigma_vi), C.byref(vm), C.byref(f2)))
         return F32(vm.value), F32(f2.value)
+
+    def power_spectrum(self, box=200.0):
+        """``xi(10, nbin)`` of CUBE/utilities/powerspectrum.f90 (linear_kbin) for the density contrast of the resident state
+        (cicpower.f90), computed on the device by the library's own kernels; needs the buffered state, single image."""
+        nbin = int(round((4 * self.nc // 2) * np.sqrt(3.0)))
+        xi = np.zeros((10, nbin), np.float64)
+        nb = C.c_int(0)
+        self._ck(self.L.cube_gpu_power_spectrum(self.h, F32(box), _p(xi), nbin, C.byref(nb)))
+        assert nb.value == nbin
+        return xi
 
     def timer_start(self):
         self._ck(self.L.cube_gpu_timer(self.h, 1, None))

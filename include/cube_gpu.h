@@ -118,6 +118,13 @@ int cube_gpu_stream_vp(cube_handle *h, void *vp);
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);
 
+/* cicpower + powerspectrum (CUBE/utilities/cicpower.f90:70-167, powerspectrum.f90:21-108 with linear_kbin) of the state resident
+ * on the device -- the z = 0 P(k) gate without bringing the particles back: cell-centred CIC on ng = nf = 4*nc nodes with the
+ * library's own deposit kernel, density contrast, r2c (cuFFT), shell sums.  xi = the reference's xi(10,nbin), stored row by row
+ * (xi[r*nbin + i]): r = 0 mode count, 1 k [h/Mpc], 2 (= 3 = 4) Delta^2(k), 5, 6 the sinc kernels, 7 r, 8 b, 9 reconstructed power;
+ * nbin = nint(nyquist*sqrt(3)) is returned in *nbin (call with nbin_cap = 0 to ask).  Needs the buffered state; single image. */
+int cube_gpu_power_spectrum(cube_handle *h, float box, double *xi, int nbin_cap, int *nbin);
+
 /* ---- diagnostics used by the parity tests and the benchmark (not part of the step loop) -------- */
 
 /* derived sizes: what[] = "np_image_max","np_tile_max","nfe","nft","nt","fine_batch","kernel_launches" */

@@ -39,7 +39,7 @@ def test_power_spectrum_z0(tables):
     G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
     got = {}
     ts = TimeStepper(Cosmology(), [0.0])
-    nstep = cafcube(G, ts, on_checkpoint=lambda z, st, s: got.update(z=z, state=st))
+    nstep = cafcube(G, ts, on_checkpoint=lambda z, st, s: got.update(z=z, state=st, sig=s))
     assert got["z"] == 0.0 and nstep > 20
     assert got["state"]["xp"].shape[0] == info["npglobal"] == final_o[0]["xp"].shape[0]
     d_o = cic_delta(final_o, 1, nc, nnt)
@@ -55,4 +55,37 @@ def test_power_spectrum_z0(tables):
     assert (growth[2][low] / growth[3][low]).min() > 100.0
     assert np.abs(ratio - 1).max() < 1e-3, (np.abs(ratio - 1).max(), ratio)
     assert xi[7][low].min() > 0.99, xi[7][low]            # and the two fields are the same field, not just the same spectrum
+    # the same gate with the spectrum of the GPU side taken ON the device by the library's own estimator (cube_gpu_power_spectrum)
+    G.particle_initialization(got["state"], got["sig"])
+    G.buffer_density(); G.buffer_x(); G.buffer_v()
+    xg = G.power_spectrum(200.0)
+    assert np.abs(xg[2][low] / xi[3][low] - 1).max() < 1e-3
     G.close(); O.close()
+
+
+def test_device_power_spectrum_equals_the_host_estimator(tables):
+    """cube_gpu_power_spectrum (own cell-centred CIC deposit in fixed point, cuFFT, f32 shell arithmetic like
+    powerspectrum.f90) against the NumPy restatement of cicpower.f90 + powerspectrum.f90 (f64) on the same state: every
+    populated shell, count and k exactly, Delta^2 and the sinc kernels to f32 round-off."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.power import cic_delta, cross_power
+    from cafproject_b200.synthetic_ic import make_clustered_ic, make_ic
+    fk, ck = tables
+    nc, nnt = 24, 2
+    for maker, kw in ((make_ic, dict(seed=7, disp_rms=0.9)), (make_clustered_ic, dict(seed=23, nblob=4, blob_sigma=0.6))):
+        states, sig, _ = maker(nn=1, nc=nc, nnt=nnt, np_nc=2, **kw)
+        G = CubeGPU(nc, nnt, fk, ck, np_nc=2)
+        try:
+            G.particle_initialization(states[0], sig)
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+            xg = G.power_spectrum(200.0)
+            assert np.array_equal(xg, G.power_spectrum(200.0)) or np.allclose(xg, G.power_spectrum(200.0), rtol=1e-12, equal_nan=True)
+        finally:
+            G.close()
+        d = cic_delta(states, 1, nc, nnt)
+        xh = cross_power(d, d, 200.0)
+        ok = xh[0] > 0
+        assert np.array_equal(xg[0], xh[0])
+        assert np.allclose(xg[1][ok], xh[1][ok], rtol=1e-6)
+        for r in (2, 5, 6):
+            assert np.allclose(xg[r][ok], xh[r][ok], rtol=2e-4), (r, np.abs(xg[r][ok] / xh[r][ok] - 1).max())
