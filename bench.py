@@ -165,18 +165,57 @@ def cpu_port_throughput(nt, steps=1, warmup=0, max_threads=32):
     return dict(value=value, unit=UNIT, cores=nth, kind="port", sample=sample, seconds=sec, ms_per_step=1e3 * sec / steps)
 
 
+def cpu_port_cfg1_image(steps=1):
+    """BASELINE.json configs[0] as CUBE/main runs it: ONE image (nc=128, nnt=2: 8 tiles of nt=64, 256^3 particles), its particle
+    loops serial (CUBE/main has no OpenMP; one coarray image = one core), the FFTs through pocketfft with every host core.  Phase
+    seconds at the boundaries CUBEnu prints (update_particle | buffers | particle_mesh)."""
+    from oracle import cube_oracle as co
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables()
+    os.environ.pop("CUBE_ORACLE_THREADS", None)
+    states, sig, _ = make_ic(nn=1, nc=128, nnt=2, np_nc=2, seed=1000)
+    npart = states[0]["xp"].shape[0]
+    O = co.Oracle(nn=1, nnt=2, nc=128, np_nc=2, fk_table=fk, ck_table=ck)
+    O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+    dt_old, dt, a_mid = np.float32(0.0), np.float32(1.0), np.float32(0.021)
+    ph = {"update_particle": 0.0, "buffer": 0.0, "particle_mesh": 0.0}
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter(); O.update_particle(dt_old, dt); t1 = time.perf_counter()
+        O.buffer_density(); O.buffer_x(); t2 = time.perf_counter()
+        O.particle_mesh(a_mid, dt); t3 = time.perf_counter()
+        O.buffer_v(); t4 = time.perf_counter()
+        ph["update_particle"] += t1 - t0; ph["buffer"] += (t2 - t1) + (t4 - t3); ph["particle_mesh"] += t3 - t2
+        dt_old = dt
+    sec = time.perf_counter() - t_all
+    O.close()
+    return dict(value=npart * steps / sec, unit=UNIT, cores=1, fft_workers=os.cpu_count() or 1, kind="port",
+                sample="%d step(s) of ONE cfg-1 image (nc=128 nnt=2 nt=64 nfe=304, %d particles), serial particle loops as in CUBE/main, "
+                       "pocketfft on all host cores" % (steps, npart),
+                seconds=sec, phase_seconds={k: v / steps for k, v in ph.items()})
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     nt = args.nc // args.nnt
     r = cpu_port_throughput(nt, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    cfg = workload_config(args, world)
+    # what this arm ran (the GPU arm's workload is named beside it: the metric is a throughput, comparable across the two)
+    cfg = dict(cfg, workload="CPU port, the reference's deployment of one coarray image per core: " + r["sample"]
+               + "; GPU arm's workload: " + cfg["workload"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 mesh / f64 particle update / int16 codes", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "restated CPU path (C + pocketfft port of CUBE/main), not the coarray-Fortran binary: no Fortran compiler exists here"}
+    if not args.no_cfg1:
+        try:   # BASELINE.md sec. 3: config 1 as one image, with phase timers and the core count
+            line["cfg1_single_image"] = cpu_port_cfg1_image(1)
+        except Exception as e:   # never lose the arm's line over the extra sample
+            line["cfg1_single_image"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -210,6 +249,8 @@ def main():
     ap.add_argument("--fine-batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the one-step sample of a whole cfg-1 image")
+    ap.add_argument("--no-late", action="store_true", help="skip the late-time leg (evolve the ICs to z=0 and time the clustered state)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -300,9 +341,10 @@ def main():
     nfine = ntile * nfe ** 3
     # compulsory bytes per step of each phase: every input read once, every output written once (DESIGN.md "roofline")
     N = G.query("nfft"); NH = N // 2 + 1; M = 4 * nt + 2
-    np_win = npart * (N / 4 / nt) ** 3          # particles inside the tiles' FFT windows (ghosts included)
-    alg = {"drift_key": 12 * npart, "drift_count": 6 * npart, "drift_place": 24 * npart, "drift_scan": 12 * nc ** 3,
-           "buffer": 32 * nc ** 3, "fine_deposit": 6 * np_win + 4 * ntile * N ** 3,
+    reg = (4 * nc + N - 4 * nt) ** 3 if batch == ntile else ntile * N ** 3   # nodes of the fine-density region(s) written per step
+    np_reg = npart * ((nc + 10) / nc) ** 3      # particles deposited once: the image plus five ghost cells each side
+    alg = {"drift_key": 18 * npart + 28 * nc ** 3, "drift_count": 8 * npart, "drift_place": 28 * npart, "drift_scan": 12 * nc ** 3,
+           "buffer": 32 * nc ** 3, "fine_deposit": 6 * np_reg + 4 * reg,
            "fine_fft_x": ntile * (4 * N ** 3 + 8 * N * N * NH), "fine_fft_y": ntile * 16 * N * N * NH,
            "fine_fft_z_green": ntile * (8 * N * N * NH + 24 * M * N * NH) + 12 * N * N * NH,
            "fine_ifft_y": ntile * 3 * (8 * M * N * NH + 8 * M * M * NH), "fine_ifft_x": ntile * 3 * (8 * M * M * NH + 4 * M ** 3),
@@ -368,6 +410,40 @@ def main():
     radius = G.query("drift_radius")
     G.close()
 
+    # ---- late-time (clustered) state: the same ICs evolved to z=0 by the product's own step loop, then timed ----------------
+    late = None
+    if world == 1 and not args.no_late:
+        from cafproject_b200.timestep import Cosmology, TimeStepper
+        G = CubeGPU(nc, nnt, fk, ck, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut())
+        G.particle_initialization(st, sig)
+        G.buffer_density(); G.buffer_x(); G.buffer_v()
+        ts = TimeStepper(Cosmology(), [0.0])
+        t0 = time.perf_counter()
+        nev = 0
+        while nev < 400 and time.perf_counter() - t0 < 120.0:
+            dto, dtn, am = ts.step()
+            G.update_particle(dto, dtn); G.buffer_density(); G.buffer_x()
+            ts.limits(G.particle_mesh(am, dtn)); G.buffer_v()
+            nev += 1
+            if ts.checkpoint_step:
+                break
+        dtl, aml = ts.dt, ts.a_mid
+        for _ in range(2):
+            G.update_particle(dtl, dtl); G.buffer_density(); G.buffer_x(); G.particle_mesh(aml, dtl); G.buffer_v()
+        torch.cuda.synchronize()
+        G.timer_start()
+        nl = 3
+        for _ in range(nl):
+            G.update_particle(dtl, dtl); G.buffer_density(); G.buffer_x(); G.particle_mesh(aml, dtl); G.buffer_v()
+        msl = G.timer_stop() / nl
+        G.set_profiling(True); G.phase_times()
+        G.update_particle(dtl, dtl); G.buffer_density(); G.buffer_x(); G.particle_mesh(aml, dtl); G.buffer_v()
+        phl = {k: v for k, v in G.phase_times().items() if v > 0}
+        late = {"z": 1.0 / float(ts.a) - 1.0, "steps_evolved": nev, "ms_per_step": msl, "value": npart / (msl * 1e-3), "unit": UNIT,
+                "drift_radius": G.query("drift_radius"), "phases_ms_per_step": phl,
+                "note": "the bench ICs evolved from z=49 by the adaptive step loop (cafcube.f90:25-46), then timed: haloes, empty cells"}
+        G.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_port_throughput(nt, steps=1, warmup=0)
@@ -378,7 +454,7 @@ def main():
                 "dtype": "f32 mesh / f64 particle update / int16 codes", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roof, "phases_ms_per_step": phases, "cpu_baseline": cpu,
-                "particles_per_gpu": int(npart), "drift_radius": radius}
+                "particles_per_gpu": int(npart), "drift_radius": radius, "late_time": late}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
