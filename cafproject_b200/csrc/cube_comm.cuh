@@ -67,6 +67,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -81,7 +82,7 @@ struct NcclApi {
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) { err = std::string("cannot open libnccl.so.2: ") + dlerror(); return false; }
 #define CUBE_NCCL_SYM(f) f = reinterpret_cast<decltype(f)>(dlsym(lib, "nccl" #f)); if (!f) { err = "libnccl.so.2 lacks nccl" #f; lib = nullptr; return false; }
-    CUBE_NCCL_SYM(GetUniqueId) CUBE_NCCL_SYM(CommInitRank) CUBE_NCCL_SYM(CommDestroy) CUBE_NCCL_SYM(Send) CUBE_NCCL_SYM(Recv)
+    CUBE_NCCL_SYM(GetUniqueId) CUBE_NCCL_SYM(CommInitRank) CUBE_NCCL_SYM(CommDestroy) CUBE_NCCL_SYM(CommAbort) CUBE_NCCL_SYM(Send) CUBE_NCCL_SYM(Recv)
     CUBE_NCCL_SYM(AllGather) CUBE_NCCL_SYM(GroupStart) CUBE_NCCL_SYM(GroupEnd) CUBE_NCCL_SYM(GetErrorString)
 #undef CUBE_NCCL_SYM
     return true;
@@ -112,6 +113,9 @@ struct NcclComm : Comm {
     err = std::string(what) + ": " + nccl_api().GetErrorString(r);
     return 1;
   }
+  // a local failure between two collectives: tear the communicator down so that the peers' pending operations end with an error
+  // instead of waiting for this image for ever (the reference `stop`s every image)
+  void abort_group() override { if (comm) { nccl_api().CommAbort(comm); comm = nullptr; } }
   int group_begin(cudaStream_t) override { return ck(nccl_api().GroupStart(), "ncclGroupStart"); }
   int send_peer(const void* p, size_t bytes, int peer) override { return ck(nccl_api().Send(p, bytes, ncclInt8, peer, comm, st_), "ncclSend"); }
   int recv_peer(void* p, size_t bytes, int peer) override { return ck(nccl_api().Recv(p, bytes, ncclInt8, peer, comm, st_), "ncclRecv"); }

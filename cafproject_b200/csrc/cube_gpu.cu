@@ -36,10 +36,13 @@ static int fail(const char* fmt, ...) {
   g_err = buf;
   return 1;
 }
+// a CUDA failure of an image that shares a communicator: abort it (cube_comm.cuh) -- an image must not return between two collectives
+// and leave the others waiting in the next one
+static void abort_current_comm();
 #define CK(call)                                                                                     \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
-    if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    if (e_ != cudaSuccess) { abort_current_comm(); return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } \
   } while (0)
 #define CF(call)                                                                                     \
   do {                                                                                               \
@@ -184,6 +187,8 @@ struct PhaseTimer {  // CUBEnu-style phase bracket (pm.f90:35,195,...) with CUDA
   }
 };
 
+static thread_local cube_handle* g_cur = nullptr;  // the handle of the API call in progress on this thread
+static void abort_current_comm() { if (g_cur && g_cur->comm) g_cur->comm->abort_group(); }
 template <class T> static cudaError_t dmalloc(T** p, long long n) { return cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T)); }
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
@@ -922,7 +927,13 @@ static int exchange_density(cube_handle* h, int* status) {
   CK(cudaStreamSynchronize(h->st));
   for (int i = 0; i <= nd; i++) { h->gbound[i] = b[i]; h->sbound[i] = b[nd + 1 + i]; }
   h->nghost = h->gbound[nd];
-  if (h->nplocal + h->nghost > h->np_image_max || h->sbound[nd] > h->sendcap) *status = 1;
+  if (h->sbound[nd] > h->sendcap) {  // the message buffer follows the state (the reference's only limit is np_image_max, below)
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaFree(h->psend)); h->psend = nullptr;
+    h->sendcap = h->sbound[nd] + h->sbound[nd] / 4 + 4096;
+    CK(cudaMalloc(&h->psend, (size_t)3 * std::max(h->zx, h->zv) * h->sendcap + 16));
+  }
+  if (h->nplocal + h->nghost > h->np_image_max) *status = 1;
   return 0;
 }
 
@@ -951,6 +962,7 @@ static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per co
 
 extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_v, float* overhead_image) {
   if (!h) return fail("null handle");
+  g_cur = h;
   CK(cudaSetDevice(h->p.device));
   const Geom& g = h->g;
   const bool multi = h->nimg > 1;
@@ -998,6 +1010,7 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
 extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t* nplocal, float* sigma_vi_new,
                                  double std_vsim[3], float* overhead_tile) {
   if (!h) return fail("null handle");
+  g_cur = h;
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("cube_gpu_update_x: state is not buffered (call cube_gpu_buffer first, cafcube.f90:17-19)");
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // an asynchronous download still reads the particle arrays
@@ -1274,6 +1287,7 @@ static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt
 extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, float* dt_fine, float* dt_coarse,
                                       float* dt_vmax, float* vmax_out) {
   if (!h) return fail("null handle");
+  g_cur = h;
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("cube_gpu_particle_mesh: state is not buffered (call cube_gpu_buffer first)");
   // a cube_gpu_download_async of vp still reads the velocities the kicks rewrite in place (positions may keep streaming)
@@ -1430,7 +1444,7 @@ extern "C" int cube_gpu_power_spectrum(cube_handle* h, float box, double* xi, in
     k_ps_contrast<<<nb, 256, 0, h->st>>>(n, rho, part + nb);
     if (cudaGetLastError() != cudaSuccess) { rc = fail("power spectrum: kernel launch failed"); break; }
     int dims[3] = {n, n, n}, rembed[3] = {n, n, n + 2}, cembed[3] = {n, n, n / 2 + 1};
-    if (cufftPlanMany(&pl, 3, dims, rembed, 1, 0, cembed, 1, 0, CUFFT_R2C, 1) != CUFFT_SUCCESS || cufftSetStream(pl, h->st) != CUFFT_SUCCESS ||
+    if (cufftPlanMany(&pl, 3, dims, rembed, 1, (int)vol, cembed, 1, (int)(vol / 2), CUFFT_R2C, 1) != CUFFT_SUCCESS || cufftSetStream(pl, h->st) != CUFFT_SUCCESS ||
         cufftExecR2C(pl, rho, (cufftComplex*)rho) != CUFFT_SUCCESS) { rc = fail("power spectrum: cuFFT failed (n=%d)", n); break; }
     if (cudaMemsetAsync(bins, 0, sizeof(double) * PS_Q * nbin, h->st) != cudaSuccess) { rc = fail("power spectrum: memset"); break; }
     const size_t smem = sizeof(double) * PS_Q * nbin;

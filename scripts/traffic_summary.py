@@ -8,7 +8,7 @@ import csv
 import json
 import sys
 
-PHASE_OF = [("k_drift_key", "drift_key"), ("k_mask_ext", "drift_key"), ("k_drift_count", "drift_count"), ("k_vfield_sq", "drift_count"),
+PHASE_OF = [("k_drift_key", "drift_key"), ("k_mask_ext", "drift_key"), ("k_drift_count", "drift_count"), ("k_flag_compact", "drift_count"), ("k_vfield_sq", "drift_count"),
             ("k_scan_", "drift_scan"), ("k_drift_place", "drift_place"), ("k_build_ext", "buffer"), ("k_tile_counts", "buffer"),
             ("k_fine_deposit", "fine_deposit"), ("k_fft_x_fwd", "fine_fft_x"), ("k_fft_y<16, 18, 1", "fine_ifft_y"), ("k_fft_y<", "fine_fft_y"),
             ("k_fft_z_green", "fine_fft_z_green"), ("k_fft_x_inv3", "fine_ifft_x"), ("k_fine_kick", "fine_kick"),
