@@ -123,4 +123,20 @@ __global__ void __launch_bounds__(PC_T) k_particle_pack(long long ng, const int*
   }
 }
 
+// the IDs of the particles I send (-DPID: buffer_v.f90 carries pid with vp), one 8-byte word per particle
+__global__ void __launch_bounds__(PC_T) k_pid_pack(long long ng, const int* __restrict__ scell_L, const long long* __restrict__ sstart,
+                                                   const long long* __restrict__ cstart_p, const long long* __restrict__ pid,
+                                                   long long* __restrict__ out) {
+  __shared__ int soff[PC_CELLS + 1];
+  __shared__ long long ssrc[PC_CELLS];
+  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  for (int t = threadIdx.x; t < PC_CELLS; t += blockDim.x) ssrc[t] = c0 + t < ng ? cstart_p[scell_L[c0 + t]] : 0;
+  const int np = chunk_setup(sstart, c0, ng, soff);
+  const long long p0 = sstart[c0];
+  for (int q = threadIdx.x; q < np; q += PC_T) {
+    const int c = chunk_find(soff, q);
+    out[p0 + q] = pid[ssrc[c] + (q - soff[c])];
+  }
+}
+
 }  // namespace cube

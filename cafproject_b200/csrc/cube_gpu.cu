@@ -108,7 +108,8 @@ struct cube_handle {
   bool buffered = false;
   // particles (double buffered)
   void *xp = nullptr, *vp = nullptr, *xp2 = nullptr, *vp2 = nullptr;  // integer(izipx) xp(3,np), integer(izipv) vp(3,np)
-  long long *pid = nullptr, *pid2 = nullptr; bool pid_valid = false;  // -DPID: optional particle IDs (cube_gpu_upload_pid), single image
+  long long *pid = nullptr, *pid2 = nullptr; bool pid_valid = false;  // -DPID: optional particle IDs (cube_gpu_upload_pid)
+  long long* pid_send = nullptr; long long pid_sendcap = 0;           // message buffer of the IDs that travel with vp (buffer_v.f90)
   unsigned short* key = nullptr;
   // coarse-cell arrays, file order
   int *rhoc_p = nullptr, *rhoc_p2 = nullptr;
@@ -785,7 +786,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   cudaStreamSynchronize(h->st);
   void* ptrs[] = {h->xp, h->vp, h->xp2, h->vp2, h->key, h->rhoc_p, h->rhoc_p2, h->vfield_p, h->vfield_p2, h->cstart_p, h->cstart_p2,
                   h->rhoc_e, h->cstart_e, h->vfield_e, h->sid_e, h->mask_s, h->mask_e, h->farblk, h->inflag, h->flist, h->nflag, h->csum, h->bsum, h->stat_partial, h->stat3, h->rank, h->tile_count, h->maxoff, h->f2max,
-                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->kick_next, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2, h->rho_own};
+                  h->vmax_bits, h->tanlut, h->dvlut, h->enc, h->tanh, h->divok, h->dvlut2, h->divok2, h->kick_next, h->Ak, h->Bk, h->F, h->kern_f, h->tw, h->r3, h->cforce, h->kern_c, h->fc, h->pid, h->pid2, h->pid_send, h->rho_own};
   for (void* q : ptrs) if (q) cudaFree(q);
   void* mptrs[] = {h->gcell_ext, h->scell_L, h->gcnt, h->scnt, h->gstart, h->sstart, h->dir_cell0, h->dir_bounds, h->hsend, h->hrecv, h->psend,
                    h->stat_partial_g, h->stageA, h->slabR, h->kernT, h->sendF, h->recvF, h->slabC, h->packT, h->T, h->T3, h->zzoff, h->zzcs};
@@ -839,7 +840,6 @@ extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, c
 extern "C" int cube_gpu_upload_pid(cube_handle* h, const int64_t* pid) {
   if (!h) return fail("null handle");
   if (!pid) return fail("cube_gpu_upload_pid: null array");
-  if (h->nimg > 1) return fail("particle IDs with several images are not built (the ghost exchange carries xp and vp only)");
   CK(cudaSetDevice(h->p.device));
   if (!h->pid) { CK(dmalloc(&h->pid, h->np_image_max)); CK(dmalloc(&h->pid2, h->np_image_max)); }
   CK(cudaMemcpyAsync(h->pid, pid, sizeof(long long) * h->nplocal, cudaMemcpyHostToDevice, h->st));
@@ -960,6 +960,31 @@ static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per co
   return 0;
 }
 
+// -DPID: the IDs of the ghost particles (buffer_v.f90:23,42,62,81,104 moves pid with vp), received behind the physical ones
+static int exchange_pid(cube_handle* h) {
+  const long long ng = h->ex.ng;
+  const int nd = (int)h->ex.dirs.size();
+  Comm* cm = h->comm.get();
+  if (h->sbound[nd] > h->pid_sendcap) {
+    if (h->pid_send) { CK(cudaStreamSynchronize(h->st)); CK(cudaFree(h->pid_send)); h->pid_send = nullptr; }
+    h->pid_sendcap = h->sbound[nd] + h->sbound[nd] / 4 + 4096;
+    CK(dmalloc(&h->pid_send, h->pid_sendcap));
+  }
+  k_pid_pack<<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, h->pid, h->pid_send); CKL();
+  h->launches++;
+  CC(cm->begin(h->st));
+  for (int i = 0; i < nd; i++) {
+    const size_t n = (size_t)(h->sbound[i + 1] - h->sbound[i]);
+    if (n) CC(cm->send(h->pid_send + h->sbound[i], n * sizeof(long long), h->ex.dirs[i].dst_rank));
+  }
+  for (int i = 0; i < nd; i++) {
+    const size_t n = (size_t)(h->gbound[i + 1] - h->gbound[i]);
+    if (n) CC(cm->recv(h->pid + h->nplocal + h->gbound[i], n * sizeof(long long), h->ex.dirs[i].src_rank));
+  }
+  CC(cm->end());
+  return 0;
+}
+
 extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_v, float* overhead_image) {
   if (!h) return fail("null handle");
   g_cur = h;
@@ -1002,7 +1027,7 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
   }
   // one image: ghost particles alias the periodic image, nothing to copy
   if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp, h->zx)) return 1; }
-  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp, h->zv)) return 1; }
+  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp, h->zv)) return 1; if (h->pid_valid && exchange_pid(h)) return 1; }
   return 0;
 }
 
@@ -1109,6 +1134,10 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     if (h->pid_valid) {  // update_particle.f90:88,106: the IDs take the same permutation
       k_pid_place<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, h->pid, h->rank, h->cstart_p, h->cstart_p2, h->pid2); CKL();
       h->launches += 1;
+      if (multi && ng) {
+        k_pid_place_g<<<nblk(ng, 256), 256, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, h->pid, h->rank, h->cstart_p2, h->pid2); CKL();
+        h->launches += 1;
+      }
     }
     double stg[2] = {0, 0};
     if (multi && ng) {

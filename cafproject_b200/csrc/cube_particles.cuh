@@ -983,7 +983,8 @@ __global__ void __launch_bounds__(1024) k_reduce_strided(const double* __restric
 }
 
 // -DPID (update_particle.f90:88 `pid_new(idx)=pid(ip)`): the particle IDs follow the permutation of pass C.  IDs are optional and off
-// the hot path: one thread per source cell, the destination arithmetic of k_drift_place_w (single image: periodic wrap).
+// the hot path: one thread per source cell, the destination arithmetic of pass C (dest_cell: periodic wrap for nn_d == 1, particles
+// that leave the image are another image's).
 __global__ void __launch_bounds__(256) k_pid_place(Geom g, const long long* __restrict__ pid, const unsigned* __restrict__ rank,
                                                    const long long* __restrict__ cstart_p, const long long* __restrict__ cstart_new,
                                                    long long* __restrict__ pid_new) {
@@ -991,21 +992,33 @@ __global__ void __launch_bounds__(256) k_pid_place(Geom g, const long long* __re
   if (L >= g.ncell_p) return;
   int tx0, ty0, tz0, i0, j0, k0;
   phys_decompose(g, L, tx0, ty0, tz0, i0, j0, k0);
-  const int nt = g.nt, nnt = g.nnt;
+  CellPos cp = {(short)tx0, (short)ty0, (short)tz0, (short)i0, (short)j0, (short)k0, 0, 0};
   const long long pend = cstart_p[L + 1];
   for (long long p = cstart_p[L]; p < pend; p++) {
     const unsigned rk = rank[p];
     if (rk == RANK_LOST) continue;
     const unsigned o = rk >> RANK_BITS;
-    int i = i0 + (int)(o & 15u) - 8, j = j0 + (int)((o >> 4) & 15u) - 8, k = k0 + (int)((o >> 8) & 15u) - 8;
-    int tx = tx0, ty = ty0, tz = tz0;
-    if (i < 0) { i += nt; tx--; } else if (i >= nt) { i -= nt; tx++; }
-    if (j < 0) { j += nt; ty--; } else if (j >= nt) { j -= nt; ty++; }
-    if (k < 0) { k += nt; tz--; } else if (k >= nt) { k -= nt; tz++; }
-    tx = tx < 0 ? tx + nnt : (tx >= nnt ? tx - nnt : tx);
-    ty = ty < 0 ? ty + nnt : (ty >= nnt ? ty - nnt : ty);
-    tz = tz < 0 ? tz + nnt : (tz >= nnt ? tz - nnt : tz);
-    const long long D = phys_index(g, tx, ty, tz, i, j, k);
+    long long D;
+    if (!dest_cell(g, cp, (int)(o & 15u) - 8, (int)((o >> 4) & 15u) - 8, (int)((o >> 8) & 15u) - 8, D)) continue;
+    pid_new[cstart_new[D] + (rk & ((1u << RANK_BITS) - 1))] = pid[p];
+  }
+}
+// the same for the ghost particles received from other images (buffer_v.f90:23,42,... carries pid with vp): one thread per ghost cell
+__global__ void __launch_bounds__(256) k_pid_place_g(Geom g, long long ng, const int* __restrict__ gcell_ext, const long long* __restrict__ gstart,
+                                                     long long base, const long long* __restrict__ pid, const unsigned* __restrict__ rank,
+                                                     const long long* __restrict__ cstart_new, long long* __restrict__ pid_new) {
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (q >= ng) return;
+  const long long e = gcell_ext[q];
+  const int x0 = (int)(e % g.ne) - NCB, y0 = (int)((e / g.ne) % g.ne) - NCB, z0 = (int)(e / ((long long)g.ne * g.ne)) - NCB;
+  const long long pend = base + gstart[q + 1];
+  for (long long p = base + gstart[q]; p < pend; p++) {
+    const unsigned rk = rank[p];
+    if (rk == RANK_LOST) continue;
+    const unsigned o = rk >> RANK_BITS;
+    const int X = x0 + (int)(o & 15u) - 8, Y = y0 + (int)((o >> 4) & 15u) - 8, Z = z0 + (int)((o >> 8) & 15u) - 8;
+    if ((unsigned)X >= (unsigned)g.nc || (unsigned)Y >= (unsigned)g.nc || (unsigned)Z >= (unsigned)g.nc) continue;
+    const long long D = phys_index(g, X / g.nt, Y / g.nt, Z / g.nt, X % g.nt, Y % g.nt, Z % g.nt);
     pid_new[cstart_new[D] + (rk & ((1u << RANK_BITS) - 1))] = pid[p];
   }
 }

@@ -94,8 +94,9 @@ int cube_gpu_download(cube_handle *h, void *xp, void *vp, int32_t *rhoc_phys, fl
 /* -DPID (CUBE/main variables.f90:44, particle_initialization.f90:56-59; on by default in CUBEnu's Makefile): optional particle
  * IDs.  upload_pid gives the IDs of the nplocal particles of the LAST cube_gpu_upload, in the same file order; they then take the
  * permutation of every cube_gpu_update_x (update_particle.f90:88,106) and download_pid returns them in the order of the current
- * disjoint state (what checkpoint.f90 writes to `zipid`).  Single image only: the ghost exchange between images carries xp and
- * vp, not IDs -- upload_pid fails on a multi-image handle.  A new cube_gpu_upload drops the IDs. */
+ * disjoint state (what checkpoint.f90 writes to `zipid`).  With several images the IDs of the ghost particles travel with vp in
+ * cube_gpu_buffer(do_v) (buffer_v.f90:23,42,62,81,104), so a particle that crosses an image boundary keeps its ID.  A new
+ * cube_gpu_upload drops the IDs. */
 int cube_gpu_upload_pid(cube_handle *h, const int64_t *pid);
 int cube_gpu_download_pid(cube_handle *h, int64_t *pid);
 

@@ -166,3 +166,55 @@ def test_full_steps_two_images(tables):
             ts.dt_fine, ts.dt_coarse, ts.dt_vmax = po["dt_fine"], po["dt_coarse"], po["dt_vmax"]
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("nn,nc,nnt", [((2, 1, 1), 24, 2), ((2, 2, 2), 24, 1)])
+def test_particle_ids_cross_image_boundaries(tables, nn, nc, nnt):
+    """-DPID with several images: the IDs travel with vp in buffer_v (buffer_v.f90:23,42,62,81,104) and take the permutation of
+    update_particle (update_particle.f90:88) -- after two drifts every image holds the IDs the oracle holds, slot for slot, and
+    all images together still hold every ID exactly once (a large step makes many particles change image)."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    nimg = nn[0] * nn[1] * nn[2]
+    states, sig, info = make_ic(nn=nn, nc=nc, nnt=nnt, np_nc=NP_NC, seed=90, disp_rms=1.5)
+    base = 0
+    for s in states:
+        n = s["xp"].shape[0]
+        s["pid"] = np.arange(base + 1, base + n + 1, dtype=np.int64)
+        base += n
+    O = co.Oracle(nn=nn, nnt=nnt, nc=nc, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+    _group[0] += 1
+    grp = _group[0]
+    lut = co.tanf_lut()
+
+    def mk(m):
+        G = CubeGPU(nc, nnt, fk, ck, nn=nn, rank=m, np_nc=NP_NC, tanf_lut=lut, local_group=grp, fine_batch=2)
+        G.particle_initialization(states[m], sig, npglobal=info["npglobal"])
+        G.buffer_density(); G.buffer_x(); G.buffer_v()
+        return G
+    Gs = run_images(nimg, mk)
+    try:
+        dt = np.float32(1.5)
+        moved = 0
+        for it in range(2):
+            O.update_particle(np.float32(0) if it == 0 else dt, dt)
+            run_images(nimg, lambda m: Gs[m].update_particle(np.float32(0) if it == 0 else dt, dt))
+            allids = []
+            for m in range(nimg):
+                so = O.store(m)
+                sg, _ = Gs[m].checkpoint()
+                assert np.array_equal(so["xp"], sg["xp"]) and np.array_equal(so["vp"], sg["vp"]), (it, m)
+                assert np.array_equal(so["pid"], sg["pid"]), (it, m)
+                allids.append(sg["pid"])
+                lo = sum(s["xp"].shape[0] for s in states[:m])
+                moved += int(((sg["pid"] <= lo) | (sg["pid"] > lo + states[m]["xp"].shape[0])).sum())
+            assert np.array_equal(np.sort(np.concatenate(allids)), np.arange(1, info["npglobal"] + 1))
+            O.buffer_density(); O.buffer_x(); O.buffer_v()
+            run_images(nimg, lambda m: (Gs[m].buffer_density(), Gs[m].buffer_x(), Gs[m].buffer_v()))
+        assert moved > 0          # the test did move particles (and their IDs) from image to image
+    finally:
+        run_images(nimg, lambda m: Gs[m].close())
+        O.close()
