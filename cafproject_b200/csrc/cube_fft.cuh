@@ -65,6 +65,32 @@ __device__ __forceinline__ void static_for(F&& f) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed complex arithmetic.  sm_100a has two-wide f32 instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2 on a
+// 64-bit register pair): a complex add is ONE instruction instead of two, a multiply by a twiddle TWO (FMUL2 + FFMA2) instead of
+// four, and ptxas folds the (re,im) swap, per-half negation and splat of an operand into the instruction's own operand modifiers
+// (R.F32x2.LO_HI.NP ...), so multiplying by +-i costs nothing extra.  The line-FFT kernels are bound by instruction issue, most of
+// it this arithmetic (profiles/r02_notes.md).  Each half is an IEEE f32 operation: same numerics as the scalar form.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long cpk;
+__device__ __forceinline__ cpk c_pack(float x, float y) { cpk r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ cpk c_pack(float2 a) { return c_pack(a.x, a.y); }
+__device__ __forceinline__ float2 c_unpack(cpk v) { float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(v)); return a; }
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { cpk r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { cpk r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+__device__ __forceinline__ float2 c_mul2(float2 a, float2 b) { cpk r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+__device__ __forceinline__ float2 c_fma2(float2 a, float2 b, float2 c) {
+  cpk r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b)), "l"(c_pack(c))); return c_unpack(r);
+}
+// a + S*i*b  (S = +1 or -1): (a.x - S b.y, a.y + S b.x)
+template <int S> __device__ __forceinline__ float2 c_add_i(float2 a, float2 b) {
+  return c_fma2(make_float2(b.y, b.x), make_float2(S > 0 ? -1.f : 1.f, S > 0 ? 1.f : -1.f), a);
+}
+// a * (c + i s)
+__device__ __forceinline__ float2 c_mul(float2 a, float c, float s) {
+  return c_fma2(make_float2(a.y, a.x), make_float2(-s, s), c_mul2(a, make_float2(c, c)));
+}
+
 // a * exp(DIR * 2 pi i T / R) with the root folded to immediates; trivial roots cost nothing
 template <int DIR, int T, int R>
 __device__ __forceinline__ float2 mul_root(float2 a) {
@@ -76,7 +102,7 @@ __device__ __forceinline__ float2 mul_root(float2 a) {
   else {
     constexpr ct_cs w = ct_cossin_turn(t, R);
     constexpr float c = (float)w.c, s = (float)(DIR > 0 ? w.s : -w.s);
-    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    return c_mul(a, c, s);
   }
 }
 
@@ -86,31 +112,28 @@ __host__ __device__ constexpr int fft_radix_of(int R) { return R % 4 == 0 ? 4 : 
 template <int P, int DIR>
 __device__ __forceinline__ void butterfly(float2 (&t)[P]) {
   if constexpr (P == 2) {
-    float2 a = t[0], b = t[1];
-    t[0] = make_float2(a.x + b.x, a.y + b.y);
-    t[1] = make_float2(a.x - b.x, a.y - b.y);
+    const float2 a = t[0], b = t[1];
+    t[0] = c_add(a, b);
+    t[1] = c_sub(a, b);
   } else if constexpr (P == 4) {
-    float2 a = make_float2(t[0].x + t[2].x, t[0].y + t[2].y), b = make_float2(t[0].x - t[2].x, t[0].y - t[2].y);
-    float2 c = make_float2(t[1].x + t[3].x, t[1].y + t[3].y), d = make_float2(t[1].x - t[3].x, t[1].y - t[3].y);
-    t[0] = make_float2(a.x + c.x, a.y + c.y);
-    t[2] = make_float2(a.x - c.x, a.y - c.y);
-    if (DIR > 0) { t[1] = make_float2(b.x - d.y, b.y + d.x); t[3] = make_float2(b.x + d.y, b.y - d.x); }   // b +- i d
-    else         { t[1] = make_float2(b.x + d.y, b.y - d.x); t[3] = make_float2(b.x - d.y, b.y + d.x); }   // b -+ i d
+    const float2 a = c_add(t[0], t[2]), b = c_sub(t[0], t[2]);
+    const float2 c = c_add(t[1], t[3]), d = c_sub(t[1], t[3]);
+    t[0] = c_add(a, c);
+    t[2] = c_sub(a, c);
+    t[1] = c_add_i<(DIR > 0 ? 1 : -1)>(b, d);   // b +- i d
+    t[3] = c_add_i<(DIR > 0 ? -1 : 1)>(b, d);   // b -+ i d
   } else if constexpr (P == 3) {
     constexpr float s0 = (float)(DIR > 0 ? 0.866025403784438646763723170752936183 : -0.866025403784438646763723170752936183);
-    float2 s = make_float2(t[1].x + t[2].x, t[1].y + t[2].y), d = make_float2(t[1].x - t[2].x, t[1].y - t[2].y);
-    float2 m = make_float2(t[0].x - 0.5f * s.x, t[0].y - 0.5f * s.y);
-    t[0] = make_float2(t[0].x + s.x, t[0].y + s.y);
-    t[1] = make_float2(m.x - s0 * d.y, m.y + s0 * d.x);
-    t[2] = make_float2(m.x + s0 * d.y, m.y - s0 * d.x);
+    const float2 s = c_add(t[1], t[2]), d = c_sub(t[1], t[2]);
+    const float2 m = c_fma2(s, make_float2(-0.5f, -0.5f), t[0]);
+    t[0] = c_add(t[0], s);
+    t[1] = c_fma2(make_float2(d.y, d.x), make_float2(-s0, s0), m);   // m + i s0 d
+    t[2] = c_fma2(make_float2(d.y, d.x), make_float2(s0, -s0), m);   // m - i s0 d
   } else {  // generic small prime (5): direct DFT with immediate roots
     float2 o[P];
     static_for<0, P>([&](auto Q) {
       float2 acc = t[0];
-      static_for<1, P>([&](auto J) {
-        float2 v = mul_root<DIR, (J.value * Q.value) % P, P>(t[J.value]);
-        acc.x += v.x; acc.y += v.y;
-      });
+      static_for<1, P>([&](auto J) { acc = c_add(acc, mul_root<DIR, (J.value * Q.value) % P, P>(t[J.value])); });
       o[Q.value] = acc;
     });
     static_for<0, P>([&](auto Q) { t[Q.value] = o[Q.value]; });
@@ -138,10 +161,7 @@ __device__ __forceinline__ void dft(float2 (&x)[R]) { dft_rec<R, DIR, 1, 0, R>(x
 
 // a * tw or a * conj(tw)
 template <int DIR>
-__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
-  if (DIR < 0) return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-  return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
-}
+__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) { return c_mul(a, w.x, DIR < 0 ? w.y : -w.y); }
 
 // ---------------------------------------------------------------------------------------------
 // CTA-level line FFT, N = R1*R2, LW lines interleaved: s[n*LW + line].  tw[t] = exp(-2 pi i t/N).
@@ -273,8 +293,8 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2)) k_fft_x_fwd(FftGeom 
     for (int k = lane; k < g.NH; k += 32) {
       const float2 zk = s[k * LW + l], zn = s[(k ? N - k : 0) * LW + l];
       float2 o;
-      if (!im) o = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      else o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      if (!im) o = c_mul2(c_add(zk, make_float2(zn.x, -zn.y)), make_float2(0.5f, 0.5f));  // (Z[k] + conj Z[N-k]) / 2
+      else { const float2 d = c_sub(zk, make_float2(zn.x, -zn.y)); o = c_mul2(make_float2(d.y, d.x), make_float2(0.5f, -0.5f)); }  // (Z[k] - conj Z[N-k]) / 2i
       row[k] = o;
     }
   }
@@ -379,7 +399,7 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
           const int kf = kz < NHZ ? kz : N - kz;
           float K = ks[(d * NHZ + kf) * FL + line];
           if (d == 2 && kz >= NHZ) K = -K;
-          w[k2] = make_float2(-X[k2].y * K, X[k2].x * K);
+          w[k2] = c_mul2(make_float2(X[k2].y, X[k2].x), make_float2(-K, K));  // i K X
         }
         ifft_step_a<R1, R2, LW>(w, s, tw, line, idx);
       }
@@ -457,12 +477,12 @@ __global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, 
 #pragma unroll
       for (int l = 0; l < 8; l++) {
         const float2 a = va[l], c = vb[l];
-        sk[l] = make_float2(a.x - c.y, a.y + c.x);
-        sm[l] = make_float2(a.x + c.y, c.x - a.y);
+        sk[l] = c_add_i<1>(a, c);                                                              // Xa + i Xb
+        sm[l] = c_add(make_float2(a.x, -a.y), make_float2(c.y, c.x));                          // conj(Xa) + i conj(Xb)
       }
     } else {
 #pragma unroll
-      for (int l = 0; l < 8; l++) sk[l] = make_float2(va[l].x - vb[l].y, va[l].y + vb[l].x);
+      for (int l = 0; l < 8; l++) sk[l] = c_add_i<1>(va[l], vb[l]);
     }
   }
   __syncthreads();
