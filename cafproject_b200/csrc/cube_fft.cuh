@@ -76,23 +76,43 @@ typedef unsigned long long cpk;
 __device__ __forceinline__ cpk c_pack(float x, float y) { cpk r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
 __device__ __forceinline__ cpk c_pack(float2 a) { return c_pack(a.x, a.y); }
 __device__ __forceinline__ float2 c_unpack(cpk v) { float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(v)); return a; }
-__device__ __forceinline__ float2 c_add(float2 a, float2 b) { cpk r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
-__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { cpk r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
-__device__ __forceinline__ float2 c_mul2(float2 a, float2 b) { cpk r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
-__device__ __forceinline__ float2 c_fma2(float2 a, float2 b, float2 c) {
-  cpk r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b)), "l"(c_pack(c))); return c_unpack(r);
-}
+// the four two-wide operations, packed (Pk) or as pairs of scalar instructions (Sc: same values; the z pass is faster with it --
+// measured 6.8 against 7.8 ms at cfg 2, its twiddle constants then ride as immediates of scalar FFMAs -- every other pass with Pk)
+struct Pk {
+  static __device__ __forceinline__ float2 add(float2 a, float2 b) { cpk r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+  static __device__ __forceinline__ float2 sub(float2 a, float2 b) { cpk r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+  static __device__ __forceinline__ float2 mul2(float2 a, float2 b) { cpk r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b))); return c_unpack(r); }
+  static __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    cpk r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(c_pack(a)), "l"(c_pack(b)), "l"(c_pack(c))); return c_unpack(r);
+  }
+};
+struct Sc {
+  static __device__ __forceinline__ float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+  static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+  static __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+  static __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+};
+struct Mx {  // packed additions, scalar multiplies (constants stay immediates)
+  static __device__ __forceinline__ float2 add(float2 a, float2 b) { return Pk::add(a, b); }
+  static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return Pk::sub(a, b); }
+  static __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return Sc::mul2(a, b); }
+  static __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return Sc::fma2(a, b, c); }
+};
+template <class M = Pk> __device__ __forceinline__ float2 c_add(float2 a, float2 b) { return M::add(a, b); }
+template <class M = Pk> __device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return M::sub(a, b); }
+template <class M = Pk> __device__ __forceinline__ float2 c_mul2(float2 a, float2 b) { return M::mul2(a, b); }
+template <class M = Pk> __device__ __forceinline__ float2 c_fma2(float2 a, float2 b, float2 c) { return M::fma2(a, b, c); }
 // a + S*i*b  (S = +1 or -1): (a.x - S b.y, a.y + S b.x)
-template <int S> __device__ __forceinline__ float2 c_add_i(float2 a, float2 b) {
-  return c_fma2(make_float2(b.y, b.x), make_float2(S > 0 ? -1.f : 1.f, S > 0 ? 1.f : -1.f), a);
+template <int S, class M = Pk> __device__ __forceinline__ float2 c_add_i(float2 a, float2 b) {
+  return M::fma2(make_float2(b.y, b.x), make_float2(S > 0 ? -1.f : 1.f, S > 0 ? 1.f : -1.f), a);
 }
 // a * (c + i s)
-__device__ __forceinline__ float2 c_mul(float2 a, float c, float s) {
-  return c_fma2(make_float2(a.y, a.x), make_float2(-s, s), c_mul2(a, make_float2(c, c)));
+template <class M = Pk> __device__ __forceinline__ float2 c_mul(float2 a, float c, float s) {
+  return M::fma2(make_float2(a.y, a.x), make_float2(-s, s), M::mul2(a, make_float2(c, c)));
 }
 
 // a * exp(DIR * 2 pi i T / R) with the root folded to immediates; trivial roots cost nothing
-template <int DIR, int T, int R>
+template <int DIR, int T, int R, class M = Pk>
 __device__ __forceinline__ float2 mul_root(float2 a) {
   constexpr int t = ((T % R) + R) % R;
   if constexpr (t == 0) return a;
@@ -102,38 +122,38 @@ __device__ __forceinline__ float2 mul_root(float2 a) {
   else {
     constexpr ct_cs w = ct_cossin_turn(t, R);
     constexpr float c = (float)w.c, s = (float)(DIR > 0 ? w.s : -w.s);
-    return c_mul(a, c, s);
+    return c_mul<M>(a, c, s);
   }
 }
 
 __host__ __device__ constexpr int fft_radix_of(int R) { return R % 4 == 0 ? 4 : R % 2 == 0 ? 2 : R % 3 == 0 ? 3 : R % 5 == 0 ? 5 : R; }
 
 // p-point butterfly, natural order in and out, root exp(DIR*2 pi i/p)
-template <int P, int DIR>
+template <int P, int DIR, class M = Pk>
 __device__ __forceinline__ void butterfly(float2 (&t)[P]) {
   if constexpr (P == 2) {
     const float2 a = t[0], b = t[1];
-    t[0] = c_add(a, b);
-    t[1] = c_sub(a, b);
+    t[0] = c_add<M>(a, b);
+    t[1] = c_sub<M>(a, b);
   } else if constexpr (P == 4) {
-    const float2 a = c_add(t[0], t[2]), b = c_sub(t[0], t[2]);
-    const float2 c = c_add(t[1], t[3]), d = c_sub(t[1], t[3]);
-    t[0] = c_add(a, c);
-    t[2] = c_sub(a, c);
-    t[1] = c_add_i<(DIR > 0 ? 1 : -1)>(b, d);   // b +- i d
-    t[3] = c_add_i<(DIR > 0 ? -1 : 1)>(b, d);   // b -+ i d
+    const float2 a = c_add<M>(t[0], t[2]), b = c_sub<M>(t[0], t[2]);
+    const float2 c = c_add<M>(t[1], t[3]), d = c_sub<M>(t[1], t[3]);
+    t[0] = c_add<M>(a, c);
+    t[2] = c_sub<M>(a, c);
+    t[1] = c_add_i<(DIR > 0 ? 1 : -1), M>(b, d);   // b +- i d
+    t[3] = c_add_i<(DIR > 0 ? -1 : 1), M>(b, d);   // b -+ i d
   } else if constexpr (P == 3) {
     constexpr float s0 = (float)(DIR > 0 ? 0.866025403784438646763723170752936183 : -0.866025403784438646763723170752936183);
-    const float2 s = c_add(t[1], t[2]), d = c_sub(t[1], t[2]);
-    const float2 m = c_fma2(s, make_float2(-0.5f, -0.5f), t[0]);
-    t[0] = c_add(t[0], s);
-    t[1] = c_fma2(make_float2(d.y, d.x), make_float2(-s0, s0), m);   // m + i s0 d
-    t[2] = c_fma2(make_float2(d.y, d.x), make_float2(s0, -s0), m);   // m - i s0 d
+    const float2 s = c_add<M>(t[1], t[2]), d = c_sub<M>(t[1], t[2]);
+    const float2 m = c_fma2<M>(s, make_float2(-0.5f, -0.5f), t[0]);
+    t[0] = c_add<M>(t[0], s);
+    t[1] = c_fma2<M>(make_float2(d.y, d.x), make_float2(-s0, s0), m);   // m + i s0 d
+    t[2] = c_fma2<M>(make_float2(d.y, d.x), make_float2(s0, -s0), m);   // m - i s0 d
   } else {  // generic small prime (5): direct DFT with immediate roots
     float2 o[P];
     static_for<0, P>([&](auto Q) {
       float2 acc = t[0];
-      static_for<1, P>([&](auto J) { acc = c_add(acc, mul_root<DIR, (J.value * Q.value) % P, P>(t[J.value])); });
+      static_for<1, P>([&](auto J) { acc = c_add<M>(acc, mul_root<DIR, (J.value * Q.value) % P, P, M>(t[J.value])); });
       o[Q.value] = acc;
     });
     static_for<0, P>([&](auto Q) { t[Q.value] = o[Q.value]; });
@@ -141,27 +161,27 @@ __device__ __forceinline__ void butterfly(float2 (&t)[P]) {
 }
 
 // In-register DFT of the R elements x[OFF + S*i] (natural order in and out), decimation in time.
-template <int R, int DIR, int S, int OFF, int NT>
+template <int R, int DIR, int S, int OFF, int NT, class M = Pk>
 __device__ __forceinline__ void dft_rec(float2 (&x)[NT]) {
   if constexpr (R > 1) {
     constexpr int p = fft_radix_of(R), m = R / p;
-    static_for<0, p>([&](auto J) { dft_rec<m, DIR, S * p, OFF + S * J.value, NT>(x); });
+    static_for<0, p>([&](auto J) { dft_rec<m, DIR, S * p, OFF + S * J.value, NT, M>(x); });
     float2 y[R];
     static_for<0, m>([&](auto K) {
       float2 t[p];
-      static_for<0, p>([&](auto J) { t[J.value] = mul_root<DIR, J.value * K.value, R>(x[OFF + S * (J.value + p * K.value)]); });
-      butterfly<p, DIR>(t);
+      static_for<0, p>([&](auto J) { t[J.value] = mul_root<DIR, J.value * K.value, R, M>(x[OFF + S * (J.value + p * K.value)]); });
+      butterfly<p, DIR, M>(t);
       static_for<0, p>([&](auto Q) { y[K.value + m * Q.value] = t[Q.value]; });
     });
     static_for<0, R>([&](auto I) { x[OFF + S * I.value] = y[I.value]; });
   }
 }
-template <int R, int DIR>
-__device__ __forceinline__ void dft(float2 (&x)[R]) { dft_rec<R, DIR, 1, 0, R>(x); }
+template <int R, int DIR, class M = Pk>
+__device__ __forceinline__ void dft(float2 (&x)[R]) { dft_rec<R, DIR, 1, 0, R, M>(x); }
 
 // a * tw or a * conj(tw)
-template <int DIR>
-__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) { return c_mul(a, w.x, DIR < 0 ? w.y : -w.y); }
+template <int DIR, class M = Pk>
+__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) { return c_mul<M>(a, w.x, DIR < 0 ? w.y : -w.y); }
 
 // ---------------------------------------------------------------------------------------------
 // CTA-level line FFT, N = R1*R2, LW lines interleaved: s[n*LW + line].  tw[t] = exp(-2 pi i t/N).
@@ -170,37 +190,37 @@ __device__ __forceinline__ float2 mul_tw(float2 a, float2 w) { return c_mul(a, w
 constexpr int FL = 16;  // lines per CTA
 
 // step A: R1-point DFTs over n1 for fixed n2 = idx, twiddle, back to the same slots (holds Y[k1][n2])
-template <int R1, int R2, int DIR, int LW>
+template <int R1, int R2, int DIR, int LW, class M = Pk>
 __device__ __forceinline__ void fft_step_a(float2* s, const float2* tw, int line, int idx) {
   if (idx < R2) {
     float2 v[R1];
 #pragma unroll
     for (int n1 = 0; n1 < R1; n1++) v[n1] = s[(n1 * R2 + idx) * LW + line];
-    dft<R1, DIR>(v);
+    dft<R1, DIR, M>(v);
 #pragma unroll
-    for (int k1 = 0; k1 < R1; k1++) s[(k1 * R2 + idx) * LW + line] = k1 ? mul_tw<DIR>(v[k1], tw[idx * k1]) : v[0];
+    for (int k1 = 0; k1 < R1; k1++) s[(k1 * R2 + idx) * LW + line] = k1 ? mul_tw<DIR, M>(v[k1], tw[idx * k1]) : v[0];
   }
 }
 // step B: R2-point DFT over n2 for fixed k1 = idx; v[k2] = X[k1 + R1*k2]
-template <int R1, int R2, int DIR, int LW>
+template <int R1, int R2, int DIR, int LW, class M = Pk>
 __device__ __forceinline__ void fft_step_b(const float2* s, int line, int idx, float2 (&v)[R2]) {
 #pragma unroll
   for (int n2 = 0; n2 < R2; n2++) v[n2] = s[(idx * R2 + n2) * LW + line];
-  dft<R2, DIR>(v);
+  dft<R2, DIR, M>(v);
 }
 // mirrored inverse, first half: from v[k2] = X[k1 + R1*k2] (registers of thread k1 = idx) to s[(k1*R2+n2)]
-template <int R1, int R2, int LW>
+template <int R1, int R2, int LW, class M = Pk>
 __device__ __forceinline__ void ifft_step_a(float2 (&v)[R2], float2* s, const float2* tw, int line, int idx) {
-  dft<R2, +1>(v);
+  dft<R2, +1, M>(v);
 #pragma unroll
-  for (int n2 = 0; n2 < R2; n2++) s[(idx * R2 + n2) * LW + line] = n2 ? mul_tw<+1>(v[n2], tw[n2 * idx]) : v[0];
+  for (int n2 = 0; n2 < R2; n2++) s[(idx * R2 + n2) * LW + line] = n2 ? mul_tw<+1, M>(v[n2], tw[n2 * idx]) : v[0];
 }
 // mirrored inverse, second half: thread n2 = idx gets v[n1] = x[n1*R2 + n2]
-template <int R1, int R2, int LW>
+template <int R1, int R2, int LW, class M = Pk>
 __device__ __forceinline__ void ifft_step_b(const float2* s, int line, int idx, float2 (&v)[R1]) {
 #pragma unroll
   for (int k1 = 0; k1 < R1; k1++) v[k1] = s[(k1 * R2 + idx) * LW + line];
-  dft<R1, +1>(v);
+  dft<R1, +1, M>(v);
 }
 
 struct FftGeom {
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), MINB) k_fft_y(FftGeo
 // own axis, even in the others: kernel_f.f90:32-38 mirrors the table that way).
 // ---------------------------------------------------------------------------------------------
 
-template <int R1, int R2>
+template <int R1, int R2, class ZM = Sc>
 __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 : 1)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
                                                                             const float* __restrict__ kern, float scale,
                                                                             const float2* __restrict__ tw_g) {
@@ -384,10 +404,10 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
     if (b + 1 < g.nbatch) { prefetch(b + 1, sbuf + ((b + 1) & 1) * N * LW); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
-    if (act) fft_step_a<R1, R2, -1, LW>(s, tw, line, idx);
+    if (act) fft_step_a<R1, R2, -1, LW, ZM>(s, tw, line, idx);
     __syncthreads();
     float2 X[R2];
-    if (act && idx < R1) fft_step_b<R1, R2, -1, LW>(s, line, idx, X);
+    if (act && idx < R1) fft_step_b<R1, R2, -1, LW, ZM>(s, line, idx, X);
 #pragma unroll 1
     for (int d = 0; d < 3; d++) {
       __syncthreads();
@@ -399,14 +419,14 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
           const int kf = kz < NHZ ? kz : N - kz;
           float K = ks[(d * NHZ + kf) * FL + line];
           if (d == 2 && kz >= NHZ) K = -K;
-          w[k2] = c_mul2(make_float2(X[k2].y, X[k2].x), make_float2(-K, K));  // i K X
+          w[k2] = make_float2(-X[k2].y * K, X[k2].x * K);  // i K X
         }
-        ifft_step_a<R1, R2, LW>(w, s, tw, line, idx);
+        ifft_step_a<R1, R2, LW, ZM>(w, s, tw, line, idx);
       }
       __syncthreads();
       if (act && idx < R2) {
         float2 v[R1];
-        ifft_step_b<R1, R2, LW>(s, line, idx, v);
+        ifft_step_b<R1, R2, LW, ZM>(s, line, idx, v);
         float2* dst = B + ((size_t)d * g.nbatch + b) * (size_t)g.M * plane + colo;
 #pragma unroll
         for (int n1 = 0; n1 < R1; n1++) {
