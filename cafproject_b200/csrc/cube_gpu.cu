@@ -104,6 +104,7 @@ struct cube_handle {
   unsigned long long* kick_next = nullptr; int kb_hot = 0; bool old_kick = false;  // merged brick kick (cube_kick.cuh)
   CUtensorMap fmap = {}; int kick_stage = 2;  // TMA view of F[batch][M][M][3][FP]
   cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
+  cudaEvent_t ev_vpack = nullptr, ev_vghost = nullptr; bool vghost_pending = false, async_vghost = true;  // buffer_v's exchange under the next drift's key pass
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
@@ -624,6 +625,8 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
     CK(cudaStreamCreateWithPriority(&h->st_coarse, cudaStreamNonBlocking, getenv("CUBE_GPU_COARSE_PRIO0") ? lo : hi));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_vpack, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_vghost, cudaEventDisableTiming));
+  h->async_vghost = getenv("CUBE_GPU_SYNC_BUFFER_V") == nullptr;
   h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;  // multi-image runs: decided after the communicator exists (below)
   CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
@@ -804,6 +807,8 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   if (h->st_coarse) { cudaStreamSynchronize(h->st_coarse); cudaStreamDestroy(h->st_coarse); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_vpack) cudaEventDestroy(h->ev_vpack);
+  if (h->ev_vghost) cudaEventDestroy(h->ev_vghost);
   for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
@@ -819,6 +824,7 @@ extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, c
   if (nplocal > h->np_image_max)
     return fail("error: too many particles in this image+buffer: %lld > %lld; please set image_buffer larger", (long long)nplocal, h->np_image_max);
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // a streamed download still reads the arrays overwritten here
+  if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); h->vghost_pending = false; }
   h->vp_stream_host = nullptr;
   h->pid_valid = false;  // a new state: its IDs, if any, come with cube_gpu_upload_pid
   CK(cudaMemcpyAsync(h->xp, xp, (size_t)3 * h->zx * nplocal, cudaMemcpyHostToDevice, h->st));
@@ -942,7 +948,8 @@ static int exchange_density(cube_handle* h, int* status) {
 }
 
 // ghost particles (buffer_x.f90 for xp, buffer_v.f90 for vp): received behind the physical particles
-static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per code */) {
+// `cst`: the stream the messages travel on (the pack kernel always runs on h->st, the messages wait for it)
+static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per code */, cudaStream_t cst) {
   char* arr = (char*)arr_v; char* psend = (char*)h->psend;
   const long long ng = h->ex.ng;
   const int nd = (int)h->ex.dirs.size();
@@ -951,7 +958,8 @@ static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per co
   else k_particle_pack<signed char><<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, (const signed char*)arr, (signed char*)psend);
   CKL();
   h->launches++;
-  CC(cm->begin(h->st));
+  if (cst != h->st) { CK(cudaEventRecord(h->ev_vpack, h->st)); CK(cudaStreamWaitEvent(cst, h->ev_vpack, 0)); }
+  CC(cm->begin(cst));
   for (int i = 0; i < nd; i++) {
     const size_t n = (size_t)(h->sbound[i + 1] - h->sbound[i]);
     if (n) CC(cm->send(psend + (size_t)3 * z * h->sbound[i], n * 3 * z, h->ex.dirs[i].dst_rank));
@@ -965,7 +973,7 @@ static int exchange_particles(cube_handle* h, void* arr_v, int z /* bytes per co
 }
 
 // -DPID: the IDs of the ghost particles (buffer_v.f90:23,42,62,81,104 moves pid with vp), received behind the physical ones
-static int exchange_pid(cube_handle* h) {
+static int exchange_pid(cube_handle* h, cudaStream_t cst) {
   const long long ng = h->ex.ng;
   const int nd = (int)h->ex.dirs.size();
   Comm* cm = h->comm.get();
@@ -976,7 +984,8 @@ static int exchange_pid(cube_handle* h) {
   }
   k_pid_pack<<<nblk(ng, PC_CELLS), PC_T, 0, h->st>>>(ng, h->scell_L, h->sstart, h->cstart_p, h->pid, h->pid_send); CKL();
   h->launches++;
-  CC(cm->begin(h->st));
+  if (cst != h->st) { CK(cudaEventRecord(h->ev_vpack, h->st)); CK(cudaStreamWaitEvent(cst, h->ev_vpack, 0)); }
+  CC(cm->begin(cst));
   for (int i = 0; i < nd; i++) {
     const size_t n = (size_t)(h->sbound[i + 1] - h->sbound[i]);
     if (n) CC(cm->send(h->pid_send + h->sbound[i], n * sizeof(long long), h->ex.dirs[i].dst_rank));
@@ -1030,8 +1039,17 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
     h->buffered = true;
   }
   // one image: ghost particles alias the periodic image, nothing to copy
-  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp, h->zx)) return 1; }
-  if (do_v && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->vp, h->zv)) return 1; if (h->pid_valid && exchange_pid(h)) return 1; }
+  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp, h->zx, h->st)) return 1; }
+  if (do_v && multi) {
+    // The ghosts' velocities (and IDs) are first read by the next update_particle's pass over the GHOST cells: the messages travel on
+    // the high-priority side stream and that pass waits for them, so they cross under the key pass of the physical cells (which
+    // only reads physical particles).  Phase profiling keeps everything on one stream.
+    PhaseTimer pt(h, PH_BUFFER);
+    cudaStream_t cst = (h->async_vghost && !h->prof) ? h->st_coarse : h->st;
+    if (exchange_particles(h, h->vp, h->zv, cst)) return 1;
+    if (h->pid_valid && exchange_pid(h, cst)) return 1;
+    if (cst != h->st) { CK(cudaEventRecord(h->ev_vghost, cst)); h->vghost_pending = true; }
+  }
   return 0;
 }
 
@@ -1064,6 +1082,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
                                                                                             h->rank, h->maxoff, h->mask_s, h->inflag, h->rhoc_p2, h->vfield_p2));
     CKL();
     h->launches++;
+    if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); h->vghost_pending = false; }  // ghost velocities from buffer_v
     if (multi && ng) {
       FMT_SWITCH(h, k_drift_key_g<F><<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, XPC(h->xp), VPC(h->vp), h->vfield_e, h->dvlut, dt_mid,
                                                                    h->key, h->rank, h->maxoff, h->mask_s + MASK_W * g.ncell_p, h->inflag));
@@ -1706,6 +1725,7 @@ extern "C" int cube_gpu_timer(cube_handle* h, int start, float* ms) {
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->p.device));
   if (start) { CK(cudaEventRecord(h->tev[0], h->st)); return 0; }
+  if (h->vghost_pending) CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0));  // the stopwatch covers a ghost exchange still in flight on the side stream
   CK(cudaEventRecord(h->tev[1], h->st));
   CK(cudaEventSynchronize(h->tev[1]));
   if (ms) CK(cudaEventElapsedTime(ms, h->tev[0], h->tev[1]));
