@@ -122,6 +122,8 @@ struct cube_handle {
   int* rhoc_e = nullptr; long long* cstart_e = nullptr; float* vfield_e = nullptr;
   int* sid_e = nullptr; unsigned *mask_s = nullptr, *mask_e = nullptr; int* farblk = nullptr; float* csum = nullptr;  // source-cell mover summaries of the drift (cube_particles.cuh)
   unsigned char* inflag = nullptr; int *flist = nullptr, *nflag = nullptr; bool count_all = false;  // destination cells with arrivals (pass B's work list)
+  int nlayer = 1;              // 1: CUBE/main's in-cell order; > 1: CUBEnu's colour passes (cube_gpu_set_drift_layers)
+  float vmax3[3] = {0, 0, 0};  // CUBEnu's vmax(3) of the last particle_mesh
   // scan scratch, reductions
   long long* bsum = nullptr; int nscan_blocks = 0;
   double* stat_partial = nullptr; double* stat3 = nullptr;
@@ -661,7 +663,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(dmalloc(&h->stat_partial, std::max<long long>(2 * 4096 * PW_W, (long long)nblk(g.ncell_p, 128)))); CK(dmalloc(&h->stat3, 8));
   CK(dmalloc(&h->rank, cap));
   CK(dmalloc(&h->tile_count, (long long)g.nnt * g.nnt * g.nnt));
-  CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 1));
+  CK(dmalloc(&h->maxoff, 1)); CK(dmalloc(&h->vmax_bits, 4));
   const int nvb = h->nvbin, vh = nvb / 2;  // table sizes of this velocity format
   CK(dmalloc(&h->tanlut, nvb)); CK(dmalloc(&h->dvlut, nvb)); CK(dmalloc(&h->enc, vh));
   CK(dmalloc(&h->tanh, vh + 4)); CK(dmalloc(&h->divok, 1)); CK(dmalloc(&h->dvlut2, nvb)); CK(dmalloc(&h->divok2, 1));
@@ -1125,7 +1127,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
       // pass B only redoes the cells that receive somebody; the others were finished by k_drift_key_chain
       const int* flist = h->count_all ? nullptr : h->flist;
       if (flist) { k_flag_compact<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g.ncell_p, h->inflag, h->flist, h->nflag); CKL(); h->launches++; }
-      FMT_SWITCH(h, const DriftCountArgs<F> A{XPC(h->xp), VPC(h->vp), h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, h->mask_e, h->farblk, h->rank, dt_mid, r};
+      FMT_SWITCH(h, const DriftCountArgs<F> A{XPC(h->xp), VPC(h->vp), h->key, h->rhoc_e, h->cstart_e, h->vfield_e, h->dvlut, h->mask_e, h->farblk, h->rank, dt_mid, r, h->nlayer};
                  if (h->count_minb == 8) k_drift_count<8, F><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, flist, h->nflag, h->rhoc_p2, h->vfield_p2);
                  else k_drift_count<5, F><<<nb, DC_T, 0, h->st>>>(g, A, h->heavy_count, flist, h->nflag, h->rhoc_p2, h->vfield_p2));
       CKL();
@@ -1373,7 +1375,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   const bool merged = !h->old_kick;  // one pass per batch does both kicks (cube_kick.cuh); else fine kick per batch, coarse kick at the end
   const bool kick_c_per_batch = merged || vp_host;
   if (build_dvlut2(h, h->sigma_vi_new)) return 1;
-  CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
+  CK(cudaMemsetAsync(h->vmax_bits, 0, 4 * sizeof(unsigned long long), h->st));
   if (vp_host) {
     CK(cudaMemcpy2DAsync(tile_start.data(), sizeof(long long), h->cstart_p, sizeof(long long) * nt3, sizeof(long long), ntile + 1,
                          cudaMemcpyDeviceToHost, h->st));
@@ -1429,16 +1431,17 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   if (build_dvlut(h, h->sigma_vi)) return 1;
   if (overlap) { CK(cudaStreamWaitEvent(h->st, h->ev_join, 0)); }
   else if (!kick_c_per_batch && coarse_mesh(h, true, a_mid, dt, nullptr)) return 1;
-  float f2c = 0; unsigned long long vb = 0;
+  float f2c = 0; unsigned long long vb4[4] = {0, 0, 0, 0};
   if (!kick_c_per_batch) {
     PhaseTimer pt(h, PH_CKICK);
     if (run_coarse_kick(h, vtab(h), vscale(h->sigma_vi), 0, g.ncell_p)) return 1;
   }
   CK(cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaMemcpyAsync(&vb, h->vmax_bits, sizeof vb, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(vb4, h->vmax_bits, sizeof vb4, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  double vmd; memcpy(&vmd, &vb, sizeof vmd);
+  double vmd; memcpy(&vmd, &vb4[0], sizeof vmd);
   const float vmax = (float)vmd;  // f32 <- max(f32, f64) is monotone, so one final rounding is the same
+  for (int d = 0; d < 3; d++) { double t; memcpy(&t, &vb4[1 + d], sizeof t); h->vmax3[d] = (float)t; }
   float f2f = 0; for (float v : f2) f2f = std::max(f2f, v);
   if (pre_in_fft) f2f = f2f / pscale / pscale;
   float vmax_all = vmax;
@@ -1649,7 +1652,7 @@ extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, f
   CK(cudaMemcpyAsync(h->fc, force_c, sizeof(float) * 3 * m * m * m, cudaMemcpyHostToDevice, h->st));
   if (build_dvlut(h, sigma_vi)) return 1;
   CK(cudaMemsetAsync(h->f2max + h->batch, 0, sizeof(unsigned), h->st));
-  CK(cudaMemsetAsync(h->vmax_bits, 0, sizeof(unsigned long long), h->st));
+  CK(cudaMemsetAsync(h->vmax_bits, 0, 4 * sizeof(unsigned long long), h->st));
   k_force_c_prefix<<<1184, 256, 0, h->st>>>(m * m * m, h->fc, a_mid, dt, h->f2max + h->batch); CKL();
   if (h->old_kick) {
     if (run_coarse_kick(h, vtab(h), vscale(sigma_vi), 0, g.ncell_p)) return 1;
@@ -1712,6 +1715,20 @@ extern "C" int cube_gpu_selftest_codes(cube_handle* h, float sigma_vi, int64_t n
   if (bad_encode) *bad_encode = (int64_t)out[0];
   if (bad_decode) *bad_decode = (int64_t)out[1];
   if (fma_division) *fma_division = (ok != 0 && h->vt_hot) ? 1 : 0;
+  return 0;
+}
+
+// CUBEnu's bookkeeping of the same arithmetic: the order in which update_xp visits the source planes and the
+// per-component vmax.  nlayer = 2*ceiling(dt_mid*sim%vz_max/ncell)+1 (CUBEnu update_particle.f90:37), 0 or 1 = CUBE/main.
+extern "C" int cube_gpu_set_drift_layers(cube_handle* h, int nlayer) {
+  if (!h) return fail("null handle");
+  if (nlayer < 0) return fail("cube_gpu_set_drift_layers: nlayer must be >= 0");
+  h->nlayer = nlayer < 1 ? 1 : nlayer;
+  return 0;
+}
+extern "C" int cube_gpu_get_vmax3(cube_handle* h, float vmax3[3]) {
+  if (!h || !vmax3) return fail("null argument");
+  for (int d = 0; d < 3; d++) vmax3[d] = h->vmax3[d];
   return 0;
 }
 

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(PC_T) k_fine_kick_p(Geom g, int tile0, int M, 
 template <class F>
 __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, double S, const typename F::XT* __restrict__ xp, typename F::VT* __restrict__ vp,
                                                           const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
-                                                          const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits,
+                                                          const float* __restrict__ Gc, unsigned long long* __restrict__ vmax_bits /* [4]: scalar, |.| per component */,
                                                           long long c_begin, long long c_end /* file-order cell range */) {
   extern __shared__ __align__(16) unsigned char pw_smem[];
   float* s_tan = reinterpret_cast<float*>(pw_smem);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
   const VDec dec = make_dec(vt, s_tan, S);
   __syncthreads();
   const int m = g.nc + 2;
-  double vm = 0.0;
+  double vm = 0.0, va0 = 0.0, va1 = 0.0, va2 = 0.0;
   for (long long c0 = c_begin + ((long long)blockIdx.x * PW_W + warp) * WC; c0 < c_end; c0 += (long long)gridDim.x * PW_W * WC) {
     long long p0;
     const int np = warp_chunk_setup(g, cstart_p, c0, c_end, ws, lane, p0);
@@ -312,12 +312,22 @@ __global__ void __launch_bounds__(PW_T, 1) k_coarse_kick_w(Geom g, VTab vt, doub
         v2 = __dadd_rn(v2, (double)kick_weight(__ldg(f + 2), wx, wy, wz));
       }
       const double vf0 = vfield_p[3 * L], vf1 = vfield_p[3 * L + 1], vf2 = vfield_p[3 * L + 2];
-      vm = fmax(vm, fmax(__dadd_rn(v0, vf0), fmax(__dadd_rn(v1, vf1), __dadd_rn(v2, vf2))));  // pm.f90:220
+      const double t0 = __dadd_rn(v0, vf0), t1 = __dadd_rn(v1, vf1), t2 = __dadd_rn(v2, vf2);
+      vm = fmax(vm, fmax(t0, fmax(t1, t2)));                                            // pm.f90:220
+      va0 = fmax(va0, fabs(t0)); va1 = fmax(va1, fabs(t1)); va2 = fmax(va2, fabs(t2));  // CUBEnu pm.f90:349: vmax(3), with abs
       store_code3(vp, p, vp_encode_lut<F::VB>(v0, S, vt.thr), vp_encode_lut<F::VB>(v1, S, vt.thr), vp_encode_lut<F::VB>(v2, S, vt.thr));
     }
   }
-  for (int o = 16; o; o >>= 1) vm = fmax(vm, __shfl_down_sync(FULL, vm, o));
-  if (lane == 0 && vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
+  for (int o = 16; o; o >>= 1) {
+    vm = fmax(vm, __shfl_down_sync(FULL, vm, o));
+    va0 = fmax(va0, __shfl_down_sync(FULL, va0, o)); va1 = fmax(va1, __shfl_down_sync(FULL, va1, o)); va2 = fmax(va2, __shfl_down_sync(FULL, va2, o));
+  }
+  if (lane == 0) {  // non-negative doubles order like their bit patterns
+    if (vm > 0.0) atomicMax(vmax_bits, (unsigned long long)__double_as_longlong(vm));
+    if (va0 > 0.0) atomicMax(vmax_bits + 1, (unsigned long long)__double_as_longlong(va0));
+    if (va1 > 0.0) atomicMax(vmax_bits + 2, (unsigned long long)__double_as_longlong(va1));
+    if (va2 > 0.0) atomicMax(vmax_bits + 3, (unsigned long long)__double_as_longlong(va2));
+  }
 }
 
 // force_c(3,0:nc+1,...) from the three inverse transforms + periodic 1-cell halo (pm.f90:176-189, single image),
@@ -654,6 +664,25 @@ __device__ __forceinline__ int dest_flags(const Geom& g, const int* __restrict__
 template <class F> struct DriftCountArgs {
   const typename F::XT* xp; const typename F::VT* vp; const unsigned short* key; const int* rhoc_e; const long long* cstart_e; const float* vfield_e;
   const double* dvlut; const unsigned* mask_e; const int* farblk; unsigned* rank; double dt_mid; int r;
+  int nlayer;  // 1: CUBE/main (source planes in storage order); > 1: CUBEnu's colour passes over k (update_particle.f90:37,55-58)
+};
+// Source planes sk in [k-r, k+r] of a destination at tile-local plane k (0-based), in the reference's traversal order.  CUBE/main
+// walks k upwards; CUBEnu walks `do ilayer=0,nlayer-1; do k=1-ncb+ilayer,nt+ncb,nlayer`: colour (sk0 + ncb) mod nlayer first, then k.
+// Usage: for (PlaneOrder po(k, r, nlayer); po.valid(); po.next()) { const int sk = po.sk; ... }
+struct PlaneOrder {
+  int sk, last, nlayer, c, c_first, first;
+  __device__ __forceinline__ PlaneOrder(int k, int r, int nl) : last(k + r), nlayer(nl < 1 ? 1 : nl), c(0), first(k - r) {
+    c_first = ((first + NCB) % nlayer + nlayer) % nlayer;
+    seek();
+  }
+  __device__ __forceinline__ void seek() {  // first plane of colour c (or of the next colour that has one)
+    for (; c < nlayer; c++) {
+      sk = first + ((c - c_first) % nlayer + nlayer) % nlayer;
+      if (sk <= last) return;
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return c < nlayer; }
+  __device__ __forceinline__ void next() { sk += nlayer; if (sk > last) { c++; seek(); } }
 };
 // one candidate particle of source cell (si,sj,sk) for destination (i,j,k): accepted? and its velocity
 template <class F>
@@ -732,8 +761,8 @@ __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountAr
       float vfn0 = (float)__dmul_rn((double)A.vfield_e[3 * e0], weight_v);  // :27
       float vfn1 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 1], weight_v);
       float vfn2 = (float)__dmul_rn((double)A.vfield_e[3 * e0 + 2], weight_v);
-      for (int sk = k - r; sk <= k + r; sk++)
-        for (int sj = j - r; sj <= j + r; sj++) {
+      for (PlaneOrder po(k, r, A.nlayer); po.valid(); po.next())
+        for (int sj = j - r, sk = po.sk; sj <= j + r; sj++) {
           long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
           for (int si = i - r; si <= i + r; si++, e++) {
             const int ddx = i - si, ddy = j - sj, ddz = k - sk;
@@ -783,8 +812,8 @@ __global__ void __launch_bounds__(DC_T, MINB) k_drift_count(Geom g, DriftCountAr
       const int dcomp = lane % 3;
       float vfn = (float)__dmul_rn((double)A.vfield_e[3 * e0 + dcomp], weight_v);
       double(*sv)[32] = s_v[wp];
-      for (int sk = k - r; sk <= k + r; sk++)
-        for (int sj = j - r; sj <= j + r; sj++) {
+      for (PlaneOrder po(k, r, A.nlayer); po.valid(); po.next())
+        for (int sj = j - r, sk = po.sk; sj <= j + r; sj++) {
           long long e = ext_index(g, X0 + i - r, Y0 + sj, Z0 + sk);
           for (int si = i - r; si <= i + r; si++, e++) {
             const int ddx = i - si, ddy = j - sj, ddz = k - sk;

@@ -79,6 +79,8 @@ def load_library():
     L.cube_gpu_exchange_plan.argtypes = [C.POINTER(CubeParams), vp, i32]
     L.cube_gpu_selftest_codes.argtypes = [vp, f32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.cube_gpu_power_spectrum.argtypes = [vp, f32, vp, i32, C.POINTER(i32)]
+    L.cube_gpu_set_drift_layers.argtypes = [vp, i32]
+    L.cube_gpu_get_vmax3.argtypes = [vp, C.POINTER(C.c_float * 3)]
     _lib = L
     return L
 
@@ -91,7 +93,7 @@ ABI_SYMBOLS = [
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
     "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
-    "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum",
+    "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum", "cube_gpu_set_drift_layers", "cube_gpu_get_vmax3",
 ]
 
 
@@ -269,7 +271,14 @@ class CubeGPU:
             self._ck(self.L.cube_gpu_stream_vp(self.h, _p(out["vp"])))
 
     # ---- step subroutines -------------------------------------------------------------------
-    def update_particle(self, dt_old, dt):
+    def update_particle(self, dt_old, dt, vz_max=None):
+        """``vz_max=None``: CUBE/main's in-cell order.  With CUBEnu's ``sim%vz_max`` the source planes are visited in
+        ``nlayer = 2*ceiling(dt_mid*vz_max/ncell)+1`` colour passes (CUBEnu update_particle.f90:37,55-58)."""
+        nlayer = 1
+        if vz_max is not None:
+            dt_mid = F32(F32(F32(dt_old) + F32(dt)) / F32(2))
+            nlayer = 2 * int(np.ceil(F32(F32(dt_mid * F32(vz_max)) / F32(4)))) + 1
+        self._ck(self.L.cube_gpu_set_drift_layers(self.h, int(nlayer)))
         npl = C.c_int64(); sig = C.c_float(); ovh = C.c_float(); st = (C.c_double * 3)()
         self._ck(self.L.cube_gpu_update_x(self.h, F32(dt_old), F32(dt), C.byref(npl), C.byref(sig), C.byref(st), C.byref(ovh)))
         self.nplocal = npl.value
@@ -291,7 +300,10 @@ class CubeGPU:
         o = [C.c_float() for _ in range(4)]
         self._ck(self.L.cube_gpu_particle_mesh(self.h, F32(a_mid), F32(dt), *[C.byref(v) for v in o]))
         self.dt_fine, self.dt_coarse, self.dt_vmax = (F32(v.value) for v in o[:3])
-        return dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000), vmax=F32(o[3].value))
+        v3 = (C.c_float * 3)()
+        self._ck(self.L.cube_gpu_get_vmax3(self.h, C.byref(v3)))
+        return dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000), vmax=F32(o[3].value),
+                    vmax3=[F32(v3[d]) for d in range(3)])   # vmax3: CUBEnu's vmax(3) (pm.f90:349,398)
 
     def step(self, dt_old, dt, a_mid):
         """cafcube.f90:27-31."""

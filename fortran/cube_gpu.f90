@@ -42,9 +42,9 @@ module cube_gpu
     end function
     ! particle_initialization.f90:11-72
     integer(c_int) function cube_gpu_upload(h, xp, vp, rhoc_phys, vfield_phys, nplocal, npglobal, sigma_vi) bind(C, name="cube_gpu_upload")
-      import :: c_int, c_ptr, c_int16_t, c_int32_t, c_int64_t, c_float
+      import :: c_int, c_ptr, c_int32_t, c_int64_t, c_float
       type(c_ptr), value :: h
-      integer(c_int16_t), intent(in) :: xp(3,*), vp(3,*)
+      type(c_ptr), value :: xp, vp                       ! c_loc(xp), c_loc(vp): integer(izipx) xp(3,*), integer(izipv) vp(3,*)
       integer(c_int32_t), intent(in) :: rhoc_phys(*)     ! rhoc(1:nt,1:nt,1:nt,:,:,:) contiguous copy
       real(c_float), intent(in) :: vfield_phys(*)        ! vfield(:,1:nt,1:nt,1:nt,:,:,:)
       integer(c_int64_t), value :: nplocal, npglobal
@@ -75,9 +75,9 @@ module cube_gpu
     end function
     ! checkpoint.f90:33-70
     integer(c_int) function cube_gpu_download(h, xp, vp, rhoc_phys, vfield_phys, nplocal, sigma_vi) bind(C, name="cube_gpu_download")
-      import :: c_int, c_ptr, c_int16_t, c_int32_t, c_int64_t, c_float
+      import :: c_int, c_ptr, c_int32_t, c_int64_t, c_float
       type(c_ptr), value :: h
-      integer(c_int16_t), intent(out) :: xp(3,*), vp(3,*)
+      type(c_ptr), value :: xp, vp                       ! c_loc of integer(izipx) xp(3,*), integer(izipv) vp(3,*); c_null_ptr = skip
       integer(c_int32_t), intent(out) :: rhoc_phys(*)
       real(c_float), intent(out) :: vfield_phys(*)
       integer(c_int64_t), intent(out) :: nplocal
@@ -99,7 +99,8 @@ module cube_gpu
       import :: c_int, c_ptr
       type(c_ptr), value :: h, vp
     end function
-    ! -DPID: IDs of the particles of the last cube_gpu_upload (file order); they follow every cube_gpu_update_x (single image)
+    ! -DPID: IDs of the particles of the last cube_gpu_upload (file order); they follow every cube_gpu_update_x and cross images
+    ! with vp in cube_gpu_buffer(do_v) (buffer_v.f90:23,42,62,81,104)
     integer(c_int) function cube_gpu_upload_pid(h, pid) bind(C, name="cube_gpu_upload_pid")
       import :: c_int, c_ptr, c_int64_t
       type(c_ptr), value :: h
@@ -109,6 +110,27 @@ module cube_gpu
       import :: c_int, c_ptr, c_int64_t
       type(c_ptr), value :: h
       integer(c_int64_t), intent(out) :: pid(*)
+    end function
+    ! cicpower + powerspectrum (CUBE/utilities/cicpower.f90, powerspectrum.f90, linear_kbin) of the resident state: xi(nbin,10)
+    ! in Fortran order = the reference's xi(10,nbin) transposed; nbin = nint(nyquist*sqrt(3.)) comes back in nbin
+    integer(c_int) function cube_gpu_power_spectrum(h, box, xi, nbin_cap, nbin) bind(C, name="cube_gpu_power_spectrum")
+      import :: c_int, c_ptr, c_float, c_double
+      type(c_ptr), value :: h
+      real(c_float), value :: box
+      real(c_double), intent(out) :: xi(*)
+      integer(c_int), value :: nbin_cap
+      integer(c_int), intent(out) :: nbin
+    end function
+    ! CUBEnu's bookkeeping: nlayer colour passes of update_xp (update_particle.f90:37,55-58) and vmax(3) (pm.f90:349,398)
+    integer(c_int) function cube_gpu_set_drift_layers(h, nlayer) bind(C, name="cube_gpu_set_drift_layers")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int), value :: nlayer
+    end function
+    integer(c_int) function cube_gpu_get_vmax3(h, vmax3) bind(C, name="cube_gpu_get_vmax3")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: h
+      real(c_float), intent(out) :: vmax3(3)
     end function
     integer(c_int) function cube_gpu_finalize(h) bind(C, name="cube_gpu_finalize")
       import :: c_int, c_ptr
@@ -136,16 +158,18 @@ contains
     error stop
   end subroutine
 
-  ! tan((pi*real(v))/real(nvbin-1)) for every 16-bit pattern, evaluated by THIS build's libm, so that
-  ! the GPU decodes velocities exactly like pm.f90:102 / update_particle.f90:42 would on this host
-  subroutine cube_gpu_make_tanf_lut(lut)
-    real(c_float), intent(out) :: lut(0:65535)
+  ! tan((pi*real(v))/real(nvbin-1)) for every pattern of an integer(izipv) code (nvbin = 2**(8*izipv) entries), evaluated by THIS
+  ! build's libm, so that the GPU decodes velocities exactly like pm.f90:102 / update_particle.f90:42 would on this host
+  subroutine cube_gpu_make_tanf_lut(lut, izipv)
+    integer, intent(in) :: izipv
+    real(c_float), intent(out) :: lut(0:2**(8*izipv)-1)
     real, parameter :: pi = 4*atan(1.)
-    integer :: u
-    integer(2) :: v
-    do u = 0, 65535
-      v = transfer(int(u, 4), v)          ! low 16 bits reinterpreted as integer(2)
-      lut(u) = tan((pi*real(v))/real(65535))
+    integer :: u, v, nvbin
+    nvbin = 2**(8*izipv)
+    do u = 0, nvbin-1
+      v = u
+      if (u >= nvbin/2) v = u - nvbin      ! the pattern read as a signed integer(izipv)
+      lut(u) = tan((pi*real(v))/real(nvbin-1))
     end do
   end subroutine
 

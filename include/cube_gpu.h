@@ -116,6 +116,14 @@ int cube_gpu_download_cells_async(cube_handle *h, int32_t *rhoc_phys, float *vfi
  * checkpoint.f90:51-58 leaves under the computation.  cube_gpu_download with NULL for vp waits for the stream. */
 int cube_gpu_stream_vp(cube_handle *h, void *vp);
 
+/* CUBEnu keeps the same arithmetic with other bookkeeping (CUBEnu/work/main/update_particle.f90:37,55-58, pm.f90:349,398):
+ * update_xp visits the source planes in `nlayer = 2*ceiling(dt_mid*sim%vz_max/ncell)+1` colour passes, which fixes the order of the
+ * particles inside a destination cell (and of the f32 additions into vfield_new), and particle_mesh keeps vmax(3) = max|v| per
+ * component.  set_drift_layers(nlayer) selects that order for the following cube_gpu_update_x calls (0 or 1 = CUBE/main's, the default);
+ * get_vmax3 returns vmax(3) of the last cube_gpu_particle_mesh (whose `vmax` argument stays CUBE/main's scalar, pm.f90:220). */
+int cube_gpu_set_drift_layers(cube_handle *h, int nlayer);
+int cube_gpu_get_vmax3(cube_handle *h, float vmax3[3]);
+
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);
 

@@ -314,3 +314,45 @@ def test_velocities_streamed_per_batch_equal_the_plain_step(tables):
     assert sa == sb
     for k in ("dt_fine", "dt_coarse", "dt_vmax"):
         assert pa[k] == pb[k], k
+
+
+def test_cubenu_order_and_vmax3(tables):
+    """CUBEnu's bookkeeping of the same arithmetic (cube_gpu_set_drift_layers / cube_gpu_get_vmax3): update_xp visits the source
+    planes in nlayer colour passes (CUBEnu update_particle.f90:37,55-58), which changes the order of the particles inside a
+    destination cell and of the f32 additions into vfield_new -- counts, positions, codes and vfield bit for bit against the
+    oracle's CUBEnu variant, on a step large enough that cells receive particles from several planes; then vmax(3) (pm.f90:349)."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=17, disp_rms=1.2)
+    dt_old, dt, a_mid = np.float32(0.9), np.float32(1.1), np.float32(0.021)
+    differs = False
+    for vz_max in (2.0, 9.0):          # nlayer = 3 and 7
+        O = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+        O.load(states, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+        G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+        G.particle_initialization(states[0], sig); G.buffer_density(); G.buffer_x(); G.buffer_v()
+        try:
+            O.update_particle(dt_old, dt, vz_max=vz_max)
+            assert O.nlayer > 1
+            G.update_particle(dt_old, dt, vz_max=vz_max)
+            so = O.store(0); sg, _ = G.checkpoint()
+            for k in ("rhoc", "xp", "vp"):
+                assert np.array_equal(so[k], sg[k]), (vz_max, k)
+            assert np.array_equal(so["vfield"].view(np.uint32), sg["vfield"].view(np.uint32))
+            # the order does matter on this state: CUBE/main's order gives other codes
+            G2 = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=co.tanf_lut())
+            G2.particle_initialization(states[0], sig); G2.buffer_density(); G2.buffer_x(); G2.buffer_v()
+            G2.update_particle(dt_old, dt)
+            s2, _ = G2.checkpoint()
+            G2.close()
+            assert np.array_equal(s2["rhoc"], sg["rhoc"])
+            differs = differs or not np.array_equal(s2["xp"], sg["xp"])
+            O.buffer_density(); O.buffer_x(); G.buffer_density(); G.buffer_x()
+            po = O.particle_mesh(a_mid, dt, keep=True)
+            G.fine_kick_with(1, 1, 1, po["meshes"]["force_f"][(0, 1, 1, 1)], a_mid, dt, O.sigma_vi, O.sigma_vi)   # any fine kick: vmax3 comes from the coarse one
+            G.coarse_kick_with(O.force_c_image(po["meshes"]["force_c"], 0), a_mid, dt, O.sigma_vi)
+        finally:
+            G.close(); O.close()
+    assert differs
