@@ -291,23 +291,27 @@ static int make_force_map(cube_handle* h) {
 }
 
 // fine kick of the tiles [tile0, tile0+nb) with the force in h->F (pm.f90:88-118); codes come in with h->dvlut's sigma
-static int run_fine_kick(cube_handle* h, int tile0, int nb, double S_new) {
+// `hm`: whose force mesh (a second species is kicked by the first species' h->F / h->fc)
+static int run_fine_kick(cube_handle* h, int tile0, int nb, double S_new, cube_handle* hm = nullptr) {
+  if (!hm) hm = h;
   const Geom& g = h->g;
   const long long nt3 = (long long)g.nt * g.nt * g.nt;
-  if (h->kick_stage == 2 && h->zx == 2 && h->zv == 2 && getenv("CUBE_GPU_FKICK_BRICK")) {
+  cudaStream_t st = hm->st;
+  if (hm == h && h->kick_stage == 2 && h->zx == 2 && h->zv == 2 && getenv("CUBE_GPU_FKICK_BRICK")) {
     const int bpt = ((g.nt + KB_X - 1) / KB_X) * ((g.nt + KB_Y - 1) / KB_Y) * ((g.nt + KB_Z - 1) / KB_Z);
     k_fine_kick_brick<<<dim3(bpt, nb), FKB_T, 0, h->st>>>(g, tile0, h->fg.M, (const short*)h->xp, (short*)h->vp, h->cstart_p, h->dvlut, h->enc, S_new, h->fmap);
   } else {
-    FMT_SWITCH(h, k_fine_kick_p<F><<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, h->st>>>(g, tile0, h->fg.M, h->fg.FP, XPC(h->xp), VPM(h->vp), h->cstart_p, h->F, h->dvlut, h->enc, S_new));
+    FMT_SWITCH(h, k_fine_kick_p<F><<<dim3(nblk(nt3, PC_CELLS), nb), PC_T, 0, st>>>(g, tile0, hm->fg.M, hm->fg.FP, XPC(h->xp), VPM(h->vp), h->cstart_p, hm->F, h->dvlut, h->enc, S_new));
   }
   CKL();
   h->launches++;
   return 0;
 }
 // coarse kick of the file-order cells [c_begin, c_end) with the force in h->fc (pm.f90:196-228)
-static int run_coarse_kick(cube_handle* h, const VTab& vt, double S, long long c_begin, long long c_end) {
-  FMT_SWITCH(h, k_coarse_kick_w<F><<<pw_grid(h, c_end - c_begin), PW_T, pw_smem_bytes(h->vt_hot), h->st>>>(h->g, vt, S, XPC(h->xp), VPM(h->vp), h->cstart_p, h->vfield_p, h->fc,
-                                                                                                       h->vmax_bits, c_begin, c_end));
+static int run_coarse_kick(cube_handle* h, const VTab& vt, double S, long long c_begin, long long c_end, cube_handle* hm = nullptr) {
+  if (!hm) hm = h;
+  FMT_SWITCH(h, k_coarse_kick_w<F><<<pw_grid(h, c_end - c_begin), PW_T, pw_smem_bytes(h->vt_hot), hm->st>>>(h->g, vt, S, XPC(h->xp), VPM(h->vp), h->cstart_p, h->vfield_p, hm->fc,
+                                                                                                        h->vmax_bits, c_begin, c_end));
   CKL();
   h->launches++;
   return 0;
@@ -1217,17 +1221,19 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
 // fine mesh of tiles [tile0, tile0+nb): deposit -> x,y forward -> z forward * i kern_f, z inverse (x3) -> y,x inverse
 // (pm.f90:44-84).  Leaves force_f of the nb tiles in h->F.
 // deposit the particles of source cells R.c0..R.c1 onto the fine-grid region R (frame: FRAME_NONE, or the tile's first cell)
-static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* out) {
+// `hp`: whose particles (a further species of a two-species run deposits into the first species' meshes, accumulate = 1)
+static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* out, cube_handle* hp = nullptr, int accumulate = 0) {
+  if (!hp) hp = h;
   PhaseTimer pt(h, PH_FDEP);
   auto launch = [&](auto cfg) {
     using C = decltype(cfg);
     const unsigned nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY, nbz = (R.n[2] + C::NZ - 1) / C::NZ;
     auto go = [&](auto xt) {
       using XT = decltype(xt);
-      if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
-      else k_fine_deposit_r<C, true, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, out);
+      if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out, accumulate);
+      else k_fine_deposit_r<C, true, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out, accumulate);
     };
-    if (h->zx == 2) go((short)0); else go((signed char)0);
+    if (hp->zx == 2) go((short)0); else go((signed char)0);
   };
   if (h->fd_brick == 888) launch(Fd888{}); else if (h->fd_brick == 844) launch(Fd844{}); else launch(Fd884{});
   CKL();
@@ -1235,7 +1241,7 @@ static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* 
   return 0;
 }
 // fine density of the tiles [tile0, tile0+nb) in h->rho; returns how the x pass finds each tile's window
-static int fine_density_batch(cube_handle* h, int tile0, int nb, RhoView& v) {
+static int fine_density_batch(cube_handle* h, int tile0, int nb, RhoView& v, cube_handle* h2 = nullptr) {
   const Geom& g = h->g;
   const int N = h->fg.N;
   v.p = h->rho; v.nnt = g.nnt; v.tile0 = tile0; v.tstep = 4 * g.nt;
@@ -1244,7 +1250,8 @@ static int fine_density_batch(cube_handle* h, int tile0, int nb, RhoView& v) {
     int k[3];
     batch_box(g, tile0, nb, v.t0, k);
     v.ldy = R.ldy; v.ldz = R.ldz; v.tvol = 0;
-    return fine_deposit(h, R, make_int3(FRAME_NONE, 0, 0), h->rho);
+    if (fine_deposit(h, R, make_int3(FRAME_NONE, 0, 0), h->rho)) return 1;
+    return h2 ? fine_deposit(h, R, make_int3(FRAME_NONE, 0, 0), h->rho, h2, 1) : 0;  // pm.f90:79-99 (NEUTRINOS): the same rho_f
   }
   v.ldy = N; v.ldz = (long long)N * N; v.tvol = (long long)N * N * N; v.t0[0] = v.t0[1] = v.t0[2] = 0;
   for (int b = 0; b < nb; b++) {  // large tiles: each in its own frame (f32 rounding of tempx, cube_kernels.cuh)
@@ -1253,13 +1260,14 @@ static int fine_density_batch(cube_handle* h, int tile0, int nb, RhoView& v) {
     for (int d = 0; d < 3; d++) { R.c0[d] = tc[d] * g.nt - (NCB - 1); R.c1[d] = (tc[d] + 1) * g.nt + (NCB - 1); R.f0[d] = 4 * tc[d] * g.nt - 16; R.n[d] = N; }
     R.ldy = N; R.ldz = (long long)N * N;
     if (fine_deposit(h, R, make_int3(tc[0] * g.nt, tc[1] * g.nt, tc[2] * g.nt), h->rho + (size_t)b * v.tvol)) return 1;
+    if (h2 && fine_deposit(h, R, make_int3(tc[0] * g.nt, tc[1] * g.nt, tc[2] * g.nt), h->rho + (size_t)b * v.tvol, h2, 1)) return 1;
   }
   return 0;
 }
 
 // leaves force_f of the nb tiles in h->F (multiplied by the kick prefix a_mid*dt/6/pi when `prefix`) and the per-tile
 // f2_max_fine in h->f2max[0..nb)
-static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid, float dt) {
+static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid, float dt, cube_handle* h2 = nullptr) {
   FftGeom f = h->fg;
   f.nbatch = nb;
   const FftPlan& pl = *h->plan;
@@ -1267,7 +1275,7 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
   const size_t smem_x = (size_t)(N * (FL + 1) + N) * sizeof(float2), smem_y = (size_t)(N * FL + N) * sizeof(float2);
   const size_t smem_z = (size_t)(2 * N * FL + N) * sizeof(float2) + (size_t)3 * (N / 2 + 1) * FL * sizeof(float);
   RhoView rv;
-  if (fine_density_batch(h, tile0, nb, rv)) return 1;
+  if (fine_density_batch(h, tile0, nb, rv, h2)) return 1;
   {
     PhaseTimer pt(h, PH_FFTX);
     pl.x_fwd<<<dim3((N + 31) / 32, N, nb), T, smem_x, h->st>>>(f, rv, h->Ak, h->tw); CKL();
@@ -1307,18 +1315,21 @@ static int set_coarse_streams(cube_handle* h, cudaStream_t st) {
 
 // coarse mesh (pm.f90:127-189): deposit -> r2c -> i kern_c -> 3 c2r -> force_c with halo.  Leaves the kick prefix
 // force_c*a_mid*dt/6/pi in h->fc, f2_max_coarse in h->f2max[batch]; raw (optional, device) gets force_c itself.
-static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw) {
+static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw, cube_handle* h2 = nullptr) {
   const Geom& g = h->g;
   const bool multi = h->nimg > 1;
   {
     PhaseTimer pt(h, PH_CDEP);
     const long long nbox = (long long)(g.nc + 2) * (g.nc + 2) * (g.nc + 2);
-    const int heavy = h->mass_p <= 8.f ? h->heavy_deposit : INT_MAX;  // REDUX sums of 32 terms stay below 2^32
-    if (h->zx == 2) k_coarse_cell_sums<short><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum);
-    else k_coarse_cell_sums<signed char><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, nbox, h->csum);
-    CKL();
-    k_coarse_gather27<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, nbox, h->csum, h->r3, multi ? g.nc : g.nc + 2); CKL();
-    h->launches += 2;
+    for (cube_handle* hp : {h, h2}) {  // every species into the same r3 (pm.f90:130-163 with NEUTRINOS)
+      if (!hp) continue;
+      const int heavy = hp->mass_p <= 8.f ? h->heavy_deposit : INT_MAX;  // REDUX sums of 32 terms stay below 2^32
+      if (hp->zx == 2) k_coarse_cell_sums<short><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const short*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, nbox, h->csum);
+      else k_coarse_cell_sums<signed char><<<nblk(nbox, CD_T), CD_T, 0, h->st>>>(g, heavy, (const signed char*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, nbox, h->csum);
+      CKL();
+      k_coarse_gather27<<<nblk(g.ncell_p, 256), 256, 0, h->st>>>(g, nbox, h->csum, h->r3, multi ? g.nc : g.nc + 2, hp != h); CKL();
+      h->launches += 2;
+    }
   }
   if (!through_force) return 0;
   PhaseTimer pt(h, PH_CFFT);
@@ -1461,6 +1472,108 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two particle species sharing the meshes (CUBEnu -DNEUTRINOS: pm.f90:79-99,160,235,356 deposit xp_nu with mass_p_nu into the same
+// rho_f / r3 and kick vp_nu with the same forces; update_particle.f90:326-353 drifts them through their own rhoc_nu / vfield_nu with
+// sigma_vi_nu).  Every species is a handle of its own -- its own codes, zip format, cell arrays, sigma_vi, capacities, ghost exchange:
+// cube_gpu_upload / update_x / buffer / download act per handle exactly as for one species.  This call is particle_mesh for both:
+// `h` owns the meshes (fine pipeline, coarse FFT), `h2`'s particles are deposited into them after h's and kicked from them.
+//   mass_p of a species: cube_gpu_set_mass_p (sim%mass_p_cdm, sim%mass_p_nu; the single-species default nf_global^3/npglobal would
+//   count the mean density twice).
+extern "C" int cube_gpu_set_mass_p(cube_handle* h, float mass_p) {
+  if (!h) return fail("null handle");
+  if (!(mass_p > 0.f)) return fail("cube_gpu_set_mass_p: mass_p must be positive");
+  h->mass_p = mass_p;
+  return 0;
+}
+
+extern "C" int cube_gpu_particle_mesh_species(cube_handle* h, cube_handle* h2, float a_mid, float dt, float* dt_fine, float* dt_coarse,
+                                              float* dt_vmax, float* vmax_out, float* dt_vmax2, float* vmax2_out) {
+  if (!h || !h2) return fail("null handle");
+  if (h == h2) return fail("cube_gpu_particle_mesh_species: the two species must be different handles");
+  g_cur = h;
+  CK(cudaSetDevice(h->p.device));
+  if (h2->p.device != h->p.device) return fail("cube_gpu_particle_mesh_species: both species must live on the same device");
+  const Geom& g = h->g;
+  if (memcmp(&h2->g, &g, sizeof(Geom)) != 0) return fail("cube_gpu_particle_mesh_species: the species differ in geometry (nn, nnt, nc, image)");
+  if (!h->buffered || !h2->buffered) return fail("cube_gpu_particle_mesh_species: both states must be buffered (call cube_gpu_buffer on each)");
+  for (cube_handle* q : {h, h2}) {
+    if (q->copy_pending && q->copy_reads_vp) { CK(cudaStreamWaitEvent(h->st, q->ev_copy[1], 0)); q->copy_reads_vp = false; }
+    q->vp_stream_host = nullptr;
+  }
+  // everything below runs on h's stream: wait for what the second species still has in flight on its own, and lend it ours
+  CK(cudaEventRecord(h2->ev_fork, h2->st)); CK(cudaStreamWaitEvent(h->st, h2->ev_fork, 0));
+  if (h2->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h2->ev_vghost, 0)); }
+  cudaStream_t st2 = h2->st;
+  h2->st = h->st;
+  int rc = 0;
+  float f2f = 0, f2c = 0, vmax[2] = {0, 0};
+  const int ntile = g.nnt * g.nnt * g.nnt;
+  std::vector<float> f2(ntile, 0.f);
+  const float pscale = ((1.0f * a_mid) * dt) / 6.0f / PI_F;
+  const bool pre_in_fft = pscale > 1e-12f && pscale < 1e12f;
+  do {
+    for (cube_handle* q : {h, h2}) {
+      if ((rc = build_dvlut(q, q->sigma_vi))) break;
+      if ((rc = build_dvlut2(q, q->sigma_vi_new))) break;
+      if (cudaMemsetAsync(q->vmax_bits, 0, 4 * sizeof(unsigned long long), h->st) != cudaSuccess) { rc = fail("memset"); break; }
+    }
+    if (rc) break;
+    if ((rc = coarse_mesh(h, true, a_mid, dt, nullptr, h2))) break;
+    for (int t0 = 0; t0 < ntile && !rc; t0 += h->batch) {
+      const int nb = std::min(h->batch, ntile - t0);
+      if ((rc = fine_mesh(h, t0, nb, pre_in_fft, a_mid, dt, h2))) break;
+      if (cudaMemcpyAsync(f2.data() + t0, h->f2max, sizeof(float) * nb, cudaMemcpyDeviceToHost, h->st) != cudaSuccess) { rc = fail("f2max copy"); break; }
+      if (!pre_in_fft) {
+        FftGeom fb = h->fg; fb.nbatch = nb;
+        k_prefix_rows<<<dim3(592, nb), 256, 0, h->st>>>(fb, h->F, a_mid, dt);
+        h->launches++;
+      }
+      PhaseTimer pt(h, PH_FKICK);
+      if ((rc = run_fine_kick(h, t0, nb, vscale(h->sigma_vi_new)))) break;                 // pm.f90:88-118
+      if ((rc = run_fine_kick(h2, t0, nb, vscale(h2->sigma_vi_new), h))) break;            // ... and its NEUTRINOS block
+    }
+    if (rc) break;
+    for (cube_handle* q : {h, h2}) {
+      q->sigma_vi = q->sigma_vi_new;  // pm.f90:122
+      if ((rc = build_dvlut(q, q->sigma_vi))) break;
+    }
+    if (rc) break;
+    {
+      PhaseTimer pt(h, PH_CKICK);
+      if ((rc = run_coarse_kick(h, vtab(h), vscale(h->sigma_vi), 0, g.ncell_p))) break;     // pm.f90:196-228
+      if ((rc = run_coarse_kick(h2, vtab(h2), vscale(h2->sigma_vi), 0, g.ncell_p, h))) break;
+    }
+    unsigned long long vb[2] = {0, 0};
+    if (cudaMemcpyAsync(&f2c, h->f2max + h->batch, sizeof(float), cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
+        cudaMemcpyAsync(&vb[0], h->vmax_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
+        cudaMemcpyAsync(&vb[1], h2->vmax_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
+        cudaStreamSynchronize(h->st) != cudaSuccess) { rc = fail("cube_gpu_particle_mesh_species: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    for (int q = 0; q < 2; q++) { double t; memcpy(&t, &vb[q], sizeof t); vmax[q] = (float)t; }
+    for (float v : f2) f2f = std::max(f2f, v);
+    if (pre_in_fft) f2f = f2f / pscale / pscale;
+  } while (0);
+  h2->st = st2;
+  if (rc) { abort_current_comm(); return 1; }
+  float vall[2] = {vmax[0], vmax[1]};
+  if (h->nimg > 1) {  // pm.f90:239-244
+    struct Rec { float f2f, f2c, v0, v1; } mine = {f2f, f2c, vmax[0], vmax[1]};
+    std::vector<Rec> all(h->nimg);
+    CC(h->comm->allgather_host(&mine, all.data(), sizeof(Rec), h->st));
+    for (int m = 0; m < h->nimg; m++) { f2f = std::max(f2f, all[m].f2f); f2c = std::max(f2c, all[m].f2c); vall[0] = std::max(vall[0], all[m].v0); vall[1] = std::max(vall[1], all[m].v1); }
+  }
+  h->last_f2max_fine = f2f;
+  const float GG = 1.0f / 6.0f / PI_F;
+  if (dt_fine) *dt_fine = sqrtf(1.0f / (sqrtf(f2f) * a_mid * GG));
+  if (dt_coarse) *dt_coarse = sqrtf((float)NCELL / (sqrtf(f2c) * a_mid * GG));
+  if (dt_vmax) *dt_vmax = 0.9f * 20 / vall[0];
+  if (dt_vmax2) *dt_vmax2 = 0.9f * 20 / vall[1];
+  if (vmax_out) *vmax_out = vmax[0];
+  if (vmax2_out) *vmax2_out = vmax[1];
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cicpower + powerspectrum (CUBE/utilities/cicpower.f90:70-167, powerspectrum.f90:21-108, linear_kbin) of the resident state, with
 // the library's own deposit kernel (cell-centred variant) and cuFFT.  xi(10,nbin) row-major like the reference's xi(10,nbin):
@@ -1490,10 +1603,10 @@ extern "C" int cube_gpu_power_spectrum(cube_handle* h, float box, double* xi, in
       const unsigned nbx = (m + C::NX - 1) / C::NX, nby = (m + C::NY - 1) / C::NY, nbz = (m + C::NZ - 1) / C::NZ;
       if (h->zx == 2) {
         if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
-        k_fine_deposit_r<C, false, short, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
+        k_fine_deposit_r<C, false, short, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep, 0);
       } else {
         if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, signed char, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
-        k_fine_deposit_r<C, false, signed char, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
+        k_fine_deposit_r<C, false, signed char, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep, 0);
       }
     }
     k_ps_extract<<<nb, 256, 0, h->st>>>(n, dep, rho, part);

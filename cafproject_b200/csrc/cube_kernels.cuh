@@ -234,7 +234,7 @@ template <int XB, bool HALF = false> __device__ __forceinline__ void fine_cic(in
 template <class C, bool FRAME, class XT, bool HALF = false>
 __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const XT* __restrict__ xp,
                                                           const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                          float mass_p, float* __restrict__ out) {
+                                                          float mass_p, float* __restrict__ out, int accumulate /* add to `out`: a further species */) {
   extern __shared__ __align__(16) unsigned fd_smem[];
   unsigned* acc = fd_smem;                                             // [NZ][PZ]
   int* pref = reinterpret_cast<int*>(fd_smem + C::ACC);                // [P2]
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
   for (int q = 0; q < C::NT / 32; q++) { const int v = s_w[q]; if (q < wp) woff += v; total += v; cmax = max(cmax, s_m[q]); }
   const int ox = bx * C::NX, oy = by * C::NY, oz = bz * C::NZ;  // brick offset inside the region
   if (total == 0) {  // empty brick: zeros, no accumulators
+    if (accumulate) return;
     for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {
       const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
       if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = 0.f;
@@ -327,8 +328,11 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
   __syncthreads();
   for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {  // one 32-float row per warp and iteration
     const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
-    if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2])
-      out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
+    if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) {
+      float* dst = out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X;
+      const float v = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
+      *dst = accumulate ? __fadd_rn(*dst, v) : v;  // one writer per node either way
+    }
   }
 }
 
@@ -478,7 +482,8 @@ __global__ void __launch_bounds__(CD_T) k_coarse_cell_sums(Geom g, int heavy, co
 }
 
 // r3(X,Y,Z) = sum over the 27 source cells (X+dx, Y+dy, Z+dz), in k, j, i order, of the partial sum each aims at this target
-__global__ void __launch_bounds__(256) k_coarse_gather27(Geom g, long long nbox, const float* __restrict__ S, float* __restrict__ r3 /*[nc][nc][ld]*/, int ld) {
+__global__ void __launch_bounds__(256) k_coarse_gather27(Geom g, long long nbox, const float* __restrict__ S, float* __restrict__ r3 /*[nc][nc][ld]*/, int ld,
+                                                         int accumulate /* add to r3: a further species (pm.f90:160, NEUTRINOS) */) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= g.ncell_p) return;
   const int X = (int)(q % g.nc), Y = (int)((q / g.nc) % g.nc), Z = (int)(q / ((long long)g.nc * g.nc));
@@ -494,7 +499,8 @@ __global__ void __launch_bounds__(256) k_coarse_gather27(Geom g, long long nbox,
         const long long b = ((long long)(Z + dz + 1) * m + (Y + dy + 1)) * m + (X + dx + 1);
         v = __fadd_rn(v, S[(((1 - dz) * 3 + (1 - dy)) * 3 + (1 - dx)) * nbox + b]);
       }
-  r3[((long long)Z * g.nc + Y) * ld + X] = v;
+  float* dst = r3 + ((long long)Z * g.nc + Y) * ld + X;
+  *dst = accumulate ? __fadd_rn(*dst, v) : v;
 }
 
 // force_c(3,0:nc+1,0:nc+1,0:nc+1) from the three inverse transforms + periodic 1-cell halo

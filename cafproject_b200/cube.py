@@ -79,6 +79,8 @@ def load_library():
     L.cube_gpu_exchange_plan.argtypes = [C.POINTER(CubeParams), vp, i32]
     L.cube_gpu_selftest_codes.argtypes = [vp, f32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.cube_gpu_power_spectrum.argtypes = [vp, f32, vp, i32, C.POINTER(i32)]
+    L.cube_gpu_set_mass_p.argtypes = [vp, f32]
+    L.cube_gpu_particle_mesh_species.argtypes = [vp, vp, f32, f32] + [C.POINTER(f32)] * 6
     L.cube_gpu_set_drift_layers.argtypes = [vp, i32]
     L.cube_gpu_get_vmax3.argtypes = [vp, C.POINTER(C.c_float * 3)]
     _lib = L
@@ -93,7 +95,7 @@ ABI_SYMBOLS = [
     "cube_gpu_coarse_density", "cube_gpu_coarse_force", "cube_gpu_coarse_kick_with", "cube_gpu_phase_count",
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
     "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
-    "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum", "cube_gpu_set_drift_layers", "cube_gpu_get_vmax3",
+    "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum", "cube_gpu_set_drift_layers", "cube_gpu_get_vmax3", "cube_gpu_set_mass_p", "cube_gpu_particle_mesh_species",
 ]
 
 
@@ -304,6 +306,20 @@ class CubeGPU:
         self._ck(self.L.cube_gpu_get_vmax3(self.h, C.byref(v3)))
         return dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000), vmax=F32(o[3].value),
                     vmax3=[F32(v3[d]) for d in range(3)])   # vmax3: CUBEnu's vmax(3) (pm.f90:349,398)
+
+    def set_mass_p(self, mass_p):
+        """Particle mass of this species (CUBEnu sim%mass_p_cdm / sim%mass_p_nu); call after particle_initialization."""
+        self._ck(self.L.cube_gpu_set_mass_p(self.h, F32(mass_p)))
+
+    def particle_mesh_species(self, other, a_mid, dt):
+        """particle_mesh for two species (CUBEnu -DNEUTRINOS): ``other``'s particles are deposited into this handle's meshes after
+        its own, both are kicked by the one force field.  Returns this species' limits plus ``dt_vmax2``/``vmax2`` of ``other``."""
+        o = [C.c_float() for _ in range(6)]
+        self._ck(self.L.cube_gpu_particle_mesh_species(self.h, other.h, F32(a_mid), F32(dt), *[C.byref(v) for v in o]))
+        self.dt_fine, self.dt_coarse, self.dt_vmax = (F32(v.value) for v in o[:3])
+        other.dt_fine, other.dt_coarse, other.dt_vmax = self.dt_fine, self.dt_coarse, F32(o[4].value)
+        return dict(dt_fine=self.dt_fine, dt_coarse=self.dt_coarse, dt_vmax=self.dt_vmax, dt_pp=F32(1000), vmax=F32(o[3].value),
+                    dt_vmax2=F32(o[4].value), vmax2=F32(o[5].value))
 
     def step(self, dt_old, dt, a_mid):
         """cafcube.f90:27-31."""

@@ -132,6 +132,19 @@ module cube_gpu
       type(c_ptr), value :: h
       real(c_float), intent(out) :: vmax3(3)
     end function
+    ! a second species (-DNEUTRINOS): one handle per species; particle_mesh for both on the first one's meshes
+    integer(c_int) function cube_gpu_set_mass_p(h, mass_p) bind(C, name="cube_gpu_set_mass_p")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: h
+      real(c_float), value :: mass_p
+    end function
+    integer(c_int) function cube_gpu_particle_mesh_species(h, h2, a_mid, dt, dt_fine, dt_coarse, dt_vmax, vmax, dt_vmax2, vmax2) &
+        bind(C, name="cube_gpu_particle_mesh_species")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: h, h2
+      real(c_float), value :: a_mid, dt
+      real(c_float), intent(out) :: dt_fine, dt_coarse, dt_vmax, vmax, dt_vmax2, vmax2
+    end function
     integer(c_int) function cube_gpu_finalize(h) bind(C, name="cube_gpu_finalize")
       import :: c_int, c_ptr
       type(c_ptr), value :: h

@@ -124,6 +124,16 @@ int cube_gpu_stream_vp(cube_handle *h, void *vp);
 int cube_gpu_set_drift_layers(cube_handle *h, int nlayer);
 int cube_gpu_get_vmax3(cube_handle *h, float vmax3[3]);
 
+/* Two particle species sharing the meshes (CUBEnu -DNEUTRINOS: pm.f90:79-99,160,235,356; update_particle.f90:326-353).  Every species is
+ * a handle of its own: its zip format, codes, rhoc/vfield, sigma_vi, capacities and ghost exchange -- cube_gpu_init / upload / update_x /
+ * buffer / download are called per species exactly as for one.  set_mass_p gives a species its particle mass (sim%mass_p_cdm,
+ * sim%mass_p_nu; the single-species default is nf_global^3/npglobal).  particle_mesh_species is particle_mesh for both: the particles
+ * of `h2` are deposited into `h`'s fine and coarse meshes after h's own, one convolution, and both species are kicked by its forces,
+ * each with its own sigma_vi / sigma_vi_new; dt_vmax2, vmax2 are the second species' (dt_vmax_nu).  Same geometry and device required. */
+int cube_gpu_set_mass_p(cube_handle *h, float mass_p);
+int cube_gpu_particle_mesh_species(cube_handle *h, cube_handle *h2, float a_mid, float dt, float *dt_fine, float *dt_coarse,
+                                   float *dt_vmax, float *vmax, float *dt_vmax2, float *vmax2);
+
 int cube_gpu_finalize(cube_handle *h);
 const char *cube_gpu_last_error(void);
 
