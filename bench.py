@@ -221,8 +221,10 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world):
     nt = args.nc // args.nnt
-    return {"workload": "CUBE LCDM %d^3 particles per image, %d image(s), nc=%d nnt=%d nt=%d nfe=%d np_nc=2 izipx=izipv=2, z=49 Zel'dovich ICs"
-                        % (2 * args.nc, world, args.nc, args.nnt, nt, 4 * nt + 48),
+    two = getattr(args, "species", 1) == 2
+    return {"workload": "CUBE LCDM %d^3 particles per image%s, %d image(s), nc=%d nnt=%d nt=%d nfe=%d np_nc=2 izipx=izipv=2, z=49 Zel'dovich ICs"
+                        % (2 * args.nc, " + as many of a second (hot, light) species on the same meshes (CUBEnu -DNEUTRINOS)" if two else "",
+                           world, args.nc, args.nnt, nt, 4 * nt + 48),
             "step": "update_particle+buffer_density+buffer_x+particle_mesh+buffer_v (cafcube.f90:27-31)",
             "l2": "state and meshes (>1.5 GB) exceed the 126 MB L2; no flush needed",
             "parallelism": "1 image" if world == 1 else
@@ -249,6 +251,7 @@ def main():
     ap.add_argument("--fine-batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--species", type=int, default=1, help="2: BASELINE.json configs[3], a second (hot, light) species of as many particles on the same meshes")
     ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the one-step sample of a whole cfg-1 image")
     ap.add_argument("--no-late", action="store_true", help="skip the late-time leg (evolve the ICs to z=0 and time the clustered state)")
     ap.add_argument("--profile", action="store_true",
@@ -294,6 +297,16 @@ def main():
     G.buffer_density(); G.buffer_x(); G.buffer_v()
     # fixed small time step so that every timed step does the same work (dt from the first PM limits)
     dt, a_mid = np.float32(0.5), np.float32(0.0205)
+    G2 = None
+    if args.species == 2:   # cfg 4: CDM + a hot light species (5 % of the mass, 3x the velocity dispersion), each in its own handle
+        s2, sig2, _ = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=4000, device="cuda", velocity_boost=3.0)
+        torch.cuda.empty_cache()
+        nccl_id2 = shared_nccl_id(device="cuda") if world > 1 else None
+        G2 = CubeGPU(nc, nnt, fk, ck, nn=image_grid(world), rank=rank, np_nc=2, device=local_rank, tanf_lut=host_tanf_lut(), nccl_id=nccl_id2, secondary=True)
+        G2.particle_initialization(s2[0], sig2, npglobal=world * npart)
+        mass = float((4 * nc) ** 3) / npart
+        G.set_mass_p(0.95 * mass); G2.set_mass_p(0.05 * mass)
+        G2.buffer_density(); G2.buffer_x(); G2.buffer_v()
 
     def barrier():
         if world > 1:
@@ -301,7 +314,16 @@ def main():
         torch.cuda.synchronize()
 
     def one_step(dt_old):
-        G.step(dt_old, dt, a_mid)
+        if G2 is None:
+            G.step(dt_old, dt, a_mid)
+            return
+        for H in (G, G2):                    # CUBEnu main.f90:102-118 with NEUTRINOS: every call for both species
+            H.update_particle(dt_old, dt)
+        for H in (G, G2):
+            H.buffer_density(); H.buffer_x()
+        G.particle_mesh_species(G2, a_mid, dt)
+        for H in (G, G2):
+            H.buffer_v()
 
     one_step(np.float32(0.0))
     for _ in range(max(0, args.warmup - 1)):
@@ -326,15 +348,23 @@ def main():
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * npart / (ms_per_step * 1e-3)
+    nspec = 2 if G2 is not None else 1
+    value = nspec * world * npart / (ms_per_step * 1e-3)
 
     # ---- per-phase timing (CUDA events on the library stream) -> dominant kernel + roofline ----
     G.set_profiling(True); G.phase_times()
+    if G2 is not None:
+        G2.set_profiling(True); G2.phase_times()
     nprof = 2
     for _ in range(nprof):
         one_step(dt)
     phases = {k: v / nprof for k, v in G.phase_times().items()}
     G.set_profiling(False)
+    if G2 is not None:   # the second species' own drift and exchange phases (its mesh phases are in the first handle's)
+        for k, v in G2.phase_times().items():
+            if v > 0:
+                phases[k + "_species2"] = v / nprof
+        G2.set_profiling(False)
     nt = nc // nnt; nfe = 4 * nt + 48
     ntile = nnt ** 3
     batch = G.query("fine_batch")
@@ -353,6 +383,8 @@ def main():
            "coarse_deposit": 6 * npart + 4 * nc ** 3, "coarse_fft_green": 50 * nc ** 3, "coarse_kick": 18 * npart + 12 * nc ** 3}
     phases = {k: v for k, v in phases.items() if v > 0}
     launches_per_step = {k: (ntile + batch - 1) // batch if k.startswith("fine") else 1 for k in phases}
+    for k in list(phases):
+        alg.setdefault(k, alg.get(k.replace("_species2", ""), 0))
     dom = max(phases, key=lambda k: phases[k])
     peak, which = measured_peak()
     dom_ms_per_launch = phases[dom] / launches_per_step[dom]
@@ -375,7 +407,9 @@ def main():
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if G2 is not None:
+        G2.close()
+    if not args.no_e2e and G2 is None:
         cur, sig_cur = G.checkpoint()
         cap = int(1.25 * cur["xp"].shape[0]) + 1024      # nplocal of an image changes from step to step when nn > 1
         pin = {k: (torch.empty((cap, 3), dtype=torch.int16).pin_memory() if k in ("xp", "vp") else torch.from_numpy(v).pin_memory())
@@ -407,12 +441,32 @@ def main():
             t = torch.tensor([sec], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); sec = float(t.item())
         e2e = {"value": world * npart * n_e2e / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * sec / n_e2e, "steps": n_e2e}
+        # one more step, untimed for the metric, with a device synchronisation after every call: where the wall clock of an e2e step goes
+        marks = []
+
+        def mark(name, t_prev):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            marks.append((name, 1e3 * (t - t_prev)))
+            return t
+        barrier()
+        t = time.perf_counter()
+        G.particle_initialization(inp, sig_cur, npglobal=world * npart); t = mark("upload", t)
+        G.buffer_density(); G.buffer_x(); G.buffer_v(); t = mark("buffer", t)
+        G.update_particle(dt, dt); t = mark("update_particle", t)
+        G.checkpoint_begin(host, xp=True, cells=True, vp_during_pm=not args.no_stream_vp)
+        G.buffer_density(); G.buffer_x(); t = mark("buffer_after_drift+xp_cells_download_so_far", t)
+        G.particle_mesh(a_mid, dt); t = mark("particle_mesh+streamed_downloads", t)
+        G.buffer_v(); t = mark("buffer_v", t)
+        inp, sig_cur = G.checkpoint(out=host, skip=("xp", "rhoc", "vfield") + (() if args.no_stream_vp else ("vp",))); t = mark("checkpoint_tail", t)
+        e2e["serialised_breakdown_ms"] = {k: round(v, 2) for k, v in marks}
+        e2e["h2d_GBps_upload_alone"] = round(h2d / 1e9 / (marks[0][1] * 1e-3), 1)
     radius = G.query("drift_radius")
     G.close()
 
     # ---- late-time (clustered) state: the same ICs evolved to z=0 by the product's own step loop, then timed ----------------
     late = None
-    if world == 1 and not args.no_late:
+    if world == 1 and not args.no_late and args.species == 1:
         from cafproject_b200.timestep import Cosmology, TimeStepper
         G = CubeGPU(nc, nnt, fk, ck, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut())
         G.particle_initialization(st, sig)

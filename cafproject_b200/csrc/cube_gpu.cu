@@ -732,6 +732,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
       batch = (int)std::max<long long>(1, std::min<long long>(64, (long long)(fr * 0.6) / (long long)per));
     }
   }
+  if (p->reserved[0] & 1) batch = 1;  // a further species of a two-species run: kicked from the first species' meshes, never uses its own
   batch = align_batch(g.nnt, std::min(batch, ntile));
   h->batch = batch;
   // pm.f90:54-58 in f32 is exact below 512 fine cells of tile-local coordinate (cells up to nt+5): then the weights do not depend
@@ -1230,8 +1231,13 @@ static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* 
     const unsigned nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY, nbz = (R.n[2] + C::NZ - 1) / C::NZ;
     auto go = [&](auto xt) {
       using XT = decltype(xt);
-      if (frame.x == FRAME_NONE) k_fine_deposit_r<C, false, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out, accumulate);
-      else k_fine_deposit_r<C, true, XT><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out, accumulate);
+#define FD_GO(FR, AC) k_fine_deposit_r<C, FR, XT, false, AC><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out)
+      if (accumulate) {
+        if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, XT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, true, XT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) return;
+        if (frame.x == FRAME_NONE) FD_GO(false, true); else FD_GO(true, true);
+      } else if (frame.x == FRAME_NONE) FD_GO(false, false); else FD_GO(true, false);
+#undef FD_GO
     };
     if (hp->zx == 2) go((short)0); else go((signed char)0);
   };
@@ -1603,10 +1609,10 @@ extern "C" int cube_gpu_power_spectrum(cube_handle* h, float box, double* xi, in
       const unsigned nbx = (m + C::NX - 1) / C::NX, nby = (m + C::NY - 1) / C::NY, nbz = (m + C::NZ - 1) / C::NZ;
       if (h->zx == 2) {
         if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
-        k_fine_deposit_r<C, false, short, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep, 0);
+        k_fine_deposit_r<C, false, short, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const short*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
       } else {
         if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, signed char, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) { rc = fail("power spectrum: kernel attribute"); break; }
-        k_fine_deposit_r<C, false, signed char, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep, 0);
+        k_fine_deposit_r<C, false, signed char, true><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(g, R, make_int3(FRAME_NONE, 0, 0), (const signed char*)h->xp, h->rhoc_e, h->cstart_e, h->mass_p, dep);
       }
     }
     k_ps_extract<<<nb, 256, 0, h->st>>>(n, dep, rho, part);
@@ -1716,8 +1722,7 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   CK(cudaSetDevice(h->p.device));
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
-  const Geom& g = h->g;
-  const long long m = h->fg.M, n = m * m * m, nt3 = (long long)g.nt * g.nt * g.nt;
+  const long long m = h->fg.M, n = m * m * m;
   float* tmp = nullptr; CK(dmalloc(&tmp, 3 * n));
   CK(cudaMemcpyAsync(tmp, force_f, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->st));
   k_force_from_ref<<<nblk(n, 256), 256, 0, h->st>>>((int)m, h->fg.FP, tmp, h->F); CKL();

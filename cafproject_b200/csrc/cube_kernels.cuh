@@ -231,10 +231,14 @@ template <int XB, bool HALF = false> __device__ __forceinline__ void fine_cic(in
   }
 }
 
-template <class C, bool FRAME, class XT, bool HALF = false>
+// ACC: add to `out` instead of overwriting it (a further species of a two-species run, pm.f90:79-99 NEUTRINOS): the lines already there
+// are prefetched to L2 before the particle loop and the write-out reads four rows ahead of its stores
+template <class C, bool FRAME, class XT, bool HALF = false, bool ACC = false>
 __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const XT* __restrict__ xp,
                                                           const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                          float mass_p, float* __restrict__ out, int accumulate /* add to `out`: a further species */) {
+                                                          float mass_p, float* __restrict__ out) {
+  constexpr int NIT = C::NX * C::NY * C::NZ / C::NT;
+  static_assert(C::NX * C::NY * C::NZ % C::NT == 0, "write-out loop");
   extern __shared__ __align__(16) unsigned fd_smem[];
   unsigned* acc = fd_smem;                                             // [NZ][PZ]
   int* pref = reinterpret_cast<int*>(fd_smem + C::ACC);                // [P2]
@@ -269,13 +273,19 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
   for (int q = 0; q < C::NT / 32; q++) { const int v = s_w[q]; if (q < wp) woff += v; total += v; cmax = max(cmax, s_m[q]); }
   const int ox = bx * C::NX, oy = by * C::NY, oz = bz * C::NZ;  // brick offset inside the region
   if (total == 0) {  // empty brick: zeros, no accumulators
-    if (accumulate) return;
-    for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {
-      const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
-      if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = 0.f;
-    }
+    if (!ACC)
+      for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {
+        const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+        if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = 0.f;
+      }
     return;
   }
+  if (ACC)
+    for (int r = t; r < 2 * C::NY * C::NZ; r += C::NT) {  // both ends of every row: a row of 32 floats touches at most two lines
+      const int Y = (r >> 1) % C::NY, Z = (r >> 1) / C::NY, X = (r & 1) * (C::NX - 1);
+      if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2])
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X));
+    }
   if (t < C::NS) pref[t] = woff + incl - n;
   for (int e = C::NS + t; e < C::P2; e += C::NT) pref[e] = total;  // sentinels: the search never steps onto them (q < total)
   for (int e = t; e < C::ACC / 4; e += C::NT) reinterpret_cast<uint4*>(acc)[e] = make_uint4(0u, 0u, 0u, 0u);
@@ -326,12 +336,25 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
     }
   }
   __syncthreads();
-  for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {  // one 32-float row per warp and iteration
-    const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
-    if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) {
-      float* dst = out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X;
+  constexpr int AH = ACC ? 4 : 1;  // rows read ahead of the stores
+  static_assert(NIT % AH == 0, "write-out loop");
+#pragma unroll 1
+  for (int it = 0; it < NIT; it += AH) {  // one 32-float row per warp and iteration
+    float* dst[AH];
+    float prev[AH];
+#pragma unroll
+    for (int u = 0; u < AH; u++) {
+      const int o = t + (it + u) * C::NT;
+      const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+      dst[u] = (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) ? out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X : nullptr;
+      prev[u] = (ACC && dst[u]) ? *dst[u] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < AH; u++) {
+      const int o = t + (it + u) * C::NT;
+      const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
       const float v = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
-      *dst = accumulate ? __fadd_rn(*dst, v) : v;  // one writer per node either way
+      if (dst[u]) *dst[u] = ACC ? __fadd_rn(prev[u], v) : v;  // one writer per node either way
     }
   }
 }

@@ -161,7 +161,7 @@ class CubeGPU:
     """One image of a CUBE run on one B200.  Mirrors the step subroutines of CUBE/main."""
 
     def __init__(self, nc, nnt, fk_table, ck_table, nn=(1, 1, 1), rank=0, np_nc=2, image_buffer=1.5, tile_buffer=2.5,
-                 device=0, fine_batch=0, tanf_lut=None, nccl_id=None, local_group=0, izipx=2, izipv=2):
+                 device=0, fine_batch=0, tanf_lut=None, nccl_id=None, local_group=0, izipx=2, izipv=2, secondary=False):
         """``nn``: image grid; ``rank``: this image (0-based, x fastest).  More than one image needs either ``nccl_id``
         (one process per GPU; the 128 bytes of :func:`nccl_unique_id` broadcast from image 1) or ``local_group`` > 0
         (every image is a host thread of this process, e.g. several images per GPU)."""
@@ -176,6 +176,7 @@ class CubeGPU:
         self.xdt, self.vdt = code_dtypes(self.izipx, self.izipv) if izipx in (1, 2) and izipv in (1, 2) else (np.int16, np.int16)
         p.np_nc, p.image_buffer, p.tile_buffer, p.device, p.fine_batch = np_nc, image_buffer, tile_buffer, device, fine_batch
         p.local_group = int(local_group)
+        p.reserved[0] = 1 if secondary else 0     # a further species: kicked from another handle's meshes (particle_mesh_species)
         self.params = p
         self.nn, self.nc, self.nnt, self.nt = nn, nc, nnt, nc // nnt
         self.nft = 4 * self.nt

@@ -47,7 +47,8 @@ typedef struct cube_params {
   int32_t fine_batch;   /* tiles per batched fine-mesh FFT, 0 = choose automatically */
   int32_t local_group;  /* 0: one process per image (NCCL when nn>1); k>0: all images of the run are host threads of THIS
                            process and share in-process group k (several images per GPU, `-fcoarray=single`-style runs) */
-  int32_t reserved[3];
+  int32_t reserved[3];  /* reserved[0] bit 0: this handle is a further species of a two-species run (cube_gpu_particle_mesh_species):
+                           its own fine-mesh pipeline is allocated for one tile only */
 } cube_params;
 
 typedef struct cube_handle cube_handle;
