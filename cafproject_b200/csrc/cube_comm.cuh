@@ -93,6 +93,7 @@ inline NcclApi& nccl_api() { static NcclApi a; return a; }
 struct NcclComm : Comm {
   ncclComm_t comm = nullptr;
   char* dbuf = nullptr;  // device staging for allgather_host
+  HostStage stage;       // host side of it: mapped memory, no copy engine (cube_common.cuh)
   static constexpr size_t kMaxGather = 256;
   int init(int rank_, int size_, const void* id128) {
     rank = rank_; size = size_;
@@ -106,6 +107,7 @@ struct NcclComm : Comm {
   }
   ~NcclComm() override {
     if (dbuf) cudaFree(dbuf);
+    stage.destroy();
     if (comm) nccl_api().CommDestroy(comm);
   }
   int ck(ncclResult_t r, const char* what) {
@@ -122,10 +124,11 @@ struct NcclComm : Comm {
   int group_end_peer() override { return ck(nccl_api().GroupEnd(), "ncclGroupEnd"); }
   int allgather_host(const void* in, void* out, size_t bytes, cudaStream_t st) override {
     if (bytes > kMaxGather) { err = "allgather_host: message too large"; return 1; }
-    if (cudaMemcpyAsync(dbuf, in, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { err = "allgather H2D"; return 1; }
+    if (stage.init() != cudaSuccess) { err = "allgather staging"; return 1; }
+    if (stage.write(dbuf, in, bytes, st) != cudaSuccess) { err = "allgather H2D"; return 1; }
     if (ck(nccl_api().AllGather(dbuf, dbuf + kMaxGather, bytes, ncclInt8, comm, st), "ncclAllGather")) return 1;
-    if (cudaMemcpyAsync(out, dbuf + kMaxGather, bytes * size, cudaMemcpyDeviceToHost, st) != cudaSuccess) { err = "allgather D2H"; return 1; }
-    if (cudaStreamSynchronize(st) != cudaSuccess) { err = "allgather sync"; return 1; }
+    if (stage.read(out, dbuf + kMaxGather, bytes * size, st) != cudaSuccess) { err = "allgather D2H"; return 1; }
+    if (stage.sync(st) != cudaSuccess) { err = "allgather sync"; return 1; }
     return 0;
   }
 };

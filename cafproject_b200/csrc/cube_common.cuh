@@ -7,6 +7,7 @@
 // device; f32 division uses __fdiv_rn.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <type_traits>
 #include <cuda_runtime.h>
 
@@ -143,5 +144,58 @@ constexpr unsigned KEY_FLAG = 0x8000u;
 __host__ __device__ inline unsigned key_pack(int dx, int dy, int dz) {
   return (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Small device<->host messages that do not use the copy engines.  A few bytes copied with cudaMemcpyAsync wait in the copy engine's
+// queue behind whatever large transfer is in flight on ANY stream -- with a checkpoint streaming out under particle_mesh, each
+// 4-byte f2_max read-back waited for the 0.8 GB of positions in front of it and the step lost all of the overlap (measured: 105 ms
+// per end-to-end step, equal to the sum of its serialised parts).  These go through mapped pinned memory instead: a one-warp kernel
+// on the compute stream moves the words, the host reads them after the stream synchronisation it does anyway.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_copy_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src, int nwords) {
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void k_copy_ll_strided(long long* __restrict__ dst, const long long* __restrict__ src, long long stride, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[(long long)i * stride];
+}
+struct HostStage {
+  static constexpr size_t CAP = 1 << 16;
+  char* buf = nullptr;  // cudaHostAllocMapped: the same address on both sides (unified addressing)
+  size_t used = 0;
+  struct Pending { void* dst; size_t off, bytes; cudaStream_t st; };
+  Pending pend[256];
+  int npend = 0;
+  cudaError_t init() { return buf ? cudaSuccess : cudaHostAlloc((void**)&buf, CAP, cudaHostAllocMapped | cudaHostAllocPortable); }
+  void destroy() { if (buf) cudaFreeHost(buf); buf = nullptr; }
+  void drop() { npend = 0; used = 0; }  // at an entry point: forget read-backs of a call that returned on an error before its sync()
+  // device -> host, words of 4 bytes; `dst` is valid after sync()
+  cudaError_t read(void* dst, const void* src, size_t bytes, cudaStream_t st, long long stride_ll = 0) {
+    const size_t need = (bytes + 15) & ~(size_t)15;
+    if (!buf || (bytes & 3) || npend == 256 || used + need > CAP) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    if (stride_ll) k_copy_ll_strided<<<1, 128, 0, st>>>((long long*)(buf + used), (const long long*)src, stride_ll, (int)(bytes / 8));
+    else k_copy_words<<<1, 128, 0, st>>>((unsigned*)(buf + used), (const unsigned*)src, (int)(bytes / 4));
+    pend[npend++] = Pending{dst, used, bytes, st};
+    used += need;
+    return cudaGetLastError();
+  }
+  cudaError_t sync(cudaStream_t st) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (int i = 0; i < npend && e == cudaSuccess; i++)
+      if (pend[i].st != st) e = cudaStreamSynchronize(pend[i].st);
+    if (e == cudaSuccess)
+      for (int i = 0; i < npend; i++) memcpy(pend[i].dst, buf + pend[i].off, pend[i].bytes);
+    npend = 0; used = 0;
+    return e;
+  }
+  // host -> device through the same memory (the caller's bytes are copied now; the kernel reads them in stream order)
+  cudaError_t write(void* dst_dev, const void* src, size_t bytes, cudaStream_t st) {
+    const size_t need = (bytes + 15) & ~(size_t)15;
+    if (!buf || (bytes & 3) || used + need > CAP) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st);
+    memcpy(buf + used, src, bytes);
+    k_copy_words<<<1, 128, 0, st>>>((unsigned*)dst_dev, (const unsigned*)(buf + used), (int)(bytes / 4));
+    used += need;
+    return cudaGetLastError();
+  }
+};
 
 }  // namespace cube

@@ -336,25 +336,32 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
     }
   }
   __syncthreads();
-  constexpr int AH = ACC ? 4 : 1;  // rows read ahead of the stores
-  static_assert(NIT % AH == 0, "write-out loop");
-#pragma unroll 1
-  for (int it = 0; it < NIT; it += AH) {  // one 32-float row per warp and iteration
-    float* dst[AH];
-    float prev[AH];
-#pragma unroll
-    for (int u = 0; u < AH; u++) {
-      const int o = t + (it + u) * C::NT;
+  if constexpr (!ACC) {
+    for (int o = t; o < C::NX * C::NY * C::NZ; o += C::NT) {  // one 32-float row per warp and iteration; one writer per node
       const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
-      dst[u] = (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) ? out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X : nullptr;
-      prev[u] = (ACC && dst[u]) ? *dst[u] : 0.f;
+      if (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2])
+        out[(long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X] = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
     }
+  } else {
+    constexpr int AH = 4;  // rows whose old values are read ahead of the stores
+    static_assert(NIT % AH == 0, "write-out loop");
+#pragma unroll 1
+    for (int it = 0; it < NIT; it += AH) {
+      float* dst[AH];
+      float prev[AH];
 #pragma unroll
-    for (int u = 0; u < AH; u++) {
-      const int o = t + (it + u) * C::NT;
-      const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
-      const float v = __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv);
-      if (dst[u]) *dst[u] = ACC ? __fadd_rn(prev[u], v) : v;  // one writer per node either way
+      for (int u = 0; u < AH; u++) {
+        const int o = t + (it + u) * C::NT;
+        const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+        dst[u] = (ox + X < R.n[0] && oy + Y < R.n[1] && oz + Z < R.n[2]) ? out + (long long)(oz + Z) * R.ldz + (long long)(oy + Y) * R.ldy + ox + X : nullptr;
+        prev[u] = dst[u] ? *dst[u] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < AH; u++) {
+        const int o = t + (it + u) * C::NT;
+        const int X = o % C::NX, Y = (o / C::NX) % C::NY, Z = o / (C::NX * C::NY);
+        if (dst[u]) *dst[u] = __fadd_rn(prev[u], __fmul_rn(__uint2float_rn(acc[Z * C::PZ + Y * C::PY + X]), inv));
+      }
     }
   }
 }
