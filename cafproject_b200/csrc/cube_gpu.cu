@@ -106,6 +106,8 @@ struct cube_handle {
   CUtensorMap fmap = {}; int kick_stage = 2;  // TMA view of F[batch][M][M][3][FP]
   cudaStream_t st_coarse = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_coarse = true;  // coarse mesh under the fine mesh
   cudaEvent_t ev_vpack = nullptr, ev_vghost = nullptr; bool vghost_pending = false, async_vghost = true;  // buffer_v's exchange under the next drift's key pass
+  cudaEvent_t ev_xghost = nullptr; bool xghost_pending = false, async_xghost = true;  // buffer_x's exchange under the fine deposit of the bricks that read no ghost cell
+  cudaStream_t st_main = nullptr;  // h->st, also while particle_mesh points h->st at the side stream
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
@@ -634,7 +636,10 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_vpack, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_vghost, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_xghost, cudaEventDisableTiming));
+  h->st_main = h->st;
   h->async_vghost = getenv("CUBE_GPU_SYNC_BUFFER_V") == nullptr;
+  h->async_xghost = getenv("CUBE_GPU_SYNC_BUFFER_X") == nullptr;
   h->overlap_coarse = getenv("CUBE_GPU_NO_OVERLAP") == nullptr;  // multi-image runs: decided after the communicator exists (below)
   CK(cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming));
   for (int i = 0; i < 2 * PH_N; i++) CK(cudaEventCreate(&h->ev[i]));
@@ -819,6 +824,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_vpack) cudaEventDestroy(h->ev_vpack);
   if (h->ev_vghost) cudaEventDestroy(h->ev_vghost);
+  if (h->ev_xghost) cudaEventDestroy(h->ev_xghost);
   for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
@@ -826,6 +832,14 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// the ghost positions of `hp` (buffer_x's messages may still be in flight on its side stream): every later launch on h's main
+// stream sees them
+static int join_xghost(cube_handle* h, cube_handle* hp = nullptr) {
+  if (!hp) hp = h;
+  if (hp->xghost_pending) { CK(cudaStreamWaitEvent(h->st_main, hp->ev_xghost, 0)); if (hp == h) hp->xghost_pending = false; }
+  return 0;
+}
+
 extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys,
                                const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
   if (!h) return fail("null handle");
@@ -836,6 +850,7 @@ extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, c
     return fail("error: too many particles in this image+buffer: %lld > %lld; please set image_buffer larger", (long long)nplocal, h->np_image_max);
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // a streamed download still reads the arrays overwritten here
   if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); h->vghost_pending = false; }
+  if (join_xghost(h)) return 1;
   h->vp_stream_host = nullptr;
   h->pid_valid = false;  // a new state: its IDs, if any, come with cube_gpu_upload_pid
   CK(cudaMemcpyAsync(h->xp, xp, (size_t)3 * h->zx * nplocal, cudaMemcpyHostToDevice, h->st));
@@ -1050,12 +1065,22 @@ extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_
     h->buffered = true;
   }
   // one image: ghost particles alias the periodic image, nothing to copy
-  if (do_x && multi) { PhaseTimer pt(h, PH_BUFFER); if (exchange_particles(h, h->xp, h->zx, h->st)) return 1; }
+  if (do_x && multi) {
+    // The ghosts' positions are first read by the fine deposit's bricks next to the image boundary and by the coarse deposit: the
+    // messages travel on the side stream while particle_mesh deposits the bricks that read no ghost cell (fine_deposit below).
+    PhaseTimer pt(h, PH_BUFFER);
+    if (join_xghost(h)) return 1;
+    if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); }  // buffer_v's messages leave from the same send buffer
+    cudaStream_t cst = (h->async_xghost && !h->prof) ? h->st_coarse : h->st;
+    if (exchange_particles(h, h->xp, h->zx, cst)) return 1;
+    if (cst != h->st) { CK(cudaEventRecord(h->ev_xghost, cst)); h->xghost_pending = true; }
+  }
   if (do_v && multi) {
     // The ghosts' velocities (and IDs) are first read by the next update_particle's pass over the GHOST cells: the messages travel on
     // the high-priority side stream and that pass waits for them, so they cross under the key pass of the physical cells (which
     // only reads physical particles).  Phase profiling keeps everything on one stream.
     PhaseTimer pt(h, PH_BUFFER);
+    if (join_xghost(h)) return 1;  // buffer_x's messages leave from the same send buffer
     cudaStream_t cst = (h->async_vghost && !h->prof) ? h->st_coarse : h->st;
     if (exchange_particles(h, h->vp, h->zv, cst)) return 1;
     if (h->pid_valid && exchange_pid(h, cst)) return 1;
@@ -1094,6 +1119,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     CKL();
     h->launches++;
     if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); h->vghost_pending = false; }  // ghost velocities from buffer_v
+    if (join_xghost(h)) return 1;
     if (multi && ng) {
       FMT_SWITCH(h, k_drift_key_g<F><<<nchunk_g, PC_T, 0, h->st>>>(g, ng, h->gcell_ext, h->gstart, h->nplocal, XPC(h->xp), VPC(h->vp), h->vfield_e, h->dvlut, dt_mid,
                                                                    h->key, h->rank, h->maxoff, h->mask_s + MASK_W * g.ncell_p, h->inflag));
@@ -1230,12 +1256,17 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
 static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* out, cube_handle* hp = nullptr, int accumulate = 0) {
   if (!hp) hp = h;
   PhaseTimer pt(h, PH_FDEP);
+  // ghost positions still in flight (buffer_x on the side stream): first the bricks that read no ghost cell, then, behind the
+  // messages, the others.  Anything else waits for the messages first.
+  const bool two_phase = hp->xghost_pending && h->st == h->st_main && frame.x == FRAME_NONE && !accumulate;
+  if (!two_phase && hp->xghost_pending && h->st == h->st_main && join_xghost(h, hp)) return 1;
+  int part = two_phase ? 1 : 0;
   auto launch = [&](auto cfg) {
     using C = decltype(cfg);
     const unsigned nbx = (R.n[0] + C::NX - 1) / C::NX, nby = (R.n[1] + C::NY - 1) / C::NY, nbz = (R.n[2] + C::NZ - 1) / C::NZ;
     auto go = [&](auto xt) {
       using XT = decltype(xt);
-#define FD_GO(FR, AC) k_fine_deposit_r<C, FR, XT, false, AC><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out)
+#define FD_GO(FR, AC) k_fine_deposit_r<C, FR, XT, false, AC><<<nbx * nby * nbz, C::NT, C::SMEM, h->st>>>(h->g, R, frame, (const XT*)hp->xp, hp->rhoc_e, hp->cstart_e, hp->mass_p, out, part)
       if (accumulate) {
         if (cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, false, XT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute((const void*)k_fine_deposit_r<C, true, XT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess) return;
@@ -1248,6 +1279,13 @@ static int fine_deposit(cube_handle* h, const FineRegion& R, int3 frame, float* 
   if (h->fd_brick == 888) launch(Fd888{}); else if (h->fd_brick == 844) launch(Fd844{}); else launch(Fd884{});
   CKL();
   h->launches++;
+  if (two_phase) {
+    if (join_xghost(h, hp)) return 1;
+    part = 2;
+    if (h->fd_brick == 888) launch(Fd888{}); else if (h->fd_brick == 844) launch(Fd844{}); else launch(Fd884{});
+    CKL();
+    h->launches++;
+  }
   return 0;
 }
 // fine density of the tiles [tile0, tile0+nb) in h->rho; returns how the x pass finds each tile's window
@@ -1330,6 +1368,9 @@ static int set_coarse_streams(cube_handle* h, cudaStream_t st) {
 static int coarse_mesh(cube_handle* h, bool through_force, float a_mid, float dt, float* raw, cube_handle* h2 = nullptr) {
   const Geom& g = h->g;
   const bool multi = h->nimg > 1;
+  // the coarse deposit reads the first layer of ghost cells: on the side stream it is queued behind buffer_x's messages already
+  for (cube_handle* hp : {h, h2})
+    if (hp && hp->xghost_pending && (h->st == h->st_main || hp != h)) CK(cudaStreamWaitEvent(h->st, hp->ev_xghost, 0));
   {
     PhaseTimer pt(h, PH_CDEP);
     const long long nbox = (long long)(g.nc + 2) * (g.nc + 2) * (g.nc + 2);
@@ -1876,6 +1917,7 @@ extern "C" int cube_gpu_timer(cube_handle* h, int start, float* ms) {
   CK(cudaSetDevice(h->p.device));
   if (start) { CK(cudaEventRecord(h->tev[0], h->st)); return 0; }
   if (h->vghost_pending) CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0));  // the stopwatch covers a ghost exchange still in flight on the side stream
+  if (h->xghost_pending) CK(cudaStreamWaitEvent(h->st, h->ev_xghost, 0));
   CK(cudaEventRecord(h->tev[1], h->st));
   CK(cudaEventSynchronize(h->tev[1]));
   if (ms) CK(cudaEventElapsedTime(ms, h->tev[0], h->tev[1]));

@@ -236,7 +236,8 @@ template <int XB, bool HALF = false> __device__ __forceinline__ void fine_cic(in
 template <class C, bool FRAME, class XT, bool HALF = false, bool ACC = false>
 __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, int3 frame0, const XT* __restrict__ xp,
                                                           const int* __restrict__ rhoc_e, const long long* __restrict__ cstart_e,
-                                                          float mass_p, float* __restrict__ out) {
+                                                          float mass_p, float* __restrict__ out,
+                                                          int part = 0 /* 1: only bricks that read no ghost cell, 2: only the others */) {
   constexpr int NIT = C::NX * C::NY * C::NZ / C::NT;
   static_assert(C::NX * C::NY * C::NZ % C::NT == 0, "write-out loop");
   extern __shared__ __align__(16) unsigned fd_smem[];
@@ -251,6 +252,10 @@ __global__ void __launch_bounds__(C::NT) k_fine_deposit_r(Geom g, FineRegion R, 
   // image-local node index of the brick's first node; its first own coarse cell
   const int N0x = R.f0[0] + bx * C::NX, N0y = R.f0[1] + by * C::NY, N0z = R.f0[2] + bz * C::NZ;
   const int cbx = N0x >> 2, cby = N0y >> 2, cbz = N0z >> 2;
+  if (part) {  // several images: the bricks away from the image boundary run while the ghost positions are still on the wire
+    const bool edge = cbx < 1 || cbx - 1 + C::SX > g.nc || cby < 1 || cby - 1 + C::SY > g.nc || cbz < 1 || cbz - 1 + C::SZ > g.nc;
+    if (edge != (part == 2)) return;
+  }
   // --- the brick's source cells: counts, starts, prefix, fullest cell
   int n = 0; long long s = 0;
   if (t < C::NS) {
