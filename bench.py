@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--fine-batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stream-upload", action="store_true", help="e2e leg: cube_gpu_upload instead of cube_gpu_upload_begin")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the CPUs next to its GPU")
     ap.add_argument("--species", type=int, default=1, help="2: BASELINE.json configs[3], a second (hot, light) species of as many particles on the same meshes")
     ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the one-step sample of a whole cfg-1 image")
@@ -440,9 +441,9 @@ def main():
         h2d = d2h = 0
 
         def e2e_step(inp, sig_cur):
-            G.particle_initialization(inp, sig_cur, npglobal=world * npart)
+            G.particle_initialization(inp, sig_cur, npglobal=world * npart, streamed=not args.no_stream_upload)
             G.buffer_density(); G.buffer_x(); G.buffer_v()
-            G.update_particle(dt, dt)
+            G.update_particle(dt, dt)      # keys each chunk of a streamed upload as it lands
             # positions, rhoc and vfield are final for this step: stream them out under particle_mesh; the velocities follow
             # tile batch by tile batch as their kicks are done
             G.checkpoint_begin(host, xp=True, cells=True, vp_during_pm=not args.no_stream_vp)

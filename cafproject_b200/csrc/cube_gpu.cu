@@ -108,6 +108,9 @@ struct cube_handle {
   cudaEvent_t ev_vpack = nullptr, ev_vghost = nullptr; bool vghost_pending = false, async_vghost = true;  // buffer_v's exchange under the next drift's key pass
   cudaEvent_t ev_xghost = nullptr; bool xghost_pending = false, async_xghost = true;  // buffer_x's exchange under the fine deposit of the bricks that read no ghost cell
   cudaStream_t st_main = nullptr;  // h->st, also while particle_mesh points h->st at the side stream
+  // cube_gpu_upload_begin: the particles arrive in UP_N chunks of up_stride cells on the copy stream; update_x keys each chunk as it lands
+  static constexpr int UP_N = 8;
+  cudaEvent_t ev_up[UP_N] = {}; int up_n = 0; long long up_stride = 0;
   long long np_image_max = 0, np_tile_max = 0;
   long long nplocal = 0, npglobal = 0;
   float sigma_vi = 0, sigma_vi_new = 0, mass_p = 0;
@@ -637,6 +640,7 @@ extern "C" int cube_gpu_init(const cube_params* p, const float* fk_table, const 
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_vpack, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_vghost, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_xghost, cudaEventDisableTiming));
+  for (auto& e : h->ev_up) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->st_main = h->st;
   h->async_vghost = getenv("CUBE_GPU_SYNC_BUFFER_V") == nullptr;
   h->async_xghost = getenv("CUBE_GPU_SYNC_BUFFER_X") == nullptr;
@@ -825,6 +829,7 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
   if (h->ev_vpack) cudaEventDestroy(h->ev_vpack);
   if (h->ev_vghost) cudaEventDestroy(h->ev_vghost);
   if (h->ev_xghost) cudaEventDestroy(h->ev_xghost);
+  for (auto e : h->ev_up) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->st);
   delete h;
@@ -832,6 +837,14 @@ extern "C" int cube_gpu_finalize(cube_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Every entry point that reads or writes the particle arrays: select the device and, after a cube_gpu_upload_begin, let the main
+// stream wait for the last chunk (the chunks are in order on the copy stream).  cube_gpu_update_x waits chunk by chunk instead.
+static int enter(cube_handle* h, bool particles = true) {
+  CK(cudaSetDevice(h->p.device));
+  if (particles && h->up_n) { CK(cudaStreamWaitEvent(h->st_main, h->ev_up[h->up_n - 1], 0)); h->up_n = 0; }
+  return 0;
+}
+
 // the ghost positions of `hp` (buffer_x's messages may still be in flight on its side stream): every later launch on h's main
 // stream sees them
 static int join_xghost(cube_handle* h, cube_handle* hp = nullptr) {
@@ -840,10 +853,10 @@ static int join_xghost(cube_handle* h, cube_handle* hp = nullptr) {
   return 0;
 }
 
-extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys,
-                               const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
+static int upload_impl(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys, const float* vfield_phys, int64_t nplocal,
+                       int64_t npglobal, float sigma_vi, bool streamed) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   h->rb.drop();
   const Geom& g = h->g;
   if (nplocal > h->np_image_max)
@@ -853,15 +866,35 @@ extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, c
   if (join_xghost(h)) return 1;
   h->vp_stream_host = nullptr;
   h->pid_valid = false;  // a new state: its IDs, if any, come with cube_gpu_upload_pid
-  CK(cudaMemcpyAsync(h->xp, xp, (size_t)3 * h->zx * nplocal, cudaMemcpyHostToDevice, h->st));
-  CK(cudaMemcpyAsync(h->vp, vp, (size_t)3 * h->zv * nplocal, cudaMemcpyHostToDevice, h->st));
+  // streamed: the cell arrays first, then the particles in UP_N chunks of whole key-pass CTAs on the copy stream, so that
+  // cube_gpu_update_x keys chunk c while chunk c+1 is on the bus
+  constexpr int UP_N = cube_handle::UP_N;
+  const long long stride = g.ncell_p / UP_N / PC_CELLS * PC_CELLS;
+  if (stride == 0) streamed = false;
+  if (!streamed) {
+    CK(cudaMemcpyAsync(h->xp, xp, (size_t)3 * h->zx * nplocal, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->vp, vp, (size_t)3 * h->zv * nplocal, cudaMemcpyHostToDevice, h->st));
+  }
   CK(cudaMemcpyAsync(h->rhoc_p, rhoc_phys, sizeof(int) * g.ncell_p, cudaMemcpyHostToDevice, h->st));
   CK(cudaMemcpyAsync(h->vfield_p, vfield_phys, sizeof(float) * 3 * g.ncell_p, cudaMemcpyHostToDevice, h->st));
   if (scan_counts(h, h->rhoc_p, g.ncell_p, h->cstart_p)) return 1;
-  long long tot = 0;
+  long long tot = 0, first[UP_N + 1];
   CK(h->rb.read(&tot, h->cstart_p + g.ncell_p, sizeof(long long), h->st));
+  if (streamed) CK(h->rb.read(first, h->cstart_p, sizeof(long long) * UP_N, h->st, stride));
   CK(h->rb.sync(h->st));
   if (tot != nplocal) return fail("cube_gpu_upload: sum(rhoc)=%lld differs from nplocal=%lld", tot, (long long)nplocal);
+  if (streamed) {  // the main stream is idle (synchronised above) and so is the copy stream (a pending download was waited for)
+    first[UP_N] = nplocal;
+    for (int c = 0; c < UP_N; c++) {
+      const size_t p0 = (size_t)first[c], n = (size_t)(first[c + 1] - first[c]);
+      if (n) {
+        CK(cudaMemcpyAsync((char*)h->xp + 3 * h->zx * p0, (const char*)xp + 3 * h->zx * p0, 3 * h->zx * n, cudaMemcpyHostToDevice, h->st_copy));
+        CK(cudaMemcpyAsync((char*)h->vp + 3 * h->zv * p0, (const char*)vp + 3 * h->zv * p0, 3 * h->zv * n, cudaMemcpyHostToDevice, h->st_copy));
+      }
+      CK(cudaEventRecord(h->ev_up[c], h->st_copy));
+    }
+    h->up_n = UP_N; h->up_stride = stride;
+  }
   h->nplocal = nplocal; h->npglobal = npglobal;
   h->sigma_vi = h->sigma_vi_new = sigma_vi;
   // mass_p=real((nf*nn)**3)/npglobal  (particle_initialization.f90:72)
@@ -870,13 +903,23 @@ extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, c
   h->buffered = false;
   return 0;
 }
+extern "C" int cube_gpu_upload(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys,
+                               const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
+  return upload_impl(h, xp, vp, rhoc_phys, vfield_phys, nplocal, npglobal, sigma_vi, false);
+}
+// The same, returning while xp and vp are still on their way: both host arrays must be page-locked and stay untouched until the
+// next call that uses the particles has returned (cube_gpu_update_x; any other entry point waits for the whole upload first).
+extern "C" int cube_gpu_upload_begin(cube_handle* h, const void* xp, const void* vp, const int32_t* rhoc_phys,
+                                     const float* vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi) {
+  return upload_impl(h, xp, vp, rhoc_phys, vfield_phys, nplocal, npglobal, sigma_vi, true);
+}
 
 // -DPID: the IDs of the nplocal particles of the last cube_gpu_upload, file order (particle_initialization.f90:56-59).  They ride
 // through update_x (the buffers of a single image hold no ghost copies, and particle_mesh does not move particles).
 extern "C" int cube_gpu_upload_pid(cube_handle* h, const int64_t* pid) {
   if (!h) return fail("null handle");
   if (!pid) return fail("cube_gpu_upload_pid: null array");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->pid) { CK(dmalloc(&h->pid, h->np_image_max)); CK(dmalloc(&h->pid2, h->np_image_max)); }
   CK(cudaMemcpyAsync(h->pid, pid, sizeof(long long) * h->nplocal, cudaMemcpyHostToDevice, h->st));
   CK(h->rb.sync(h->st));
@@ -886,7 +929,7 @@ extern "C" int cube_gpu_upload_pid(cube_handle* h, const int64_t* pid) {
 extern "C" int cube_gpu_download_pid(cube_handle* h, int64_t* pid) {
   if (!h) return fail("null handle");
   if (!h->pid_valid) return fail("no particle IDs were uploaded for this state");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   CK(cudaMemcpyAsync(pid, h->pid, sizeof(long long) * h->nplocal, cudaMemcpyDeviceToHost, h->st));
   CK(h->rb.sync(h->st));
   return 0;
@@ -897,7 +940,7 @@ extern "C" int cube_gpu_download_pid(cube_handle* h, int64_t* pid) {
 // (e.g. xp right after update_x: particle_mesh does not change positions).  cube_gpu_download waits for it.
 extern "C" int cube_gpu_download_async(cube_handle* h, void* xp, void* vp) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   CK(cudaEventRecord(h->ev_copy[0], h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
   if (xp) CK(cudaMemcpyAsync(xp, h->xp, (size_t)3 * h->zx * h->nplocal, cudaMemcpyDeviceToHost, h->st_copy));
@@ -909,7 +952,7 @@ extern "C" int cube_gpu_download_async(cube_handle* h, void* xp, void* vp) {
 
 extern "C" int cube_gpu_download_cells_async(cube_handle* h, int32_t* rhoc_phys, float* vfield_phys) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   const Geom& g = h->g;
   CK(cudaEventRecord(h->ev_copy[0], h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_copy[0], 0));
@@ -929,7 +972,7 @@ extern "C" int cube_gpu_stream_vp(cube_handle* h, void* vp) {
 extern "C" int cube_gpu_download(cube_handle* h, void* xp, void* vp, int32_t* rhoc_phys, float* vfield_phys,
                                  int64_t* nplocal, float* sigma_vi) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   const Geom& g = h->g;
   if (h->copy_pending) { CK(cudaEventSynchronize(h->ev_copy[1])); h->copy_pending = false; h->copy_reads_vp = false; }
   if (xp) CK(cudaMemcpyAsync(xp, h->xp, (size_t)3 * h->zx * h->nplocal, cudaMemcpyDeviceToHost, h->st));
@@ -1027,7 +1070,7 @@ static int exchange_pid(cube_handle* h, cudaStream_t cst) {
 extern "C" int cube_gpu_buffer(cube_handle* h, int do_density, int do_x, int do_v, float* overhead_image) {
   if (!h) return fail("null handle");
   g_cur = h; h->rb.drop();
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h, h->nimg > 1 && (do_x || do_v))) return 1;  // buffer_density reads the cell arrays only; one image's ghosts are aliases
   const Geom& g = h->g;
   const bool multi = h->nimg > 1;
   if (do_density) {
@@ -1094,7 +1137,7 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
                                  double std_vsim[3], float* overhead_tile) {
   if (!h) return fail("null handle");
   g_cur = h; h->rb.drop();
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h, false)) return 1;  // a streamed upload is waited for chunk by chunk, below
   if (!h->buffered) return fail("cube_gpu_update_x: state is not buffered (call cube_gpu_buffer first, cafcube.f90:17-19)");
   if (h->copy_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); }  // an asynchronous download still reads the particle arrays
   const Geom& g = h->g;
@@ -1114,10 +1157,16 @@ extern "C" int cube_gpu_update_x(cube_handle* h, float dt_old, float dt, int64_t
     PhaseTimer pt(h, PH_KEY);
     CK(cudaMemsetAsync(h->inflag, 0, (size_t)g.ncell_p, h->st));
     CK(cudaMemsetAsync(h->nflag, 0, sizeof(int), h->st));
-    FMT_SWITCH(h, k_drift_key_chain<F><<<nblk(g.ncell_p, PC_CELLS), PC_T, KC_SMEM, h->st>>>(g, XPC(h->xp), VPC(h->vp), h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key,
-                                                                                            h->rank, h->maxoff, h->mask_s, h->inflag, h->rhoc_p2, h->vfield_p2));
-    CKL();
-    h->launches++;
+    const int nup = std::max(1, h->up_n);
+    for (int c = 0; c < nup; c++) {  // one launch, or one per chunk of a streamed upload as it lands (cube_gpu_upload_begin)
+      const long long cb = h->up_n ? c * h->up_stride : 0, ce = (h->up_n && c + 1 < nup) ? cb + h->up_stride : g.ncell_p;
+      if (h->up_n) CK(cudaStreamWaitEvent(h->st, h->ev_up[c], 0));
+      FMT_SWITCH(h, k_drift_key_chain<F><<<nblk(ce - cb, PC_CELLS), PC_T, KC_SMEM, h->st>>>(g, XPC(h->xp), VPC(h->vp), h->cstart_p, h->vfield_p, h->dvlut, dt_mid, h->key,
+                                                                                       h->rank, h->maxoff, h->mask_s, h->inflag, h->rhoc_p2, h->vfield_p2, cb));
+      CKL();
+      h->launches++;
+    }
+    h->up_n = 0;
     if (h->vghost_pending) { CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0)); h->vghost_pending = false; }  // ghost velocities from buffer_v
     if (join_xghost(h)) return 1;
     if (multi && ng) {
@@ -1408,7 +1457,7 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
                                       float* dt_vmax, float* vmax_out) {
   if (!h) return fail("null handle");
   g_cur = h; h->rb.drop();
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("cube_gpu_particle_mesh: state is not buffered (call cube_gpu_buffer first)");
   // a cube_gpu_download_async of vp still reads the velocities the kicks rewrite in place (positions may keep streaming)
   if (h->copy_pending && h->copy_reads_vp) { CK(cudaStreamWaitEvent(h->st, h->ev_copy[1], 0)); h->copy_reads_vp = false; }
@@ -1554,7 +1603,7 @@ extern "C" int cube_gpu_particle_mesh_species(cube_handle* h, cube_handle* h2, f
   if (!h || !h2) return fail("null handle");
   if (h == h2) return fail("cube_gpu_particle_mesh_species: the two species must be different handles");
   g_cur = h; h->rb.drop();
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (h2->p.device != h->p.device) return fail("cube_gpu_particle_mesh_species: both species must live on the same device");
   const Geom& g = h->g;
   if (memcmp(&h2->g, &g, sizeof(Geom)) != 0) return fail("cube_gpu_particle_mesh_species: the species differ in geometry (nn, nnt, nc, image)");
@@ -1641,7 +1690,7 @@ extern "C" int cube_gpu_particle_mesh_species(cube_handle* h, cube_handle* h2, f
 // rows 0 count, 1 k [h/Mpc], 2 = 3 = 4 Delta^2 (auto power), 5-6 kernels, 7 r = 1, 8 b = 1, 9 = row 2.  Single image.
 extern "C" int cube_gpu_power_spectrum(cube_handle* h, float box, double* xi, int nbin_cap, int* nbin_out) {
   if (!h || !xi) return fail("null argument");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("cube_gpu_power_spectrum: state is not buffered (call cube_gpu_buffer first)");
   if (h->nimg > 1) return fail("cube_gpu_power_spectrum: single image (a distributed transform of the global fine grid is not built)");
   const Geom& g = h->g;
@@ -1721,14 +1770,14 @@ extern "C" int64_t cube_gpu_query(cube_handle* h, const char* what) {
   return -1;
 }
 extern "C" int cube_gpu_get_kern_f(cube_handle* h, float* out) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   const FftGeom& f = h->fg;  // strip the kx pitch: out(N/2+1, N, N, 3)
   CK(cudaMemcpy2D(out, sizeof(float) * f.NH, h->kern_f, sizeof(float) * f.P, sizeof(float) * f.NH, (size_t)3 * f.N * f.N,
                   cudaMemcpyDeviceToHost));
   return 0;
 }
 extern "C" int cube_gpu_get_kern_c(cube_handle* h, float* out) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (h->nimg > 1) return fail("cube_gpu_get_kern_c: single-image diagnostic (the distributed kern_c lives in the transposed k-space layout)");
   CK(cudaMemcpy(out, h->kern_c, sizeof(float) * 3 * h->cnk, cudaMemcpyDeviceToHost));
   return 0;
@@ -1740,7 +1789,7 @@ static int tile_index(cube_handle* h, int itx, int ity, int itz, int* t) {
   return 0;
 }
 extern "C" int cube_gpu_fine_density(cube_handle* h, int itx, int ity, int itz, float* rho_f) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
   // diagnostic: deposit on the reference's whole padded grid rho_f(nfe+2,nfe,nfe) instead of the FFT window
@@ -1760,7 +1809,7 @@ extern "C" int cube_gpu_fine_density(cube_handle* h, int itx, int ity, int itz, 
   return 0;
 }
 extern "C" int cube_gpu_fine_force(cube_handle* h, int itx, int ity, int itz, float* force_f) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
   if (fine_mesh(h, t, 1, false, 0.f, 0.f)) return 1;
@@ -1774,7 +1823,7 @@ extern "C" int cube_gpu_fine_force(cube_handle* h, int itx, int ity, int itz, fl
 }
 extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz, const float* force_f, float a_mid, float dt,
                                        float sigma_vi, float sigma_vi_new, float* f2_max) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("state is not buffered");
   int t; if (tile_index(h, itx, ity, itz, &t)) return 1;
   const long long m = h->fg.M, n = m * m * m;
@@ -1796,7 +1845,7 @@ extern "C" int cube_gpu_fine_kick_with(cube_handle* h, int itx, int ity, int itz
   return 0;
 }
 extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("state is not buffered");
   const Geom& g = h->g;
   if (coarse_mesh(h, false, 0.f, 0.f, nullptr)) return 1;
@@ -1806,7 +1855,7 @@ extern "C" int cube_gpu_coarse_density(cube_handle* h, float* r3) {
   return 0;
 }
 extern "C" int cube_gpu_coarse_force(cube_handle* h, float* force_c) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (!h->buffered) return fail("state is not buffered");
   const long long m = h->g.nc + 2;
   float* raw = nullptr; CK(dmalloc(&raw, 3 * m * m * m));
@@ -1818,7 +1867,7 @@ extern "C" int cube_gpu_coarse_force(cube_handle* h, float* force_c) {
 }
 extern "C" int cube_gpu_coarse_kick_with(cube_handle* h, const float* force_c, float a_mid, float dt, float sigma_vi, float* vmax,
                                          float* f2_max) {
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   h->rb.drop();
   if (!h->buffered) return fail("state is not buffered");
   const Geom& g = h->g;
@@ -1869,7 +1918,7 @@ extern "C" int cube_gpu_exchange_plan(const cube_params* p, int64_t* out, int ca
 // table-driven velocity code conversions against their defining formulas (see k_selftest_encode / k_selftest_decode)
 extern "C" int cube_gpu_selftest_codes(cube_handle* h, float sigma_vi, int64_t nsweep, int64_t* bad_encode, int64_t* bad_decode, int* fma_division) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (build_dvlut(h, sigma_vi)) return 1;
   unsigned long long* cnt = nullptr; CK(dmalloc(&cnt, 2));
   CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->st));
@@ -1914,7 +1963,7 @@ extern "C" int cube_gpu_phase_times(cube_handle* h, float* ms) {
 }
 extern "C" int cube_gpu_timer(cube_handle* h, int start, float* ms) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->p.device));
+  if (enter(h)) return 1;
   if (start) { CK(cudaEventRecord(h->tev[0], h->st)); return 0; }
   if (h->vghost_pending) CK(cudaStreamWaitEvent(h->st, h->ev_vghost, 0));  // the stopwatch covers a ghost exchange still in flight on the side stream
   if (h->xghost_pending) CK(cudaStreamWaitEvent(h->st, h->ev_xghost, 0));

@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(PC_T, 4) k_drift_key_chain(Geom g, const typen
                                                             const long long* __restrict__ cstart_p, const float* __restrict__ vfield_p,
                                                             const double* __restrict__ dvlut, double dt_mid, unsigned short* __restrict__ key,
                                                             unsigned* __restrict__ rank, int* __restrict__ maxoff, unsigned* __restrict__ mask_s,
-                                                            unsigned char* __restrict__ inflag, int* __restrict__ rhoc_new, float* __restrict__ vfield_new) {
+                                                            unsigned char* __restrict__ inflag, int* __restrict__ rhoc_new, float* __restrict__ vfield_new,
+                                                            long long cell_base /* first cell of this launch: a streamed upload is keyed chunk by chunk */) {
   extern __shared__ __align__(16) unsigned char kc_smem[];
   double* sv = reinterpret_cast<double*>(kc_smem);                               // [3][KC_CAPV] velocities of the chunk's particles
   unsigned char* scl = reinterpret_cast<unsigned char*>(sv + 3 * KC_CAPV);       // [KC_CAPV] cell of the particle | 0x80 = leaves its cell
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(PC_T, 4) k_drift_key_chain(Geom g, const typen
   __shared__ float svf[PC_CELLS * 3];
   __shared__ int s_cnt[PC_CELLS];  // movers of the cell
   static_assert(PC_CELLS <= 128, "cell index and mover flag share a byte");
-  const long long c0 = (long long)blockIdx.x * PC_CELLS;
+  const long long c0 = cell_base + (long long)blockIdx.x * PC_CELLS;
   for (int t = threadIdx.x; t < PC_CELLS * MASK_W; t += PC_T) smask[t] = 0u;
   for (int t = threadIdx.x; t < PC_CELLS * 3; t += PC_T) svf[t] = c0 * 3 + t < g.ncell_p * 3 ? vfield_p[c0 * 3 + t] : 0.f;
   for (int t = threadIdx.x; t < PC_CELLS; t += PC_T) s_cnt[t] = 0;

@@ -48,6 +48,7 @@ def load_library():
     vp, i64, f32, i32 = C.c_void_p, C.c_int64, C.c_float, C.c_int
     L.cube_gpu_init.argtypes = [C.POINTER(CubeParams), vp, vp, vp, vp, C.POINTER(vp)]
     L.cube_gpu_upload.argtypes = [vp, vp, vp, vp, vp, i64, i64, f32]
+    L.cube_gpu_upload_begin.argtypes = [vp, vp, vp, vp, vp, i64, i64, f32]
     L.cube_gpu_update_x.argtypes = [vp, f32, f32, C.POINTER(i64), C.POINTER(f32), C.POINTER(C.c_double * 3), C.POINTER(f32)]
     L.cube_gpu_buffer.argtypes = [vp, i32, i32, i32, C.POINTER(f32)]
     L.cube_gpu_particle_mesh.argtypes = [vp, f32, f32] + [C.POINTER(f32)] * 4
@@ -96,6 +97,7 @@ ABI_SYMBOLS = [
     "cube_gpu_phase_name", "cube_gpu_phase_times", "cube_gpu_set_profiling", "cube_gpu_timer", "cube_gpu_nccl_unique_id",
     "cube_gpu_exchange_plan", "cube_gpu_download_async", "cube_gpu_download_cells_async", "cube_gpu_stream_vp", "cube_gpu_selftest_codes",
     "cube_gpu_upload_pid", "cube_gpu_download_pid", "cube_gpu_power_spectrum", "cube_gpu_set_drift_layers", "cube_gpu_get_vmax3", "cube_gpu_set_mass_p", "cube_gpu_particle_mesh_species",
+    "cube_gpu_upload_begin",
 ]
 
 
@@ -220,7 +222,9 @@ class CubeGPU:
         return be.value, bd.value, ok.value
 
     # ---- particle_initialization / checkpoint ------------------------------------------------
-    def particle_initialization(self, state, sigma_vi, npglobal=None):
+    def particle_initialization(self, state, sigma_vi, npglobal=None, streamed=False):
+        """``streamed``: return while xp and vp (page-locked arrays, left untouched until the next ``update_particle`` has returned)
+        are still being copied; ``update_particle`` then keys them chunk by chunk as they land (cube_gpu_upload_begin)."""
         if np.asarray(state["xp"]).dtype != self.xdt or np.asarray(state["vp"]).dtype != self.vdt:
             # particle_initialization.f90:14-18: a run built for (izipx, izipv) stops on a state in another format
             raise RuntimeError("zip format incompatable: this run has izipx=%d izipv=%d, the state holds %s/%s"
@@ -228,7 +232,9 @@ class CubeGPU:
         xp = np.ascontiguousarray(state["xp"], self.xdt); vp = np.ascontiguousarray(state["vp"], self.vdt)
         rc = np.ascontiguousarray(state["rhoc"], np.int32); vf = np.ascontiguousarray(state["vfield"], np.float32)
         n = xp.shape[0]
-        self._ck(self.L.cube_gpu_upload(self.h, _p(xp), _p(vp), _p(rc), _p(vf), n, npglobal or n, F32(sigma_vi)))
+        up = self.L.cube_gpu_upload_begin if streamed else self.L.cube_gpu_upload
+        self._ck(up(self.h, _p(xp), _p(vp), _p(rc), _p(vf), n, npglobal or n, F32(sigma_vi)))
+        self._upload_keep = (xp, vp) if streamed else None     # the arrays the copy engine is still reading
         self.nplocal = n
         self.sigma_vi = F32(sigma_vi)
         self.has_pid = "pid" in state

@@ -50,6 +50,16 @@ module cube_gpu
       integer(c_int64_t), value :: nplocal, npglobal
       real(c_float), value :: sigma_vi
     end function
+    ! the same, returning while xp and vp (page-locked, untouched until cube_gpu_update_x has returned) are still being copied
+    integer(c_int) function cube_gpu_upload_begin(h, xp, vp, rhoc_phys, vfield_phys, nplocal, npglobal, sigma_vi) bind(C, name="cube_gpu_upload_begin")
+      import :: c_int, c_ptr, c_int32_t, c_int64_t, c_float
+      type(c_ptr), value :: h
+      type(c_ptr), value :: xp, vp                       ! c_loc(xp), c_loc(vp): integer(izipx) xp(3,*), integer(izipv) vp(3,*)
+      integer(c_int32_t), intent(in) :: rhoc_phys(*)     ! rhoc(1:nt,1:nt,1:nt,:,:,:) contiguous copy
+      real(c_float), intent(in) :: vfield_phys(*)        ! vfield(:,1:nt,1:nt,1:nt,:,:,:)
+      integer(c_int64_t), value :: nplocal, npglobal
+      real(c_float), value :: sigma_vi
+    end function
     ! update_particle.f90:1-213
     integer(c_int) function cube_gpu_update_x(h, dt_old, dt, nplocal, sigma_vi_new, std_vsim, overhead_tile) bind(C, name="cube_gpu_update_x")
       import :: c_int, c_ptr, c_int64_t, c_float, c_double

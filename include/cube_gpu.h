@@ -74,6 +74,12 @@ int cube_gpu_nccl_unique_id(void *id128);
 int cube_gpu_upload(cube_handle *h, const void *xp, const void *vp, const int32_t *rhoc_phys,
                     const float *vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi);
 
+/* The same, returning while xp and vp are still on the bus (the cell arrays and their scan are done): xp and vp must be page-locked
+ * and stay unchanged until the next call that uses the particles has returned.  cube_gpu_update_x keys the particles chunk by
+ * chunk as they land (its first pass then runs under the transfer); every other entry point first waits for the whole upload. */
+int cube_gpu_upload_begin(cube_handle *h, const void *xp, const void *vp, const int32_t *rhoc_phys,
+                          const float *vfield_phys, int64_t nplocal, int64_t npglobal, float sigma_vi);
+
 /* update_particle (update_particle.f90:1-213): drift + cell re-sort + vfield rebuild + sigma statistics.
  * in: buffered state; out: disjoint state.  std_vsim = {std_vsim, std_vsim_c, std_vsim_res}. */
 int cube_gpu_update_x(cube_handle *h, float dt_old, float dt, int64_t *nplocal, float *sigma_vi_new,

@@ -316,6 +316,37 @@ def test_velocities_streamed_per_batch_equal_the_plain_step(tables):
         assert pa[k] == pb[k], k
 
 
+def test_streamed_upload_equals_the_plain_one(tables):
+    """cube_gpu_upload_begin: the particles arrive in chunks on the copy stream and update_x keys every chunk as it lands -- the
+    same state after the drift as with cube_gpu_upload; a checkpoint taken right after the streamed upload (an entry point that
+    waits for the whole of it) returns what was uploaded."""
+    import torch
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    fk, ck = tables
+    states, sig, _ = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=19, disp_rms=0.7)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in states[0].items()}
+    dt = np.float32(0.9)
+    out = []
+    for streamed in (False, True):
+        G = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC)
+        G.particle_initialization(pin, sig, streamed=streamed)
+        if streamed:
+            back, _ = G.checkpoint()
+            for k in ("xp", "vp", "rhoc", "vfield"):
+                assert np.array_equal(back[k], states[0][k]), k
+            G.particle_initialization(pin, sig, streamed=True)    # again: this time update_particle meets the chunks
+        G.buffer_density(); G.buffer_x(); G.buffer_v()
+        u = G.update_particle(np.float32(0), dt)
+        st, _ = G.checkpoint()
+        out.append((st, u))
+        G.close()
+    (a, ua), (b, ub) = out
+    for k in ("xp", "vp", "rhoc", "vfield"):
+        assert np.array_equal(a[k], b[k]), k
+    assert ua == ub
+
+
 def test_cubenu_order_and_vmax3(tables):
     """CUBEnu's bookkeeping of the same arithmetic (cube_gpu_set_drift_layers / cube_gpu_get_vmax3): update_xp visits the source
     planes in nlayer colour passes (CUBEnu update_particle.f90:37,55-58), which changes the order of the particles inside a
