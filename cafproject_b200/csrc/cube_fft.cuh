@@ -369,15 +369,17 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), MINB) k_fft_y(FftGeo
 // own axis, even in the others: kernel_f.f90:32-38 mirrors the table that way).
 // ---------------------------------------------------------------------------------------------
 
-template <int R1, int R2, class ZM = Sc>
-__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 : 1)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
+// NB = 2: the next tile's lines are prefetched into the other half of a double buffer; NB = 1: one buffer, so that three CTAs fit an
+// SM (N <= 320) and cover each other's loads instead
+template <int R1, int R2, class ZM = Sc, int NB = 2>
+__global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? (NB == 1 ? 3 : 2) : 1)) k_fft_z_green(FftGeom g, const float2* __restrict__ A, float2* __restrict__ B,
                                                                             const float* __restrict__ kern, float scale,
                                                                             const float2* __restrict__ tw_g) {
   constexpr int N = R1 * R2, LW = FL, NT = FL * (R1 > R2 ? R1 : R2), NHZ = N / 2 + 1;
   extern __shared__ float2 smem[];
-  float2* sbuf = smem;                                          // [2][N][16]
-  float2* tw = smem + 2 * N * LW;                               // [N]
-  float* ks = reinterpret_cast<float*>(smem + 2 * N * LW + N);  // [3][NHZ][16]
+  float2* sbuf = smem;                                           // [NB][N][16]
+  float2* tw = smem + NB * N * LW;                               // [N]
+  float* ks = reinterpret_cast<float*>(smem + NB * N * LW + N);  // [3][NHZ][16]
   const int tid = threadIdx.x, line = tid % FL, idx = tid / FL;
   const int kx0 = blockIdx.x * FL, kx = kx0 + line, ky = blockIdx.y;
   const bool act = kx < g.NH;
@@ -392,17 +394,22 @@ __global__ void __launch_bounds__(FL * (R1 > R2 ? R1 : R2), (R1 * R2 <= 320 ? 2 
     }
     cp_async_commit();
   };
-  prefetch(0, sbuf);
+  if (NB == 2) prefetch(0, sbuf);
   load_tw(tw, tw_g, N);
   for (int q = idx; q < 3 * NHZ; q += NT / FL) {
     const int d = q / NHZ, kz = q - d * NHZ;
     ks[q * FL + line] = act ? kern[((size_t)(d * N + kz) * N + ky) * g.P + kx] * scale : 0.f;
   }
   for (int b = 0; b < g.nbatch; b++) {
-    float2* s = sbuf + (b & 1) * N * LW;
+    float2* s = sbuf + (NB == 2 ? (b & 1) : 0) * N * LW;
     __syncthreads();  // the other buffer's readers (tile b-1) are done; also orders the ks/tw fill
-    if (b + 1 < g.nbatch) { prefetch(b + 1, sbuf + ((b + 1) & 1) * N * LW); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    if (NB == 2) {
+      if (b + 1 < g.nbatch) { prefetch(b + 1, sbuf + ((b + 1) & 1) * N * LW); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+    } else {
+      prefetch(b, s);
+      cp_async_wait<0>();
+    }
     __syncthreads();
     if (act) fft_step_a<R1, R2, -1, LW, ZM>(s, tw, line, idx);
     __syncthreads();
@@ -459,7 +466,7 @@ template <int R1, int R2> struct X3Cfg {
   static constexpr size_t SMEM = (size_t)(BUF + N) * sizeof(float2);
 };
 template <int R1, int R2>
-__global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 2) k_fft_x_inv3(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
+__global__ void __launch_bounds__(X3Cfg<R1, R2>::NT, 3) k_fft_x_inv3(FftGeom g, const float2* __restrict__ B, float* __restrict__ F,
                                                                      const float2* __restrict__ tw_g, unsigned* __restrict__ f2max) {
   using C = X3Cfg<R1, R2>;
   constexpr int N = C::N, NT = C::NT, NHC = N / 2 + 1, TP = C::TP;

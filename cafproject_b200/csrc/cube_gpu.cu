@@ -77,7 +77,7 @@ struct FftPlan {
   void (*y_inv)(FftGeom, float2*, const float2*);
   void (*z_green)(FftGeom, const float2*, float2*, const float*, float, const float2*);
   void (*z_green_pk)(FftGeom, const float2*, float2*, const float*, float, const float2*);  // A/B variants of the z pass's arithmetic
-  void (*z_green_mx)(FftGeom, const float2*, float2*, const float*, float, const float2*);
+  void (*z_green_mx)(FftGeom, const float2*, float2*, const float*, float, const float2*);  // single-buffered, three CTAs per SM ("sb")
   void (*x_inv)(FftGeom, const float2*, float*, const float2*, unsigned*);
   int x_inv_threads; size_t x_inv_smem;
   int N() const { return R1 * R2; }
@@ -85,7 +85,7 @@ struct FftPlan {
 };
 template <int R1, int R2> static FftPlan make_plan() {
   return {R1, R2, k_fft_x_fwd<R1, R2>, k_fft_y<R1, R2, -1>, k_fft_y<R1, R2, +1, (R1 * R2 <= 320 ? 4 : 0)>,
-          k_fft_z_green<R1, R2>, k_fft_z_green<R1, R2, Pk>, k_fft_z_green<R1, R2, Mx>, k_fft_x_inv3<R1, R2>,
+          k_fft_z_green<R1, R2>, k_fft_z_green<R1, R2, Pk>, k_fft_z_green<R1, R2, Sc, 1>, k_fft_x_inv3<R1, R2>,
           X3Cfg<R1, R2>::NT, X3Cfg<R1, R2>::SMEM};
 }
 // N must be >= nft + 32 (see cube_fft.cuh); nt = 12,16,24,32,48,64,128 map to 80,96,128,160,256,288,576
@@ -1389,8 +1389,9 @@ static int fine_mesh(cube_handle* h, int tile0, int nb, bool prefix, float a_mid
     float scale = 1.0f / ((float)N * (float)N * (float)N);
     if (prefix) scale *= ((1.0f * a_mid) * dt) / 6.0f / PI_F;
     const char* zg = getenv("CUBE_GPU_ZG");
-    auto zk = zg && !strcmp(zg, "pk") ? pl.z_green_pk : zg && !strcmp(zg, "mx") ? pl.z_green_mx : pl.z_green;
-    zk<<<dim3(f.P / FL, N), T, smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
+    const bool sb = zg && !strcmp(zg, "sb");
+    auto zk = zg && !strcmp(zg, "pk") ? pl.z_green_pk : sb ? pl.z_green_mx : pl.z_green;
+    zk<<<dim3(f.P / FL, N), T, sb ? smem_z - (size_t)N * FL * sizeof(float2) : smem_z, h->st>>>(f, h->Ak, h->Bk, h->kern_f, scale, h->tw); CKL();
   }
   {
     PhaseTimer pt(h, PH_IFFTY);
