@@ -1484,7 +1484,10 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
   // streamed velocities (cube_gpu_stream_vp): smaller batches, coarse kick per batch, the batch's vp out under the next batch
   void* const vp_host = h->vp_stream_host;
   h->vp_stream_host = nullptr;
-  const int step_batch = vp_host ? align_batch(g.nnt, std::max(1, std::min(h->batch, (ntile + 7) / 8))) : h->batch;  // the last batch's velocities are the exposed tail
+  // streamed velocities: batches of a quarter of the tiles, then 1/8, then 1/16 + 1/16 -- a batch's velocities leave under the next
+  // batch, the last batch's are the exposed tail, and every launch of the z pass reloads its Green table (0.75 tiles' worth)
+  const int step_batch = vp_host ? align_batch(g.nnt, std::max(1, std::min(h->batch, (ntile + 3) / 4))) : h->batch;
+  const int step_min = vp_host ? align_batch(g.nnt, std::max(1, std::min(step_batch, (ntile + 15) / 16))) : h->batch;
   std::vector<long long> tile_start(ntile + 1, 0);
   const bool merged = !h->old_kick;  // one pass per batch does both kicks (cube_kick.cuh); else fine kick per batch, coarse kick at the end
   const bool kick_c_per_batch = merged || vp_host;
@@ -1514,8 +1517,9 @@ extern "C" int cube_gpu_particle_mesh(cube_handle* h, float a_mid, float dt, flo
                      h->rho_n * sizeof(float) + h->B_n * step_batch * sizeof(float2) <= h->B_n * h->batch * sizeof(float2);
   if (split) h->rho = reinterpret_cast<float*>(h->Bk + h->B_n * step_batch);
   RhoView group;
-  for (int t0 = 0; t0 < ntile; t0 += step_batch) {
-    const int nb = std::min(step_batch, ntile - t0);
+  for (int t0 = 0, nb = 0; t0 < ntile; t0 += nb) {
+    nb = std::min(step_batch, ntile - t0);
+    if (vp_host && ntile - t0 <= step_batch && nb > step_min) nb = std::max(step_min, align_batch(g.nnt, nb / 2));  // the tapering tail
     if (split && t0 % h->batch == 0 && fine_density_batch(h, t0, std::min(h->batch, ntile - t0), group)) return 1;
     if (fine_mesh(h, t0, nb, pre_in_fft, a_mid, dt, nullptr, split ? &group : nullptr)) return 1;
     CK(h->rb.read(f2.data() + t0, h->f2max, sizeof(float) * nb, h->st));

@@ -218,3 +218,69 @@ def test_particle_ids_cross_image_boundaries(tables, nn, nc, nnt):
     finally:
         run_images(nimg, lambda m: Gs[m].close())
         O.close()
+
+
+def test_two_species_on_two_images(tables):
+    """cube_gpu_particle_mesh_species with several images (BASELINE cfg 4's shape): every image holds both species, each species
+    has its own ghost exchange, the coarse density of both goes through one distributed transform.  By construction as in
+    test_gpu_two_species.py: the particles of a one-species 2x1x1 state dealt alternately to two species reproduce the
+    one-species kick (codes within the rare one-unit flips) and time-step limits; then both species drift and nobody is lost."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    from test_gpu_two_species import _split
+    fk, ck = tables
+    nn, nc, nnt = (2, 1, 1), 24, 2
+    nimg = 2
+    states, sig, info = make_ic(nn=nn, nc=nc, nnt=nnt, np_nc=NP_NC, seed=77, disp_rms=0.8)
+    npg = info["npglobal"]
+    lut = co.tanf_lut()
+    a_mid, dt = np.float32(0.021), np.float32(0.8)
+    mass_p = float((4 * nc) ** 3 * nimg) / npg
+    _group[0] += 3
+    g1, ga, gb = _group[0] - 2, _group[0] - 1, _group[0]
+
+    def one(m):
+        G = CubeGPU(nc, nnt, fk, ck, nn=nn, rank=m, np_nc=NP_NC, tanf_lut=lut, local_group=g1, fine_batch=2)
+        try:
+            G.particle_initialization(states[m], sig, npglobal=npg)
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+            pm = G.particle_mesh(a_mid, dt)
+            st, _ = G.checkpoint()
+            return pm, {k: np.array(v, copy=True) for k, v in st.items()}
+        finally:
+            G.close()
+    ref = run_images(nimg, one)
+    halves = [_split(states[m]) for m in range(nimg)]
+    npa = sum(h[0][1]["xp"].shape[0] for h in halves); npb = sum(h[1][1]["xp"].shape[0] for h in halves)
+
+    def two(m):
+        GA = CubeGPU(nc, nnt, fk, ck, nn=nn, rank=m, np_nc=NP_NC, tanf_lut=lut, local_group=ga, fine_batch=2)
+        GB = CubeGPU(nc, nnt, fk, ck, nn=nn, rank=m, np_nc=NP_NC, tanf_lut=lut, local_group=gb, fine_batch=2, secondary=True)
+        try:
+            for Gs, (mask, s), npgs in ((GA, halves[m][0], npa), (GB, halves[m][1], npb)):
+                Gs.particle_initialization(s, sig, npglobal=npgs)
+                Gs.set_mass_p(mass_p)
+                Gs.buffer_density(); Gs.buffer_x(); Gs.buffer_v()
+            pm = GA.particle_mesh_species(GB, a_mid, dt)
+            for Gs in (GA, GB):
+                Gs.buffer_v()
+            ca, _ = GA.checkpoint(); cb, _ = GB.checkpoint()
+            ca = {k: np.array(v, copy=True) for k, v in ca.items()}; cb = {k: np.array(v, copy=True) for k, v in cb.items()}
+            for Gs in (GA, GB):
+                Gs.buffer_density(); Gs.buffer_x(); Gs.buffer_v()
+            ua = GA.update_particle(dt, dt); ub = GB.update_particle(dt, dt)
+            return pm, ca, cb, ua["nplocal"], ub["nplocal"]
+        finally:
+            GA.close(); GB.close()
+    got = run_images(nimg, two)
+    for m in range(nimg):
+        pm1, st1 = ref[m]
+        pm2, ca, cb, _, _ = got[m]
+        for k in ("dt_fine", "dt_coarse"):
+            assert abs(float(pm2[k]) - float(pm1[k])) <= 1e-5 * float(pm1[k]), (m, k)
+        for (mask, _), c in ((halves[m][0], ca), (halves[m][1], cb)):
+            assert np.array_equal(c["xp"], st1["xp"][mask])
+            dv = np.abs(c["vp"].astype(np.int32) - st1["vp"][mask].astype(np.int32))
+            assert dv.max() <= 2 and (dv != 0).mean() < 1e-3, (m, dv.max(), (dv != 0).mean())
+    assert sum(g[3] for g in got) == npa and sum(g[4] for g in got) == npb
