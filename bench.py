@@ -491,15 +491,16 @@ def main():
 
     # ---- late-time (clustered) state: the same ICs evolved to z=0 by the product's own step loop, then timed ----------------
     late = None
-    if world == 1 and not args.no_late and args.species == 1:
+    if not args.no_late and args.species == 1:
         from cafproject_b200.timestep import Cosmology, TimeStepper
-        G = CubeGPU(nc, nnt, fk, ck, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut())
-        G.particle_initialization(st, sig)
+        G = CubeGPU(nc, nnt, fk, ck, nn=image_grid(world), rank=rank, np_nc=2, device=local_rank, fine_batch=args.fine_batch, tanf_lut=host_tanf_lut(),
+                    nccl_id=shared_nccl_id(device="cuda") if world > 1 else None)
+        G.particle_initialization(st, sig, npglobal=world * npart)
         G.buffer_density(); G.buffer_x(); G.buffer_v()
         ts = TimeStepper(Cosmology(), [0.0])
         t0 = time.perf_counter()
         nev = 0
-        while nev < 400 and time.perf_counter() - t0 < 120.0:
+        while nev < 400 and (world > 1 or time.perf_counter() - t0 < 120.0):   # (every image must take the same number of steps)
             dto, dtn, am = ts.step()
             G.update_particle(dto, dtn); G.buffer_density(); G.buffer_x()
             ts.limits(G.particle_mesh(am, dtn)); G.buffer_v()
@@ -515,10 +516,12 @@ def main():
         for _ in range(nl):
             G.update_particle(dtl, dtl); G.buffer_density(); G.buffer_x(); G.particle_mesh(aml, dtl); G.buffer_v()
         msl = G.timer_stop() / nl
+        if world > 1:
+            t = torch.tensor([msl], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); msl = float(t.item())
         G.set_profiling(True); G.phase_times()
         G.update_particle(dtl, dtl); G.buffer_density(); G.buffer_x(); G.particle_mesh(aml, dtl); G.buffer_v()
         phl = {k: v for k, v in G.phase_times().items() if v > 0}
-        late = {"z": 1.0 / float(ts.a) - 1.0, "steps_evolved": nev, "ms_per_step": msl, "value": npart / (msl * 1e-3), "unit": UNIT,
+        late = {"z": 1.0 / float(ts.a) - 1.0, "steps_evolved": nev, "ms_per_step": msl, "value": world * npart / (msl * 1e-3), "unit": UNIT,
                 "drift_radius": G.query("drift_radius"), "phases_ms_per_step": phl,
                 "note": "the bench ICs evolved from z=49 by the adaptive step loop (cafcube.f90:25-46), then timed: haloes, empty cells"}
         G.close()
