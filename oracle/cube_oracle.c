@@ -209,6 +209,8 @@ float oracle_get_sigma_vi_new(ctx_t *c) { return c->sigma_vi_new; }
 void oracle_set_sigma_vi(ctx_t *c, float s) { c->sigma_vi = s; }
 void oracle_set_sigma_vi_new(ctx_t *c, float s) { c->sigma_vi_new = s; }
 float oracle_mass_p(ctx_t *c) { return c->mass_p; }
+/* a species of a multi-species run carries its own particle mass (CUBEnu pm.f90:79-99 deposits mass_p_cdm / mass_p_nu) */
+void oracle_set_mass_p(ctx_t *c, float mp) { c->mass_p = mp; }
 i64 oracle_npglobal(ctx_t *c) { return c->npglobal; }
 int oracle_error(ctx_t *c) { return c->error; }
 const char *oracle_errmsg(ctx_t *c) { return c->errmsg; }

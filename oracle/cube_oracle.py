@@ -74,6 +74,7 @@ def lib():
             getattr(L, "oracle_" + name).restype = f32
             getattr(L, "oracle_" + name).argtypes = [vp]
         L.oracle_set_sigma_vi.argtypes = [vp, f32]
+        L.oracle_set_mass_p.argtypes = [vp, f32]
         L.oracle_set_sigma_vi_new.argtypes = [vp, f32]
         L.oracle_vmax.restype = f32
         L.oracle_vmax.argtypes = [vp, i64]
@@ -601,6 +602,9 @@ class Oracle:
             out["meshes"] = kept
         return out
 
+    def set_mass_p(self, mass_p):
+        lib().oracle_set_mass_p(self.h, F32(mass_p))
+
     # ---- whole step, cafcube.f90:26-31 --------------------------------------------------------
     def step(self, dt_old, dt, a_mid, keep=False):
         up = self.update_particle(dt_old, dt)
@@ -608,3 +612,40 @@ class Oracle:
         pm = self.particle_mesh(a_mid, dt, keep=keep)
         self.buffer_v()
         return up, pm
+
+
+def particle_mesh_two_species(A, B, a_mid, dt):
+    """``particle_mesh`` of a two-species run as CUBEnu's pm.f90 reads with NEUTRINOS (pm.f90:79-99: both species are deposited
+    into the same rho_f; :130-163: and into the same r3; :196-228 and its neutrino twin: each species is kicked from the common
+    force with its own sigma_vi), composed from the one-species restatement: ``A`` and ``B`` are two :class:`Oracle` objects on
+    the same geometry holding one species each (own ``mass_p``, own ``sigma_vi``).  The reference adds the second species'
+    terms into the array that already holds the first one's; here the two deposits are summed afterwards (f32 round-off of a
+    different grouping, far below the 1e-6 density gate).  That build does not compile upstream, so this is a
+    reading of the code, unpinned.  Returns the dt limits over both species."""
+    L = lib()
+    a_mid, dt = F32(a_mid), F32(dt)
+    assert (A.nn, A.nnt, A.nc) == (B.nn, B.nnt, B.nc)
+    for O in (A, B):
+        L.oracle_pm_begin(O.h)
+    for m in range(A.nimg):
+        for tz in range(1, A.nnt + 1):
+            for ty in range(1, A.nnt + 1):
+                for tx in range(1, A.nnt + 1):
+                    rho = A.fine_density(m, tx, ty, tz) + B.fine_density(m, tx, ty, tz)
+                    ff = A.fine_force(rho)
+                    for O in (A, B):
+                        L.oracle_fine_kick(O.h, m, tx, ty, tz, _ptr(ff), a_mid, dt)
+    for O in (A, B):
+        L.oracle_pm_fine_end(O.h)
+    fcg = A.coarse_force(A.coarse_density() + B.coarse_density())
+    for m in range(A.nimg):
+        fc = A.force_c_image(fcg, m)
+        for O in (A, B):
+            L.oracle_coarse_kick(O.h, m, _ptr(fc), a_mid, dt)
+    GG = F32(1.0) / F32(6.0) / PI_F
+    t = A.nnt ** 3
+    f2f = max(float(np.ctypeslib.as_array((C.c_float * t).from_address(L.oracle_f2_max_fine(A.h, m))).max()) for m in range(A.nimg))
+    f2c = max(float(L.oracle_f2_max_coarse(A.h, m)) for m in range(A.nimg))
+    vmax = [max(float(L.oracle_vmax(O.h, m)) for m in range(O.nimg)) for O in (A, B)]
+    return dict(dt_fine=np.sqrt(F32(1.0) / (np.sqrt(F32(f2f)) * a_mid * GG)), dt_coarse=np.sqrt(F32(A.ncell) / (np.sqrt(F32(f2c)) * a_mid * GG)),
+                dt_vmax=F32(0.9) * F32(20) / F32(max(vmax)), vmax=F32(vmax[0]), vmax2=F32(vmax[1]))

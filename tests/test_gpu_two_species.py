@@ -10,6 +10,8 @@ one-unit flips of codes that sit on a quantiser boundary.  Then each species dri
 import numpy as np
 import pytest
 
+from conftest import physical
+
 pytestmark = pytest.mark.gpu
 
 NC, NNT, NP_NC = 24, 2, 2
@@ -80,6 +82,58 @@ def test_two_species_equal_the_one_species_run(tables):
         assert ua["nplocal"] + ub["nplocal"] == n
     finally:
         GA.close(); GB.close()
+
+
+def test_two_species_against_the_composed_oracle(tables):
+    """Two DIFFERENT species (own particles, own mass -- 90 % / 10 % of the total -- own velocity dispersion and sigma_vi, as CDM and
+    a hot light species) against CUBEnu's two-species particle_mesh as composed from the one-species restatement
+    (oracle/cube_oracle.py::particle_mesh_two_species; that build does not compile upstream: parity unpinned).  Each side computes
+    its own FFTs, so the gates are those of a full step (test_gpu_parity.py::test_full_steps): time-step limits to 1e-4, velocity
+    codes equal except for rare flips of codes on a quantiser boundary."""
+    from cafproject_b200.cube import CubeGPU
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    fk, ck = tables
+    sa, sig_a, ia = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=71, disp_rms=0.8)
+    sb, sig_b, ib = make_ic(nn=1, nc=NC, nnt=NNT, np_nc=NP_NC, seed=72, disp_rms=0.8, velocity_boost=3.0)
+    assert sig_b > 2 * sig_a
+    na, nb = sa[0]["xp"].shape[0], sb[0]["xp"].shape[0]
+    nf3 = float((4 * NC) ** 3)
+    mass_a, mass_b = np.float32(0.9 * nf3 / na), np.float32(0.1 * nf3 / nb)
+    a_mid, dt = np.float32(0.021), np.float32(0.8)
+    OA = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    OB = co.Oracle(nn=1, nnt=NNT, nc=NC, np_nc=NP_NC, fk_table=fk, ck_table=ck)
+    lut = co.tanf_lut()
+    GA = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=lut)
+    GB = CubeGPU(NC, NNT, fk, ck, np_nc=NP_NC, tanf_lut=lut, secondary=True)
+    try:
+        for O, st, sig, mp in ((OA, sa, sig_a, mass_a), (OB, sb, sig_b, mass_b)):
+            O.load(st, sig); O.set_mass_p(mp)
+            O.buffer_density(); O.buffer_x(); O.buffer_v()
+        po = co.particle_mesh_two_species(OA, OB, a_mid, dt)
+        for G, st, sig, mp in ((GA, sa, sig_a, mass_a), (GB, sb, sig_b, mass_b)):
+            G.particle_initialization(st[0], sig); G.set_mass_p(mp)
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+        pg = GA.particle_mesh_species(GB, a_mid, dt)
+        for k in ("dt_fine", "dt_coarse"):
+            assert abs(float(pg[k]) - float(po[k])) <= 1e-4 * float(po[k]), (k, pg[k], po[k])
+        for k in ("vmax", "vmax2"):
+            assert abs(float(pg[k]) - float(po[k])) <= 1e-3 * float(po[k]), (k, pg[k], po[k])
+        assert float(pg["vmax2"]) > 1.5 * float(pg["vmax"])        # the second species is the hot one
+        for G, O, name in ((GA, OA, "A"), (GB, OB, "B")):
+            got, _ = G.checkpoint()
+            vo = physical(O, "vp", 0)
+            assert np.array_equal(got["xp"], physical(O, "xp", 0)), name
+            dv = np.abs(got["vp"].astype(np.int32) - vo.astype(np.int32))
+            assert dv.max() <= 2 and (dv != 0).mean() < 2e-3, (name, dv.max(), (dv != 0).mean())
+        # the deposit did weigh the species: with equal masses instead the forces (and dt_fine) differ
+        for G, st, sig in ((GA, sa, sig_a), (GB, sb, sig_b)):
+            G.particle_initialization(st[0], sig); G.set_mass_p(np.float32(0.5 * nf3 / na))
+            G.buffer_density(); G.buffer_x(); G.buffer_v()
+        pe = GA.particle_mesh_species(GB, a_mid, dt)
+        assert abs(float(pe["dt_fine"]) - float(po["dt_fine"])) > 1e-3 * float(po["dt_fine"])
+    finally:
+        GA.close(); GB.close(); OA.close(); OB.close()
 
 
 def test_species_must_share_the_geometry(tables):

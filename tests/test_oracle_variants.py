@@ -443,3 +443,39 @@ def test_extreme_velocity_codes_round_trip(co):
             assert np.isfinite(v) and L.oracle_probe_vencode(O.h, v, F32(0.2)) == c
         assert L.oracle_probe_vencode(O.h, 1e300, F32(0.2)) == top and L.oracle_probe_vencode(O.h, -1e300, F32(0.2)) == -top
         O.close()
+
+
+def test_two_species_composition_reduces_to_one_species(tables):
+    """oracle.particle_mesh_two_species (CUBEnu pm.f90 with NEUTRINOS, composed from the one-species restatement) on a one-species
+    state dealt alternately to two species of the same particle mass and sigma_vi: the same time-step limits and, up to rare flips of
+    codes on a quantiser boundary (the two deposits are summed in another order), the same kicked velocities as particle_mesh."""
+    from cafproject_b200.synthetic_ic import make_ic
+    from oracle import cube_oracle as co
+    from test_gpu_two_species import _split
+    fk, ck = tables
+    nc, nnt = 24, 2
+    st, sig, _ = make_ic(nn=1, nc=nc, nnt=nnt, np_nc=2, seed=5, disp_rms=0.7)
+    a_mid, dt = np.float32(0.021), np.float32(0.8)
+    O = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    A = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    B = co.Oracle(nn=1, nnt=nnt, nc=nc, np_nc=2, fk_table=fk, ck_table=ck)
+    try:
+        O.load(st, sig); O.buffer_density(); O.buffer_x(); O.buffer_v()
+        p1 = O.particle_mesh(a_mid, dt)
+        (ma, sa), (mb, sb) = _split(st[0])
+        for X, s in ((A, sa), (B, sb)):
+            X.load([s], sig); X.set_mass_p(O.mass_p)
+            assert X.mass_p == O.mass_p
+            X.buffer_density(); X.buffer_x(); X.buffer_v()
+        p2 = co.particle_mesh_two_species(A, B, a_mid, dt)
+        for k in ("dt_fine", "dt_coarse", "dt_vmax"):
+            assert abs(float(p1[k]) - float(p2[k])) <= 1e-6 * float(p1[k]), k
+        assert max(float(p2["vmax"]), float(p2["vmax2"])) == float(max(p1["vmax"]))
+        v1 = physical(O, "vp")
+        for m, X in ((ma, A), (mb, B)):
+            assert np.array_equal(physical(X, "xp"), physical(O, "xp")[m])
+            dv = np.abs(v1[m].astype(np.int32) - physical(X, "vp").astype(np.int32))
+            assert dv.max() <= 2 and (dv != 0).mean() < 2e-3
+        assert A.sigma_vi == O.sigma_vi and B.sigma_vi == O.sigma_vi     # pm.f90:122 on both
+    finally:
+        O.close(); A.close(); B.close()
